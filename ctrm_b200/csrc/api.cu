@@ -1,0 +1,817 @@
+// C-ABI of libctrm_b200 (include/ctrm_b200.h): context, uploads, stage entry points, the graph-captured
+// roll-out driver and the host-buffer wrappers with the pybind11 helpers' call shapes.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+int ctrm_fail(int code, const char* what) {
+  g_last_error = what ? what : "";
+  return code;
+}
+int ctrm_fail_cuda(cudaError_t e, const char* what) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what ? what : "?");
+  g_last_error = buf;
+  return CTRM_ERR_CUDA;
+}
+
+#define CHECK(expr)         \
+  do {                      \
+    int _r = (expr);        \
+    if (_r != 0) return _r; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct DevArena {  // tracked device allocations
+  std::vector<void*> ptrs;
+  template <typename T>
+  int alloc(T** out, size_t n) {
+    *out = nullptr;
+    if (n == 0) n = 1;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e != cudaSuccess) return ctrm_fail_cuda(e, "cudaMalloc");
+    ptrs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return 0;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+struct ctrm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;  // internal non-blocking stream of the driver (graph capture is illegal on stream 0)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+  // weights
+  DevArena w_arena;
+  DevModel model{};
+  bool have_weights = false;
+  // batch (static part) + per-step tensors
+  DevArena b_arena;
+  Batch bt{};
+  bool have_batch = false;
+  std::vector<int32_t> h_agent_off, h_obs_off;
+  std::vector<double> h_speeds;
+  // roll-out state + roadmap store (sized by params)
+  DevArena r_arena;
+  int r_L = 0, r_S = 0, r_W = 0, r_K = 0, r_NT = 0, r_MT = 0, r_att = 0;
+  bool r_trace = false;
+  // tables
+  DevArena t_arena;
+  // results
+  DevArena c_arena;
+  int32_t* d_tfin = nullptr;
+  int64_t *d_agent_nv = nullptr, *d_agent_ne = nullptr, *d_totals = nullptr;
+  int64_t totals[3] = {0, 0, 0};
+  bool have_result = false;
+  bool trace = false;
+  int32_t* h_ndone = nullptr;  // pinned
+  float ms[3] = {0, 0, 0};
+  int64_t steps = 0, launches = 0;
+};
+
+static int sync_in(ctrm_ctx* c, cudaStream_t user) {
+  CTRM_CUDA_OK(cudaEventRecord(c->ev_in, user));
+  CTRM_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
+  return 0;
+}
+static int sync_out(ctrm_ctx* c, cudaStream_t user) {
+  CTRM_CUDA_OK(cudaEventRecord(c->ev_out, c->stream));
+  CTRM_CUDA_OK(cudaStreamWaitEvent(user, c->ev_out, 0));
+  return 0;
+}
+
+extern "C" int ctrm_abi_version(void) { return CTRM_B200_ABI_VERSION; }
+
+extern "C" const char* ctrm_last_error(const ctrm_ctx*) { return g_last_error.c_str(); }
+
+extern "C" int ctrm_ctx_create(int device, ctrm_ctx** out) {
+  if (!out) return ctrm_fail(CTRM_ERR_ARG, "ctrm_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return ctrm_fail_cuda(e, "cudaGetDeviceCount (no CUDA device: ctrm_b200 has no CPU fallback)");
+  if (device < 0 || device >= n) return ctrm_fail(CTRM_ERR_ARG, "ctrm_ctx_create: no such device");
+  CTRM_CUDA_OK(cudaSetDevice(device));
+  ctrm_ctx* c = new ctrm_ctx();
+  c->device = device;
+  CTRM_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CTRM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+  CTRM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+  for (int i = 0; i < 4; ++i) CTRM_CUDA_OK(cudaEventCreate(&c->ev_t[i]));
+  CTRM_CUDA_OK(cudaMallocHost(&c->h_ndone, sizeof(int32_t)));
+  *out = c;
+  return 0;
+}
+
+extern "C" void ctrm_ctx_destroy(ctrm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->w_arena.release();
+  c->b_arena.release();
+  c->r_arena.release();
+  c->t_arena.release();
+  c->c_arena.release();
+  if (c->h_ndone) cudaFreeHost(c->h_ndone);
+  for (int i = 0; i < 4; ++i)
+    if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  if (c->ev_out) cudaEventDestroy(c->ev_out);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+static int check_desc(const ctrm_model_desc* d) {
+  if (!d) return ctrm_fail(CTRM_ERR_ARG, "model desc is NULL");
+  if (d->dim_hidden != 32 || d->dim_message != 32 || d->dim_attention != 10 || d->dim_latent != 64 || d->dim_ind != 3)
+    return ctrm_fail(CTRM_ERR_ARG, "unsupported network dims (need hidden 32, message 32, attention 10, latent 64, ind 3)");
+  if (d->fov_size < 1 || (d->fov_size & 1) == 0 || d->fov_size > 63) return ctrm_fail(CTRM_ERR_ARG, "fov_size must be odd, <= 63");
+  if (d->map_size < 1 || d->map_size > 255) return ctrm_fail(CTRM_ERR_ARG, "map_size must be in 1..255 (reference limit)");
+  return 0;
+}
+
+extern "C" int ctrm_weight_offsets(const ctrm_model_desc* d, ctrm_weight_offsets_t* o) {
+  CHECK(check_desc(d));
+  if (!o) return ctrm_fail(CTRM_ERR_ARG, "out is NULL");
+  int p = 0;
+  auto take = [&](int n) {
+    int r = p;
+    p += (n + 3) & ~3;  // keep every block 16-byte aligned
+    return r;
+  };
+  const int KD = 2 * d->fov_size * d->fov_size;
+  o->fov_w0 = take(KD * 64); o->fov_b0 = take(64);
+  o->fovs_w1 = take(32 * 32); o->fovs_b1 = take(32); o->fovs_w2 = take(32 * 32); o->fovs_b2 = take(32);
+  o->fovv_w1 = take(32 * 32); o->fovv_b1 = take(32); o->fovv_w2 = take(32 * 32); o->fovv_b2 = take(32);
+  o->ag_w0i = take(11 * 32); o->ag_w0v = take(32 * 32); o->ag_b0 = take(32);
+  o->ag_w1 = take(32 * 32); o->ag_b1 = take(32);
+  o->ag_w2 = take(32 * 44); o->ag_b2 = take(44);
+  o->ind_w0 = take(72 * 32); o->ind_b0 = take(32); o->ind_w1 = take(32 * 32); o->ind_b1 = take(32);
+  o->ind_w2 = take(32 * 4); o->ind_b2 = take(4);
+  o->enc_w0 = take(75 * 32); o->enc_b0 = take(32); o->enc_w1 = take(32 * 32); o->enc_b1 = take(32);
+  o->enc_w2 = take(32 * 64); o->enc_b2 = take(64);
+  o->dec_w0 = take(139 * 32); o->dec_b0 = take(32); o->dec_w1 = take(32 * 32); o->dec_b1 = take(32);
+  o->dec_w2 = take(32 * 4); o->dec_b2 = take(4);
+  o->total = p;
+  return 0;
+}
+
+extern "C" int ctrm_load_weights(ctrm_ctx* c, const ctrm_model_desc* d, const float* h_blob, size_t n_floats) {
+  if (!c || !h_blob) return ctrm_fail(CTRM_ERR_ARG, "ctrm_load_weights: NULL argument");
+  ctrm_weight_offsets_t off;
+  CHECK(ctrm_weight_offsets(d, &off));
+  if (n_floats != (size_t)off.total) return ctrm_fail(CTRM_ERR_ARG, "ctrm_load_weights: blob size does not match ctrm_weight_offsets");
+  CTRM_CUDA_OK(cudaSetDevice(c->device));
+  CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->w_arena.release();
+  float* blob = nullptr;
+  CHECK(c->w_arena.alloc(&blob, n_floats));
+  CTRM_CUDA_OK(cudaMemcpy(blob, h_blob, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+  c->model.blob = blob;
+  c->model.off = off;
+  c->model.desc = *d;
+  c->have_weights = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// instances
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(DevArena& ar, T** dptr, const T* h, size_t n, cudaStream_t st) {
+  CHECK(ar.alloc(dptr, n));
+  if (n) CTRM_CUDA_OK(cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+// disk((r,r), r) on a (2r+1)^2 grid: k^2 + l^2 < r^2  (learning/fov.py:48-56; identical to skimage's float test)
+static void disk_stencil(int r, int ld, uint8_t* out) {
+  for (int k = -r; k <= r; ++k)
+    for (int l = -r; l <= r; ++l) out[(k + r) * ld + (l + r)] = (k * k + l * l < r * r) ? 1 : 0;
+}
+
+static int cost_to_go_device(const uint8_t* d_occ, int M, const std::vector<uint8_t>& stencils, const std::vector<int32_t>& st_r,
+                             int st_ld, const std::vector<int32_t>& pm_inst, const std::vector<int32_t>& pm_st,
+                             const std::vector<int32_t>& agent_pm, const double* d_goals, int A, uint16_t* d_ctg,
+                             cudaStream_t st) {
+  DevArena tmp;
+  uint8_t* d_st = nullptr;
+  int32_t *d_str = nullptr, *d_pmi = nullptr, *d_pms = nullptr, *d_apm = nullptr;
+  uint32_t* d_pmask = nullptr;
+  int rc = 0;
+  const int P = (int)pm_inst.size(), MW = (M + 31) / 32;
+  do {
+    if ((rc = upload(tmp, &d_st, stencils.data(), stencils.size(), st))) break;
+    if ((rc = upload(tmp, &d_str, st_r.data(), st_r.size(), st))) break;
+    if ((rc = upload(tmp, &d_pmi, pm_inst.data(), pm_inst.size(), st))) break;
+    if ((rc = upload(tmp, &d_pms, pm_st.data(), pm_st.size(), st))) break;
+    if ((rc = upload(tmp, &d_apm, agent_pm.data(), agent_pm.size(), st))) break;
+    if ((rc = tmp.alloc(&d_pmask, (size_t)P * M * MW))) break;
+    if ((rc = launch_passable_masks(d_occ, M, d_st, d_str, st_ld, d_pmi, d_pms, P, d_pmask, st))) break;
+    if ((rc = launch_wavefront(d_pmask, d_apm, d_goals, A, M, d_ctg, st))) break;
+    cudaError_t e = cudaStreamSynchronize(st);  // the host vectors and temporaries die here
+    if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "cost_to_go sync");
+  } while (0);
+  tmp.release();
+  return rc;
+}
+
+extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents, const double* starts, const double* goals,
+                                     const double* speeds, const double* speeds2, const double* rads, const int32_t* n_obs,
+                                     const double* obs_xyr, void* user_stream) {
+  if (!c || B <= 0 || !n_agents || !starts || !goals || !speeds || !speeds2 || !rads || !n_obs)
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_upload_instances: NULL / empty argument");
+  if (!c->have_weights) return ctrm_fail(CTRM_ERR_STATE, "ctrm_upload_instances: load weights first (map_size / fov_size come from the model)");
+  CTRM_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CHECK(sync_in(c, (cudaStream_t)user_stream));
+  CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  c->b_arena.release();
+  c->r_arena.release();
+  c->r_L = c->r_S = 0;
+  c->have_batch = false;
+  c->have_result = false;
+  const int M = c->model.desc.map_size, F = c->model.desc.fov_size;
+  std::vector<int32_t>& aoff = c->h_agent_off;
+  std::vector<int32_t>& ooff = c->h_obs_off;
+  aoff.assign(B + 1, 0);
+  ooff.assign(B + 1, 0);
+  int n_max = 0;
+  for (int b = 0; b < B; ++b) {
+    if (n_agents[b] < 1 || n_obs[b] < 0) return ctrm_fail(CTRM_ERR_ARG, "ctrm_upload_instances: bad agent / obstacle count");
+    aoff[b + 1] = aoff[b] + n_agents[b];
+    ooff[b + 1] = ooff[b] + n_obs[b];
+    if (n_agents[b] > n_max) n_max = n_agents[b];
+  }
+  const int A = aoff[B], O = ooff[B];
+  if (O > 0 && !obs_xyr) return ctrm_fail(CTRM_ERR_ARG, "ctrm_upload_instances: obstacles missing");
+  std::vector<int32_t> ainst(A);
+  for (int b = 0; b < B; ++b)
+    for (int a = aoff[b]; a < aoff[b + 1]; ++a) ainst[a] = b;
+  c->h_speeds.assign(speeds, speeds + A);
+  // footprint stencils r = ceil(rad * M) (learning/fov.py:48) and the (instance, r) pairs that need a passability mask
+  std::vector<int32_t> st_r;
+  std::map<int, int> r_to_st;
+  std::map<std::pair<int, int>, int> pm_of;
+  std::vector<int32_t> pm_inst, pm_st, agent_pm(A);
+  int rmax = 0;
+  for (int a = 0; a < A; ++a) {
+    int r = (int)std::ceil(rads[a] * (double)M);
+    if (r < 0 || r > 127) return ctrm_fail(CTRM_ERR_ARG, "ctrm_upload_instances: agent radius out of range");
+    if (!r_to_st.count(r)) {
+      r_to_st[r] = (int)st_r.size();
+      st_r.push_back(r);
+      if (r > rmax) rmax = r;
+    }
+    auto key = std::make_pair(ainst[a], r_to_st[r]);
+    if (!pm_of.count(key)) {
+      pm_of[key] = (int)pm_inst.size();
+      pm_inst.push_back(key.first);
+      pm_st.push_back(key.second);
+    }
+    agent_pm[a] = pm_of[key];
+  }
+  const int st_ld = 2 * rmax + 1;
+  std::vector<uint8_t> stencils(st_r.size() * (size_t)st_ld * st_ld, 0);
+  for (size_t i = 0; i < st_r.size(); ++i) disk_stencil(st_r[i], st_ld, stencils.data() + i * (size_t)st_ld * st_ld);
+
+  Batch& bt = c->bt;
+  bt = Batch{};
+  bt.B = B; bt.A = A; bt.O = O; bt.M = M; bt.F = F; bt.n_max = n_max;
+  DevArena& ar = c->b_arena;
+  int32_t *d_aoff, *d_ooff, *d_ainst;
+  double *d_starts, *d_goals, *d_speeds, *d_speeds2, *d_rads, *d_obs, *d_merge2;
+  CHECK(upload(ar, &d_aoff, aoff.data(), (size_t)B + 1, st));
+  CHECK(upload(ar, &d_ooff, ooff.data(), (size_t)B + 1, st));
+  CHECK(upload(ar, &d_ainst, ainst.data(), (size_t)A, st));
+  CHECK(upload(ar, &d_starts, starts, (size_t)2 * A, st));
+  CHECK(upload(ar, &d_goals, goals, (size_t)2 * A, st));
+  CHECK(upload(ar, &d_speeds, speeds, (size_t)A, st));
+  CHECK(upload(ar, &d_speeds2, speeds2, (size_t)A, st));
+  CHECK(upload(ar, &d_rads, rads, (size_t)A, st));
+  CHECK(upload(ar, &d_obs, obs_xyr, (size_t)3 * O, st));
+  CHECK(ar.alloc(&d_merge2, (size_t)A));
+  bt.agent_off = d_aoff; bt.obs_off = d_ooff; bt.agent_inst = d_ainst;
+  bt.starts = d_starts; bt.goals = d_goals; bt.speeds = d_speeds; bt.speeds2 = d_speeds2; bt.rads = d_rads;
+  bt.obs_xyr = d_obs; bt.merge2 = d_merge2;
+  uint8_t* d_occ;
+  uint16_t* d_ctg;
+  CHECK(ar.alloc(&d_occ, (size_t)B * M * M + 16));
+  CHECK(ar.alloc(&d_ctg, (size_t)A * M * M));
+  bt.occ = d_occ; bt.ctg = d_ctg;
+  // per-step tensors (A-sized)
+  CHECK(ar.alloc(&bt.fov, (size_t)A * 2 * F * F + 8));
+  CHECK(ar.alloc(&bt.e_self, (size_t)A * 32));
+  CHECK(ar.alloc(&bt.e_vain, (size_t)A * 32));
+  CHECK(ar.alloc(&bt.vain_proj, (size_t)A * 32));
+  CHECK(ar.alloc(&bt.X, (size_t)A * CTRM_DIM_X));
+  CHECK(ar.alloc(&bt.cv_logits, (size_t)A * 64));
+  CHECK(ar.alloc(&bt.cv_dec0, (size_t)A * 32));
+  CHECK(ar.alloc(&bt.ind, (size_t)A));
+  CHECK(ar.alloc(&bt.cur, (size_t)2 * A));
+  CHECK(ar.alloc(&bt.prev, (size_t)2 * A));
+  CHECK(ar.alloc(&bt.nxt, (size_t)2 * A));
+  CHECK(ar.alloc(&bt.loc_pred, (size_t)2 * A));
+  CHECK(ar.alloc(&bt.arrived, (size_t)A));
+  CHECK(ar.alloc(&bt.k_traj, (size_t)B));
+  CHECK(ar.alloc(&bt.t, (size_t)B));
+  CHECK(ar.alloc(&bt.makespan, (size_t)B));
+  CHECK(ar.alloc(&bt.done, (size_t)B));
+  CHECK(ar.alloc(&bt.cnt_collide, (size_t)B));
+  CHECK(ar.alloc(&bt.n_done, (size_t)1));
+  CHECK(ar.alloc(&bt.nlayers, (size_t)A));
+  CHECK(ar.alloc(&c->d_tfin, (size_t)B));
+  CHECK(ar.alloc(&c->d_agent_nv, (size_t)A));
+  CHECK(ar.alloc(&c->d_agent_ne, (size_t)A));
+  CHECK(ar.alloc(&c->d_totals, (size_t)4));
+  CTRM_CUDA_OK(cudaMemsetAsync(bt.done, 0, (size_t)B, st));
+  // occupancy raster + cost-to-go for every goal (Format2D_CTRM_Input.set_instance, format_input.py:200-210)
+  {
+    DevArena tmp;
+    int4* d_cells = nullptr;
+    int rc = tmp.alloc(&d_cells, (size_t)O);
+    if (!rc) rc = launch_obs_to_cells(d_obs, O, M, d_cells, st);
+    if (!rc) rc = launch_raster_occupancy(d_cells, d_ooff, B, M, d_occ, st);
+    if (!rc) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "raster sync");
+    }
+    tmp.release();
+    CHECK(rc);
+  }
+  CHECK(cost_to_go_device(d_occ, M, stencils, st_r, st_ld, pm_inst, pm_st, agent_pm, d_goals, A, d_ctg, st));
+  c->have_batch = true;
+  CHECK(sync_out(c, (cudaStream_t)user_stream));
+  return 0;
+}
+
+extern "C" int ctrm_get_device_view(ctrm_ctx* c, ctrm_device_view* v) {
+  if (!c || !v) return ctrm_fail(CTRM_ERR_ARG, "NULL argument");
+  if (!c->have_batch) return ctrm_fail(CTRM_ERR_STATE, "no batch uploaded");
+  const Batch& bt = c->bt;
+  v->B = bt.B; v->A = bt.A; v->O = bt.O; v->M = bt.M; v->F = bt.F; v->L = bt.L; v->S = bt.S; v->W = bt.W;
+  v->d_agent_off = bt.agent_off; v->d_obs_off = bt.obs_off; v->d_agent_inst = bt.agent_inst;
+  v->d_starts = bt.starts; v->d_goals = bt.goals; v->d_speeds = bt.speeds; v->d_speeds2 = bt.speeds2; v->d_rads = bt.rads;
+  v->d_obs_xyr = bt.obs_xyr; v->d_occ = bt.occ; v->d_ctg = bt.ctg;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int ctrm_collide_segments(const double* d_from, const double* d_to, const double* d_rad, const int32_t* d_seg_inst,
+                                     int64_t n_seg, const double* d_obs_xyr, const int32_t* d_obs_off, uint8_t* d_verdict,
+                                     int32_t* d_survivors, int32_t* d_n_survivors, void* stream) {
+  if (n_seg < 0 || (n_seg > 0 && (!d_from || !d_to || !d_rad || !d_obs_off || !d_verdict)))
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_collide_segments: NULL argument");
+  if ((d_survivors == nullptr) != (d_n_survivors == nullptr))
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_collide_segments: survivors and n_survivors go together");
+  return launch_collide_segments(d_from, d_to, d_rad, d_seg_inst, n_seg, d_obs_xyr, d_obs_off, d_verdict, d_survivors,
+                                 d_n_survivors, (cudaStream_t)stream);
+}
+
+extern "C" int ctrm_collide_sphere_pairs(const double* f1, const double* t1, const double* r1, const double* f2, const double* t2,
+                                         const double* r2, int dim, int64_t n, uint8_t* verdict, void* stream) {
+  if (n < 0 || (n > 0 && (!f1 || !t1 || !r1 || !f2 || !t2 || !r2 || !verdict)))
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_collide_sphere_pairs: NULL argument");
+  return launch_collide_pairs(f1, t1, r1, f2, t2, r2, dim, n, verdict, (cudaStream_t)stream);
+}
+
+extern "C" int ctrm_raster_occupancy(const double* d_obs_xyr, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, void* stream) {
+  if (B <= 0 || M < 1 || M > 255 || !d_obs_off || !d_occ) return ctrm_fail(CTRM_ERR_ARG, "ctrm_raster_occupancy: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t O = 0;
+  CTRM_CUDA_OK(cudaMemcpyAsync(&O, d_obs_off + B, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  int4* d_cells = nullptr;
+  CTRM_CUDA_OK(cudaMallocAsync(&d_cells, sizeof(int4) * (size_t)(O > 0 ? O : 1), st));
+  int rc = launch_obs_to_cells(d_obs_xyr, O, M, d_cells, st);
+  if (!rc) rc = launch_raster_occupancy(d_cells, d_obs_off, B, M, d_occ, st);
+  cudaFreeAsync(d_cells, st);
+  return rc;
+}
+
+extern "C" int ctrm_cost_to_go(const uint8_t* d_occ, const int32_t* d_agent_inst, const double* d_goals,
+                               const int32_t* d_stencil_r, int A, int M, uint16_t* d_ctg, void* stream) {
+  if (A <= 0 || M < 1 || M > 255 || !d_occ || !d_agent_inst || !d_goals || !d_stencil_r || !d_ctg)
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_cost_to_go: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int32_t> inst(A), rr(A);
+  CTRM_CUDA_OK(cudaMemcpyAsync(inst.data(), d_agent_inst, sizeof(int32_t) * A, cudaMemcpyDeviceToHost, st));
+  CTRM_CUDA_OK(cudaMemcpyAsync(rr.data(), d_stencil_r, sizeof(int32_t) * A, cudaMemcpyDeviceToHost, st));
+  CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<int32_t> st_r, pm_inst, pm_st, agent_pm(A);
+  std::map<int, int> r_to_st;
+  std::map<std::pair<int, int>, int> pm_of;
+  int rmax = 0;
+  for (int a = 0; a < A; ++a) {
+    int r = rr[a];
+    if (r < 0 || r > 127) return ctrm_fail(CTRM_ERR_ARG, "ctrm_cost_to_go: stencil radius out of range");
+    if (!r_to_st.count(r)) { r_to_st[r] = (int)st_r.size(); st_r.push_back(r); if (r > rmax) rmax = r; }
+    auto key = std::make_pair(inst[a], r_to_st[r]);
+    if (!pm_of.count(key)) { pm_of[key] = (int)pm_inst.size(); pm_inst.push_back(key.first); pm_st.push_back(key.second); }
+    agent_pm[a] = pm_of[key];
+  }
+  const int st_ld = 2 * rmax + 1;
+  std::vector<uint8_t> stencils(st_r.size() * (size_t)st_ld * st_ld, 0);
+  for (size_t i = 0; i < st_r.size(); ++i) disk_stencil(st_r[i], st_ld, stencils.data() + i * (size_t)st_ld * st_ld);
+  return cost_to_go_device(d_occ, M, stencils, st_r, st_ld, pm_inst, pm_st, agent_pm, d_goals, A, d_ctg, st);
+}
+
+extern "C" int ctrm_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
+                               int A, int M, int F, float* d_fov, void* stream) {
+  if (A <= 0 || M < 1 || M > 255 || F < 1 || (F & 1) == 0 || F > 63 || !d_occ || !d_ctg || !d_agent_inst || !d_pos || !d_fov)
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_fov_raster: bad argument");
+  if ((reinterpret_cast<uintptr_t>(d_fov) & 15) != 0) return ctrm_fail(CTRM_ERR_ARG, "ctrm_fov_raster: d_fov must be 16-byte aligned");
+  return launch_fov_raster(d_occ, d_ctg, d_agent_inst, d_pos, nullptr, A, M, F, d_fov, (cudaStream_t)stream);
+}
+
+extern "C" int ctrm_encode_features(ctrm_ctx* c, const float* d_fov, const double* d_cur, const double* d_prev, float* d_X,
+                                    void* stream) {
+  if (!c || !d_fov || !d_cur || !d_prev || !d_X) return ctrm_fail(CTRM_ERR_ARG, "ctrm_encode_features: NULL argument");
+  if (!c->have_weights || !c->have_batch) return ctrm_fail(CTRM_ERR_STATE, "ctrm_encode_features: weights and instances first");
+  cudaStream_t st = (cudaStream_t)stream;
+  Batch bt = c->bt;
+  bt.done = nullptr;
+  CHECK(launch_fov_encode(c->model, d_fov, bt.agent_inst, nullptr, bt.A, bt.e_self, bt.e_vain, bt.vain_proj, st));
+  CHECK(launch_agent_comm(c->model, bt, d_cur, d_prev, bt.e_self, bt.vain_proj, d_X, st));
+  return 0;
+}
+
+extern "C" int ctrm_cvae_sample(ctrm_ctx* c, const float* d_X, const float* d_uniforms, int K, uint64_t seed, int k_traj, int t,
+                                float* d_samples, int32_t* d_ind, void* stream) {
+  if (!c || !d_X || !d_samples || K < 1) return ctrm_fail(CTRM_ERR_ARG, "ctrm_cvae_sample: bad argument");
+  if (!c->have_weights || !c->have_batch) return ctrm_fail(CTRM_ERR_STATE, "ctrm_cvae_sample: weights and instances first");
+  Batch bt = c->bt;
+  bt.done = nullptr;
+  bt.K = K;
+  bt.dim_ind = c->model.desc.dim_ind;
+  bt.seed_lo = (uint32_t)(seed & 0xFFFFFFFFu);
+  bt.seed_hi = (uint32_t)(seed >> 32);
+  bt.inst_base = 0;
+  return launch_cvae_sample_ex(c->model, bt, d_X, d_uniforms, 0, k_traj, t, bt.cv_logits, bt.cv_dec0, nullptr, d_samples, d_ind,
+                               (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the driver
+// ------------------------------------------------------------------------------------------------
+extern "C" int ctrm_trace_enable(ctrm_ctx* c, int enable) {
+  if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
+  c->trace = enable != 0;
+  return 0;
+}
+
+static int ensure_rollout_store(ctrm_ctx* c, const ctrm_params* p, int K) {
+  Batch& bt = c->bt;
+  const int L = p->max_T + 2;
+  const int W = (p->N_traj + 1 + 31) / 32;
+  const int S = 32 * W;
+  const bool same = c->r_L == L && c->r_S == S && c->r_K == K && c->r_NT == p->N_traj && c->r_MT == p->max_T &&
+                    c->r_att == p->max_attempt && c->r_trace == c->trace;
+  bt.L = L; bt.S = S; bt.W = W; bt.K = K;
+  if (same) return 0;
+  c->r_arena.release();
+  DevArena& ar = c->r_arena;
+  const size_t slots = (size_t)bt.A * L * S;
+  CHECK(ar.alloc(&bt.vpos, slots * 2));
+  CHECK(ar.alloc(&bt.vcnt, (size_t)bt.A * L));
+  CHECK(ar.alloc(&bt.cmask, slots * W));
+  CHECK(ar.alloc(&bt.pmask, slots * W));
+  CHECK(ar.alloc(&bt.samples, (size_t)bt.A * K * 3));
+  bt.tr_samples = nullptr; bt.tr_loc_pred = nullptr; bt.tr_loc_next = nullptr;
+  if (c->trace) {
+    const size_t steps = (size_t)p->N_traj * p->max_T;
+    CHECK(ar.alloc(&bt.tr_samples, steps * bt.A * K * 3));
+    CHECK(ar.alloc(&bt.tr_loc_pred, steps * bt.A * 2));
+    CHECK(ar.alloc(&bt.tr_loc_next, steps * bt.A * 2));
+  }
+  c->r_L = L; c->r_S = S; c->r_W = W; c->r_K = K; c->r_NT = p->N_traj; c->r_MT = p->max_T; c->r_att = p->max_attempt;
+  c->r_trace = c->trace;
+  return 0;
+}
+
+// one roll-out step for every unfinished instance; `nn` = run the networks (skipped for teacher-forced runs
+// that do not trace the CVAE output)
+static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, int* n_kernels) {
+  int k = 0;
+  if (nn) {
+    CHECK(launch_fov_raster(bt.occ, bt.ctg, bt.agent_inst, bt.cur, bt.done, bt.A, bt.M, bt.F, bt.fov, st)); ++k;
+    CHECK(launch_fov_encode(c->model, bt.fov, bt.agent_inst, bt.done, bt.A, bt.e_self, nullptr, bt.vain_proj, st)); ++k;
+    CHECK(launch_agent_comm(c->model, bt, bt.cur, bt.prev, bt.e_self, bt.vain_proj, bt.X, st)); ++k;
+    CHECK(launch_cvae_sample_ex(c->model, bt, bt.X, nullptr, 1, 0, 0, bt.cv_logits, bt.cv_dec0, nullptr, bt.samples,
+                                bt.ind, st));
+    k += 2;
+  }
+  CHECK(launch_select(bt, st)); ++k;
+  CHECK(launch_merge(bt, st)); ++k;
+  CHECK(launch_advance(bt, st)); ++k;
+  *n_kernels = k;
+  return 0;
+}
+
+extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm_tables* tb, void* user_stream) {
+  if (!c || !p) return ctrm_fail(CTRM_ERR_ARG, "ctrm_build_roadmaps: NULL argument");
+  if (!c->have_weights || !c->have_batch) return ctrm_fail(CTRM_ERR_STATE, "ctrm_build_roadmaps: weights and instances first");
+  if (p->N_traj < 0 || p->N_traj > 32 * CTRM_MAX_W - 1) return ctrm_fail(CTRM_ERR_ARG, "N_traj must be in 0..127");
+  if (p->max_T < 1 || p->max_T > 4096) return ctrm_fail(CTRM_ERR_ARG, "max_T must be in 1..4096");
+  if (p->max_attempt < 0 || p->max_attempt > 255) return ctrm_fail(CTRM_ERR_ARG, "max_attempt must be in 0..255");
+  if (p->randomize_indicator)
+    return ctrm_fail(CTRM_ERR_ARG, "randomize_indicator=True is not supported (per-row random indicators, learned_sampler.py:93-97)");
+  const int K = p->K > 0 ? p->K : c->model.desc.dim_ind;
+  if (K > 4096) return ctrm_fail(CTRM_ERR_ARG, "K too large");
+  if (p->rng_mode == 1 && (!tb || !tb->h_gate || (p->max_attempt > 0 && !tb->h_rw)))
+    return ctrm_fail(CTRM_ERR_ARG, "rng_mode 1 needs the gate and rw tables");
+  CTRM_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CHECK(sync_in(c, (cudaStream_t)user_stream));
+  CHECK(ensure_rollout_store(c, p, K));
+  Batch& bt = c->bt;
+  bt.max_T = p->max_T; bt.N_traj = p->N_traj; bt.max_attempt = p->max_attempt;
+  bt.dim_ind = c->model.desc.dim_ind; bt.randomize_indicator = 0;
+  bt.rng_mode = p->rng_mode;
+  bt.seed_lo = (uint32_t)(p->seed & 0xFFFFFFFFu); bt.seed_hi = (uint32_t)(p->seed >> 32);
+  bt.inst_base = p->instance_id_base;
+  bt.prob_after_goal = p->prob_uniform_sampling_after_goal;
+  c->have_result = false;
+  // tables
+  CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  c->t_arena.release();
+  bt.tab_gate = bt.tab_rw = bt.tab_step = nullptr;
+  bt.tab_teacher = bt.tab_uniforms = nullptr;
+  const size_t steps_max = (size_t)p->N_traj * p->max_T;
+  {
+    const int MT1 = p->max_T + 1;
+    std::vector<double> prw((size_t)MT1 * MT1, 0.0);
+    if (tb && tb->h_p_rw) {
+      memcpy(prw.data(), tb->h_p_rw, prw.size() * sizeof(double));
+    } else {
+      for (int t = 1; t <= p->max_T; ++t)
+        for (int D = 1; D <= p->max_T; ++D)
+          prw[(size_t)t * MT1 + D] =
+              (1.0 - std::exp(-p->prob_uniform_gamma * t / D)) * (1.0 - p->prob_uniform_bias) + p->prob_uniform_bias;
+    }
+    double* d = nullptr;
+    CHECK(upload(c->t_arena, &d, prw.data(), prw.size(), st));
+    bt.p_rw = d;
+    std::vector<double> m2(bt.A);
+    if (tb && tb->h_merge2) {
+      memcpy(m2.data(), tb->h_merge2, m2.size() * sizeof(double));
+    } else {
+      for (int a = 0; a < bt.A; ++a) {
+        double md = p->merge_distance_rate * c->h_speeds[a];
+        m2[a] = md * md;
+      }
+    }
+    CTRM_CUDA_OK(cudaMemcpyAsync(const_cast<double*>(bt.merge2), m2.data(), m2.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  if (tb) {
+    double* d = nullptr;
+    float* f = nullptr;
+    if (tb->h_gate) { CHECK(upload(c->t_arena, &d, tb->h_gate, steps_max * bt.A, st)); bt.tab_gate = d; }
+    if (tb->h_rw && p->max_attempt > 0) { CHECK(upload(c->t_arena, &d, tb->h_rw, steps_max * bt.A * p->max_attempt * 3, st)); bt.tab_rw = d; }
+    if (tb->h_step) { CHECK(upload(c->t_arena, &d, tb->h_step, steps_max * bt.B, st)); bt.tab_step = d; }
+    if (tb->h_teacher) { CHECK(upload(c->t_arena, &f, tb->h_teacher, steps_max * bt.A * K * 3, st)); bt.tab_teacher = f; }
+    if (tb->h_uniforms) { CHECK(upload(c->t_arena, &f, tb->h_uniforms, steps_max * bt.A * K * 64, st)); bt.tab_uniforms = f; }
+    CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  if (bt.tab_uniforms != nullptr)
+    return ctrm_fail(CTRM_ERR_ARG, "per-step uniform tables are only supported through ctrm_cvae_sample (stage entry point)");
+  const bool nn = (bt.tab_teacher == nullptr) || c->trace;
+  // reset the roadmap store and the roll-out state
+  CTRM_CUDA_OK(cudaEventRecord(c->ev_t[0], st));
+  const size_t slots = (size_t)bt.A * bt.L * bt.S;
+  CTRM_CUDA_OK(cudaMemsetAsync(bt.vcnt, 0, (size_t)bt.A * bt.L * sizeof(int32_t), st));
+  CTRM_CUDA_OK(cudaMemsetAsync(bt.cmask, 0, slots * bt.W * sizeof(uint32_t), st));
+  CTRM_CUDA_OK(cudaMemsetAsync(bt.pmask, 0, slots * bt.W * sizeof(uint32_t), st));
+  if (c->trace) {
+    CTRM_CUDA_OK(cudaMemsetAsync(bt.tr_samples, 0xFF, steps_max * bt.A * K * 3 * sizeof(float), st));
+    CTRM_CUDA_OK(cudaMemsetAsync(bt.tr_loc_pred, 0xFF, steps_max * bt.A * 2 * sizeof(double), st));
+    CTRM_CUDA_OK(cudaMemsetAsync(bt.tr_loc_next, 0xFF, steps_max * bt.A * 2 * sizeof(double), st));
+  }
+  CHECK(launch_rollout_init(bt, st));
+  int64_t launches = 1;
+  // capture one step as a CUDA graph, then replay it; n_done is polled every `chunk` replays
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int per_step = 0;
+  CTRM_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_step(c, bt, nn, st, &per_step);
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return ctrm_fail_cuda(ce, "cudaStreamEndCapture");
+  ce = cudaGraphInstantiate(&gexec, graph, 0);
+  if (ce != cudaSuccess) { cudaGraphDestroy(graph); return ctrm_fail_cuda(ce, "cudaGraphInstantiate"); }
+  CTRM_CUDA_OK(cudaEventRecord(c->ev_t[1], st));
+  const int chunk = 32;
+  int64_t steps = 0;
+  rc = 0;
+  while ((size_t)steps < steps_max) {
+    int n = (int)std::min<size_t>(chunk, steps_max - steps);
+    for (int i = 0; i < n && !rc; ++i) {
+      ce = cudaGraphLaunch(gexec, st);
+      if (ce != cudaSuccess) rc = ctrm_fail_cuda(ce, "cudaGraphLaunch");
+    }
+    if (rc) break;
+    steps += n;
+    ce = cudaMemcpyAsync(c->h_ndone, bt.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "roll-out step loop"); break; }
+    if (*c->h_ndone >= bt.B) break;
+  }
+  cudaGraphExecDestroy(gexec);
+  cudaGraphDestroy(graph);
+  CHECK(rc);
+  launches += steps * per_step;
+  CTRM_CUDA_OK(cudaEventRecord(c->ev_t[2], st));
+  // format_trms + append_goals, then CSR sizes
+  CHECK(launch_finalize(bt, c->d_tfin, st));
+  CHECK(launch_csr_count(bt, c->d_agent_nv, c->d_agent_ne, c->d_totals, st));
+  launches += 6;
+  CTRM_CUDA_OK(cudaEventRecord(c->ev_t[3], st));
+  CTRM_CUDA_OK(cudaMemcpyAsync(c->totals, c->d_totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  CTRM_CUDA_OK(cudaEventElapsedTime(&c->ms[0], c->ev_t[0], c->ev_t[3]));
+  CTRM_CUDA_OK(cudaEventElapsedTime(&c->ms[1], c->ev_t[1], c->ev_t[2]));
+  CTRM_CUDA_OK(cudaEventElapsedTime(&c->ms[2], c->ev_t[2], c->ev_t[3]));
+  c->steps = steps;
+  c->launches = launches;
+  c->have_result = true;
+  CHECK(sync_out(c, (cudaStream_t)user_stream));
+  return 0;
+}
+
+extern "C" int ctrm_result_sizes(ctrm_ctx* c, int64_t* nv, int64_t* ne, int64_t* nl) {
+  if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
+  if (!c->have_result) return ctrm_fail(CTRM_ERR_STATE, "no result: call ctrm_build_roadmaps first");
+  if (nv) *nv = c->totals[0];
+  if (ne) *ne = c->totals[1];
+  if (nl) *nl = c->totals[2];
+  return 0;
+}
+
+extern "C" int ctrm_export_csr(ctrm_ctx* c, int32_t* layer_ptr, double* pos, int64_t* eptr, int32_t* eidx, int32_t* n_layers,
+                               int64_t* cnt_collide, int dst_is_device, void* user_stream) {
+  if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
+  if (!c->have_result) return ctrm_fail(CTRM_ERR_STATE, "no result: call ctrm_build_roadmaps first");
+  CTRM_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CHECK(sync_in(c, (cudaStream_t)user_stream));
+  const Batch& bt = c->bt;
+  const int64_t nv = c->totals[0], ne = c->totals[1];
+  const size_t nlp = (size_t)bt.A * bt.L + 1;
+  const cudaMemcpyKind kind = dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  int32_t *d_lp = layer_ptr, *d_ei = eidx;
+  double* d_pos = pos;
+  int64_t* d_ep = eptr;
+  c->c_arena.release();
+  if (!dst_is_device || !layer_ptr) CHECK(c->c_arena.alloc(&d_lp, nlp));
+  if (!dst_is_device || !pos) CHECK(c->c_arena.alloc(&d_pos, (size_t)2 * nv));
+  if (!dst_is_device || !eptr) CHECK(c->c_arena.alloc(&d_ep, (size_t)nv + 1));
+  if (!dst_is_device || !eidx) CHECK(c->c_arena.alloc(&d_ei, (size_t)ne));
+  CHECK(launch_csr_fill(bt, c->d_agent_nv, c->d_agent_ne, c->d_totals, d_lp, d_pos, d_ep, d_ei, st));
+  if (!dst_is_device) {
+    if (layer_ptr) CTRM_CUDA_OK(cudaMemcpyAsync(layer_ptr, d_lp, nlp * sizeof(int32_t), kind, st));
+    if (pos) CTRM_CUDA_OK(cudaMemcpyAsync(pos, d_pos, (size_t)2 * nv * sizeof(double), kind, st));
+    if (eptr) CTRM_CUDA_OK(cudaMemcpyAsync(eptr, d_ep, ((size_t)nv + 1) * sizeof(int64_t), kind, st));
+    if (eidx) CTRM_CUDA_OK(cudaMemcpyAsync(eidx, d_ei, (size_t)ne * sizeof(int32_t), kind, st));
+  }
+  if (n_layers) CTRM_CUDA_OK(cudaMemcpyAsync(n_layers, bt.nlayers, (size_t)bt.A * sizeof(int32_t), kind, st));
+  if (cnt_collide) CTRM_CUDA_OK(cudaMemcpyAsync(cnt_collide, bt.cnt_collide, (size_t)bt.B * sizeof(int64_t), kind, st));
+  if (!dst_is_device) CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  CHECK(sync_out(c, (cudaStream_t)user_stream));
+  return 0;
+}
+
+extern "C" int ctrm_trace_read(ctrm_ctx* c, float* h_samples, double* h_loc_pred, double* h_loc_next) {
+  if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
+  if (!c->have_result || !c->r_trace || !c->bt.tr_samples) return ctrm_fail(CTRM_ERR_STATE, "no trace recorded");
+  const Batch& bt = c->bt;
+  const size_t steps = (size_t)bt.N_traj * bt.max_T;
+  CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (h_samples) CTRM_CUDA_OK(cudaMemcpy(h_samples, bt.tr_samples, steps * bt.A * bt.K * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (h_loc_pred) CTRM_CUDA_OK(cudaMemcpy(h_loc_pred, bt.tr_loc_pred, steps * bt.A * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h_loc_next) CTRM_CUDA_OK(cudaMemcpy(h_loc_next, bt.tr_loc_next, steps * bt.A * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ctrm_last_timing(ctrm_ctx* c, float ms[3], int64_t* steps, int64_t* launches) {
+  if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
+  if (ms) { ms[0] = c->ms[0]; ms[1] = c->ms[1]; ms[2] = c->ms[2]; }
+  if (steps) *steps = c->steps;
+  if (launches) *launches = c->launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer wrappers with the pybind11 helpers' call shapes (B = 1); GPU only
+// ------------------------------------------------------------------------------------------------
+extern "C" int ctrm_host_continuous_collide_spheres(const double* from1, const double* to1, double rad1, const double* from2,
+                                                    const double* to2, double rad2, int dim, int* out) {
+  if (!from1 || !to1 || !from2 || !to2 || !out || (dim != 2 && dim != 3)) return ctrm_fail(CTRM_ERR_ARG, "bad argument");
+  double h[14];
+  for (int i = 0; i < dim; ++i) { h[i] = from1[i]; h[3 + i] = to1[i]; h[6 + i] = from2[i]; h[9 + i] = to2[i]; }
+  h[12] = rad1; h[13] = rad2;
+  double* d = nullptr;
+  uint8_t* dv = nullptr;
+  CTRM_CUDA_OK(cudaMalloc(&d, sizeof(h)));
+  CTRM_CUDA_OK(cudaMalloc(&dv, 16));
+  int rc = 0;
+  cudaError_t e = cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "memcpy");
+  // the [n][dim] layout with n = 1: from1 at d, to1 at d+3, from2 at d+6, to2 at d+9
+  if (!rc) rc = launch_collide_pairs(d, d + 3, d + 12, d + 6, d + 9, d + 13, dim, 1, dv, nullptr);
+  uint8_t v = 0;
+  if (!rc) {
+    e = cudaMemcpy(&v, dv, 1, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "memcpy");
+  }
+  cudaFree(d);
+  cudaFree(dv);
+  *out = v ? 1 : 0;
+  return rc;
+}
+
+extern "C" int ctrm_host_cost_to_go_2d(const double* goal, const int32_t* occ, int M, const int32_t* agent, int agent_size,
+                                       int32_t* out) {
+  if (!goal || !occ || !agent || !out || M < 1 || M > 255 || agent_size < 1 || (agent_size & 1) == 0 || agent_size > 255)
+    return ctrm_fail(CTRM_ERR_ARG, "bad argument");
+  const int r = (agent_size - 1) / 2;
+  std::vector<uint8_t> occ8((size_t)M * M), st8((size_t)agent_size * agent_size);
+  for (size_t i = 0; i < occ8.size(); ++i) occ8[i] = occ[i] == 1 ? 1 : 0;  // the reference tests `== 1` (cost_to_go.cpp:68)
+  for (size_t i = 0; i < st8.size(); ++i) st8[i] = agent[i] == 1 ? 1 : 0;
+  DevArena ar;
+  uint8_t* d_occ = nullptr;
+  double* d_goal = nullptr;
+  uint16_t* d_ctg = nullptr;
+  int rc = upload(ar, &d_occ, occ8.data(), occ8.size(), (cudaStream_t) nullptr);
+  if (!rc) rc = upload(ar, &d_goal, goal, 2, (cudaStream_t) nullptr);
+  if (!rc) rc = ar.alloc(&d_ctg, (size_t)M * M);
+  std::vector<int32_t> st_r{r}, pm_inst{0}, pm_st{0}, agent_pm{0};
+  if (!rc) rc = cost_to_go_device(d_occ, M, st8, st_r, agent_size, pm_inst, pm_st, agent_pm, d_goal, 1, d_ctg, nullptr);
+  std::vector<uint16_t> h((size_t)M * M);
+  if (!rc) {
+    cudaError_t e = cudaMemcpy(h.data(), d_ctg, h.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "memcpy");
+  }
+  ar.release();
+  if (!rc)
+    for (size_t i = 0; i < h.size(); ++i) out[i] = (int32_t)h[i];
+  return rc;
+}
+
+extern "C" int ctrm_host_fov2d(const double* pos, const int32_t* occ, const int32_t* ctg, int M, int F, int32_t* out) {
+  if (!pos || !occ || !ctg || !out || M < 1 || M > 255 || F < 1 || (F & 1) == 0 || F > 63) return ctrm_fail(CTRM_ERR_ARG, "bad argument");
+  std::vector<uint8_t> occ8((size_t)M * M);
+  std::vector<uint16_t> ctg16((size_t)M * M);
+  for (size_t i = 0; i < occ8.size(); ++i) {
+    occ8[i] = (uint8_t)(occ[i] & 1);
+    // the reference sees inf as INT_MIN: `_c >= 0` is its reachability test (cost_to_go.cpp:176-179)
+    ctg16[i] = (ctg[i] < 0 || ctg[i] >= 65535) ? (uint16_t)65535 : (uint16_t)ctg[i];
+  }
+  DevArena ar;
+  uint8_t* d_occ = nullptr;
+  uint16_t* d_ctg = nullptr;
+  double* d_pos = nullptr;
+  int32_t* d_inst = nullptr;
+  float* d_fov = nullptr;
+  const int32_t zero = 0;
+  const size_t n = (size_t)2 * F * F;
+  int rc = upload(ar, &d_occ, occ8.data(), occ8.size(), (cudaStream_t) nullptr);
+  if (!rc) rc = upload(ar, &d_ctg, ctg16.data(), ctg16.size(), (cudaStream_t) nullptr);
+  if (!rc) rc = upload(ar, &d_pos, pos, 2, (cudaStream_t) nullptr);
+  if (!rc) rc = upload(ar, &d_inst, &zero, 1, (cudaStream_t) nullptr);
+  if (!rc) rc = ar.alloc(&d_fov, n + 8);
+  if (!rc) rc = launch_fov_raster(d_occ, d_ctg, d_inst, d_pos, nullptr, 1, M, F, d_fov, nullptr);
+  std::vector<float> h(n);
+  if (!rc) {
+    cudaError_t e = cudaMemcpy(h.data(), d_fov, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "memcpy");
+  }
+  ar.release();
+  if (!rc)
+    for (size_t i = 0; i < n; ++i) out[i] = (int32_t)h[i];
+  return rc;
+}

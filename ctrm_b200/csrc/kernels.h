@@ -1,0 +1,93 @@
+// Internal declarations shared by the .cu translation units of libctrm_b200 (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ctrm_b200.h"
+
+#define CTRM_MAX_W 4          // adjacency bitmask words per vertex: slots S = 32*W >= N_traj + 1  (N_traj <= 127)
+#define CTRM_DIM_X 72         // [self_info 8 | fov_self 32 | comm 32]   (format_input.py:354-355)
+#define CTRM_DIM_H 32
+#define CTRM_DIM_INFO 11      // compiled.py:30-97
+
+// device-side view of the weights
+struct DevModel {
+  const float* blob;
+  ctrm_weight_offsets_t off;
+  ctrm_model_desc desc;
+};
+
+// device-side view of one uploaded batch and its roll-out state; passed to kernels by value
+struct Batch {
+  int B, A, O, M, F, L, S, W, K;
+  int n_max;  // largest num_agents of the batch
+  int max_T, N_traj, max_attempt, dim_ind, randomize_indicator;
+  // static problem data (flat over agents / obstacles)
+  const int32_t *agent_off, *obs_off, *agent_inst;
+  const double *starts, *goals, *speeds, *speeds2, *merge2, *rads, *obs_xyr;
+  const uint8_t* occ;   // [B][M][M]
+  const uint16_t* ctg;  // [A][M][M]
+  // roll-out state
+  double *cur, *prev, *nxt, *loc_pred;  // [A][2]
+  uint8_t* arrived;                     // [A]
+  int32_t *k_traj, *t, *makespan;       // [B]   makespan 0 = None
+  uint8_t* done;                        // [B]
+  unsigned long long* cnt_collide;      // [B]   StaticObjects.cnt_continuous_collide
+  int32_t* n_done;                      // [1]
+  // per-step tensors
+  float *fov, *e_self, *e_vain, *vain_proj, *X, *samples;
+  float *cv_logits, *cv_dec0;  // [A][64], [A][32]
+  int32_t* ind;  // [A]
+  // timed roadmaps: V[t][i] / E[t][i] as fixed slots + bitmask adjacency
+  double* vpos;     // [A][L][S][2]
+  int32_t* vcnt;    // [A][L]
+  uint32_t* cmask;  // [A][L][S][W]  bit j: edge (t,i) -> (t+1,j)
+  uint32_t* pmask;  // [A][L][S][W]  bit j: edge (t-1,j) -> (t,i)
+  int32_t* nlayers; // [A] len(trm.V)
+  // randomness
+  int rng_mode;
+  uint32_t seed_lo, seed_hi, inst_base;
+  const double *tab_gate, *tab_rw, *tab_step;
+  const float *tab_teacher, *tab_uniforms;
+  const double* p_rw;  // [(max_T+1)][(max_T+1)]  p_rw[t][D], D = makespan or max_T
+  double prob_after_goal;
+  // optional trace
+  float* tr_samples;
+  double *tr_loc_pred, *tr_loc_next;
+};
+
+__host__ __device__ inline size_t vslot(const Batch& bt, int a, int t, int s) { return ((size_t)a * bt.L + t) * bt.S + s; }
+
+// ---- launchers (each returns 0 or a negative ctrm_status) ----
+int launch_obs_to_cells(const double* d_obs_xyr, int O, int M, int4* d_cells, cudaStream_t st);
+int launch_raster_occupancy(const int4* d_cells, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, cudaStream_t st);
+int launch_passable_masks(const uint8_t* d_occ, int M, const uint8_t* d_stencils, const int32_t* d_stencil_r, int st_ld,
+                          const int32_t* d_pm_inst, const int32_t* d_pm_stencil, int P, uint32_t* d_pmask, cudaStream_t st);
+int launch_wavefront(const uint32_t* d_pmask, const int32_t* d_agent_pm, const double* d_goals, int A, int M,
+                     uint16_t* d_ctg, cudaStream_t st);
+int launch_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
+                      const uint8_t* d_skip_inst, int A, int M, int F, float* d_fov, cudaStream_t st);
+
+int launch_collide_segments(const double* d_from, const double* d_to, const double* d_rad, const int32_t* d_seg_inst,
+                            int64_t n, const double* d_obs_xyr, const int32_t* d_obs_off, uint8_t* d_verdict,
+                            int32_t* d_survivors, int32_t* d_n_survivors, cudaStream_t st);
+int launch_collide_pairs(const double* f1, const double* t1, const double* r1, const double* f2, const double* t2,
+                         const double* r2, int dim, int64_t n, uint8_t* verdict, cudaStream_t st);
+
+int launch_fov_encode(const DevModel& m, const float* d_fov, const int32_t* d_agent_inst, const uint8_t* d_skip_inst, int A,
+                      float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st);
+int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, const double* d_prev, const float* d_e_self,
+                      const float* d_vain_proj, float* d_X, cudaStream_t st);
+int launch_cvae_sample_ex(const DevModel& m, const Batch& bt, const float* d_X, const float* d_uniforms, int use_state_kt,
+                          int kt_fixed, int t_fixed, float* d_logits, float* d_dec0, const int32_t* d_ind_override, float* d_samples, int32_t* d_ind,
+                          cudaStream_t st);
+
+int launch_select(const Batch& bt, cudaStream_t st);
+int launch_merge(const Batch& bt, cudaStream_t st);
+int launch_advance(const Batch& bt, cudaStream_t st);
+int launch_rollout_init(const Batch& bt, cudaStream_t st);
+
+int launch_finalize(const Batch& bt, int32_t* d_tfin, cudaStream_t st);
+int launch_csr_count(const Batch& bt, int64_t* d_agent_nv, int64_t* d_agent_ne, int64_t* d_totals, cudaStream_t st);
+int launch_csr_fill(const Batch& bt, const int64_t* d_agent_v0, const int64_t* d_agent_e0, const int64_t* d_totals,
+                    int32_t* d_layer_ptr, double* d_pos, int64_t* d_eptr, int32_t* d_eidx, cudaStream_t st);

@@ -1,0 +1,316 @@
+// Occupancy raster, footprint passability masks, batched cost-to-go wavefront and FOV raster.
+//   reference: StaticObjects.draw_2d (environment/static_objects.py:173-187), ObstacleSphere.draw_2d
+//   (environment/obstacle.py:63-81), get_approx_cost_to_go_matrix_2d (learning/fov.py:34-63),
+//   getCostToGo2D (cpp_helper/cost_to_go_wrapper/src/cost_to_go.cpp:25-107),
+//   getFov2dOccupancyCost (cost_to_go.cpp:109-186).
+// All integer/bit work: results are bit-exact by construction.
+#include "common.cuh"
+#include "kernels.h"
+
+// ------------------------------------------------------------------------------------------------
+// obstacle -> integer disk (X, Y, R):  X = int(M*x), Y = int(M*y), R = int(M*rad)   (obstacle.py:73-77)
+// ------------------------------------------------------------------------------------------------
+__global__ void obs_to_cells_kernel(const double* __restrict__ obs_xyr, int O, int M, int4* __restrict__ cells) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  double m = (double)M;
+  int X = (int)f64mul(m, obs_xyr[3 * o + 0]);  // int() truncates toward zero
+  int Y = (int)f64mul(m, obs_xyr[3 * o + 1]);
+  int R = (int)f64mul(m, obs_xyr[3 * o + 2]);
+  cells[o] = make_int4(X, Y, R * R, R);
+}
+
+// occ[b][x][y] = any_o ( (x-X)^2 + (y-Y)^2 < R^2 ) — the integer form of skimage.draw.disk's float test
+// ((r-r0)/R)^2 + ((c-c0)/R)^2 < 1 (exhaustively identical for R <= 40, SURVEY §8a note (i); R = 0 is empty).
+// One thread produces 16 consecutive bytes of the flat [B][M][M] array and stores them as one uint4.
+__global__ void __launch_bounds__(256) raster_occupancy_kernel(const int4* __restrict__ cells,
+                                                               const int32_t* __restrict__ obs_off, int B, int M,
+                                                               uint8_t* __restrict__ occ) {
+  const long long total = (long long)B * M * M;
+  const int MM = M * M;
+  for (long long chunk = (long long)blockIdx.x * blockDim.x + threadIdx.x; chunk * 16 < total;
+       chunk += (long long)gridDim.x * blockDim.x) {
+    long long base = chunk * 16;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    int b = (int)(base / MM);
+    int rem = (int)(base - (long long)b * MM);
+    int x = rem / M, y = rem - x * M;
+    int o0 = obs_off[b], o1 = obs_off[b + 1];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (base + j < total) {
+        uint32_t v = 0u;
+        for (int o = o0; o < o1; ++o) {
+          int4 c = __ldg(&cells[o]);
+          int dx = x - c.x, dy = y - c.y;
+          v |= (uint32_t)(dx * dx + dy * dy < c.z);
+        }
+        w[j >> 2] |= v << (8 * (j & 3));
+        if (++y == M) {
+          y = 0;
+          if (++x == M) {
+            x = 0;
+            ++b;
+            if (b < B) { o0 = obs_off[b]; o1 = obs_off[b + 1]; }
+          }
+        }
+      }
+    }
+    if (base + 16 <= total) {
+      *reinterpret_cast<uint4*>(occ + base) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      for (int j = 0; base + j < total; ++j) occ[base + j] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// passability masks: bit (x, y) of mask p set iff the agent footprint centred on (x,y) is collision-free
+// (cost_to_go.cpp:68-97): occ[x][y]==0 and no stencil cell with agent==1 is outside the map or occupied.
+// One warp per (mask p, row x, word w); lane = y & 31; ballot packs the word.  MW = ceil(M/32).
+// stencils: [n_st][st_ld*st_ld] uint8, the (2r+1)^2 footprint stored top-left aligned with leading dim st_ld.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) passable_mask_kernel(const uint8_t* __restrict__ occ, int M, int MW,
+                                                            const uint8_t* __restrict__ stencils,
+                                                            const int32_t* __restrict__ stencil_r, int st_ld,
+                                                            const int32_t* __restrict__ pm_inst,
+                                                            const int32_t* __restrict__ pm_stencil, int P,
+                                                            uint32_t* __restrict__ pmask) {
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  long long nwarps = (long long)P * M * MW;
+  if (warp >= nwarps) return;
+  int w = (int)(warp % MW);
+  long long t = warp / MW;
+  int x = (int)(t % M);
+  int p = (int)(t / M);
+  int y = w * 32 + lane;
+  const uint8_t* o = occ + (size_t)pm_inst[p] * M * M;
+  int st = pm_stencil[p];
+  int r = stencil_r[st];
+  const uint8_t* s = stencils + (size_t)st * st_ld * st_ld;
+  bool ok = false;
+  if (y < M) {
+    ok = (o[x * M + y] == 0);
+    for (int k = -r; ok && k <= r; ++k) {
+      int xk = x + k;
+      for (int l = -r; l <= r; ++l) {
+        if (s[(k + r) * st_ld + (l + r)] == 0) continue;
+        int yl = y + l;
+        if (xk < 0 || xk >= M || yl < 0 || yl >= M) { ok = false; break; }
+        if (o[xk * M + yl] != 0) { ok = false; break; }
+      }
+    }
+  }
+  uint32_t bits = __ballot_sync(0xFFFFFFFFu, ok);
+  if (lane == 0) pmask[((size_t)p * M + x) * MW + w] = bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cost-to-go wavefront: one warp per goal, the whole M x M bit grid lives in registers.
+// Lane l owns rows [l*RPL, (l+1)*RPL), each row MW words.  Per level:
+//   new = (N|S|E|W neighbours of the frontier) & passable & ~visited ; ctg[new cells] = level.
+// BFS hop counts are independent of the expansion order, so this equals the reference's std::queue BFS.
+// The goal cell gets 0 unconditionally (cost_to_go.cpp:50) and is expanded even if not passable itself.
+// ------------------------------------------------------------------------------------------------
+template <int RPL, int MW>
+__global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restrict__ pmask,
+                                                        const int32_t* __restrict__ agent_pm,
+                                                        const double* __restrict__ goals, int A, int M,
+                                                        uint16_t* __restrict__ ctg) {
+  int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (a >= A) return;
+  const uint32_t* pm = pmask + (size_t)agent_pm[a] * M * MW;
+  uint16_t* out = ctg + (size_t)a * M * M;
+  uint32_t pass[RPL][MW], vis[RPL][MW], fr[RPL][MW];
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) {
+    int x = lane * RPL + r;
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+      pass[r][w] = (x < M) ? __ldg(&pm[x * MW + w]) : 0u;
+      vis[r][w] = 0u;
+      fr[r][w] = 0u;
+    }
+  }
+  int gx = grid_cell(goals[2 * a + 0], M), gy = grid_cell(goals[2 * a + 1], M);
+  if (gx >= M || gy >= M) return;  // asserts are compiled out in the reference; field stays unreachable
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) {
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+      if (lane * RPL + r == gx && w == (gy >> 5)) {
+        fr[r][w] = 1u << (gy & 31);
+        vis[r][w] = fr[r][w];
+      }
+    }
+  }
+  if (lane == gx / RPL) out[gx * M + gy] = 0;
+  for (int level = 1; level < 65535; ++level) {
+    uint32_t nw[RPL][MW];
+    uint32_t any = 0u;
+    // rows across lane boundaries
+    uint32_t up_in[MW], dn_in[MW];
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+      up_in[w] = __shfl_up_sync(0xFFFFFFFFu, fr[RPL - 1][w], 1);  // row x-1 of my first row
+      dn_in[w] = __shfl_down_sync(0xFFFFFFFFu, fr[0][w], 1);      // row x+1 of my last row
+      if (lane == 0) up_in[w] = 0u;
+      if (lane == 31) dn_in[w] = 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+#pragma unroll
+      for (int w = 0; w < MW; ++w) {
+        uint32_t f = fr[r][w];
+        uint32_t lo = (w > 0) ? fr[r][w - 1] : 0u;
+        uint32_t hi = (w < MW - 1) ? fr[r][w + 1] : 0u;
+        uint32_t nb = (f << 1) | (lo >> 31) | (f >> 1) | (hi << 31);
+        nb |= (r > 0) ? fr[r - 1][w] : up_in[w];
+        nb |= (r < RPL - 1) ? fr[r + 1][w] : dn_in[w];
+        uint32_t n = nb & pass[r][w] & ~vis[r][w];
+        nw[r][w] = n;
+        any |= n;
+      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, any != 0u)) break;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+#pragma unroll
+      for (int w = 0; w < MW; ++w) {
+        uint32_t n = nw[r][w];
+        vis[r][w] |= n;
+        fr[r][w] = n;
+        uint16_t* row = out + (size_t)(lane * RPL + r) * M + w * 32;
+        while (n) {
+          int bit = __ffs(n) - 1;
+          n &= n - 1;
+          row[bit] = (uint16_t)level;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FOV raster (cost_to_go.cpp:109-186, flatten layout) for all agents: fov[a][x_fov*F + y_fov] = 1 - occ,
+// fov[a][F^2 + ...] = reach(x,y) && (!reach(c) || ctg[x,y] < ctg[c]); out-of-map cells stay 0; float32.
+// One warp rasterises one agent's 2F^2 values into shared memory; the block (APB agents) then streams its
+// contiguous APB*2F^2 floats out with coalesced 16-byte stores (APB even keeps every block base 16B aligned).
+// ------------------------------------------------------------------------------------------------
+template <int APB>
+__global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __restrict__ occ,
+                                                              const uint16_t* __restrict__ ctg,
+                                                              const int32_t* __restrict__ agent_inst,
+                                                              const double* __restrict__ pos,
+                                                              const uint8_t* __restrict__ skip_inst, int A, int M,
+                                                              int F, float* __restrict__ fov) {
+  extern __shared__ __align__(16) float tile[];  // [APB][2F^2]
+  const int FF = F * F, ROW = 2 * FF;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int a0 = blockIdx.x * APB;
+  int a = a0 + warp;
+  bool live = false;
+  if (a < A) {
+    int b = agent_inst[a];
+    live = (skip_inst == nullptr) || (skip_inst[b] == 0);
+    float* t = tile + warp * ROW;
+    if (live) {
+      const uint8_t* o = occ + (size_t)b * M * M;
+      const uint16_t* c = ctg + (size_t)a * M * M;
+      int cx = grid_cell(pos[2 * a + 0], M), cy = grid_cell(pos[2 * a + 1], M);
+      int buf = (F - 1) / 2;
+      // a position outside [0,1] wraps through uint16 in the reference; such crops are entirely outside the map
+      bool centre_in = cx < M && cy < M;
+      int cc = centre_in ? (int)c[cx * M + cy] : CTRM_UNREACH;
+      bool c_reach = cc != CTRM_UNREACH;
+      for (int i = lane; i < FF; i += 32) {
+        int xf = i / F, yf = i - xf * F;
+        int x = cx - buf + xf, y = cy - buf + yf;
+        float v0 = 0.f, v1 = 0.f;
+        if (centre_in && x >= 0 && x < M && y >= 0 && y < M) {
+          v0 = (float)(1 - (int)o[x * M + y]);
+          int _c = (int)c[x * M + y];
+          v1 = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 1.f : 0.f;
+        }
+        t[i] = v0;
+        t[FF + i] = v1;
+      }
+    } else {
+      for (int i = lane; i < ROW; i += 32) t[i] = 0.f;  // finished instance: row is never consumed
+    }
+  }
+  // a block whose agents all belong to finished instances writes nothing
+  if (!__syncthreads_or(live)) return;
+  int n_rows = min(APB, A - a0);
+  size_t base = (size_t)a0 * ROW;  // floats; APB even -> base*4 bytes is a multiple of 16
+  int n_f = n_rows * ROW;
+  int n_v = n_f >> 2;
+  float4* dst = reinterpret_cast<float4*>(fov + base);
+  const float4* src = reinterpret_cast<const float4*>(tile);
+  for (int v = threadIdx.x; v < n_v; v += blockDim.x) dst[v] = src[v];
+  for (int i = n_v * 4 + threadIdx.x; i < n_f; i += blockDim.x) fov[base + i] = tile[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+int launch_obs_to_cells(const double* d_obs_xyr, int O, int M, int4* d_cells, cudaStream_t st) {
+  if (O <= 0) return 0;
+  obs_to_cells_kernel<<<(O + 127) / 128, 128, 0, st>>>(d_obs_xyr, O, M, d_cells);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_raster_occupancy(const int4* d_cells, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, cudaStream_t st) {
+  long long chunks = ((long long)B * M * M + 15) / 16;
+  int blocks = (int)((chunks + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  raster_occupancy_kernel<<<blocks, 256, 0, st>>>(d_cells, d_obs_off, B, M, d_occ);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_passable_masks(const uint8_t* d_occ, int M, const uint8_t* d_stencils, const int32_t* d_stencil_r, int st_ld,
+                          const int32_t* d_pm_inst, const int32_t* d_pm_stencil, int P, uint32_t* d_pmask, cudaStream_t st) {
+  int MW = (M + 31) / 32;
+  long long threads = (long long)P * M * MW * 32;
+  if (threads <= 0) return 0;
+  passable_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_occ, M, MW, d_stencils, d_stencil_r, st_ld,
+                                                                       d_pm_inst, d_pm_stencil, P, d_pmask);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_wavefront(const uint32_t* d_pmask, const int32_t* d_agent_pm, const double* d_goals, int A, int M,
+                     uint16_t* d_ctg, cudaStream_t st) {
+  if (A <= 0) return 0;
+  CTRM_CUDA_OK(cudaMemsetAsync(d_ctg, 0xFF, (size_t)A * M * M * sizeof(uint16_t), st));
+  int blocks = (A + 3) / 4;
+  if (M <= 160) wavefront_kernel<5, 5><<<blocks, 128, 0, st>>>(d_pmask, d_agent_pm, d_goals, A, M, d_ctg);
+  else if (M <= 256) wavefront_kernel<8, 8><<<blocks, 128, 0, st>>>(d_pmask, d_agent_pm, d_goals, A, M, d_ctg);
+  else return ctrm_fail(-1, "map_size > 255 unsupported (reference limit, cost_to_go.cpp:47)");
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int APB>
+static int launch_fov_raster_t(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
+                               const uint8_t* d_skip_inst, int A, int M, int F, float* d_fov, cudaStream_t st) {
+  size_t smem = (size_t)APB * 2 * F * F * sizeof(float);
+  if (smem > 48 * 1024)
+    CTRM_CUDA_OK(cudaFuncSetAttribute(fov_raster_kernel<APB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fov_raster_kernel<APB><<<(A + APB - 1) / APB, APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F,
+                                                                   d_fov);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
+                      const uint8_t* d_skip_inst, int A, int M, int F, float* d_fov, cudaStream_t st) {
+  if (A <= 0) return 0;
+  if (F <= 27) return launch_fov_raster_t<8>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, d_fov, st);
+  return launch_fov_raster_t<2>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, d_fov, st);
+}

@@ -1,0 +1,397 @@
+// The per-step roll-out kernels behind get_timed_roadmaps_multiple_paths_with_learned_indicator
+// (roadmap_learned/learned_sampler.py:65-196):
+//   select  : candidate validation, gate logic and random walk (learned_sampler.py:114-168; valid_edge closure
+//             :127-132; valid_move roadmap/utils.py:18-42; collisions static_objects.py:108-138)
+//   merge   : merge_samples (roadmap_learned/utils.py:21-137) on a slot/bitmask timed roadmap, then the goal test
+//             (learned_sampler.py:182-183)
+//   advance : roll-out bookkeeping (learned_sampler.py:186-196, :65-73)
+// One warp per agent (select, merge) / per instance (advance).  Every instance carries its own (k_traj, t).
+// All geometry is fp64 without FMA in the reference's operation order: verdicts and topology are bit-exact.
+#include "common.cuh"
+#include "geometry.cuh"
+#include "kernels.h"
+
+#define RO_WARPS 4
+
+__device__ __forceinline__ size_t step_index(const Batch& bt, int kt, int t) { return (size_t)kt * bt.max_T + (t - 1); }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void rollout_init_kernel(Batch bt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < bt.A) {
+    double sx = bt.starts[2 * i], sy = bt.starts[2 * i + 1];
+    bt.cur[2 * i] = sx; bt.cur[2 * i + 1] = sy;
+    bt.prev[2 * i] = sx; bt.prev[2 * i + 1] = sy;
+    bt.nxt[2 * i] = sx; bt.nxt[2 * i + 1] = sy;
+    bt.arrived[i] = 0;
+    bt.nlayers[i] = 1;  // TimedRoadmap(start): V = [[start]], E = [[[]]]  (timed_roadmap.py:59-65)
+    bt.vcnt[(size_t)i * bt.L] = 1;
+    size_t s = vslot(bt, i, 0, 0);
+    bt.vpos[2 * s] = sx;
+    bt.vpos[2 * s + 1] = sy;
+  }
+  if (i < bt.B) {
+    bt.k_traj[i] = 0;
+    bt.t[i] = 1;
+    bt.makespan[i] = 0;
+    bt.done[i] = (bt.N_traj <= 0) ? 1 : 0;
+    bt.cnt_collide[i] = 0ULL;
+  }
+  if (i == 0) *bt.n_done = (bt.N_traj <= 0) ? bt.B : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// select: loc_pred for every agent
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RO_WARPS * 32) select_kernel(Batch bt) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= bt.A) return;
+  const int b = bt.agent_inst[a];
+  if (bt.done[b]) return;
+  const int t = bt.t[b], kt = bt.k_traj[b];
+  const int a0 = bt.agent_off[b], il = a - a0;
+  const int N = bt.agent_off[b + 1] - a0;
+  const int o0 = bt.obs_off[b], nO = bt.obs_off[b + 1] - o0;
+  const double cx = bt.cur[2 * a], cy = bt.cur[2 * a + 1];
+  const double speed = bt.speeds[a], speed2 = bt.speeds2[a], rad = bt.rads[a];
+  const bool arrived = bt.arrived[a] != 0;
+  const size_t si = step_index(bt, kt, t);
+  const uint32_t c0 = bt.inst_base + (uint32_t)b, c1 = rng_ctr1(kt, t);
+  // prob_random_walk (learned_sampler.py:84-91), tabulated by the host over (t, makespan)
+  const int D = bt.makespan[b] ? bt.makespan[b] : bt.max_T;
+  const double p_rw = bt.p_rw[(size_t)t * (bt.max_T + 1) + D];
+  double u_gate;
+  if (bt.rng_mode == 1) {
+    u_gate = bt.tab_gate[si * bt.A + a];
+  } else {
+    uint4 w = philox4x32(c0, c1, (uint32_t)il, rng_ctr3(STREAM_GATE, 0), bt.seed_lo, bt.seed_hi);
+    u_gate = u64_to_f64(w.x, w.y);
+  }
+  const bool learned = (!arrived && u_gate < p_rw) || (arrived && u_gate > bt.prob_after_goal) || (kt < bt.dim_ind);
+  const int nL = learned ? bt.K : 0;
+  const int C = nL + bt.max_attempt;
+  (void)N;
+  bool found = false;
+  double lx = cx, ly = cy;  // fallback of sample_uniform_i: stay (learned_sampler.py:145)
+  unsigned int count = 0;
+  for (int g0 = 0; g0 < C && !found; g0 += 32) {
+    const int c = g0 + lane;
+    double x = cx, y = cy;
+    bool pre = false;
+    if (c < C) {
+      if (c < nL) {
+        const float* s3 = (bt.tab_teacher != nullptr) ? bt.tab_teacher + ((si * bt.A + a) * (size_t)bt.K + c) * 3
+                                                      : bt.samples + ((size_t)a * bt.K + c) * 3;
+        // Y = cur (f64) + SAMPLES[:, :2] * SAMPLES[:, 2] (f32 product)   learned_sampler.py:114-121
+        x = f64add(cx, (double)__fmul_rn(s3[0], s3[2]));
+        y = f64add(cy, (double)__fmul_rn(s3[1], s3[2]));
+      } else {
+        const int att = c - nL;
+        double u_mag, sn, cs;
+        if (bt.rng_mode == 1) {
+          const double* r = bt.tab_rw + ((si * bt.A + a) * (size_t)bt.max_attempt + att) * 3;
+          u_mag = r[0]; sn = r[1]; cs = r[2];
+        } else {
+          uint4 w = philox4x32(c0, c1, (uint32_t)il, rng_ctr3(STREAM_RW, (uint32_t)att), bt.seed_lo, bt.seed_hi);
+          u_mag = u64_to_f64(w.x, w.y);
+          det_sincos_2pi(u64_to_f64(w.z, w.w), &sn, &cs);
+        }
+        // mag = speed * U ; loc = [sin, cos] * mag + cur   (learned_sampler.py:137-142)
+        double mag = f64mul(speed, u_mag);
+        x = f64add(f64mul(sn, mag), cx);
+        y = f64add(f64mul(cs, mag), cy);
+      }
+      pre = bounds_ok(x, y, rad) && speed_ok(cx, cy, x, y, speed, speed2);
+    }
+    const uint32_t pre_mask = __ballot_sync(0xFFFFFFFFu, pre);
+    // swept tests of the pre-checked candidates, flattened over (candidate, obstacle) pairs across the warp
+    const int npairs = __popc(pre_mask) * nO;
+    uint32_t coll = 0u;
+    for (int p0 = 0; p0 < npairs; p0 += 32) {
+      const int p = p0 + lane;
+      const bool act = p < npairs;
+      const int ci = act ? p / nO : 0;
+      uint32_t pm = pre_mask;
+      for (int q = 0; q < ci; ++q) pm &= pm - 1;  // drop the ci lowest set bits
+      const int src = act ? (__ffs(pm) - 1) : 0;
+      const double tx = __shfl_sync(0xFFFFFFFFu, x, src), ty = __shfl_sync(0xFFFFFFFFu, y, src);
+      if (act) {
+        const int o = o0 + (p - ci * nO);
+        const double ox = __ldg(&bt.obs_xyr[3 * o]), oy = __ldg(&bt.obs_xyr[3 * o + 1]);
+        const double rs = f64add(rad, __ldg(&bt.obs_xyr[3 * o + 2]));
+        if (!sweep_far(cx, cy, tx, ty, ox, oy, rs) && sweep_static(cx, cy, tx, ty, ox, oy, rs)) coll |= 1u << src;
+      }
+    }
+    coll = __reduce_or_sync(0xFFFFFFFFu, coll);
+    const uint32_t valid = pre_mask & ~coll;
+    if (valid) {
+      const int first = __ffs(valid) - 1;
+      count += __popc(pre_mask & ((2u << first) - 1u));
+      lx = __shfl_sync(0xFFFFFFFFu, x, first);
+      ly = __shfl_sync(0xFFFFFFFFu, y, first);
+      found = true;
+    } else {
+      count += __popc(pre_mask);
+    }
+  }
+  if (lane == 0) {
+    bt.loc_pred[2 * a] = lx;
+    bt.loc_pred[2 * a + 1] = ly;
+    if (count) atomicAdd(&bt.cnt_collide[b], (unsigned long long)count);
+    if (bt.tr_loc_pred != nullptr) {
+      bt.tr_loc_pred[2 * (si * bt.A + a)] = lx;
+      bt.tr_loc_pred[2 * (si * bt.A + a) + 1] = ly;
+    }
+  }
+  if (bt.tr_samples != nullptr && bt.samples != nullptr) {
+    for (int i = lane; i < bt.K * 3; i += 32)
+      bt.tr_samples[(si * bt.A + a) * (size_t)bt.K * 3 + i] = bt.samples[(size_t)a * bt.K * 3 + i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge: insert loc_pred into the agent's timed roadmap or merge it with a compatible vertex
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RO_WARPS * 32) merge_kernel(Batch bt) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= bt.A) return;
+  const int b = bt.agent_inst[a];
+  if (bt.done[b]) return;
+  const int t = bt.t[b], kt = bt.k_traj[b];
+  const int o0 = bt.obs_off[b], o1 = bt.obs_off[b + 1];
+  const double lx = bt.loc_pred[2 * a], ly = bt.loc_pred[2 * a + 1];
+  const double speed = bt.speeds[a], speed2 = bt.speeds2[a], merge2 = bt.merge2[a], rad = bt.rads[a];
+  const double gx = bt.goals[2 * a], gy = bt.goals[2 * a + 1];
+  const int W = bt.W;
+  const int nl = bt.nlayers[a];
+  const bool has_t = nl > t, has_next = nl > t + 1;
+  unsigned int count = 0;
+  uint32_t P[CTRM_MAX_W], Cm[CTRM_MAX_W], Mg[CTRM_MAX_W];
+#pragma unroll
+  for (int w = 0; w < CTRM_MAX_W; ++w) { P[w] = 0u; Cm[w] = 0u; Mg[w] = 0u; }
+  // parents: V[t-1] within speed and collision free, tested as (parent -> loc)   utils.py:58-69
+  {
+    const int n = bt.vcnt[(size_t)a * bt.L + (t - 1)];
+#pragma unroll
+    for (int w = 0; w < CTRM_MAX_W; ++w) {
+      if (w < W && w * 32 < n) {
+        const int s = w * 32 + lane;
+        bool cand = false, ok = false;
+        if (s < n) {
+          const size_t v = vslot(bt, a, t - 1, s);
+          const double px = bt.vpos[2 * v], py = bt.vpos[2 * v + 1];
+          cand = dist2(px, py, lx, ly) <= speed2;
+          if (cand) ok = !any_obstacle_hit(px, py, lx, ly, rad, bt.obs_xyr, o0, o1);
+        }
+        count += __popc(__ballot_sync(0xFFFFFFFFu, cand));
+        P[w] = __ballot_sync(0xFFFFFFFFu, ok);
+      }
+    }
+  }
+  // children: V[t+1], tested as (child -> loc)   utils.py:72-84
+  if (has_next) {
+    const int n = bt.vcnt[(size_t)a * bt.L + (t + 1)];
+#pragma unroll
+    for (int w = 0; w < CTRM_MAX_W; ++w) {
+      if (w < W && w * 32 < n) {
+        const int s = w * 32 + lane;
+        bool cand = false, ok = false;
+        if (s < n) {
+          const size_t v = vslot(bt, a, t + 1, s);
+          const double px = bt.vpos[2 * v], py = bt.vpos[2 * v + 1];
+          cand = dist2(px, py, lx, ly) <= speed2;
+          if (cand) ok = !any_obstacle_hit(px, py, lx, ly, rad, bt.obs_xyr, o0, o1);
+        }
+        count += __popc(__ballot_sync(0xFFFFFFFFu, cand));
+        Cm[w] = __ballot_sync(0xFFFFFFFFu, ok);
+      }
+    }
+  }
+  const int n_t = has_t ? bt.vcnt[(size_t)a * bt.L + t] : 0;
+  // merge candidates: V[t] within merge_distance   utils.py:86-89
+#pragma unroll
+  for (int w = 0; w < CTRM_MAX_W; ++w) {
+    if (w < W && w * 32 < n_t) {
+      const int s = w * 32 + lane;
+      bool cand = false;
+      if (s < n_t) {
+        const size_t v = vslot(bt, a, t, s);
+        cand = dist2(bt.vpos[2 * v], bt.vpos[2 * v + 1], lx, ly) <= merge2;
+      }
+      Mg[w] = __ballot_sync(0xFFFFFFFFu, cand);
+    }
+  }
+  // rules (utils.py:94-133), candidates in index order; everything below is warp-uniform
+  double rx = lx, ry = ly;
+  int target = -1;       // vertex of layer t that receives loc (replace) or -1
+  bool add_edges = false, resolved = false;
+  const double h_loc = dist2(lx, ly, gx, gy);
+#pragma unroll
+  for (int w = 0; w < CTRM_MAX_W; ++w) {
+    uint32_t m = (w < W) ? Mg[w] : 0u;
+    while (m && !resolved) {
+      const int u = w * 32 + __ffs(m) - 1;
+      m &= m - 1;
+      const size_t v = vslot(bt, a, t, u);
+      bool eq = true, sup = true, sub = true;
+      for (int q = 0; q < W; ++q) {
+        const uint32_t pu = bt.pmask[v * W + q], cu = bt.cmask[v * W + q];
+        eq = eq && pu == P[q] && cu == Cm[q];
+        sup = sup && (P[q] & ~pu) == 0u && (Cm[q] & ~cu) == 0u;
+        sub = sub && (pu & ~P[q]) == 0u && (cu & ~Cm[q]) == 0u;
+      }
+      const double ux = bt.vpos[2 * v], uy = bt.vpos[2 * v + 1];
+      if (eq) {
+        if (h_loc < dist2(ux, uy, gx, gy)) target = u;  // replace u by loc
+        else { rx = ux; ry = uy; }                       // abandon loc
+        resolved = true;
+      } else if (sup) {
+        rx = ux; ry = uy;
+        resolved = true;
+      } else if (sub) {
+        target = u;
+        add_edges = true;
+        resolved = true;
+      }
+    }
+  }
+  if (!resolved) {  // trm.append_sample(loc, t, parents, children)   utils.py:136, timed_roadmap.py:67-104
+    target = n_t;
+    add_edges = true;
+    if (target >= bt.S) target = -1;  // cannot happen: one insert per (k_traj, t, agent) and S >= N_traj + 1
+  }
+  if (target >= 0) {
+    const size_t v = vslot(bt, a, t, target);
+    if (lane == 0) {
+      bt.vpos[2 * v] = lx;
+      bt.vpos[2 * v + 1] = ly;
+      if (!resolved) {
+        bt.vcnt[(size_t)a * bt.L + t] = n_t + 1;
+        if (nl < t + 1) bt.nlayers[a] = t + 1;
+      }
+    }
+    if (add_edges) {
+      const uint32_t tbit = 1u << (target & 31);
+      const int tw = target >> 5;
+#pragma unroll
+      for (int w = 0; w < CTRM_MAX_W; ++w) {
+        if (w < W) {
+          const uint32_t pu = resolved ? bt.pmask[v * W + w] : 0u;
+          const uint32_t cu = resolved ? bt.cmask[v * W + w] : 0u;
+          const int s = w * 32 + lane;
+          if ((P[w] & ~pu) >> lane & 1u) bt.cmask[vslot(bt, a, t - 1, s) * W + tw] |= tbit;   // E[t-1][p].append(u)
+          if ((Cm[w] & ~cu) >> lane & 1u) bt.pmask[vslot(bt, a, t + 1, s) * W + tw] |= tbit;  // mirror of E[t][u] += ...
+          __syncwarp();
+          if (lane == 0) {
+            bt.pmask[v * W + w] = pu | P[w];
+            bt.cmask[v * W + w] = cu | Cm[w];
+          }
+        }
+      }
+    }
+  }
+  // goal test: valid_edge(loc_next, goal)   learned_sampler.py:182-183
+  bool arr = false;
+  if (bounds_ok(gx, gy, rad) && speed_ok(rx, ry, gx, gy, speed, speed2)) {
+    count += 1;
+    bool hit = false;
+    for (int o = o0 + lane; o < o1; o += 32) {
+      const double ox = __ldg(&bt.obs_xyr[3 * o]), oy = __ldg(&bt.obs_xyr[3 * o + 1]);
+      const double rs = f64add(rad, __ldg(&bt.obs_xyr[3 * o + 2]));
+      hit = hit || (!sweep_far(rx, ry, gx, gy, ox, oy, rs) && sweep_static(rx, ry, gx, gy, ox, oy, rs));
+    }
+    arr = !__any_sync(0xFFFFFFFFu, hit);
+  }
+  if (lane == 0) {
+    bt.nxt[2 * a] = rx;
+    bt.nxt[2 * a + 1] = ry;
+    if (arr) bt.arrived[a] = 1;
+    if (count) atomicAdd(&bt.cnt_collide[b], (unsigned long long)count);
+    if (bt.tr_loc_next != nullptr) {
+      const size_t si = step_index(bt, kt, t);
+      bt.tr_loc_next[2 * (si * bt.A + a)] = rx;
+      bt.tr_loc_next[2 * (si * bt.A + a) + 1] = ry;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// advance: one warp per instance
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RO_WARPS * 32) advance_kernel(Batch bt) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= bt.B) return;
+  if (bt.done[b]) return;
+  const int a0 = bt.agent_off[b], N = bt.agent_off[b + 1] - a0;
+  bool all = true;
+  for (int i = lane; i < N; i += 32) all = all && (bt.arrived[a0 + i] != 0);
+  all = __all_sync(0xFFFFFFFFu, all);
+  const int t = bt.t[b];
+  bool end_roll = false;
+  if (all) {  // learned_sampler.py:186-191
+    if (lane == 0) bt.makespan[b] = bt.makespan[b] ? max(bt.makespan[b], t) : t;
+    end_roll = true;
+  } else if (t >= bt.max_T) {
+    end_roll = true;
+  }
+  if (!end_roll) {  // learned_sampler.py:194-196
+    for (int i = lane; i < N; i += 32) {
+      const int a = a0 + i;
+      bt.prev[2 * a] = bt.cur[2 * a];
+      bt.prev[2 * a + 1] = bt.cur[2 * a + 1];
+      bt.cur[2 * a] = bt.nxt[2 * a];
+      bt.cur[2 * a + 1] = bt.nxt[2 * a + 1];
+    }
+    if (lane == 0) bt.t[b] = t + 1;
+  } else {
+    const int kt = bt.k_traj[b] + 1;
+    if (kt >= bt.N_traj) {
+      if (lane == 0) {
+        bt.k_traj[b] = kt;
+        bt.done[b] = 1;
+        atomicAdd(bt.n_done, 1);
+      }
+    } else {  // next roll-out restarts from the starts (learned_sampler.py:68-73)
+      for (int i = lane; i < N; i += 32) {
+        const int a = a0 + i;
+        const double sx = bt.starts[2 * a], sy = bt.starts[2 * a + 1];
+        bt.cur[2 * a] = sx; bt.cur[2 * a + 1] = sy;
+        bt.prev[2 * a] = sx; bt.prev[2 * a + 1] = sy;
+        bt.arrived[a] = 0;
+      }
+      if (lane == 0) {
+        bt.k_traj[b] = kt;
+        bt.t[b] = 1;
+      }
+    }
+  }
+}
+
+int launch_rollout_init(const Batch& bt, cudaStream_t st) {
+  int n = bt.A > bt.B ? bt.A : bt.B;
+  if (n <= 0) return 0;
+  rollout_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(bt);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_select(const Batch& bt, cudaStream_t st) {
+  if (bt.A <= 0) return 0;
+  select_kernel<<<(bt.A + RO_WARPS - 1) / RO_WARPS, RO_WARPS * 32, 0, st>>>(bt);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_merge(const Batch& bt, cudaStream_t st) {
+  if (bt.A <= 0) return 0;
+  merge_kernel<<<(bt.A + RO_WARPS - 1) / RO_WARPS, RO_WARPS * 32, 0, st>>>(bt);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_advance(const Batch& bt, cudaStream_t st) {
+  if (bt.B <= 0) return 0;
+  advance_kernel<<<(bt.B + RO_WARPS - 1) / RO_WARPS, RO_WARPS * 32, 0, st>>>(bt);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,243 @@
+/*
+ * ctrm_b200 — C-ABI of the B200-native timed-roadmap construction path.
+ *
+ * This header is the drop-in boundary: plain pointers and sizes, no torch / pybind11 types.
+ * Every entry point cites the interface of the reference (omron-sinicx/ctrm, paths relative to the
+ * reference checkout) that it replaces.  All functions return 0 on success and a negative
+ * ctrm_status on failure; they never throw and never take ownership of caller memory.
+ * `stream` arguments are a cudaStream_t passed as void* (NULL = the legacy default stream).
+ * Pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ *
+ * There is no CPU fallback anywhere behind this interface: without a CUDA device every compute entry
+ * point returns CTRM_ERR_CUDA.
+ */
+#ifndef CTRM_B200_H
+#define CTRM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTRM_B200_ABI_VERSION 1
+#define CTRM_UNREACHABLE 65535u /* cost_to_go.cpp:36 max_cost */
+
+typedef enum {
+  CTRM_OK = 0,
+  CTRM_ERR_ARG = -1,   /* bad argument (null pointer, size out of the supported range) */
+  CTRM_ERR_CUDA = -2,  /* a CUDA call failed; see ctrm_last_error() */
+  CTRM_ERR_STATE = -3, /* call order violated (e.g. build before weights / instances were loaded) */
+  CTRM_ERR_ALLOC = -4
+} ctrm_status;
+
+typedef struct ctrm_ctx ctrm_ctx;
+
+/* ---- hyper-parameters of the trained networks (learning/model/*.py, format_input.py:84-142) ---- */
+typedef struct {
+  int32_t fov_size;      /* F, odd; trained config 19  (fov_encoder.py:16-22)              */
+  int32_t map_size;      /* M <= 255 (cost_to_go.cpp:47 uint16 cell index); trained 160    */
+  int32_t dim_hidden;    /* 32: every hidden layer of every net (must be 32)               */
+  int32_t dim_message;   /* 32 (agent_encoder.py:18-24)                                    */
+  int32_t dim_attention; /* 10                                                             */
+  int32_t dim_ind;       /* 3  (format_output.py:80-81)                                    */
+  int32_t dim_latent;    /* 64 (cvae.py:23-37)                                             */
+  int32_t num_neighbors; /* 15 (format_input.py:96)                                        */
+  int32_t use_k_neighbor;
+  int32_t include_self_attention;
+  float temp;            /* 2.0 Gumbel-softmax temperature (cvae.py:133)                   */
+} ctrm_model_desc;
+
+/* ---- sampler parameters: the keyword arguments of
+ *      get_timed_roadmaps_multiple_paths_with_learned_indicator (learned_sampler.py:19-31) ---- */
+typedef struct {
+  double prob_uniform_sampling_after_goal; /* 0.9 */
+  double prob_uniform_bias;                /* 0.0 */
+  double prob_uniform_gamma;               /* 5.0 */
+  int32_t max_T;                           /* 64  */
+  int32_t N_traj;                          /* 25  */
+  int32_t max_attempt;                     /* 3   */
+  int32_t randomize_indicator;             /* 0   */
+  double merge_distance_rate;              /* 0.25 */
+  int32_t K;                               /* candidates per agent-step; 0 -> dim_ind (reference couples them,
+                                              learned_sampler.py:82) */
+  int32_t rng_mode;                        /* 0 = counter-based Philox4x32-10 keyed (instance,k_traj,t,agent,..);
+                                              1 = explicit host tables (replay of a recorded reference run) */
+  uint64_t seed;                           /* Philox key (rng_mode 0) */
+  uint32_t instance_id_base;               /* Philox counter word 0 of instance b is instance_id_base + b */
+} ctrm_params;
+
+/* explicit randomness / teacher forcing for parity runs (all optional, HOST pointers, flat over the batch's
+ * agents A = sum n_agents; index [k_traj][t-1][agent(flat)]...):
+ *   gate     [N_traj][max_T][A]               f64  np.random.rand() of learned_sampler.py:150-155
+ *   rw       [N_traj][max_T][A][max_attempt][3] f64 (u_mag, sin(theta), cos(theta)) of :137-141
+ *   step     [N_traj][max_T][B]               f64  the always-consumed draw of :93
+ *   teacher  [N_traj][max_T][A][K][3]         f32  SAMPLES to use INSTEAD of the CVAE output (:107-113)
+ *   uniforms [N_traj][max_T][A][K][dim_latent] f32 torch.rand of RelaxedOneHotCategorical.rsample (cvae.py:133-136)
+ */
+typedef struct {
+  const double* h_gate;
+  const double* h_rw;
+  const double* h_step;
+  const float* h_teacher;
+  const float* h_uniforms;
+  /* host-computed constants, so that libm-dependent values are the caller's (numpy / CPython) own:
+   *   p_rw   [(max_T+1)][(max_T+1)] f64  prob_random_walk(t, D) of learned_sampler.py:84-91, D = makespan or max_T
+   *   merge2 [A] f64  (merge_distance_rate * max_speed) ** 2 of roadmap_learned/utils.py:86-88
+   * NULL -> computed by the library with C `exp` / a plain product. */
+  const double* h_p_rw;
+  const double* h_merge2;
+} ctrm_tables;
+
+/* ------------------------------------------------------------------------------------------------
+ * context
+ * ---------------------------------------------------------------------------------------------- */
+int ctrm_abi_version(void);
+/* one context per (process, device, caller thread).  */
+int ctrm_ctx_create(int device, ctrm_ctx** out);
+void ctrm_ctx_destroy(ctrm_ctx* ctx);
+const char* ctrm_last_error(const ctrm_ctx* ctx); /* ctx may be NULL: process-wide last error */
+
+/* replaces learning/utils.py:32-53 `reconstruct` + model/__init__.py:19-59 (the device half): upload the
+ * five networks as one fp32 blob.  BatchNorm (eval mode) is already folded into the preceding Linear by
+ * the host (ctrm_b200/weights.py); every matrix is stored [in][out_padded] row-major.  The blob layout is
+ * fixed by ctrm_weight_offsets() so host and device agree. */
+typedef struct {
+  /* offsets in floats into the blob; *_w matrices are [in][ld], biases [ld] */
+  int32_t fov_w0, fov_b0;       /* [2F^2][64]  first layers of fov_encoder_self (cols 0..31) | _vain (32..63) */
+  int32_t fovs_w1, fovs_b1, fovs_w2, fovs_b2; /* self: [32][32] x2 */
+  int32_t fovv_w1, fovv_b1, fovv_w2, fovv_b2; /* vain: [32][32] x2 */
+  int32_t ag_w0i, ag_w0v, ag_b0; /* agent encoder layer 0 split: [11][32] (others_info part), [32][32] (fov_vain part) */
+  int32_t ag_w1, ag_b1;          /* [32][32] */
+  int32_t ag_w2, ag_b2;          /* [32][44] (42 = message 32 + attention 10, padded to 44) */
+  int32_t ind_w0, ind_b0, ind_w1, ind_b1, ind_w2, ind_b2; /* indicator 72->32->32->3(ld 4), BN folded */
+  int32_t enc_w0, enc_b0, enc_w1, enc_b1, enc_w2, enc_b2; /* encoder_input 75->32->32->64 */
+  int32_t dec_w0, dec_b0, dec_w1, dec_b1, dec_w2, dec_b2; /* decoder 139->32->32->3(ld 4) */
+  int32_t total;
+} ctrm_weight_offsets_t;
+int ctrm_weight_offsets(const ctrm_model_desc* desc, ctrm_weight_offsets_t* out);
+int ctrm_load_weights(ctrm_ctx* ctx, const ctrm_model_desc* desc, const float* h_blob, size_t n_floats);
+
+/* replaces environment/instance.py:17-46 + Format2D_CTRM_Input.set_instance (format_input.py:200-210):
+ * copies B problem definitions (fp64, SoA, flat over agents / obstacles), rasterises the occupancy maps
+ * and runs the batched cost-to-go wavefront for every goal.  speeds2[a] = max_speed**2 and
+ * merge2 are computed by the host in Python-float arithmetic (roadmap/utils.py:40, utils.py:86-88). */
+int ctrm_upload_instances(ctrm_ctx* ctx, int B, const int32_t* h_n_agents, const double* h_starts /*[A][2]*/,
+                          const double* h_goals /*[A][2]*/, const double* h_speeds /*[A]*/,
+                          const double* h_speeds2 /*[A]*/, const double* h_rads /*[A]*/,
+                          const int32_t* h_n_obs, const double* h_obs_xyr /*[O][3]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * stage entry points (device pointers; each is one kernel family that can be profiled alone)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces sphere_collision_check_wrapper.continuousCollideSpheres (collision_check.cpp:16-58) as used by
+ * StaticObjects.collide_continuous_sphere (static_objects.py:108-138): for each of n_seg swept circles
+ * (from,to,rad) of instance seg_inst[s], verdict[s] = any over that instance's obstacles.  fp64, the
+ * reference's operation order, no FMA.  d_survivors (optional) receives the compacted indices of the
+ * NON-colliding segments in ascending order (warp ballot + prefix scan), *d_n_survivors their count. */
+int ctrm_collide_segments(const double* d_from /*[n][2]*/, const double* d_to /*[n][2]*/, const double* d_rad /*[n]*/,
+                          const int32_t* d_seg_inst /*[n] or NULL (all instance 0)*/, int64_t n_seg,
+                          const double* d_obs_xyr /*[O][3]*/, const int32_t* d_obs_off /*[B+1]*/,
+                          uint8_t* d_verdict /*[n]*/, int32_t* d_survivors /*[n] or NULL*/,
+                          int32_t* d_n_survivors /*[1] or NULL*/, void* stream);
+
+/* general pairwise form of the same test (both spheres moving; dim 2 or 3) — the full signature of
+ * continuousCollideSpheres(from1,to1,rad1,from2,to2,rad2) batched over n pairs. */
+int ctrm_collide_sphere_pairs(const double* d_from1, const double* d_to1, const double* d_rad1, const double* d_from2,
+                              const double* d_to2, const double* d_rad2, int dim, int64_t n, uint8_t* d_verdict,
+                              void* stream);
+
+/* replaces StaticObjects.draw_2d (static_objects.py:173-187) / ObstacleSphere.draw_2d (obstacle.py:63-81):
+ * occ[b][x][y] in {0,1}, uint8, first axis x. */
+int ctrm_raster_occupancy(const double* d_obs_xyr, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, void* stream);
+
+/* replaces get_approx_cost_to_go_matrix_2d (learning/fov.py:34-63) + getCostToGo2D (cost_to_go.cpp:25-107),
+ * batched over A goals: ctg[a][x][y] uint16 hop count, 65535 = unreachable.  Agent footprint stencil
+ * r = ceil(rad*M) (r computed by the HOST in Python float arithmetic -> d_stencil_r). */
+int ctrm_cost_to_go(const uint8_t* d_occ /*[B][M][M]*/, const int32_t* d_agent_inst /*[A]*/,
+                    const double* d_goals /*[A][2]*/, const int32_t* d_stencil_r /*[A]*/, int A, int M,
+                    uint16_t* d_ctg /*[A][M][M]*/, void* stream);
+
+/* replaces getFov2dOccupancyCost (cost_to_go.cpp:109-186) + torch.tensor(...).float() (format_input.py:299-308)
+ * for all agents at once: fov[a][0..2F^2) float32 {0,1}, flatten layout idx = x_fov*F + y_fov, channel 1 at F^2. */
+int ctrm_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos /*[A][2]*/,
+                    int A, int M, int F, float* d_fov /*[A][2F^2]*/, void* stream);
+
+/* replaces Format2D_CTRM_Input.get_feature_one_step after the FOV crop (format_input.py:311-357):
+ * FOV encoders, numba get_arr_others_info (compiled.py:30-97), AgentEncoder, get_comm (format_input.py:212-277),
+ * get_self_info (compiled.py:100-125).  X[a][72] = [self_info 8 | fov_self 32 | comm 32].  Uses the ctx's
+ * uploaded weights and instance table (agent offsets, goals, rads, speeds). */
+int ctrm_encode_features(ctrm_ctx* ctx, const float* d_fov /*[A][2F^2]*/, const double* d_cur /*[A][2]*/,
+                         const double* d_prev /*[A][2]*/, float* d_X /*[A][72]*/, void* stream);
+
+/* replaces indicator+argmax+one_hot (learned_sampler.py:99-104) and CTRMNet.sample (cvae.py:128-138) for K copies
+ * per agent: samples[a][k][3] = (dx,dy,mag).  d_uniforms [A][K][dim_latent] may be NULL -> Philox stream 8 keyed
+ * by (seed; instance, k_traj, t, row k*N+i, column/4).
+ * d_ind (optional) receives the argmax indicator per agent. */
+int ctrm_cvae_sample(ctrm_ctx* ctx, const float* d_X /*[A][72]*/, const float* d_uniforms, int K, uint64_t seed,
+                     int k_traj, int t, float* d_samples /*[A][K][3]*/, int32_t* d_ind /*[A] or NULL*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * the fused driver: replaces get_timed_roadmaps_multiple_paths_with_learned_indicator
+ * (learned_sampler.py:19-204) incl. merge_samples / format_trms / append_goals (roadmap_learned/utils.py:21-174)
+ * for the whole uploaded batch.  The step loop (FOV raster -> encoders -> CVAE -> candidate validation ->
+ * merge/edge building -> advance) is captured once in a CUDA graph and replayed; every instance carries its
+ * own (k_traj, t) so finished roll-outs never wait for the others.
+ * ---------------------------------------------------------------------------------------------- */
+int ctrm_build_roadmaps(ctrm_ctx* ctx, const ctrm_params* params, const ctrm_tables* tables /*or NULL*/, void* stream);
+
+/* after ctrm_build_roadmaps: totals of the CSR result (format after append_goals). */
+int ctrm_result_sizes(ctrm_ctx* ctx, int64_t* n_vertices, int64_t* n_edges, int64_t* n_layers_total);
+
+/* CSR export.  Vertex order: instance, agent, layer t, index i (the reference's V[t][i]);
+ *   layer_ptr [A*(L)+1]   first vertex of (agent a, layer t) at layer_ptr[a*L + t], L = max_T+2; layers beyond an
+ *                         agent's length are empty
+ *   pos       [nv][2] f64 ;  eptr [nv+1] ; eidx [ne]  = indices into the NEXT layer, ascending
+ *   n_layers  [A] = len(trm.V) ;  cnt_collide [B] = StaticObjects.cnt_continuous_collide (static_objects.py:72-75)
+ * dst_is_device selects whether the destination pointers are device or host memory. */
+int ctrm_export_csr(ctrm_ctx* ctx, int32_t* layer_ptr, double* pos, int64_t* eptr, int32_t* eidx, int32_t* n_layers,
+                    int64_t* cnt_collide, int dst_is_device, void* stream);
+
+/* per-step trace for parity tests (optional): when enabled before ctrm_build_roadmaps, the driver records for every
+ * executed (instance, k_traj, t): samples computed by the CVAE [N_traj][max_T][A][K][3] f32, loc_pred and loc_next
+ * [N_traj][max_T][A][2] f64 (NaN where the step was not executed). */
+int ctrm_trace_enable(ctrm_ctx* ctx, int enable);
+int ctrm_trace_read(ctrm_ctx* ctx, float* h_samples, double* h_loc_pred, double* h_loc_next);
+
+/* device timing of the last ctrm_build_roadmaps, measured with CUDA events on its stream:
+ * ms[0] = total, ms[1] = step loop, ms[2] = finalisation; steps = graph replays; launches = kernels launched. */
+int ctrm_last_timing(ctrm_ctx* ctx, float ms[3], int64_t* steps, int64_t* launches);
+
+/* raw views of the context's device state for stage-level tests (valid until the next upload) */
+typedef struct {
+  int32_t B, A, O, M, F, L, S, W;
+  const int32_t *d_agent_off, *d_obs_off, *d_agent_inst;
+  const double *d_starts, *d_goals, *d_speeds, *d_speeds2, *d_rads, *d_obs_xyr;
+  const uint8_t* d_occ;
+  const uint16_t* d_ctg;
+} ctrm_device_view;
+int ctrm_get_device_view(ctrm_ctx* ctx, ctrm_device_view* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * host-buffer convenience wrappers with the pybind11 modules' exact call shapes (B = 1); they copy in,
+ * launch the kernels above on the GPU and copy out.
+ * ---------------------------------------------------------------------------------------------- */
+/* sphere_collision_check_wrapper.continuousCollideSpheres(from1,to1,rad1,from2,to2,rad2) -> bool
+ * (collision_check.cpp:16-24, :60-67) */
+int ctrm_host_continuous_collide_spheres(const double* from1, const double* to1, double rad1, const double* from2,
+                                         const double* to2, double rad2, int dim, int* out_collide);
+/* cost_to_go_wrapper.getCostToGo2D(goal, occupancy_map, occupancy_agent) -> int32[M][M] (cost_to_go.cpp:25-107);
+ * occupancy_agent is the (2r+1)^2 stencil. */
+int ctrm_host_cost_to_go_2d(const double* goal, const int32_t* occupancy_map, int M, const int32_t* occupancy_agent,
+                            int agent_size, int32_t* out_cost /*[M][M]*/);
+/* cost_to_go_wrapper.getFov2dOccupancyCost(current_pos, occupancy_map, cost_to_go, fov_size, flatten)
+ * (cost_to_go.cpp:109-186); cost_to_go passed as int32 with negative = unreachable (the reference's inf -> INT_MIN). */
+int ctrm_host_fov2d(const double* pos, const int32_t* occupancy_map, const int32_t* cost_to_go, int M, int F,
+                    int32_t* out_fov /*[2][F][F]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTRM_B200_H */
