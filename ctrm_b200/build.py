@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "build")
 SOURCES = ["api.cu", "raster.cu", "collide.cu", "encode.cu", "cvae.cu", "rollout.cu", "finalize.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+         "--expt-relaxed-constexpr"]
 
 
 def _deps():

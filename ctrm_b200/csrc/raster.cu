@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restri
   int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (a >= A) return;
-  const uint32_t* pm = pmask + (size_t)agent_pm[a] * M * MW;
+  const int mw = (M + 31) >> 5;  // words per row of the mask as written by passable_mask_kernel
+  const uint32_t* pm = pmask + (size_t)agent_pm[a] * M * mw;
   uint16_t* out = ctg + (size_t)a * M * M;
   uint32_t pass[RPL][MW], vis[RPL][MW], fr[RPL][MW];
 #pragma unroll
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restri
     int x = lane * RPL + r;
 #pragma unroll
     for (int w = 0; w < MW; ++w) {
-      pass[r][w] = (x < M) ? __ldg(&pm[x * MW + w]) : 0u;
+      pass[r][w] = (x < M && w < mw) ? __ldg(&pm[x * mw + w]) : 0u;
       vis[r][w] = 0u;
       fr[r][w] = 0u;
     }

@@ -1,0 +1,296 @@
+"""Stage-level parity of the CUDA kernels (called through the C-ABI) against the reference's golden vectors
+(tests/golden/ref_stage.npz, ref_trace_demo.npz — produced by the unmodified reference, oracle/gen_golden.py) and
+against the oracle on seeded inputs.  Integer / verdict outputs must be bit-exact; fp32 network outputs within
+1e-5 relative (BASELINE.json north_star) using helpers.rel_err."""
+import math
+
+import numpy as np
+import pytest
+
+import ctrm_oracle as O
+from helpers import instance_from_oins, oins_from_npz, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _t():
+    import torch
+
+    return torch
+
+
+def _dev(a):
+    torch = _t()
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _stream():
+    return _t().cuda.current_stream().cuda_stream
+
+
+def _lib():
+    from ctrm_b200 import _lib
+
+    return _lib, _lib.load()
+
+
+# ---------------------------------------------------------------------------------------------- collision
+def test_collide_pairs_golden(stage_gold):
+    L, lib = _lib()
+    z = stage_gold
+    n = len(z["s3.verdict"])
+    f1, t1, c = _dev(z["s3.f1"]), _dev(z["s3.t1"]), _dev(z["s3.c"])
+    r1, r2 = _dev(z["s3.r1"]), _dev(z["s3.r2"])
+    out = _t().zeros(n, dtype=_t().uint8, device="cuda")
+    L.check(lib.ctrm_collide_sphere_pairs(f1.data_ptr(), t1.data_ptr(), r1.data_ptr(), c.data_ptr(), c.data_ptr(),
+                                          r2.data_ptr(), 2, n, out.data_ptr(), _stream()))
+    assert np.array_equal(out.cpu().numpy().astype(bool), z["s3.verdict"])
+
+
+def test_collide_segments_golden_and_compaction(stage_gold):
+    L, lib = _lib()
+    torch = _t()
+    z = stage_gold
+    n = len(z["s3.verdict"])
+    # one obstacle per segment: instance s holds obstacle s; r1 is the agent radius of segment s
+    obs = _dev(np.concatenate([z["s3.c"], z["s3.r2"][:, None]], axis=1))
+    off = _dev(np.arange(n + 1, dtype=np.int32))
+    inst = _dev(np.arange(n, dtype=np.int32))
+    f1, t1, r1 = _dev(z["s3.f1"]), _dev(z["s3.t1"]), _dev(z["s3.r1"])
+    out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    surv = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    nsurv = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.check(lib.ctrm_collide_segments(f1.data_ptr(), t1.data_ptr(), r1.data_ptr(), inst.data_ptr(), n, obs.data_ptr(),
+                                      off.data_ptr(), out.data_ptr(), surv.data_ptr(), nsurv.data_ptr(), _stream()))
+    v = out.cpu().numpy().astype(bool)
+    assert np.array_equal(v, z["s3.verdict"])
+    k = int(nsurv.item())
+    assert k == int((~v).sum())
+    assert np.array_equal(surv[:k].cpu().numpy(), np.nonzero(~v)[0])
+
+
+def test_collide_segments_random_vs_oracle():
+    L, lib = _lib()
+    torch = _t()
+    rng = np.random.RandomState(5)
+    B, n, Omax = 7, 200000, 12
+    nobs = rng.randint(0, Omax, size=B)
+    nobs[3] = 0  # an instance without obstacles never collides
+    off = np.concatenate([[0], np.cumsum(nobs)]).astype(np.int32)
+    obs = np.concatenate([rng.rand(off[-1], 2), rng.rand(off[-1], 1) * 0.04 + 0.02], axis=1)
+    inst = rng.randint(0, B, size=n).astype(np.int32)
+    f = rng.rand(n, 2)
+    t = f + (rng.rand(n, 2) - 0.5) * 0.07
+    t[:1000] = f[:1000]
+    r = rng.rand(n) * 0.02 + 0.01
+    out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d = [_dev(x) for x in (f, t, r, inst, obs if len(obs) else np.zeros((1, 3)), off)]
+    L.check(lib.ctrm_collide_segments(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, d[4].data_ptr(),
+                                      d[5].data_ptr(), out.data_ptr(), None, None, _stream()))
+    want = np.zeros(n, dtype=bool)
+    for b in range(B):
+        m = inst == b
+        if nobs[b] == 0 or not m.any():
+            continue
+        o = obs[off[b]:off[b + 1]]
+        hit = O.sweep_collide(f[m][:, None, :], t[m][:, None, :], r[m][:, None], o[None, :, :2], o[None, :, :2], o[None, :, 2])
+        want[m] = hit.any(axis=1)
+    assert np.array_equal(out.cpu().numpy().astype(bool), want)
+    assert 0.02 < want.mean() < 0.9
+
+
+def test_pybind_shim_collision_reference_cases():
+    """tests/environment/test_fcl_utils.py:73-104 of the reference: crossing (True) vs parallel (False), 2-D and 3-D"""
+    from ctrm_b200.shims import sphere_collision_check_wrapper as scw
+
+    assert scw.continuousCollideSpheres(np.array([0.0, 0.0]), np.array([1.0, 1.0]), 0.1, np.array([1.0, 0.0]),
+                                        np.array([0.0, 1.0]), 0.1) is True
+    assert scw.continuousCollideSpheres(np.array([0.0, 0.0]), np.array([1.0, 0.0]), 0.1, np.array([0.0, 1.0]),
+                                        np.array([1.0, 1.0]), 0.1) is False
+    assert scw.continuousCollideSpheres(np.array([0.0, 0.0, 0.0]), np.array([1.0, 1.0, 1.0]), 0.1, np.array([1.0, 0.0, 0.0]),
+                                        np.array([0.0, 1.0, 1.0]), 0.1) is True
+    assert scw.continuousCollideSpheres(np.array([0.0, 0.0, 0.0]), np.array([1.0, 0.0, 0.0]), 0.1, np.array([0.0, 1.0, 1.0]),
+                                        np.array([1.0, 1.0, 1.0]), 0.1) is False
+
+
+def test_static_objects_thresholds():
+    """tests/environment/test_static_objects.py:7-35 (continuous half): touching at rad collides, rad-0.01 does not"""
+    from ctrm_b200.environment import ObstacleSphere, StaticObjects
+
+    objs = StaticObjects([ObstacleSphere(pos=np.array([0.5, 0.5]), rad=0.1)])
+    rad = 0.1
+    assert objs.collide_continuous_sphere(np.array([0.0, 0.5 - 0.1 - rad]), np.array([1.0, 0.5 - 0.1 - rad]), rad)
+    assert not objs.collide_continuous_sphere(np.array([0.0, 0.5 - 0.1 - rad]), np.array([1.0, 0.5 - 0.1 - rad]), rad - 0.01)
+    assert objs.cnt_continuous_collide == 2
+
+
+# ---------------------------------------------------------------------------------------------- raster / wavefront / FOV
+def test_occupancy_ctg_fov_golden(stage_gold):
+    L, lib = _lib()
+    torch = _t()
+    z = stage_gold
+    M, F = 160, 19
+    oi = oins_from_npz(z, "s1.")
+    N = oi.num_agents
+    obs = _dev(np.concatenate([oi.obs_pos, oi.obs_rad[:, None]], axis=1))
+    off = _dev(np.array([0, len(oi.obs_rad)], dtype=np.int32))
+    occ = torch.zeros(M * M + 16, dtype=torch.uint8, device="cuda")
+    L.check(lib.ctrm_raster_occupancy(obs.data_ptr(), off.data_ptr(), 1, M, occ.data_ptr(), _stream()))
+    assert np.array_equal(occ[:M * M].cpu().numpy().reshape(M, M), z["s1.occ"])
+    inst = torch.zeros(N, dtype=torch.int32, device="cuda")
+    goals = _dev(oi.goals)
+    r = _dev(np.array([math.ceil(x * M) for x in oi.rads], dtype=np.int32))
+    assert len(set(r.cpu().tolist())) > 1  # hetero radii: several passability masks
+    ctg = torch.zeros(N * M * M, dtype=torch.int16, device="cuda")
+    L.check(lib.ctrm_cost_to_go(occ.data_ptr(), inst.data_ptr(), goals.data_ptr(), r.data_ptr(), N, M, ctg.data_ptr(), _stream()))
+    got = ctg.cpu().numpy().view(np.uint16).reshape(N, M, M)
+    assert np.array_equal(got, z["s1.ctg"])
+    # FOV: every golden point for every agent's cost field
+    pts = z["s1.pts"]
+    P = len(pts)
+    pos = _dev(np.tile(pts, (N, 1)))                       # row a*P + p
+    ctg_rep = ctg.view(N, M * M).repeat_interleave(P, dim=0).contiguous()
+    inst2 = torch.zeros(N * P, dtype=torch.int32, device="cuda")
+    fov = torch.zeros(N * P * 2 * F * F + 8, dtype=torch.float32, device="cuda")
+    L.check(lib.ctrm_fov_raster(occ.data_ptr(), ctg_rep.data_ptr(), inst2.data_ptr(), pos.data_ptr(), N * P, M, F,
+                                fov.data_ptr(), _stream()))
+    got = fov[:N * P * 2 * F * F].cpu().numpy().reshape(N, P, 2 * F * F)
+    assert np.array_equal(got, z["s1.fov"].astype(np.float32))
+
+
+def test_pybind_shims_reference_test_vectors(stage_gold):
+    """the reference's own tests/learning/test_fov.py:29-94 through the drop-in modules: cost 30 at the start cell and
+    both 2x5x5 golden FOVs (values as evaluated by the reference, s4.*)"""
+    from ctrm_b200.shims import cost_to_go_wrapper as cw
+
+    z = stage_gold
+    occ = z["s4.occ"].astype(np.float32)
+    stencil = O.agent_stencil(0.05, 16)
+    ctg = cw.getCostToGo2D(np.array([1.0, 1.0]), occ, stencil)
+    assert ctg.dtype == np.int32 and ctg.shape == (16, 16)
+    assert np.array_equal(ctg, z["s4.ctg"].astype(np.int32))
+    assert ctg[0, 0] == 30
+    ctg_f = np.where(ctg == 65535, np.inf, ctg).astype(np.float32)  # learning/fov.py:60-62
+    f00 = cw.getFov2dOccupancyCost(np.array([0.0, 0.0]), occ, ctg_f, 5, False)
+    f01 = cw.getFov2dOccupancyCost(np.array([0.0, 1.0]), occ, ctg_f, 5, False)
+    assert f00.shape == (2, 5, 5)
+    assert np.array_equal(f00, z["s4.fov00"].astype(np.int32).reshape(2, 5, 5))
+    assert np.array_equal(f01, z["s4.fov01"].astype(np.int32).reshape(2, 5, 5))
+    flat = cw.getFov2dOccupancyCost(np.array([0.0, 1.0]), occ, ctg_f, 5, True)
+    assert np.array_equal(flat, f01.reshape(-1))
+
+
+def test_wavefront_edge_cases():
+    """blocked goal cell, walled-off region, goal on the map border, M not a multiple of 32 — vs the oracle BFS"""
+    L, lib = _lib()
+    torch = _t()
+    rng = np.random.RandomState(11)
+    for M in (16, 50, 160, 250):
+        occ = (rng.rand(M, M) < 0.18).astype(np.uint8)
+        occ[M // 2, :] = 1
+        occ[M // 2, M // 3] = 0  # a single door in a wall
+        goals = np.array([[0.999, 0.999], [0.0, 0.0], [0.5, 0.25], [1.0, 0.3], [0.31, 0.77]])
+        rads = np.array([0.0, 1.0 / M, 0.4 / M, 1.5 / M, 2.2 / M])
+        N = len(goals)
+        d_occ = torch.zeros(M * M + 16, dtype=torch.uint8, device="cuda")
+        d_occ[:M * M] = _dev(occ.reshape(-1))
+        inst = torch.zeros(N, dtype=torch.int32, device="cuda")
+        r = _dev(np.array([math.ceil(x * M) for x in rads], dtype=np.int32))
+        ctg = torch.zeros(N * M * M, dtype=torch.int16, device="cuda")
+        L.check(lib.ctrm_cost_to_go(d_occ.data_ptr(), inst.data_ptr(), _dev(goals).data_ptr(), r.data_ptr(), N, M,
+                                    ctg.data_ptr(), _stream()))
+        got = ctg.cpu().numpy().view(np.uint16).reshape(N, M, M)
+        for a in range(N):
+            want = O.cost_to_go(goals[a], occ, rads[a])
+            assert np.array_equal(got[a].astype(np.int32), want), (M, a)
+
+
+# ---------------------------------------------------------------------------------------------- networks
+def _demo_setup(builder, trace_gold):
+    oi = oins_from_npz(trace_gold)
+    builder.upload([instance_from_oins(oi)])
+    return oi, builder.device_view()
+
+
+def test_set_instance_matches_oracle(builder, trace_gold, oracle_weights):
+    """Format2D_CTRM_Input.set_instance of the demo instance, observed through the F=19 crops the first roll-out step
+    reads (centre = the start positions) and through crops centred on every goal"""
+    torch = _t()
+    L, lib = _lib()
+    oi, v = _demo_setup(builder, trace_gold)
+    occ, ctgs = O.set_instance(oracle_weights, oi)
+    M, F = v.M, v.F
+    for pts, dptr in ((oi.starts, v.d_starts), (oi.goals, v.d_goals)):
+        fov = torch.zeros(v.A * 2 * F * F + 8, dtype=torch.float32, device="cuda")
+        L.check(lib.ctrm_fov_raster(v.d_occ, v.d_ctg, v.d_agent_inst, dptr, v.A, M, F, fov.data_ptr(), _stream()))
+        want = O.fov_crop_batch(pts, occ, ctgs, F).astype(np.float32)
+        assert np.array_equal(fov[:v.A * 2 * F * F].cpu().numpy().reshape(v.A, -1), want)
+
+
+def test_encode_features_vs_reference(builder, trace_gold):
+    """X of get_feature_one_step at the recorded steps of the REFERENCE run (nn_X) within 1e-5 relative"""
+    L, lib = _lib()
+    torch = _t()
+    z = trace_gold
+    oi, v = _demo_setup(builder, z)
+    F, M, A = v.F, v.M, v.A
+    worst = 0.0
+    for j, s in enumerate(z["nn_steps"]):
+        cur, prev = _dev(z["cur"][s]), _dev(z["prev"][s])
+        fov = torch.zeros(A * 2 * F * F + 8, dtype=torch.float32, device="cuda")
+        X = torch.zeros(A * 72, dtype=torch.float32, device="cuda")
+        L.check(lib.ctrm_fov_raster(v.d_occ, v.d_ctg, v.d_agent_inst, cur.data_ptr(), A, M, F, fov.data_ptr(), _stream()))
+        L.check(lib.ctrm_encode_features(builder.ctx, fov.data_ptr(), cur.data_ptr(), prev.data_ptr(), X.data_ptr(), _stream()))
+        got = X.cpu().numpy().reshape(A, 72)
+        ref = z["nn_X"][j]
+        assert np.array_equal(got[:, :8], ref[:, :8]) or rel_err(got[:, :8], ref[:, :8]) < 1e-7  # fp64 -> fp32 features
+        for lo, hi in ((0, 8), (8, 40), (40, 72)):
+            worst = max(worst, rel_err(got[:, lo:hi], ref[:, lo:hi]))
+    assert worst <= TOL, worst
+
+
+def test_cvae_sample_vs_reference(builder, trace_gold):
+    """indicator + CTRMNet.sample with the reference's own X and torch.rand uniforms: SAMPLES within 1e-5 relative,
+    indicators identical"""
+    L, lib = _lib()
+    torch = _t()
+    z = trace_gold
+    oi, v = _demo_setup(builder, z)
+    A, K = v.A, 3
+    worst = 0.0
+    for j, s in enumerate(z["nn_steps"]):
+        X = _dev(z["nn_X"][j].astype(np.float32))
+        U = z["nn_U"][j].reshape(K, A, 64).transpose(1, 0, 2)  # reference row k*N+i -> [i][k]
+        dU = _dev(U.astype(np.float32))
+        out = torch.zeros(A * K * 3, dtype=torch.float32, device="cuda")
+        ind = torch.zeros(A, dtype=torch.int32, device="cuda")
+        L.check(lib.ctrm_cvae_sample(builder.ctx, X.data_ptr(), dU.data_ptr(), K, 0, 0, 0, out.data_ptr(), ind.data_ptr(),
+                                     _stream()))
+        got = out.cpu().numpy().reshape(A, K, 3)
+        ref = z["SAMPLES"][s].reshape(K, A, 3).transpose(1, 0, 2)
+        ref_ind = z["IND"][s].reshape(K, A, 3)[0].argmax(-1)
+        assert np.array_equal(ind.cpu().numpy(), ref_ind)
+        worst = max(worst, rel_err(got, ref))
+    assert worst <= TOL, worst
+
+
+def test_cvae_philox_uniforms_match_oracle_tables(builder, trace_gold, oracle_weights):
+    """device Philox stream 8 == oracle/rng_tables.PhiloxTables.gumbel_uniforms (same keys, same float32 mapping)"""
+    from rng_tables import PhiloxTables
+
+    L, lib = _lib()
+    torch = _t()
+    z = trace_gold
+    oi, v = _demo_setup(builder, z)
+    A, K = v.A, 3
+    X = _dev(z["nn_X"][0].astype(np.float32))
+    seed, kt, t = 0x1234567890ABCDEF, 2, 17
+    out = torch.zeros(A * K * 3, dtype=torch.float32, device="cuda")
+    L.check(lib.ctrm_cvae_sample(builder.ctx, X.data_ptr(), None, K, seed, kt, t, out.data_ptr(), None, _stream()))
+    U = PhiloxTables(seed, 0).gumbel_uniforms(kt, t, K * A, 64)
+    Xk = _t().from_numpy(np.concatenate([z["nn_X"][0]] * K).astype(np.float32))
+    with torch.no_grad():
+        IND, _ = O.indicator_onehot(oracle_weights, Xk)
+        ref = O.cvae_sample(oracle_weights, Xk, IND, U).numpy().reshape(K, A, 3).transpose(1, 0, 2)
+    assert rel_err(out.cpu().numpy().reshape(A, K, 3), ref) <= TOL
