@@ -80,6 +80,9 @@ SIGNATURES = {
     "ctrm_trace_enable": (C.c_int, [V, C.c_int]),
     "ctrm_trace_read": (C.c_int, [V, V, V, V]),
     "ctrm_last_timing": (C.c_int, [V, V, c_i64p, c_i64p]),
+    "ctrm_get_instance_steps": (C.c_int, [V, V]),
+    "ctrm_set_profile": (C.c_int, [V, C.c_int]),
+    "ctrm_last_kernel_times": (C.c_int, [V, V, V]),
     "ctrm_get_device_view": (C.c_int, [V, C.POINTER(DeviceView)]),
     "ctrm_host_continuous_collide_spheres": (C.c_int, [V, V, C.c_double, V, V, C.c_double, C.c_int, C.POINTER(C.c_int)]),
     "ctrm_host_cost_to_go_2d": (C.c_int, [V, V, C.c_int, V, C.c_int, V]),

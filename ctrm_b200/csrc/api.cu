@@ -85,6 +85,9 @@ struct ctrm_ctx {
   int32_t* h_ndone = nullptr;  // pinned
   float ms[3] = {0, 0, 0};
   int64_t steps = 0, launches = 0;
+  bool profile = false;
+  double kernel_ms[16] = {0};
+  int64_t kernel_n[16] = {0};
 };
 
 static int sync_in(ctrm_ctx* c, cudaStream_t user) {
@@ -340,6 +343,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&bt.done, (size_t)B));
   CHECK(ar.alloc(&bt.cnt_collide, (size_t)B));
   CHECK(ar.alloc(&bt.n_done, (size_t)1));
+  CHECK(ar.alloc(&bt.steps_done, (size_t)B));
   CHECK(ar.alloc(&bt.nlayers, (size_t)A));
   CHECK(ar.alloc(&c->d_tfin, (size_t)B));
   CHECK(ar.alloc(&c->d_agent_nv, (size_t)A));
@@ -470,8 +474,8 @@ extern "C" int ctrm_cvae_sample(ctrm_ctx* c, const float* d_X, const float* d_un
   bt.seed_lo = (uint32_t)(seed & 0xFFFFFFFFu);
   bt.seed_hi = (uint32_t)(seed >> 32);
   bt.inst_base = 0;
-  return launch_cvae_sample_ex(c->model, bt, d_X, d_uniforms, 0, k_traj, t, bt.cv_logits, bt.cv_dec0, nullptr, d_samples, d_ind,
-                               (cudaStream_t)stream);
+  CHECK(launch_cvae_prior(c->model, bt, d_X, bt.cv_logits, bt.cv_dec0, d_ind, (cudaStream_t)stream));
+  return launch_cvae_decode(c->model, bt, bt.cv_logits, bt.cv_dec0, d_uniforms, 0, k_traj, t, d_samples, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,21 +516,76 @@ static int ensure_rollout_store(ctrm_ctx* c, const ctrm_params* p, int K) {
   return 0;
 }
 
+// kernel ids of the per-kernel timing table (ctrm_last_kernel_times)
+enum { KID_FOV_RASTER = 0, KID_FOV_ENCODE, KID_AGENT_COMM, KID_CVAE_PRIOR, KID_CVAE_DECODE, KID_SELECT, KID_MERGE, KID_ADVANCE,
+       KID_STEP_COUNT };
+
+// profile mode: the step runs eagerly with a CUDA event after every kernel
+struct StepProfiler {
+  std::vector<cudaEvent_t> ev;  // [chunk][KID_STEP_COUNT + 1]
+  int chunk = 0, cur = 0;
+  double ms[KID_STEP_COUNT] = {0};
+  int64_t n[KID_STEP_COUNT] = {0};
+  bool seen[KID_STEP_COUNT] = {false};
+  int init(int chunk_) {
+    chunk = chunk_;
+    ev.resize((size_t)chunk * (KID_STEP_COUNT + 1));
+    for (auto& e : ev) CTRM_CUDA_OK(cudaEventCreate(&e));
+    return 0;
+  }
+  cudaEvent_t at(int step, int k) { return ev[(size_t)step * (KID_STEP_COUNT + 1) + k]; }
+  int flush(int steps_in_chunk, const bool* ran) {  // after a stream sync
+    for (int s = 0; s < steps_in_chunk; ++s) {
+      int prev = 0;
+      for (int k = 0; k < KID_STEP_COUNT; ++k) {
+        if (!ran[k]) continue;
+        float t = 0.f;
+        CTRM_CUDA_OK(cudaEventElapsedTime(&t, at(s, prev), at(s, k + 1)));
+        ms[k] += t;
+        n[k] += 1;
+        prev = k + 1;
+      }
+    }
+    return 0;
+  }
+  void destroy() {
+    for (auto& e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
+
 // one roll-out step for every unfinished instance; `nn` = run the networks (skipped for teacher-forced runs
 // that do not trace the CVAE output)
-static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, int* n_kernels) {
+static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, int* n_kernels, StepProfiler* prof = nullptr,
+                        int pstep = 0, bool* ran = nullptr) {
   int k = 0;
+  auto mark = [&](int kid) -> int {
+    ++k;
+    if (prof) {
+      CTRM_CUDA_OK(cudaEventRecord(prof->at(pstep, kid + 1), st));
+      ran[kid] = true;
+    }
+    return 0;
+  };
+  if (prof) CTRM_CUDA_OK(cudaEventRecord(prof->at(pstep, 0), st));
   if (nn) {
-    CHECK(launch_fov_raster(bt.occ, bt.ctg, bt.agent_inst, bt.cur, bt.done, bt.A, bt.M, bt.F, bt.fov, st)); ++k;
-    CHECK(launch_fov_encode(c->model, bt.fov, bt.agent_inst, bt.done, bt.A, bt.e_self, nullptr, bt.vain_proj, st)); ++k;
-    CHECK(launch_agent_comm(c->model, bt, bt.cur, bt.prev, bt.e_self, bt.vain_proj, bt.X, st)); ++k;
-    CHECK(launch_cvae_sample_ex(c->model, bt, bt.X, nullptr, 1, 0, 0, bt.cv_logits, bt.cv_dec0, nullptr, bt.samples,
-                                bt.ind, st));
-    k += 2;
+    CHECK(launch_fov_raster(bt.occ, bt.ctg, bt.agent_inst, bt.cur, bt.done, bt.A, bt.M, bt.F, bt.fov, st));
+    CHECK(mark(KID_FOV_RASTER));
+    CHECK(launch_fov_encode(c->model, bt.fov, bt.agent_inst, bt.done, bt.A, bt.e_self, nullptr, bt.vain_proj, st));
+    CHECK(mark(KID_FOV_ENCODE));
+    CHECK(launch_agent_comm(c->model, bt, bt.cur, bt.prev, bt.e_self, bt.vain_proj, bt.X, st));
+    CHECK(mark(KID_AGENT_COMM));
+    CHECK(launch_cvae_prior(c->model, bt, bt.X, bt.cv_logits, bt.cv_dec0, bt.ind, st));
+    CHECK(mark(KID_CVAE_PRIOR));
+    CHECK(launch_cvae_decode(c->model, bt, bt.cv_logits, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st));
+    CHECK(mark(KID_CVAE_DECODE));
   }
-  CHECK(launch_select(bt, st)); ++k;
-  CHECK(launch_merge(bt, st)); ++k;
-  CHECK(launch_advance(bt, st)); ++k;
+  CHECK(launch_select(bt, st));
+  CHECK(mark(KID_SELECT));
+  CHECK(launch_merge(bt, st));
+  CHECK(mark(KID_MERGE));
+  CHECK(launch_advance(bt, st));
+  CHECK(mark(KID_ADVANCE));
   *n_kernels = k;
   return 0;
 }
@@ -613,36 +672,58 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   }
   CHECK(launch_rollout_init(bt, st));
   int64_t launches = 1;
-  // capture one step as a CUDA graph, then replay it; n_done is polled every `chunk` replays
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
-  int per_step = 0;
-  CTRM_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  int rc = enqueue_step(c, bt, nn, st, &per_step);
-  cudaError_t ce = cudaStreamEndCapture(st, &graph);
-  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-  if (ce != cudaSuccess) return ctrm_fail_cuda(ce, "cudaStreamEndCapture");
-  ce = cudaGraphInstantiate(&gexec, graph, 0);
-  if (ce != cudaSuccess) { cudaGraphDestroy(graph); return ctrm_fail_cuda(ce, "cudaGraphInstantiate"); }
-  CTRM_CUDA_OK(cudaEventRecord(c->ev_t[1], st));
+  // capture one step as a CUDA graph, then replay it; n_done is polled every `chunk` replays.
+  // profile mode runs the same kernels eagerly with an event after each one (per-kernel durations).
   const int chunk = 32;
+  int per_step = 0;
   int64_t steps = 0;
-  rc = 0;
-  while ((size_t)steps < steps_max) {
-    int n = (int)std::min<size_t>(chunk, steps_max - steps);
-    for (int i = 0; i < n && !rc; ++i) {
-      ce = cudaGraphLaunch(gexec, st);
-      if (ce != cudaSuccess) rc = ctrm_fail_cuda(ce, "cudaGraphLaunch");
+  int rc = 0;
+  cudaError_t ce = cudaSuccess;
+  if (!c->profile) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    CTRM_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_step(c, bt, nn, st, &per_step);
+    ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return ctrm_fail_cuda(ce, "cudaStreamEndCapture");
+    ce = cudaGraphInstantiate(&gexec, graph, 0);
+    if (ce != cudaSuccess) { cudaGraphDestroy(graph); return ctrm_fail_cuda(ce, "cudaGraphInstantiate"); }
+    CTRM_CUDA_OK(cudaEventRecord(c->ev_t[1], st));
+    while ((size_t)steps < steps_max) {
+      int n = (int)std::min<size_t>(chunk, steps_max - steps);
+      for (int i = 0; i < n && !rc; ++i) {
+        ce = cudaGraphLaunch(gexec, st);
+        if (ce != cudaSuccess) rc = ctrm_fail_cuda(ce, "cudaGraphLaunch");
+      }
+      if (rc) break;
+      steps += n;
+      ce = cudaMemcpyAsync(c->h_ndone, bt.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "roll-out step loop"); break; }
+      if (*c->h_ndone >= bt.B) break;
     }
-    if (rc) break;
-    steps += n;
-    ce = cudaMemcpyAsync(c->h_ndone, bt.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "roll-out step loop"); break; }
-    if (*c->h_ndone >= bt.B) break;
+    cudaGraphExecDestroy(gexec);
+    cudaGraphDestroy(graph);
+  } else {
+    StepProfiler prof;
+    CHECK(prof.init(chunk));
+    bool ran[KID_STEP_COUNT] = {false};
+    CTRM_CUDA_OK(cudaEventRecord(c->ev_t[1], st));
+    while ((size_t)steps < steps_max && !rc) {
+      int n = (int)std::min<size_t>(chunk, steps_max - steps);
+      for (int i = 0; i < n && !rc; ++i) rc = enqueue_step(c, bt, nn, st, &per_step, &prof, i, ran);
+      if (rc) break;
+      steps += n;
+      ce = cudaMemcpyAsync(c->h_ndone, bt.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "roll-out step loop (profile)"); break; }
+      rc = prof.flush(n, ran);
+      if (*c->h_ndone >= bt.B) break;
+    }
+    for (int k = 0; k < KID_STEP_COUNT; ++k) { c->kernel_ms[k] = prof.ms[k]; c->kernel_n[k] = prof.n[k]; }
+    prof.destroy();
   }
-  cudaGraphExecDestroy(gexec);
-  cudaGraphDestroy(graph);
   CHECK(rc);
   launches += steps * per_step;
   CTRM_CUDA_OK(cudaEventRecord(c->ev_t[2], st));
@@ -714,6 +795,26 @@ extern "C" int ctrm_trace_read(ctrm_ctx* c, float* h_samples, double* h_loc_pred
   if (h_samples) CTRM_CUDA_OK(cudaMemcpy(h_samples, bt.tr_samples, steps * bt.A * bt.K * 3 * sizeof(float), cudaMemcpyDeviceToHost));
   if (h_loc_pred) CTRM_CUDA_OK(cudaMemcpy(h_loc_pred, bt.tr_loc_pred, steps * bt.A * 2 * sizeof(double), cudaMemcpyDeviceToHost));
   if (h_loc_next) CTRM_CUDA_OK(cudaMemcpy(h_loc_next, bt.tr_loc_next, steps * bt.A * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ctrm_get_instance_steps(ctrm_ctx* c, int32_t* h_steps) {
+  if (!c || !h_steps) return ctrm_fail(CTRM_ERR_ARG, "NULL argument");
+  if (!c->have_result) return ctrm_fail(CTRM_ERR_STATE, "no result");
+  CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  CTRM_CUDA_OK(cudaMemcpy(h_steps, c->bt.steps_done, (size_t)c->bt.B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ctrm_set_profile(ctrm_ctx* c, int enable) {
+  if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
+  c->profile = enable != 0;
+  return 0;
+}
+
+extern "C" int ctrm_last_kernel_times(ctrm_ctx* c, double ms[8], int64_t launches[8]) {
+  if (!c || !ms || !launches) return ctrm_fail(CTRM_ERR_ARG, "NULL argument");
+  for (int k = 0; k < KID_STEP_COUNT; ++k) { ms[k] = c->kernel_ms[k]; launches[k] = c->kernel_n[k]; }
   return 0;
 }
 

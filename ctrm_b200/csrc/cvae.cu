@@ -221,22 +221,27 @@ __global__ void __launch_bounds__(CV_T) cvae_decode_kernel(Batch bt, int K, cons
 }
 
 // scratch owned by the caller: logits [A][64], dec0 [A][32]
-int launch_cvae_sample_ex(const DevModel& m, const Batch& bt, const float* d_X, const float* d_uniforms, int use_state_kt,
-                          int kt_fixed, int t_fixed, float* d_logits, float* d_dec0, const int32_t* d_ind_override, float* d_samples, int32_t* d_ind,
-                          cudaStream_t st) {
+int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,
+                      cudaStream_t st) {
   if (bt.A <= 0) return 0;
-  const int K = bt.K;
   int w_lo = m.off.ind_w0, w_hi = m.off.total;
   size_t smem1 = (size_t)(w_hi - w_lo + CTRM_DIM_X * CV_T) * sizeof(float);
-  size_t smem2 = (size_t)(64 * 32 + 32 * 32 + 32 * 4 + 32 + 4 + 64 * CV_T) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     CTRM_CUDA_OK(cudaFuncSetAttribute(cvae_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     attr = true;
   }
   cvae_prior_kernel<<<(bt.A + CV_T - 1) / CV_T, CV_T, smem1, st>>>(bt, d_X, m.blob, m.off, w_lo, w_hi, d_logits, d_dec0, d_ind,
-                                                                  d_ind_override);
+                                                                  nullptr);
   CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits, const float* d_dec0, const float* d_uniforms,
+                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st) {
+  if (bt.A <= 0) return 0;
+  const int K = bt.K;
+  size_t smem2 = (size_t)(64 * 32 + 32 * 32 + 32 * 4 + 32 + 4 + 64 * CV_T) * sizeof(float);
   long long rows = (long long)bt.A * K;
   cvae_decode_kernel<<<(unsigned)((rows + CV_T - 1) / CV_T), CV_T, smem2, st>>>(bt, K, d_logits, d_dec0, d_uniforms, use_state_kt,
                                                                               kt_fixed, t_fixed, m.desc.temp, m.blob, m.off, d_samples);

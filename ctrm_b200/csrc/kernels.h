@@ -34,6 +34,7 @@ struct Batch {
   uint8_t* done;                        // [B]
   unsigned long long* cnt_collide;      // [B]   StaticObjects.cnt_continuous_collide
   int32_t* n_done;                      // [1]
+  int32_t* steps_done;                  // [B] executed roll-out steps (bench accounting)
   // per-step tensors
   float *fov, *e_self, *e_vain, *vain_proj, *X, *samples;
   float *cv_logits, *cv_dec0;  // [A][64], [A][32]
@@ -78,9 +79,10 @@ int launch_fov_encode(const DevModel& m, const float* d_fov, const int32_t* d_ag
                       float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st);
 int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, const double* d_prev, const float* d_e_self,
                       const float* d_vain_proj, float* d_X, cudaStream_t st);
-int launch_cvae_sample_ex(const DevModel& m, const Batch& bt, const float* d_X, const float* d_uniforms, int use_state_kt,
-                          int kt_fixed, int t_fixed, float* d_logits, float* d_dec0, const int32_t* d_ind_override, float* d_samples, int32_t* d_ind,
-                          cudaStream_t st);
+int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,
+                      cudaStream_t st);
+int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits, const float* d_dec0, const float* d_uniforms,
+                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st);
 
 int launch_select(const Batch& bt, cudaStream_t st);
 int launch_merge(const Batch& bt, cudaStream_t st);

@@ -36,6 +36,7 @@ __global__ void rollout_init_kernel(Batch bt) {
     bt.makespan[i] = 0;
     bt.done[i] = (bt.N_traj <= 0) ? 1 : 0;
     bt.cnt_collide[i] = 0ULL;
+    bt.steps_done[i] = 0;
   }
   if (i == 0) *bt.n_done = (bt.N_traj <= 0) ? bt.B : 0;
 }
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) advance_kernel(Batch bt) {
   for (int i = lane; i < N; i += 32) all = all && (bt.arrived[a0 + i] != 0);
   all = __all_sync(0xFFFFFFFFu, all);
   const int t = bt.t[b];
+  if (lane == 0) bt.steps_done[b] += 1;
   bool end_roll = false;
   if (all) {  // learned_sampler.py:186-191
     if (lane == 0) bt.makespan[b] = bt.makespan[b] ? max(bt.makespan[b], t) : t;

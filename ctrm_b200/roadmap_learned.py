@@ -178,6 +178,46 @@ class RoadmapBuilder:
         agent_off = np.concatenate([[0], np.cumsum(p["n_agents"])]).astype(np.int32)
         return CSRRoadmaps(agent_off, L, layer_ptr, pos, eptr, eidx, n_layers, cnt, self.timing())
 
+    KERNELS = ("fov_raster", "fov_encode", "agent_comm", "cvae_prior", "cvae_decode", "select", "merge", "advance")
+
+    def set_profile(self, enable: bool):
+        """eager launches with a CUDA event after every kernel (per-kernel device times, see kernel_times)"""
+        _lib.check(self.lib.ctrm_set_profile(self.ctx, int(enable)), "ctrm_set_profile")
+
+    def kernel_times(self) -> dict:
+        ms = (C.c_double * 8)()
+        n = (C.c_int64 * 8)()
+        _lib.check(self.lib.ctrm_last_kernel_times(self.ctx, C.cast(ms, C.c_void_p), C.cast(n, C.c_void_p)),
+                   "ctrm_last_kernel_times")
+        return {k: dict(ms=ms[i], launches=n[i]) for i, k in enumerate(self.KERNELS)}
+
+    def instance_steps(self) -> np.ndarray:
+        out = np.zeros(len(self._uploaded["n_agents"]), dtype=np.int32)
+        _lib.check(self.lib.ctrm_get_instance_steps(self.ctx, _lib.ptr(out)), "ctrm_get_instance_steps")
+        return out
+
+    def export_device(self, stream: int = 0) -> dict:
+        """CSR result as torch CUDA tensors (no D2H): used for the multi-GPU gather and the device-resident timing"""
+        import torch
+
+        p = self._uploaded
+        nv, ne, _ = self.result_sizes()
+        A = int(p["n_agents"].sum())
+        B = len(p["n_agents"])
+        L = self._last["max_T"] + 2
+        dev = torch.device("cuda", self.device)
+        out = dict(layer_ptr=torch.empty(A * L + 1, dtype=torch.int32, device=dev),
+                   pos=torch.empty((nv, 2), dtype=torch.float64, device=dev),
+                   eptr=torch.empty(nv + 1, dtype=torch.int64, device=dev),
+                   eidx=torch.empty(max(ne, 1), dtype=torch.int32, device=dev),
+                   n_layers=torch.empty(A, dtype=torch.int32, device=dev),
+                   cnt_collide=torch.empty(B, dtype=torch.int64, device=dev))
+        _lib.check(self.lib.ctrm_export_csr(self.ctx, out["layer_ptr"].data_ptr(), out["pos"].data_ptr(), out["eptr"].data_ptr(),
+                                            out["eidx"].data_ptr(), out["n_layers"].data_ptr(), out["cnt_collide"].data_ptr(), 1,
+                                            stream), "ctrm_export_csr")
+        out["eidx"] = out["eidx"][:ne]
+        return out
+
     def read_trace(self):
         """(samples [N_traj][max_T][A][K][3] f32, loc_pred, loc_next [N_traj][max_T][A][2] f64); NaN = not executed"""
         p = self._uploaded

@@ -210,6 +210,15 @@ int ctrm_trace_read(ctrm_ctx* ctx, float* h_samples, double* h_loc_pred, double*
  * ms[0] = total, ms[1] = step loop, ms[2] = finalisation; steps = graph replays; launches = kernels launched. */
 int ctrm_last_timing(ctrm_ctx* ctx, float ms[3], int64_t* steps, int64_t* launches);
 
+/* profile mode: the next ctrm_build_roadmaps calls launch every step kernel eagerly (no CUDA graph) with a CUDA event
+ * after each kernel on the driver's stream; ctrm_last_kernel_times returns the summed device time (ms) and the
+ * launch count per kernel, in the order fov_raster, fov_encode, agent_comm, cvae_prior, cvae_decode, select, merge,
+ * advance.  Used by bench.py for the roofline of the dominant kernel. */
+/* executed roll-out steps per instance of the last build (sum over its N_traj roll-outs) */
+int ctrm_get_instance_steps(ctrm_ctx* ctx, int32_t* h_steps /*[B]*/);
+int ctrm_set_profile(ctrm_ctx* ctx, int enable);
+int ctrm_last_kernel_times(ctrm_ctx* ctx, double ms[8], int64_t launches[8]);
+
 /* raw views of the context's device state for stage-level tests (valid until the next upload) */
 typedef struct {
   int32_t B, A, O, M, F, L, S, W;

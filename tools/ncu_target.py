@@ -1,0 +1,18 @@
+"""Short single-GPU run of the hot path for ncu: one batch of synthetic aamas22 instances, a few roll-outs.
+    python tools/ncu_target.py [batch] [n_traj]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import PARAMS, WEIGHTS, make_instances  # noqa: E402
+
+from ctrm_b200 import RoadmapBuilder  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+NT = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+b = RoadmapBuilder(WEIGHTS, 0)
+prm = dict(PARAMS, N_traj=NT)
+csr = b.build(make_instances(B, 0), seed=1, **prm)
+print("vertices", csr.n_vertices, "edges", csr.n_edges, csr.timing)
