@@ -194,6 +194,13 @@ extern "C" int ctrm_load_weights(ctrm_ctx* c, const ctrm_model_desc* d, const fl
   c->model.blob = blob;
   c->model.off = off;
   c->model.desc = *d;
+  {
+    float mxw = 0.f;
+    for (int i = 0; i < 64 * 32; ++i) mxw = std::fmax(mxw, std::fabs(h_blob[off.dec_w0 + i]));
+    int e = 0;
+    while (std::ldexp(1.0f, e) <= mxw && e < 30) ++e;
+    c->model.dec_w0z_exp = e;
+  }
   c->have_weights = true;
   return 0;
 }

@@ -4,8 +4,8 @@
 //   (torch.distributions: probs normalised, logits = log(clamp(probs)), Gumbel noise from clamped uniforms,
 //   softmax((logits+g)/temp)) -> decoder (cvae.py:72-76).  BatchNorm runs in eval mode (model/__init__.py:53) and
 //   is folded into the preceding Linear by the host.
-// Two kernels: cvae_prior (one thread per agent: the parts shared by the K copies) and cvae_decode (one thread
-// per (agent, copy) row: Gumbel-softmax + decoder MLP).
+// cvae_prior: one thread per agent, the parts shared by the K copies.  The per-copy Gumbel-softmax + decoder MLP runs on
+// the tensor cores: cvae_tc.cu.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -129,97 +129,6 @@ __global__ void __launch_bounds__(CV_T) cvae_prior_kernel(Batch bt, const float*
 #undef WP
 }
 
-// ------------------------------------------------------------------------------------------------
-// decode: one thread per (agent a, copy k).  u -> Gumbel -> z = softmax((logits + g)/temp) -> decoder.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CV_T) cvae_decode_kernel(Batch bt, int K, const float* __restrict__ logits,
-                                                           const float* __restrict__ dec0, const float* __restrict__ uniforms,
-                                                           int use_state_kt, int kt_fixed, int t_fixed, float temp, const float* __restrict__ blob,
-                                                           ctrm_weight_offsets_t off, float* __restrict__ samples) {
-  extern __shared__ __align__(16) float smem[];
-  float* W0 = smem;               // [64][32] z rows of the decoder's first layer
-  float* W1 = W0 + 64 * 32;       // [32][32]
-  float* W2 = W1 + 32 * 32;       // [32][4]
-  float* B1 = W2 + 32 * 4;        // [32]
-  float* B2 = B1 + 32;            // [4]
-  float* zs = B2 + 4;             // [64][CV_T]
-  for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) W0[i] = __ldg(&blob[off.dec_w0 + i]);
-  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) W1[i] = __ldg(&blob[off.dec_w1 + i]);
-  for (int i = threadIdx.x; i < 32 * 4; i += blockDim.x) W2[i] = __ldg(&blob[off.dec_w2 + i]);
-  for (int i = threadIdx.x; i < 32; i += blockDim.x) B1[i] = __ldg(&blob[off.dec_b1 + i]);
-  for (int i = threadIdx.x; i < 4; i += blockDim.x) B2[i] = __ldg(&blob[off.dec_b2 + i]);
-  __syncthreads();
-  const int tid = threadIdx.x;
-  const long long row = (long long)blockIdx.x * CV_T + tid;
-  if (row >= (long long)bt.A * K) return;
-  const int a = (int)(row / K), k = (int)(row - (long long)a * K);
-  const int b = bt.agent_inst[a];
-  if (bt.done != nullptr && bt.done[b]) return;
-  const float eps = 1.1920928955078125e-07f;
-  const float* lg = logits + (size_t)a * 64;
-  // uniforms: explicit [A][K][64] or Philox stream 8 keyed (instance, k_traj|t, reference row k*N+i, column/4)
-  const float* urow = nullptr;
-  uint32_t c0 = 0, c1 = 0, c2 = 0;
-  if (uniforms != nullptr) {
-    urow = uniforms + (size_t)row * 64;
-  } else {
-    int N = bt.agent_off[b + 1] - bt.agent_off[b], il = a - bt.agent_off[b];
-    int kt = use_state_kt ? bt.k_traj[b] : kt_fixed, tt = use_state_kt ? bt.t[b] : t_fixed;
-    c0 = bt.inst_base + (uint32_t)b;
-    c1 = rng_ctr1(kt, tt);
-    c2 = (uint32_t)(k * N + il);
-  }
-  float mx = -INFINITY;
-#pragma unroll 4
-  for (int q = 0; q < 16; ++q) {
-    float u4[4];
-    if (urow != nullptr) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(urow + q * 4));
-      u4[0] = v.x; u4[1] = v.y; u4[2] = v.z; u4[3] = v.w;
-    } else {
-      uint4 w = philox4x32(c0, c1, c2, rng_ctr3(STREAM_GUMBEL, (uint32_t)q), bt.seed_lo, bt.seed_hi);
-      u4[0] = u32_to_f32(w.x); u4[1] = u32_to_f32(w.y); u4[2] = u32_to_f32(w.z); u4[3] = u32_to_f32(w.w);
-    }
-    float4 l4 = __ldg(reinterpret_cast<const float4*>(lg + q * 4));
-    float l[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float u = fminf(fmaxf(u4[j], eps), 1.f - eps);
-      float g = -logf(-logf(u));
-      float s = (l[j] + g) / temp;
-      zs[(q * 4 + j) * CV_T + tid] = s;
-      mx = fmaxf(mx, s);
-    }
-  }
-  float se = 0.f;
-  for (int c = 0; c < 64; ++c) se += expf(zs[c * CV_T + tid] - mx);
-  const float lse = mx + logf(se);
-  float h1[32], h2[32];
-  {
-    const float4* d0 = reinterpret_cast<const float4*>(dec0 + (size_t)a * 32);
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      float4 v = __ldg(&d0[j4]);
-      h1[j4 * 4] = v.x; h1[j4 * 4 + 1] = v.y; h1[j4 * 4 + 2] = v.z; h1[j4 * 4 + 3] = v.w;
-    }
-  }
-  for (int c = 0; c < 64; ++c) {
-    float z = expf(zs[c * CV_T + tid] - lse);
-    fma_row<32, 32>(z, W0 + c * 32, h1);
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) h1[j] = fmaxf(h1[j], 0.f);
-  dense32<32, 32>(h1, W1, B1, h2);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) h2[j] = fmaxf(h2[j], 0.f);
-  float o[4];
-  dense32<3, 4>(h2, W2, B2, o);
-  float* out = samples + (size_t)row * 3;
-  out[0] = o[0];
-  out[1] = o[1];
-  out[2] = o[2];
-}
-
 // scratch owned by the caller: logits [A][64], dec0 [A][32]
 int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,
                       cudaStream_t st) {
@@ -233,18 +142,6 @@ int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, floa
   }
   cvae_prior_kernel<<<(bt.A + CV_T - 1) / CV_T, CV_T, smem1, st>>>(bt, d_X, m.blob, m.off, w_lo, w_hi, d_logits, d_dec0, d_ind,
                                                                   nullptr);
-  CTRM_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits, const float* d_dec0, const float* d_uniforms,
-                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st) {
-  if (bt.A <= 0) return 0;
-  const int K = bt.K;
-  size_t smem2 = (size_t)(64 * 32 + 32 * 32 + 32 * 4 + 32 + 4 + 64 * CV_T) * sizeof(float);
-  long long rows = (long long)bt.A * K;
-  cvae_decode_kernel<<<(unsigned)((rows + CV_T - 1) / CV_T), CV_T, smem2, st>>>(bt, K, d_logits, d_dec0, d_uniforms, use_state_kt,
-                                                                              kt_fixed, t_fixed, m.desc.temp, m.blob, m.off, d_samples);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,245 @@
+// CVAE decoder on the 5th-generation tensor cores (tcgen05 + TMEM), fused with the Gumbel-softmax that produces its
+// input.  reference: RelaxedOneHotCategorical(temp).rsample() + CTRMNet.decoder (learning/model/cvae.py:72-76, :133-137).
+//
+// One CTA = 128 threads = one 128-row tile at a time (row = (agent, copy)); thread r owns row r and TMEM lane r.
+//   1. thread r: Philox uniforms -> Gumbel noise -> z = softmax((logits + g)/temp)   (64 values, fp32)
+//      z is split exactly into three bf16 parts and written to shared memory in the UMMA K-major canonical layout
+//   2. one thread issues 4 k-steps x 6 tcgen05.mma (BF16x3): D0[128x32] = z[128x64] . W0z[64x32]  -> TMEM cols 0..31
+//   3. thread r: tcgen05.ld its 32 accumulators, + dec0[agent] (x-part of layer 0 and folded BatchNorm bias, from
+//      cvae_prior), ReLU, split, back to shared memory as the next A operand
+//   4. D1[128x32] = h1 . W1 (2 k-steps x 6 MMAs) -> TMEM cols 32..63
+//   5. thread r: ld, + b1, ReLU, the 32x3 output layer on CUDA cores, store (dx, dy, mag)
+// Weights are split and staged once per (persistent) CTA.  fp32-accurate: see tc.cuh.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc.cuh"
+
+#define DT_THREADS 128
+// shared memory: z digit tiles 4 x 16 KB (K = 64; tiles 2 and 3 double as the fp32 scratch of the softmax, and the whole
+// region is reused for the three bf16 parts of h1, K = 32) | W0 digit tiles 4 x 4 KB | W1 parts 3 x 2 KB | W2, b1, b2 |
+// mbarrier, TMEM slot
+#define DT_A_PART 16384u
+#define DT_H_PART 8192u
+#define DT_W0_PART 4096u
+#define DT_W1_PART 2048u
+#define DT_SMEM (4 * 16384 + 4 * 4096 + 3 * 2048 + (128 + 32 + 4) * 4 + 16)
+#define DT_TMEM_COLS 256  // 4 x 32 layer-0 digit accumulators + 32 layer-1
+
+// 8 fp32 values of row r, columns k0..k0+7, parked as two 16-byte halves in the slots of digit tiles 2 and 3
+__device__ __forceinline__ void park8(uint8_t* At, int r, int k0, const float* v) {
+  const uint32_t off = tc::elem_offset(r, k0, 64);
+  uint32_t lo[4], hi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t a = __float_as_uint(v[2 * j]), b = __float_as_uint(v[2 * j + 1]);
+    lo[j] = (a & 0xFFFFu) | (b << 16);
+    hi[j] = (a >> 16) | (b & 0xFFFF0000u);
+  }
+  *reinterpret_cast<uint4*>(At + 2 * DT_A_PART + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  *reinterpret_cast<uint4*>(At + 3 * DT_A_PART + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+}
+__device__ __forceinline__ void unpark8(const uint8_t* At, int r, int k0, float* v) {
+  const uint32_t off = tc::elem_offset(r, k0, 64);
+  const uint4 l4 = *reinterpret_cast<const uint4*>(At + 2 * DT_A_PART + off);
+  const uint4 h4 = *reinterpret_cast<const uint4*>(At + 3 * DT_A_PART + off);
+  const uint32_t lo[4] = {l4.x, l4.y, l4.z, l4.w}, hi[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float((lo[j] & 0xFFFFu) | (hi[j] << 16));
+    v[2 * j + 1] = __uint_as_float((lo[j] >> 16) | (hi[j] & 0xFFFF0000u));
+  }
+}
+
+__global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, int K, const float* __restrict__ logits,
+                                                                    const float* __restrict__ dec0,
+                                                                    const float* __restrict__ uniforms, int use_state_kt,
+                                                                    int kt_fixed, int t_fixed, float temp, int w0_exp,
+                                                                    const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                    float* __restrict__ samples, int n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* At = smem;                       // z digits 1..4, [128 x 64] bf16 each
+  uint8_t* W0t = At + 4 * DT_A_PART;        // W0z digits 1..4, [32 x 64]
+  uint8_t* W1t = W0t + 4 * DT_W0_PART;      // W1 parts 1..3, [32 x 32]
+  float* W2 = reinterpret_cast<float*>(W1t + 3 * DT_W1_PART);  // [32][4]
+  float* B1 = W2 + 128;
+  float* B2 = B1 + 32;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(B2 + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // |W0z| < 2^w0_exp (host): digit scale 2^(7 - w0_exp) puts every weight in [-128, 128]
+  tc::stage_weight_digits(blob + off.dec_w0, 32, 0, 64, 32, 32, 64, exp2f((float)(7 - w0_exp)), W0t, tid, DT_THREADS);
+  tc::stage_weight_split(blob + off.dec_w1, 32, 0, 32, 32, 32, 32, W1t, tid, DT_THREADS);
+  for (int i = tid; i < 128; i += DT_THREADS) W2[i] = __ldg(&blob[off.dec_w2 + i]);
+  if (tid < 32) B1[tid] = __ldg(&blob[off.dec_b1 + tid]);
+  if (tid < 4) B2[tid] = __ldg(&blob[off.dec_b2 + tid]);
+  if (warp == 0) tc::tmem_alloc(tmem_slot, DT_TMEM_COLS);
+  if (tid == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t mb = tc::smem_u32(mbar);
+  const uint32_t sA = tc::smem_u32(At), sW0 = tc::smem_u32(W0t), sW1 = tc::smem_u32(W1t);
+  uint32_t phase = 0;
+  const float eps = 1.1920928955078125e-07f;
+  const long long n_rows = (long long)bt.A * K;
+  // accumulator g (digit index sum, 0-based) carries weight 256^-(g+1) * 2^(w0_exp - 7)
+  double acc_scale[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) acc_scale[g] = exp2((double)(w0_exp - 7 - 8 * (g + 1)));
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row = (long long)tile * 128 + tid;
+    bool live = row < n_rows;
+    int a = 0, k = 0, b = 0;
+    if (live) {
+      a = (int)(row / K);
+      k = (int)(row - (long long)a * K);
+      b = bt.agent_inst[a];
+      live = !(bt.done != nullptr && bt.done[b]);
+    }
+    // a tile whose rows all belong to finished instances is skipped entirely
+    if (!__syncthreads_or(live)) continue;
+    if (live) {
+      const float* lg = logits + (size_t)a * 64;
+      const float* urow = nullptr;
+      uint32_t c0 = 0, c1 = 0, c2 = 0;
+      if (uniforms != nullptr) {
+        urow = uniforms + (size_t)row * 64;
+      } else {
+        const int N = bt.agent_off[b + 1] - bt.agent_off[b], il = a - bt.agent_off[b];
+        const int kt = use_state_kt ? bt.k_traj[b] : kt_fixed, tt = use_state_kt ? bt.t[b] : t_fixed;
+        c0 = bt.inst_base + (uint32_t)b;
+        c1 = rng_ctr1(kt, tt);
+        c2 = (uint32_t)(k * N + il);  // the reference's row order k*N + i (learned_sampler.py:82)
+      }
+      float mx = -INFINITY;
+      for (int q = 0; q < 8; ++q) {
+        float u8[8], s[8];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          if (urow != nullptr) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(urow + q * 8 + h2 * 4));
+            u8[h2 * 4 + 0] = v.x; u8[h2 * 4 + 1] = v.y; u8[h2 * 4 + 2] = v.z; u8[h2 * 4 + 3] = v.w;
+          } else {
+            const uint4 w = philox4x32(c0, c1, c2, rng_ctr3(STREAM_GUMBEL, (uint32_t)(q * 2 + h2)), bt.seed_lo, bt.seed_hi);
+            u8[h2 * 4 + 0] = u32_to_f32(w.x); u8[h2 * 4 + 1] = u32_to_f32(w.y);
+            u8[h2 * 4 + 2] = u32_to_f32(w.z); u8[h2 * 4 + 3] = u32_to_f32(w.w);
+          }
+        }
+        const float4 la = __ldg(reinterpret_cast<const float4*>(lg + q * 8)), lb = __ldg(reinterpret_cast<const float4*>(lg + q * 8 + 4));
+        const float l[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float u = fminf(fmaxf(u8[j], eps), 1.f - eps);
+          const float g = -logf(-logf(u));
+          s[j] = (l[j] + g) / temp;
+          mx = fmaxf(mx, s[j]);
+        }
+        park8(At, tid, q * 8, s);
+      }
+      float se = 0.f;
+      for (int q = 0; q < 8; ++q) {
+        float s[8];
+        unpark8(At, tid, q * 8, s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) se += expf(s[j] - mx);
+      }
+      const float lse = mx + logf(se);  // torch: z = exp(scores - logsumexp(scores))
+      for (int q = 0; q < 8; ++q) {
+        float s[8];
+        unpark8(At, tid, q * 8, s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = fminf(expf(s[j] - lse), 1.f);
+        tc::store_digits8_unit(At, DT_A_PART, tid, q * 8, 64, s);
+      }
+    } else {
+      const float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int q = 0; q < 8; ++q) tc::store_digits8_unit(At, DT_A_PART, tid, q * 8, 64, v);
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::mma_digits4(tbase, 32, sA, DT_A_PART, sW0, DT_W0_PART, 64, 32);
+      tc::commit(mb);
+    }
+    tc::mbar_wait(mb, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+    // combine the four exact digit accumulators in fp64, add the x-part / bias, round once to fp32
+    float h[32];
+    {
+      double pre[32];
+      const float4* d0 = reinterpret_cast<const float4*>(dec0 + (size_t)a * 32);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 v = live ? __ldg(&d0[j4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pre[j4 * 4 + 0] = (double)v.x; pre[j4 * 4 + 1] = (double)v.y; pre[j4 * 4 + 2] = (double)v.z; pre[j4 * 4 + 3] = (double)v.w;
+      }
+#pragma unroll
+      for (int g = 3; g >= 0; --g) {
+        tc::tmem_ld32(tbase, warp, 32 * g, h);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pre[j] = fma((double)h[j], acc_scale[g], pre[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = fmaxf((float)pre[j], 0.f);
+    }
+    // h1 becomes the A operand of layer 1 (K = 32), reusing the digit tiles (layer 0 has completed)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tc::store_split8(At, At + DT_H_PART, At + 2 * DT_H_PART, tid, q * 8, 32, h + q * 8);
+    tc::fence_before_sync();
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::mma_bf16x3(tbase + 128, sA, DT_H_PART, sW1, DT_W1_PART, 32, 32, false);
+      tc::commit(mb);
+    }
+    tc::mbar_wait(mb, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+    tc::tmem_ld32(tbase, warp, 128, h);
+    if (live) {
+      float o0 = B2[0], o1 = B2[1], o2 = B2[2];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float v = fmaxf(h[j] + B1[j], 0.f);
+        const float4 w = *reinterpret_cast<const float4*>(&W2[j * 4]);
+        o0 = fmaf(v, w.x, o0);
+        o1 = fmaf(v, w.y, o1);
+        o2 = fmaf(v, w.z, o2);
+      }
+      float* out = samples + (size_t)row * 3;
+      out[0] = o0;
+      out[1] = o1;
+      out[2] = o2;
+    }
+    tc::fence_before_sync();
+    __syncthreads();  // every TMEM / shared-memory read of this tile is done before the next tile overwrites them
+    tc::fence_after_sync();
+  }
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, DT_TMEM_COLS);
+}
+
+int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits, const float* d_dec0, const float* d_uniforms,
+                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st) {
+  if (bt.A <= 0) return 0;
+  const int K = bt.K;
+  const long long rows = (long long)bt.A * K;
+  const int n_tiles = (int)((rows + 127) / 128);
+  static bool attr = false;
+  if (!attr) {
+    CTRM_CUDA_OK(cudaFuncSetAttribute(cvae_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+    attr = true;
+  }
+  const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent: two CTAs per SM
+  cvae_decode_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(bt, K, d_logits, d_dec0, d_uniforms, use_state_kt, kt_fixed, t_fixed,
+                                                          m.desc.temp, m.dec_w0z_exp, m.blob, m.off, d_samples, n_tiles);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}

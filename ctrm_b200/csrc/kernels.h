@@ -15,6 +15,7 @@ struct DevModel {
   const float* blob;
   ctrm_weight_offsets_t off;
   ctrm_model_desc desc;
+  int dec_w0z_exp;  // |decoder W0[0:64]| < 2^dec_w0z_exp (digit scale of the exact tensor-core product, tc.cuh)
 };
 
 // device-side view of one uploaded batch and its roll-out state; passed to kernels by value
