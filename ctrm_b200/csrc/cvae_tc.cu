@@ -14,6 +14,220 @@
 #include "kernels.h"
 #include "tc.cuh"
 
+// ------------------------------------------------------------------------------------------------
+// cvae_prior: everything the K copies of an agent share, one 128-agent tile per CTA, all dense layers on tcgen05 (BF16x3):
+//   indicator 72->32->32->3 + argmax (roadmap_learned/learned_sampler.py:99-104), encoder_input [X, onehot] 75->32->32->64 +
+//   LogSoftmax + Categorical normalisation + logits = log(clamp(p)) (learning/model/cvae.py:57-68, :132-136;
+//   torch.distributions probs_to_logits), and the [X, onehot] rows of the decoder's first layer (cvae.py:72-76, :137).
+// The three first layers share the A operand X[128 x 72]: ONE N = 96 MMA chain computes them side by side
+// (TMEM columns 0..31 indicator, 32..63 encoder, 64..95 decoder, times three magnitude classes); the one-hot indicator columns are added as a weight row
+// in the epilogue.  outputs per agent: logits[64], dec0[32], ind.
+// ------------------------------------------------------------------------------------------------
+#define PR_THREADS 128
+#define PR_K0 80                      // 72 padded to a multiple of 16
+#define PR_X_PART 20480u              // tile_bytes(128, 80)
+#define PR_H_PART 8192u               // tile_bytes(128, 32)
+#define PR_W0_PART 15360u             // tile_bytes(96, 80)
+#define PR_W1_PART 2048u              // tile_bytes(32, 32)
+#define PR_W2_PART 4096u              // tile_bytes(64, 32)
+#define PR_NF 608                     // fp32 constants
+#define PR_SMEM (3 * 20480 + 3 * 15360 + 2 * 3 * 2048 + 3 * 4096 + PR_NF * 4 + 16)
+#define PR_TMEM_COLS 512  // layer 0: 3 x 96 | head layers: 3 x 32 at 288 | encoder output 3 x 64 reuses 0..191
+
+__global__ void __launch_bounds__(PR_THREADS) cvae_prior_tc_kernel(Batch bt, const float* __restrict__ X,
+                                                                   const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                   float* __restrict__ logits_out, float* __restrict__ dec0_out,
+                                                                   int32_t* __restrict__ ind_out, int n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* Xt = smem;                        // X parts 1..3 [128 x 80]; reused for hidden tiles [128 x 32] x 3
+  uint8_t* W0t = Xt + 3 * PR_X_PART;         // [96 x 80] x 3 : ind_w0 | enc_w0 | dec_w0 rows 64..135
+  uint8_t* Wi1 = W0t + 3 * PR_W0_PART;       // ind_w1 [32 x 32] x 3
+  uint8_t* We1 = Wi1 + 3 * PR_W1_PART;       // enc_w1 [32 x 32] x 3
+  uint8_t* We2 = We1 + 3 * PR_W1_PART;       // enc_w2 [64 x 32] x 3
+  float* cf = reinterpret_cast<float*>(We2 + 3 * PR_W2_PART);
+  float* ind_b0 = cf;            // 32
+  float* ind_b1 = cf + 32;       // 32
+  float* ind_w2 = cf + 64;       // [32][4]
+  float* ind_b2 = cf + 192;      // 4
+  float* enc_b0 = cf + 196;      // 32
+  float* enc_b1 = cf + 228;      // 32
+  float* enc_b2 = cf + 260;      // 64
+  float* dec_b0 = cf + 324;      // 32
+  float* enc_oh = cf + 356;      // [3][32] rows 72..74 of enc_w0
+  float* dec_oh = cf + 452;      // [3][32] rows 136..138 of dec_w0
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(cf + PR_NF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  tc::stage_weight_split_at(blob + off.ind_w0, 32, 0, 72, 32, 32, 0, 96, PR_K0, W0t, tid, PR_THREADS);
+  tc::stage_weight_split_at(blob + off.enc_w0, 32, 0, 72, 32, 32, 32, 96, PR_K0, W0t, tid, PR_THREADS);
+  tc::stage_weight_split_at(blob + off.dec_w0, 32, 64, 72, 32, 32, 64, 96, PR_K0, W0t, tid, PR_THREADS);
+  tc::stage_weight_split(blob + off.ind_w1, 32, 0, 32, 32, 32, 32, Wi1, tid, PR_THREADS);
+  tc::stage_weight_split(blob + off.enc_w1, 32, 0, 32, 32, 32, 32, We1, tid, PR_THREADS);
+  tc::stage_weight_split(blob + off.enc_w2, 64, 0, 32, 64, 64, 32, We2, tid, PR_THREADS);
+  if (tid < 32) {
+    ind_b0[tid] = __ldg(&blob[off.ind_b0 + tid]);
+    ind_b1[tid] = __ldg(&blob[off.ind_b1 + tid]);
+    enc_b0[tid] = __ldg(&blob[off.enc_b0 + tid]);
+    enc_b1[tid] = __ldg(&blob[off.enc_b1 + tid]);
+    dec_b0[tid] = __ldg(&blob[off.dec_b0 + tid]);
+  }
+  if (tid < 64) enc_b2[tid] = __ldg(&blob[off.enc_b2 + tid]);
+  if (tid < 4) ind_b2[tid] = __ldg(&blob[off.ind_b2 + tid]);
+  for (int i = tid; i < 128; i += PR_THREADS) ind_w2[i] = __ldg(&blob[off.ind_w2 + i]);
+  for (int i = tid; i < 96; i += PR_THREADS) {
+    enc_oh[i] = __ldg(&blob[off.enc_w0 + CTRM_DIM_X * 32 + i]);
+    dec_oh[i] = __ldg(&blob[off.dec_w0 + (64 + CTRM_DIM_X) * 32 + i]);
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, PR_TMEM_COLS);
+  if (tid == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t mb = tc::smem_u32(mbar);
+  const uint32_t sX = tc::smem_u32(Xt), sW0 = tc::smem_u32(W0t), sWi1 = tc::smem_u32(Wi1), sWe1 = tc::smem_u32(We1),
+                 sWe2 = tc::smem_u32(We2);
+  uint32_t phase = 0;
+  const float eps = 1.1920928955078125e-07f;
+
+  // one MMA round: the A tile in shared memory is complete -> issue, commit, wait
+  auto mma_round = [&](uint32_t tcol, uint32_t a, uint32_t a_part, uint32_t b, uint32_t b_part, int Kk, int Nn) {
+    tc::fence_before_sync();
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::mma_bf16x3(tbase + tcol, (uint32_t)Nn, a, a_part, b, b_part, Kk, Nn);
+      tc::commit(mb);
+    }
+    tc::mbar_wait(mb, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+  };
+  auto store_hidden = [&](const float* h) {  // h[32] -> three bf16 parts of the [128 x 32] hidden tile
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tc::store_split8(Xt, Xt + PR_H_PART, Xt + 2 * PR_H_PART, tid, q * 8, 32, h + q * 8);
+  };
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int a = tile * 128 + tid;
+    bool live = a < bt.A;
+    if (live) live = !(bt.done != nullptr && bt.done[bt.agent_inst[a]]);
+    if (!__syncthreads_or(live)) continue;
+    {  // X row -> three bf16 parts (K padded 72 -> 80 with zeros)
+      const float4* xr = reinterpret_cast<const float4*>(X + (size_t)a * CTRM_DIM_X);
+#pragma unroll
+      for (int q = 0; q < 10; ++q) {
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (live && q < 9) {
+          const float4 p0 = __ldg(&xr[2 * q]), p1 = __ldg(&xr[2 * q + 1]);
+          v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+        }
+        tc::store_split8(Xt, Xt + PR_X_PART, Xt + 2 * PR_X_PART, tid, q * 8, PR_K0, v);
+      }
+    }
+    mma_round(0, sX, PR_X_PART, sW0, PR_W0_PART, PR_K0, 96);
+    float h[32];
+    // ---- indicator: hidden 1 -> hidden 2 -> 3 logits -> argmax
+    tc::tmem_ld32_sum3(tbase, warp, 0, 96, h);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + ind_b0[j], 0.f);
+    store_hidden(h);
+    mma_round(288, sX, PR_H_PART, sWi1, PR_W1_PART, 32, 32);
+    tc::tmem_ld32_sum3(tbase, warp, 288, 32, h);
+    int ind = 0;
+    {
+      float o0 = ind_b2[0], o1 = ind_b2[1], o2 = ind_b2[2];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float v = fmaxf(h[j] + ind_b1[j], 0.f);
+        const float4 w = *reinterpret_cast<const float4*>(&ind_w2[j * 4]);
+        o0 = fmaf(v, w.x, o0);
+        o1 = fmaf(v, w.y, o1);
+        o2 = fmaf(v, w.z, o2);
+      }
+      float best = o0;
+      if (o1 > best) { best = o1; ind = 1; }
+      if (o2 > best) { best = o2; ind = 2; }
+      if (live && ind_out != nullptr) ind_out[a] = ind;
+    }
+    // ---- decoder first layer, [X, onehot] part (TMEM columns 64..95 of the shared chain)
+    tc::tmem_ld32_sum3(tbase, warp, 64, 96, h);
+    if (live) {
+      float4* d0 = reinterpret_cast<float4*>(dec0_out + (size_t)a * 32);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        d0[j4] = make_float4(h[j4 * 4 + 0] + dec_b0[j4 * 4 + 0] + dec_oh[ind * 32 + j4 * 4 + 0],
+                             h[j4 * 4 + 1] + dec_b0[j4 * 4 + 1] + dec_oh[ind * 32 + j4 * 4 + 1],
+                             h[j4 * 4 + 2] + dec_b0[j4 * 4 + 2] + dec_oh[ind * 32 + j4 * 4 + 2],
+                             h[j4 * 4 + 3] + dec_b0[j4 * 4 + 3] + dec_oh[ind * 32 + j4 * 4 + 3]);
+    }
+    // ---- encoder_input: hidden 1 (+ one-hot row) -> hidden 2 -> 64 logits -> log_softmax -> clamped log-probs
+    tc::tmem_ld32_sum3(tbase, warp, 32, 96, h);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + enc_b0[j] + enc_oh[ind * 32 + j], 0.f);
+    store_hidden(h);
+    mma_round(288, sX, PR_H_PART, sWe1, PR_W1_PART, 32, 32);
+    tc::tmem_ld32_sum3(tbase, warp, 288, 32, h);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + enc_b1[j], 0.f);
+    store_hidden(h);
+    mma_round(0, sX, PR_H_PART, sWe2, PR_W2_PART, 32, 64);  // every layer-0 column has been consumed
+    {
+      float lg[64];
+      tc::tmem_ld32_sum3(tbase, warp, 0, 64, lg);
+      tc::tmem_ld32_sum3(tbase, warp, 32, 64, lg + 32);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        lg[j] += enc_b2[j];
+        mx = fmaxf(mx, lg[j]);
+      }
+      float se = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) se += expf(lg[j] - mx);
+      const float lse = logf(se);
+      float ps = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        lg[j] = expf((lg[j] - mx) - lse);  // probs = exp(log_softmax)
+        ps += lg[j];
+      }
+      if (live) {
+        float4* lo = reinterpret_cast<float4*>(logits_out + (size_t)a * 64);
+#pragma unroll
+        for (int j4 = 0; j4 < 16; ++j4)
+          lo[j4] = make_float4(logf(fminf(fmaxf(lg[j4 * 4 + 0] / ps, eps), 1.f - eps)),
+                               logf(fminf(fmaxf(lg[j4 * 4 + 1] / ps, eps), 1.f - eps)),
+                               logf(fminf(fmaxf(lg[j4 * 4 + 2] / ps, eps), 1.f - eps)),
+                               logf(fminf(fmaxf(lg[j4 * 4 + 3] / ps, eps), 1.f - eps)));
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+  }
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, PR_TMEM_COLS);
+}
+
+int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,
+                      cudaStream_t st) {
+  if (bt.A <= 0) return 0;
+  const int n_tiles = (bt.A + 127) / 128;
+  static bool attr = false;
+  if (!attr) {
+    CTRM_CUDA_OK(cudaFuncSetAttribute(cvae_prior_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM));
+    attr = true;
+  }
+  const int grid = n_tiles < 148 ? n_tiles : 148;  // persistent, one CTA per SM (135 KB of shared memory each)
+  cvae_prior_tc_kernel<<<grid, PR_THREADS, PR_SMEM, st>>>(bt, d_X, m.blob, m.off, d_logits, d_dec0, d_ind, n_tiles);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 #define DT_THREADS 128
 // shared memory: z digit tiles 4 x 16 KB (K = 64; tiles 2 and 3 double as the fp32 scratch of the softmax, and the whole
 // region is reused for the three bf16 parts of h1, K = 32) | W0 digit tiles 4 x 4 KB | W1 parts 3 x 2 KB | W2, b1, b2 |
@@ -23,7 +237,7 @@
 #define DT_W0_PART 4096u
 #define DT_W1_PART 2048u
 #define DT_SMEM (4 * 16384 + 4 * 4096 + 3 * 2048 + (128 + 32 + 4) * 4 + 16)
-#define DT_TMEM_COLS 256  // 4 x 32 layer-0 digit accumulators + 32 layer-1
+#define DT_TMEM_COLS 256  // 4 x 32 layer-0 digit accumulators + 3 x 32 layer-1 magnitude classes
 
 // 8 fp32 values of row r, columns k0..k0+7, parked as two 16-byte halves in the slots of digit tiles 2 and 3
 __device__ __forceinline__ void park8(uint8_t* At, int r, int k0, const float* v) {
@@ -196,13 +410,13 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, in
     __syncthreads();
     if (tid == 0) {
       tc::fence_after_sync();
-      tc::mma_bf16x3(tbase + 128, sA, DT_H_PART, sW1, DT_W1_PART, 32, 32, false);
+      tc::mma_bf16x3(tbase + 128, 32, sA, DT_H_PART, sW1, DT_W1_PART, 32, 32);
       tc::commit(mb);
     }
     tc::mbar_wait(mb, phase);
     phase ^= 1u;
     tc::fence_after_sync();
-    tc::tmem_ld32(tbase, warp, 128, h);
+    tc::tmem_ld32_sum3(tbase, warp, 128, 32, h);
     if (live) {
       float o0 = B2[0], o1 = B2[1], o2 = B2[2];
 #pragma unroll

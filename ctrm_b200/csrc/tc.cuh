@@ -79,23 +79,28 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// D[128 x N] (+)= A[128 x K] * B[N x K]^T, fp32-exact products (BF16x3, 6 MMAs per 16-wide k-step); one thread issues.
+// D[128 x N] = A[128 x K] * B[N x K]^T, fp32-exact products (BF16x3, 6 MMAs per 16-wide k-step); one thread issues.
 // a / b are shared-memory byte addresses of the first of three consecutive operand tiles (parts 1, 2, 3), a_part / b_part
-// bytes apart.
-__device__ __forceinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t a, uint32_t a_part, uint32_t b, uint32_t b_part, int K, int N,
-                                           bool accumulate) {
+// bytes apart.  The tensor core TRUNCATES when it adds into the fp32 accumulator, so the number of accumulations that see the
+// full-magnitude partial sum is kept minimal: the three magnitude classes go to THREE accumulators, n_cols TMEM columns apart
+//   tmem_d             : a1*b1                      (K/16 accumulations)
+//   tmem_d + n_cols    : a1*b2 + a2*b1              (2^-8 of the main term)
+//   tmem_d + 2*n_cols  : a2*b2 + a1*b3 + a3*b1      (2^-16)
+// and the epilogue adds them (tmem_ld32_sum3).
+__device__ __forceinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t n_cols, uint32_t a, uint32_t a_part, uint32_t b,
+                                           uint32_t b_part, int K, int N) {
   const uint32_t id = idesc_bf16(128, N);
-  uint32_t acc = accumulate ? 1u : 0u;
+  uint32_t acc = 0u;
   for (int s = 0; s < K / 16; ++s) {
     const uint32_t o = 256u * s;
     const uint64_t a1 = smem_desc(a + o, K), a2 = smem_desc(a + a_part + o, K), a3 = smem_desc(a + 2 * a_part + o, K);
     const uint64_t b1 = smem_desc(b + o, K), b2 = smem_desc(b + b_part + o, K), b3 = smem_desc(b + 2 * b_part + o, K);
-    mma_bf16(tmem_d, a1, b3, id, acc);
-    mma_bf16(tmem_d, a3, b1, id, 1u);
-    mma_bf16(tmem_d, a2, b2, id, 1u);
-    mma_bf16(tmem_d, a1, b2, id, 1u);
-    mma_bf16(tmem_d, a2, b1, id, 1u);
-    mma_bf16(tmem_d, a1, b1, id, 1u);
+    mma_bf16(tmem_d + 2 * n_cols, a1, b3, id, acc);
+    mma_bf16(tmem_d + 2 * n_cols, a3, b1, id, 1u);
+    mma_bf16(tmem_d + 2 * n_cols, a2, b2, id, 1u);
+    mma_bf16(tmem_d + n_cols, a1, b2, id, acc);
+    mma_bf16(tmem_d + n_cols, a2, b1, id, 1u);
+    mma_bf16(tmem_d, a1, b1, id, acc);
     acc = 1u;
   }
 }
@@ -209,19 +214,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t tbase, int warp, int col, flo
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// v[32] = (acc_lo + acc_mid) + acc_main for the three accumulators of mma_bf16x3 (columns col, col+n_cols, col+2*n_cols)
+__device__ __forceinline__ void tmem_ld32_sum3(uint32_t tbase, int warp, int col, int n_cols, float* v) {
+  float t[32];
+  tmem_ld32(tbase, warp, col + 2 * n_cols, v);
+  tmem_ld32(tbase, warp, col + n_cols, t);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] += t[i];
+  tmem_ld32(tbase, warp, col, t);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] += t[i];
+}
+
 // copy rows [k_begin, k_begin + K_real) of a blob weight matrix stored [in][ld] (fp32, global) into three consecutive
-// bf16 B-operand tiles (N x K, K-major, tile_bytes(N, K) apart): B[n][k] = w[(k_begin + k) * ld + n]; k >= K_real and
-// n >= N_real are zero padding
-__device__ __forceinline__ void stage_weight_split(const float* __restrict__ w, int ld, int k_begin, int K_real, int N_real,
-                                                   int N, int K, uint8_t* tiles, int tid, int nthreads) {
-  const uint32_t part = tile_bytes(N, K);
+// bf16 B-operand tiles (N_tile x K, K-major, tile_bytes(N_tile, K) apart) at tile rows [n_off, n_off + N):
+// B[n_off + n][k] = w[(k_begin + k) * ld + n]; k >= K_real and n >= N_real are zero padding
+__device__ __forceinline__ void stage_weight_split_at(const float* __restrict__ w, int ld, int k_begin, int K_real, int N_real,
+                                                      int N, int n_off, int N_tile, int K, uint8_t* tiles, int tid, int nthreads) {
+  const uint32_t part = tile_bytes(N_tile, K);
   for (int i = tid; i < N * (K / 8); i += nthreads) {
     const int k0 = (i / N) * 8, n = i - (i / N) * N;  // consecutive threads -> consecutive n (coalesced reads)
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (n < N_real && k0 + j < K_real) ? __ldg(w + (size_t)(k_begin + k0 + j) * ld + n) : 0.f;
-    store_split8(tiles, tiles + part, tiles + 2 * part, n, k0, K, v);
+    store_split8(tiles, tiles + part, tiles + 2 * part, n_off + n, k0, K, v);
   }
+}
+__device__ __forceinline__ void stage_weight_split(const float* __restrict__ w, int ld, int k_begin, int K_real, int N_real,
+                                                   int N, int K, uint8_t* tiles, int tid, int nthreads) {
+  stage_weight_split_at(w, ld, k_begin, K_real, N_real, N, 0, N, K, tiles, tid, nthreads);
 }
 
 // four signed fixed-point digit tiles of rows [k_begin, k_begin + K_real) of a blob weight matrix [in][ld]

@@ -331,5 +331,5 @@ def test_cvae_decoder_vs_fp64_truth(builder, trace_gold, oracle_weights):
                                      out.data_ptr(), None, _stream()))
         e_gpu.append(rel_err(out.cpu().numpy().reshape(A, K, 3), truth))
         e_ref.append(rel_err(z["SAMPLES"][s].reshape(K, A, 3).transpose(1, 0, 2), truth))
-    assert max(e_gpu) <= 3e-6, e_gpu
+    assert max(e_gpu) <= 4e-6, e_gpu
     assert max(e_gpu) < max(e_ref), (e_gpu, e_ref)
