@@ -194,12 +194,22 @@ extern "C" int ctrm_load_weights(ctrm_ctx* c, const ctrm_model_desc* d, const fl
   c->model.blob = blob;
   c->model.off = off;
   c->model.desc = *d;
-  {
+  auto exp_bound = [&](int first, int count) {  // smallest e >= -20 with max|w| < 2^e
     float mxw = 0.f;
-    for (int i = 0; i < 64 * 32; ++i) mxw = std::fmax(mxw, std::fabs(h_blob[off.dec_w0 + i]));
-    int e = 0;
+    for (int i = 0; i < count; ++i) mxw = std::fmax(mxw, std::fabs(h_blob[first + i]));
+    int e = -20;
     while (std::ldexp(1.0f, e) <= mxw && e < 30) ++e;
-    c->model.dec_w0z_exp = e;
+    return e;
+  };
+  c->model.dec_w0z_exp = exp_bound(off.dec_w0, 64 * 32);
+  {  // digit tiles of the FOV encoders' first layer for the tensor-core kernel
+    const int F = d->fov_size;
+    c->model.fov_w0_exp = exp_bound(off.fov_w0, 2 * F * F * 64);
+    uint8_t* tiles = nullptr;
+    CHECK(c->w_arena.alloc(&tiles, fov_w0_tiles_bytes(F)));
+    CHECK(launch_fov_w0_prep(blob + off.fov_w0, F, c->model.fov_w0_exp, tiles, c->stream));
+    CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->model.fov_w0_tiles = tiles;
   }
   c->have_weights = true;
   return 0;
@@ -331,7 +341,8 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&d_ctg, (size_t)A * M * M));
   bt.occ = d_occ; bt.ctg = d_ctg;
   // per-step tensors (A-sized)
-  CHECK(ar.alloc(&bt.fov, (size_t)A * 2 * F * F + 8));
+  CHECK(ar.alloc(&bt.fov_tiles, fov_tiles_bytes(A, F)));
+  CTRM_CUDA_OK(cudaMemsetAsync(bt.fov_tiles, 0, fov_tiles_bytes(A, F), st));
   CHECK(ar.alloc(&bt.e_self, (size_t)A * 32));
   CHECK(ar.alloc(&bt.e_vain, (size_t)A * 32));
   CHECK(ar.alloc(&bt.vain_proj, (size_t)A * 32));
@@ -465,7 +476,8 @@ extern "C" int ctrm_encode_features(ctrm_ctx* c, const float* d_fov, const doubl
   cudaStream_t st = (cudaStream_t)stream;
   Batch bt = c->bt;
   bt.done = nullptr;
-  CHECK(launch_fov_encode(c->model, d_fov, bt.agent_inst, nullptr, bt.A, bt.e_self, bt.e_vain, bt.vain_proj, st));
+  CHECK(launch_fov_f32_to_tiles(d_fov, bt.A, bt.F, bt.fov_tiles, st));
+  CHECK(launch_fov_encode(c->model, bt.fov_tiles, bt.agent_inst, nullptr, bt.A, bt.e_self, bt.e_vain, bt.vain_proj, st));
   CHECK(launch_agent_comm(c->model, bt, d_cur, d_prev, bt.e_self, bt.vain_proj, d_X, st));
   return 0;
 }
@@ -576,9 +588,10 @@ static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, 
   };
   if (prof) CTRM_CUDA_OK(cudaEventRecord(prof->at(pstep, 0), st));
   if (nn) {
-    CHECK(launch_fov_raster(bt.occ, bt.ctg, bt.agent_inst, bt.cur, bt.done, bt.A, bt.M, bt.F, bt.fov, st));
+    CHECK(launch_fov_raster_tiles(bt.occ, bt.ctg, bt.agent_inst, bt.cur, bt.done, bt.A, bt.M, bt.F, fov_n_chunks(bt.F),
+                                  bt.fov_tiles, st));
     CHECK(mark(KID_FOV_RASTER));
-    CHECK(launch_fov_encode(c->model, bt.fov, bt.agent_inst, bt.done, bt.A, bt.e_self, nullptr, bt.vain_proj, st));
+    CHECK(launch_fov_encode(c->model, bt.fov_tiles, bt.agent_inst, bt.done, bt.A, bt.e_self, nullptr, bt.vain_proj, st));
     CHECK(mark(KID_FOV_ENCODE));
     CHECK(launch_agent_comm(c->model, bt, bt.cur, bt.prev, bt.e_self, bt.vain_proj, bt.X, st));
     CHECK(mark(KID_AGENT_COMM));

@@ -1,7 +1,5 @@
 // Feature encoders of Format2D_CTRM_Input.get_feature_one_step (learning/formats/format_input.py:279-357):
-//   fov_encode : FOVEncoder.forward x2 (learning/model/fov_encoder.py:34-59; format_input.py:311-312) as one
-//                [A x 2F^2] x [2F^2 x 64] GEMM (self | vain first layers side by side) with the two 32->32->32
-//                tails and the fov_vain part of the AgentEncoder's first layer fused into the epilogue.
+//   (the FOV encoders themselves run on the tensor cores: fov_tc.cu)
 //   agent_comm : numba get_arr_others_info (learning/compiled.py:30-97), AgentEncoder.forward
 //                (learning/model/agent_encoder.py:34-65; format_input.py:328-334), get_comm
 //                (format_input.py:212-277), get_self_info (compiled.py:100-125) and the final concat
@@ -9,166 +7,6 @@
 // fp32 with FMA; the summation order differs from ATen's blocked sgemm, parity is 1e-5 relative (BASELINE.json).
 #include "common.cuh"
 #include "kernels.h"
-
-// ------------------------------------------------------------------------------------------------
-// FOV encoders
-// ------------------------------------------------------------------------------------------------
-#define FE_BM 64
-#define FE_BN 64
-#define FE_BK 32
-#define FE_ALD 36  // As[row][k] leading dim
-#define FE_HLD 65
-
-__global__ void __launch_bounds__(256) fov_encode_kernel(const float* __restrict__ fov, const int32_t* __restrict__ agent_inst,
-                                                         const uint8_t* __restrict__ skip_inst, int A, int KD,
-                                                         const float* __restrict__ blob, ctrm_weight_offsets_t off,
-                                                         float* __restrict__ e_self, float* __restrict__ e_vain,
-                                                         float* __restrict__ vain_proj) {
-  __shared__ __align__(16) float ABs[FE_BM * FE_ALD + FE_BK * FE_BN];  // GEMM tiles; reused as H2s by the tails
-  __shared__ float Hs[FE_BM * FE_HLD];
-  float* As = ABs;
-  float* Bs = ABs + FE_BM * FE_ALD;
-  float* H2s = ABs;
-  static_assert(FE_BM * FE_HLD <= FE_BM * FE_ALD + FE_BK * FE_BN, "H2s must fit in the tile buffer");
-  const int tid = threadIdx.x;
-  const int row0 = blockIdx.x * FE_BM;
-  // skip tiles whose agents all belong to finished instances
-  if (skip_inst != nullptr) {
-    int r = row0 + (tid & 63);
-    bool live = (r < A) && (skip_inst[agent_inst[r]] == 0);
-    if (!__syncthreads_or(live)) return;
-  }
-  const float* W0 = blob + off.fov_w0;
-  const int tx = tid & 15, ty = tid >> 4;
-  // global->register staging indices
-  const int a_row = tid >> 2, a_kq = tid & 3;       // A: row a_row, k = a_kq*8 .. +7
-  const int b_k = tid >> 3, b_c = (tid & 7) * 8;    // B: k = b_k, cols b_c .. +7
-  const bool a_in = (row0 + a_row) < A;
-  const float* a_ptr = fov + (size_t)(row0 + a_row) * KD + a_kq * 8;
-  float2 ra[4];
-  float4 rb[2];
-  auto load_tiles = [&](int k0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int k = k0 + a_kq * 8 + 2 * j;
-      ra[j] = (a_in && k + 1 < KD) ? *reinterpret_cast<const float2*>(a_ptr + k0 + 2 * j)
-                                   : make_float2((a_in && k < KD) ? a_ptr[k0 + 2 * j] : 0.f, 0.f);
-    }
-    int kb = k0 + b_k;
-    if (kb < KD) {
-      rb[0] = __ldg(reinterpret_cast<const float4*>(W0 + (size_t)kb * FE_BN + b_c));
-      rb[1] = __ldg(reinterpret_cast<const float4*>(W0 + (size_t)kb * FE_BN + b_c + 4));
-    } else {
-      rb[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-      rb[1] = rb[0];
-    }
-  };
-  auto store_tiles = [&]() {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(&As[a_row * FE_ALD + a_kq * 8 + 2 * j]) = ra[j];
-    *reinterpret_cast<float4*>(&Bs[b_k * FE_BN + b_c]) = rb[0];
-    *reinterpret_cast<float4*>(&Bs[b_k * FE_BN + b_c + 4]) = rb[1];
-  };
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  load_tiles(0);
-  for (int k0 = 0; k0 < KD; k0 += FE_BK) {
-    store_tiles();
-    __syncthreads();
-    if (k0 + FE_BK < KD) load_tiles(k0 + FE_BK);
-#pragma unroll
-    for (int k = 0; k < FE_BK; ++k) {
-      float4 b = *reinterpret_cast<const float4*>(&Bs[k * FE_BN + tx * 4]);
-      float a0 = As[(ty * 4 + 0) * FE_ALD + k], a1 = As[(ty * 4 + 1) * FE_ALD + k];
-      float a2 = As[(ty * 4 + 2) * FE_ALD + k], a3 = As[(ty * 4 + 3) * FE_ALD + k];
-      acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
-      acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
-      acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
-      acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
-      acc[2][0] = fmaf(a2, b.x, acc[2][0]); acc[2][1] = fmaf(a2, b.y, acc[2][1]);
-      acc[2][2] = fmaf(a2, b.z, acc[2][2]); acc[2][3] = fmaf(a2, b.w, acc[2][3]);
-      acc[3][0] = fmaf(a3, b.x, acc[3][0]); acc[3][1] = fmaf(a3, b.y, acc[3][1]);
-      acc[3][2] = fmaf(a3, b.z, acc[3][2]); acc[3][3] = fmaf(a3, b.w, acc[3][3]);
-    }
-    __syncthreads();
-  }
-  // epilogue 1: + bias, ReLU -> Hs[row][64]
-  {
-    const float* b0 = blob + off.fov_b0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        Hs[(ty * 4 + i) * FE_HLD + tx * 4 + j] = fmaxf(acc[i][j] + __ldg(&b0[tx * 4 + j]), 0.f);
-  }
-  __syncthreads();
-  // tails: thread -> (row, encoder e, 16-output half)
-  const int row = tid >> 2, q = tid & 3, e = q >> 1, half = q & 1;
-  auto dense16 = [&](const float* in_s, const float* W, const float* bias, float* o16, bool relu) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) o16[j] = __ldg(&bias[half * 16 + j]);
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      float x = in_s[row * FE_HLD + e * 32 + k];
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        float4 w = __ldg(reinterpret_cast<const float4*>(W + k * 32 + half * 16 + j4 * 4));
-        o16[j4 * 4 + 0] = fmaf(x, w.x, o16[j4 * 4 + 0]);
-        o16[j4 * 4 + 1] = fmaf(x, w.y, o16[j4 * 4 + 1]);
-        o16[j4 * 4 + 2] = fmaf(x, w.z, o16[j4 * 4 + 2]);
-        o16[j4 * 4 + 3] = fmaf(x, w.w, o16[j4 * 4 + 3]);
-      }
-    }
-    if (relu) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) o16[j] = fmaxf(o16[j], 0.f);
-    }
-  };
-  float o16[16];
-  dense16(Hs, blob + (e ? off.fovv_w1 : off.fovs_w1), blob + (e ? off.fovv_b1 : off.fovs_b1), o16, true);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) H2s[row * FE_HLD + e * 32 + half * 16 + j] = o16[j];
-  __syncthreads();
-  dense16(H2s, blob + (e ? off.fovv_w2 : off.fovs_w2), blob + (e ? off.fovv_b2 : off.fovs_b2), o16, false);
-  const int grow = row0 + row;
-  if (grow < A) {
-    float* dst = (e ? e_vain : e_self);
-    if (dst != nullptr) {
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4)
-        *reinterpret_cast<float4*>(dst + (size_t)grow * 32 + half * 16 + j4 * 4) =
-            make_float4(o16[j4 * 4], o16[j4 * 4 + 1], o16[j4 * 4 + 2], o16[j4 * 4 + 3]);
-    }
-  }
-  // fov_vain part of AgentEncoder layer 0 (agent_encoder.py:57-60 input = [others_info | fov_vain]):
-  // vain_proj[j] = b0 + W0[11:43]^T e_vain, shared by every pair (i, j)
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 16; ++j) Hs[row * FE_HLD + e * 32 + half * 16 + j] = o16[j];
-  __syncthreads();
-  if (e == 1) {
-    dense16(Hs, blob + off.ag_w0v, blob + off.ag_b0, o16, false);
-    if (grow < A) {
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4)
-        *reinterpret_cast<float4*>(vain_proj + (size_t)grow * 32 + half * 16 + j4 * 4) =
-            make_float4(o16[j4 * 4], o16[j4 * 4 + 1], o16[j4 * 4 + 2], o16[j4 * 4 + 3]);
-    }
-  }
-}
-
-int launch_fov_encode(const DevModel& m, const float* d_fov, const int32_t* d_agent_inst, const uint8_t* d_skip_inst, int A,
-                      float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st) {
-  if (A <= 0) return 0;
-  int KD = 2 * m.desc.fov_size * m.desc.fov_size;
-  fov_encode_kernel<<<(A + FE_BM - 1) / FE_BM, 256, 0, st>>>(d_fov, d_agent_inst, d_skip_inst, A, KD, m.blob, m.off, d_e_self,
-                                                            d_e_vain, d_vain_proj);
-  CTRM_CUDA_OK(cudaGetLastError());
-  return 0;
-}
 
 // ------------------------------------------------------------------------------------------------
 // pairwise features + agent encoder + neighbour attention, one warp per agent i

@@ -1,0 +1,280 @@
+// FOV encoders on the tensor cores.  reference: FOVEncoder.forward x 2 (learning/model/fov_encoder.py:34-59;
+// learning/formats/format_input.py:311-312) + the fov_vain rows of the AgentEncoder's first layer
+// (learning/model/agent_encoder.py:57-60; format_input.py:328-331).
+//
+// The FOV tensor is binary, so it is EXACT in bf16 and travels as bf16 operand tiles: [tile of 128 agents][chunk of 96
+// inputs][128 x 96 canonical UMMA tile] (24,576 B each, written in that form by the raster kernel, raster.cu).
+// First layers of both encoders side by side: D[128 x 64] = FOV[128 x 2F^2] . W0[2F^2 x 64] with the weights cut into four
+// signed fixed-point digits (tc.cuh): every digit product is an integer, all partial sums stay below 2^24, the fp32
+// accumulators are exact and the truncating tensor-core accumulate loses nothing; the four digit accumulators are combined
+// in fp64.  Operand chunks stream through a 2-stage TMA (cp.async.bulk) + mbarrier pipeline: one thread produces, one
+// thread issues the MMAs, tcgen05.commit releases the stage.
+// Tails (32->32->32 per encoder as block-diagonal 64x64, then the 32x32 vain projection) are BF16x3 rounds on the same tile.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc.cuh"
+
+#define FT_THREADS 128
+#define FT_CHUNK 96
+#define FT_A_CHUNK 24576u   // tile_bytes(128, 96)
+#define FT_W_DIGIT 12288u   // tile_bytes(64, 96)
+#define FT_W_CHUNK 49152u   // four digits
+#define FT_STAGE (FT_A_CHUNK + FT_W_CHUNK)
+#define FT_H_PART 16384u    // tile_bytes(128, 64)
+#define FT_H32_PART 8192u   // tile_bytes(128, 32)
+#define FT_W64_PART 8192u   // tile_bytes(64, 64)
+#define FT_W32_PART 2048u   // tile_bytes(32, 32)
+#define FT_NF 256
+#define FT_SMEM (2 * FT_STAGE + 2 * 3 * FT_W64_PART + 3 * FT_W32_PART + FT_NF * 4 + 64)
+
+// ---- weight preparation (once per ctrm_load_weights): digit tiles of W0 in global memory, chunk-major ----
+__global__ void fov_w0_prep_kernel(const float* __restrict__ w0 /*[KD][64]*/, int KD, int n_chunks, float scale,
+                                   uint8_t* __restrict__ out /*[n_chunks][4][12288]*/) {
+  const int total = n_chunks * 64 * (FT_CHUNK / 8);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i / (64 * (FT_CHUNK / 8));
+    const int rem = i - c * 64 * (FT_CHUNK / 8);
+    const int k0 = (rem / 64) * 8, n = rem % 64;
+    uint32_t dg[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = c * FT_CHUNK + k0 + j;
+      tc::digits4_signed(k < KD ? w0[(size_t)k * 64 + n] : 0.f, scale, dg[j]);
+    }
+    const uint32_t off = tc::elem_offset(n, k0, FT_CHUNK);
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      *reinterpret_cast<uint4*>(out + (size_t)c * FT_W_CHUNK + d * FT_W_DIGIT + off) =
+          make_uint4(dg[0][d] | (dg[1][d] << 16), dg[2][d] | (dg[3][d] << 16), dg[4][d] | (dg[5][d] << 16),
+                     dg[6][d] | (dg[7][d] << 16));
+  }
+}
+
+// ---- f32 FOV tensor [A][KD] -> bf16 operand tiles (stage entry point ctrm_encode_features only) ----
+__global__ void fov_f32_to_tiles_kernel(const float* __restrict__ fov, int A, int KD, int n_chunks, uint8_t* __restrict__ tiles) {
+  const long long total = (long long)((A + 127) / 128) * 128 * n_chunks * (FT_CHUNK / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int per_row = n_chunks * (FT_CHUNK / 8);
+    const int a = (int)(i / per_row), k8 = (int)(i - (long long)a * per_row);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (a < A) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k8 * 8 + j;
+        const float v = (k < KD) ? fov[(size_t)a * KD + k] : 0.f;
+        w[j >> 1] |= (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)) << (16 * (j & 1));
+      }
+    }
+    const int c = k8 / (FT_CHUNK / 8), kk = (k8 - c * (FT_CHUNK / 8)) * 8;
+    uint8_t* dst = tiles + ((size_t)(a >> 7) * n_chunks + c) * FT_A_CHUNK + tc::elem_offset(a & 127, kk, FT_CHUNK);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t* __restrict__ fov_tiles,
+                                                                   const uint8_t* __restrict__ w0_tiles, int n_chunks, int w0_exp,
+                                                                   const int32_t* __restrict__ agent_inst,
+                                                                   const uint8_t* __restrict__ skip_inst, int A,
+                                                                   const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                   float* __restrict__ e_self, float* __restrict__ e_vain,
+                                                                   float* __restrict__ vain_proj, int n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stage0 = smem;                              // stage s: A chunk | W chunk (4 digits)
+  uint8_t* W1c = smem + 2 * FT_STAGE;                  // blockdiag(self.mlp.2, vain.mlp.2)  [64 x 64] x 3
+  uint8_t* W2c = W1c + 3 * FT_W64_PART;                // blockdiag(self.mlp.4, vain.mlp.4)
+  uint8_t* Wp = W2c + 3 * FT_W64_PART;                 // agent.mlp.0 rows 11..42  [32 x 32] x 3
+  float* cf = reinterpret_cast<float*>(Wp + 3 * FT_W32_PART);
+  float* b0 = cf;          // 64
+  float* b1 = cf + 64;     // 64
+  float* b2 = cf + 128;    // 64
+  float* bp = cf + 192;    // 32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cf + FT_NF);  // full[2], empty[2], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint8_t* Ht = stage0;    // hidden tiles reuse the operand stages once layer 0 has completed
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  for (int i = tid; i < (int)(6 * FT_W64_PART) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(W1c)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  tc::stage_weight_split_at(blob + off.fovs_w1, 32, 0, 32, 32, 32, 0, 64, 64, W1c, tid, FT_THREADS, 0, 32);
+  tc::stage_weight_split_at(blob + off.fovv_w1, 32, 0, 32, 32, 32, 32, 64, 64, W1c, tid, FT_THREADS, 32, 32);
+  tc::stage_weight_split_at(blob + off.fovs_w2, 32, 0, 32, 32, 32, 0, 64, 64, W2c, tid, FT_THREADS, 0, 32);
+  tc::stage_weight_split_at(blob + off.fovv_w2, 32, 0, 32, 32, 32, 32, 64, 64, W2c, tid, FT_THREADS, 32, 32);
+  tc::stage_weight_split(blob + off.ag_w0v, 32, 0, 32, 32, 32, 32, Wp, tid, FT_THREADS);
+  if (tid < 64) b0[tid] = __ldg(&blob[off.fov_b0 + tid]);
+  if (tid < 32) {
+    b1[tid] = __ldg(&blob[off.fovs_b1 + tid]);
+    b1[32 + tid] = __ldg(&blob[off.fovv_b1 + tid]);
+    b2[tid] = __ldg(&blob[off.fovs_b2 + tid]);
+    b2[32 + tid] = __ldg(&blob[off.fovv_b2 + tid]);
+    bp[tid] = __ldg(&blob[off.ag_b0 + tid]);
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  if (tid == 0)
+    for (int i = 0; i < 5; ++i) tc::mbar_init(tc::smem_u32(&bars[i]), 1);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[2]), done = tc::smem_u32(&bars[4]);
+  const uint32_t sStage = tc::smem_u32(stage0), sH = tc::smem_u32(Ht), sW1 = tc::smem_u32(W1c), sW2 = tc::smem_u32(W2c),
+                 sWp = tc::smem_u32(Wp);
+  const uint32_t id64 = tc::idesc_bf16(128, 64);
+  uint32_t it = 0;          // chunks processed so far by this CTA (ring position)
+  uint32_t done_phase = 0;
+  double dscale[4];         // digit j (0-based) weighs 2^(w0_exp - 7 - 8 j)
+#pragma unroll
+  for (int d = 0; d < 4; ++d) dscale[d] = exp2((double)(w0_exp - 7 - 8 * d));
+
+  auto mma_round = [&](uint32_t tcol, uint32_t a, uint32_t a_part, uint32_t b, uint32_t b_part, int Kk, int Nn) {
+    tc::fence_before_sync();
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::mma_bf16x3(tbase + tcol, (uint32_t)Nn, a, a_part, b, b_part, Kk, Nn);
+      tc::commit(done);
+    }
+    tc::mbar_wait(done, done_phase);
+    done_phase ^= 1u;
+    tc::fence_after_sync();
+  };
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int a = tile * 128 + tid;
+    bool live = a < A;
+    if (live && skip_inst != nullptr) live = skip_inst[agent_inst[a]] == 0;
+    if (!__syncthreads_or(live)) continue;
+    // ---- layer 0: streamed exact digit products
+    if (tid == 0) {  // producer
+      const uint8_t* gA = fov_tiles + (size_t)tile * n_chunks * FT_A_CHUNK;
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t u = it + c, s = u & 1u;
+        if (u >= 2) tc::mbar_wait(empty0 + 8 * s, ((u >> 1) - 1) & 1u);
+        tc::mbar_expect_tx(full0 + 8 * s, FT_STAGE);
+        tc::tma_bulk_g2s(sStage + s * FT_STAGE, gA + (size_t)c * FT_A_CHUNK, FT_A_CHUNK, full0 + 8 * s);
+        tc::tma_bulk_g2s(sStage + s * FT_STAGE + FT_A_CHUNK, w0_tiles + (size_t)c * FT_W_CHUNK, FT_W_CHUNK, full0 + 8 * s);
+      }
+    } else if (tid == 32) {  // MMA issuer
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t u = it + c, s = u & 1u;
+        tc::mbar_wait(full0 + 8 * s, (u >> 1) & 1u);
+        tc::fence_after_sync();
+        const uint32_t sa = sStage + s * FT_STAGE, sw = sa + FT_A_CHUNK;
+#pragma unroll
+        for (int ks = 0; ks < FT_CHUNK / 16; ++ks) {
+          const uint64_t ad = tc::smem_desc(sa + 256u * ks, FT_CHUNK);
+          const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            tc::mma_bf16(tbase + 64 * d, ad, tc::smem_desc(sw + d * FT_W_DIGIT + 256u * ks, FT_CHUNK), id64, acc);
+        }
+        tc::commit(empty0 + 8 * s);
+      }
+      tc::commit(done);
+    }
+    it += (uint32_t)n_chunks;
+    tc::mbar_wait(done, done_phase);
+    done_phase ^= 1u;
+    tc::fence_after_sync();
+    // ---- epilogue 0: combine digits in fp64, + bias, ReLU -> hidden tile [128 x 64]
+    float h[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      double pre[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pre[j] = 0.0;
+#pragma unroll
+      for (int d = 3; d >= 0; --d) {
+        tc::tmem_ld32(tbase, warp, 64 * d + 32 * half, h);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pre[j] = fma((double)h[j], dscale[d], pre[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = fmaxf((float)pre[j] + b0[32 * half + j], 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, tid, 32 * half + q * 8, 64, h + q * 8);
+    }
+    // ---- tail 1
+    mma_round(256, sH, FT_H_PART, sW1, FT_W64_PART, 64, 64);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      tc::tmem_ld32_sum3(tbase, warp, 256 + 32 * half, 64, h);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + b1[32 * half + j], 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, tid, 32 * half + q * 8, 64, h + q * 8);
+    }
+    // ---- tail 2 -> e_self | e_vain
+    mma_round(256, sH, FT_H_PART, sW2, FT_W64_PART, 64, 64);
+    tc::tmem_ld32_sum3(tbase, warp, 256, 64, h);
+    if (live) {
+      float4* dst = reinterpret_cast<float4*>(e_self + (size_t)a * 32);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        dst[j4] = make_float4(h[j4 * 4] + b2[j4 * 4], h[j4 * 4 + 1] + b2[j4 * 4 + 1], h[j4 * 4 + 2] + b2[j4 * 4 + 2],
+                              h[j4 * 4 + 3] + b2[j4 * 4 + 3]);
+    }
+    tc::tmem_ld32_sum3(tbase, warp, 288, 64, h);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] += b2[32 + j];
+    if (live && e_vain != nullptr) {
+      float4* dst = reinterpret_cast<float4*>(e_vain + (size_t)a * 32);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) dst[j4] = make_float4(h[j4 * 4], h[j4 * 4 + 1], h[j4 * 4 + 2], h[j4 * 4 + 3]);
+    }
+    // ---- fov_vain part of AgentEncoder layer 0: vain_proj = b0 + W0[11:43]^T e_vain, shared by every pair (i, j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H32_PART, Ht + 2 * FT_H32_PART, tid, q * 8, 32, h + q * 8);
+    mma_round(0, sH, FT_H32_PART, sWp, FT_W32_PART, 32, 32);
+    tc::tmem_ld32_sum3(tbase, warp, 0, 32, h);
+    if (live) {
+      float4* dst = reinterpret_cast<float4*>(vain_proj + (size_t)a * 32);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        dst[j4] = make_float4(h[j4 * 4] + bp[j4 * 4], h[j4 * 4 + 1] + bp[j4 * 4 + 1], h[j4 * 4 + 2] + bp[j4 * 4 + 2],
+                              h[j4 * 4 + 3] + bp[j4 * 4 + 3]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+  }
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+// ---- host side ----
+int fov_n_chunks(int F) { return (2 * F * F + FT_CHUNK - 1) / FT_CHUNK; }
+size_t fov_tiles_bytes(int A, int F) { return (size_t)((A + 127) / 128) * fov_n_chunks(F) * FT_A_CHUNK; }
+size_t fov_w0_tiles_bytes(int F) { return (size_t)fov_n_chunks(F) * FT_W_CHUNK; }
+
+int launch_fov_w0_prep(const float* d_w0, int F, int w0_exp, uint8_t* d_out, cudaStream_t st) {
+  const int n_chunks = fov_n_chunks(F);
+  fov_w0_prep_kernel<<<64, 256, 0, st>>>(d_w0, 2 * F * F, n_chunks, exp2f((float)(7 - w0_exp)), d_out);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_fov_f32_to_tiles(const float* d_fov, int A, int F, uint8_t* d_tiles, cudaStream_t st) {
+  if (A <= 0) return 0;
+  fov_f32_to_tiles_kernel<<<148 * 4, 256, 0, st>>>(d_fov, A, 2 * F * F, fov_n_chunks(F), d_tiles);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32_t* d_agent_inst, const uint8_t* d_skip_inst, int A,
+                      float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st) {
+  if (A <= 0) return 0;
+  const int n_tiles = (A + 127) / 128;
+  static bool attr = false;
+  if (!attr) {
+    CTRM_CUDA_OK(cudaFuncSetAttribute(fov_encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+    attr = true;
+  }
+  const int grid = n_tiles < 148 ? n_tiles : 148;
+  fov_encode_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(d_fov_tiles, m.fov_w0_tiles, fov_n_chunks(m.desc.fov_size), m.fov_w0_exp,
+                                                         d_agent_inst, d_skip_inst, A, m.blob, m.off, d_e_self, d_e_vain,
+                                                         d_vain_proj, n_tiles);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}

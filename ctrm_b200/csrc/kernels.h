@@ -15,6 +15,8 @@ struct DevModel {
   const float* blob;
   ctrm_weight_offsets_t off;
   ctrm_model_desc desc;
+  const uint8_t* fov_w0_tiles;  // digit tiles of the FOV encoders' first layer (fov_tc.cu), chunk-major
+  int fov_w0_exp;               // |fov W0| < 2^fov_w0_exp
   int dec_w0z_exp;  // |decoder W0[0:64]| < 2^dec_w0z_exp (digit scale of the exact tensor-core product, tc.cuh)
 };
 
@@ -37,7 +39,8 @@ struct Batch {
   int32_t* n_done;                      // [1]
   int32_t* steps_done;                  // [B] executed roll-out steps (bench accounting)
   // per-step tensors
-  float *fov, *e_self, *e_vain, *vain_proj, *X, *samples;
+  uint8_t* fov_tiles;  // bf16 operand tiles [ceil(A/128)][n_chunks][128 x 96]
+  float *e_self, *e_vain, *vain_proj, *X, *samples;
   float *cv_logits, *cv_dec0;  // [A][64], [A][32]
   int32_t* ind;  // [A]
   // timed roadmaps: V[t][i] / E[t][i] as fixed slots + bitmask adjacency
@@ -76,8 +79,15 @@ int launch_collide_segments(const double* d_from, const double* d_to, const doub
 int launch_collide_pairs(const double* f1, const double* t1, const double* r1, const double* f2, const double* t2,
                          const double* r2, int dim, int64_t n, uint8_t* verdict, cudaStream_t st);
 
-int launch_fov_encode(const DevModel& m, const float* d_fov, const int32_t* d_agent_inst, const uint8_t* d_skip_inst, int A,
-                      float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st);
+int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
+                            const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, uint8_t* d_tiles, cudaStream_t st);
+int fov_n_chunks(int F);
+size_t fov_tiles_bytes(int A, int F);
+size_t fov_w0_tiles_bytes(int F);
+int launch_fov_w0_prep(const float* d_w0, int F, int w0_exp, uint8_t* d_out, cudaStream_t st);
+int launch_fov_f32_to_tiles(const float* d_fov, int A, int F, uint8_t* d_tiles, cudaStream_t st);
+int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32_t* d_agent_inst, const uint8_t* d_skip_inst,
+                      int A, float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st);
 int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, const double* d_prev, const float* d_e_self,
                       const float* d_vain_proj, float* d_X, cudaStream_t st);
 int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,

@@ -255,6 +255,68 @@ __global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// FOV raster, operand-tile output for the tensor-core encoders (fov_tc.cu): the same crop, written as bf16 {0, 1} into
+// [tile of 128 agents][chunk of 96 inputs][128 x 96 canonical UMMA tile].  A block rasterises 8 consecutive agents into
+// shared memory; 8 rows x 16 bytes are one 128-byte line of a core matrix, so every global store is a full line.
+// ------------------------------------------------------------------------------------------------
+#define RT_APB 8
+#define RT_CHUNK 96
+__global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uint8_t* __restrict__ occ,
+                                                                      const uint16_t* __restrict__ ctg,
+                                                                      const int32_t* __restrict__ agent_inst,
+                                                                      const double* __restrict__ pos,
+                                                                      const uint8_t* __restrict__ skip_inst, int A, int M, int F,
+                                                                      int n_chunks, uint8_t* __restrict__ tiles) {
+  extern __shared__ __align__(16) uint8_t rt_smem[];
+  const int FF = F * F, KD = 2 * FF, Kpad = n_chunks * RT_CHUNK;
+  const int row_bytes = Kpad * 2 + 16;  // +16: rows land in different banks for the 16-byte read-out
+  __shared__ int live_row[RT_APB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a0 = blockIdx.x * RT_APB, a = a0 + warp;
+  uint16_t* t = reinterpret_cast<uint16_t*>(rt_smem + (size_t)warp * row_bytes);
+  bool live = false;
+  if (a < A) {
+    const int b = agent_inst[a];
+    live = (skip_inst == nullptr) || (skip_inst[b] == 0);
+    if (live) {
+      const uint8_t* o = occ + (size_t)b * M * M;
+      const uint16_t* c = ctg + (size_t)a * M * M;
+      const int cx = grid_cell(pos[2 * a + 0], M), cy = grid_cell(pos[2 * a + 1], M);
+      const int buf = (F - 1) / 2;
+      const bool centre_in = cx < M && cy < M;
+      const int cc = centre_in ? (int)c[cx * M + cy] : CTRM_UNREACH;
+      const bool c_reach = cc != CTRM_UNREACH;
+      for (int i = lane; i < FF; i += 32) {
+        const int xf = i / F, yf = i - xf * F;
+        const int x = cx - buf + xf, y = cy - buf + yf;
+        uint16_t v0 = 0, v1 = 0;
+        if (centre_in && x >= 0 && x < M && y >= 0 && y < M) {
+          v0 = o[x * M + y] ? 0 : 0x3F80;  // bf16 1.0
+          const int _c = (int)c[x * M + y];
+          v1 = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 0x3F80 : 0;
+        }
+        t[i] = v0;
+        t[FF + i] = v1;
+      }
+      for (int i = KD + lane; i < Kpad; i += 32) t[i] = 0;
+    }
+  }
+  if (lane == 0) live_row[warp] = live ? 1 : 0;
+  if (!__syncthreads_or(live)) return;
+  const int n16 = RT_APB * (Kpad / 8);
+  for (int idx = threadIdx.x; idx < n16; idx += blockDim.x) {
+    const int rr = idx & (RT_APB - 1), k8 = idx >> 3;
+    if (!live_row[rr]) continue;  // finished instance (or beyond A: zero-filled at upload): nothing to write
+    const int ar = a0 + rr;
+    const int c = k8 / (RT_CHUNK / 8), kk = (k8 - c * (RT_CHUNK / 8)) * 8;
+    const int r = ar & 127;
+    const size_t off = ((size_t)(ar >> 7) * n_chunks + c) * (size_t)(128 * RT_CHUNK * 2) +
+                       (size_t)(r >> 3) * (RT_CHUNK / 8) * 128 + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16;
+    *reinterpret_cast<uint4*>(tiles + off) = *reinterpret_cast<const uint4*>(rt_smem + (size_t)rr * row_bytes + (size_t)k8 * 16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
 int launch_obs_to_cells(const double* d_obs_xyr, int O, int M, int4* d_cells, cudaStream_t st) {
@@ -314,4 +376,19 @@ int launch_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t
   if (A <= 0) return 0;
   if (F <= 27) return launch_fov_raster_t<8>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, d_fov, st);
   return launch_fov_raster_t<2>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, d_fov, st);
+}
+
+int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
+                            const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, uint8_t* d_tiles, cudaStream_t st) {
+  if (A <= 0) return 0;
+  const size_t smem = (size_t)RT_APB * ((size_t)n_chunks * RT_CHUNK * 2 + 16);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CTRM_CUDA_OK(cudaFuncSetAttribute(fov_raster_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  fov_raster_tiles_kernel<<<(A + RT_APB - 1) / RT_APB, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A,
+                                                                             M, F, n_chunks, d_tiles);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
 }

@@ -186,6 +186,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine, completion counted on the mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
 // ---- TMEM ----
 // whole warp executes; ncols power of two >= 32; the base address lands in *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
@@ -230,14 +240,16 @@ __device__ __forceinline__ void tmem_ld32_sum3(uint32_t tbase, int warp, int col
 // bf16 B-operand tiles (N_tile x K, K-major, tile_bytes(N_tile, K) apart) at tile rows [n_off, n_off + N):
 // B[n_off + n][k] = w[(k_begin + k) * ld + n]; k >= K_real and n >= N_real are zero padding
 __device__ __forceinline__ void stage_weight_split_at(const float* __restrict__ w, int ld, int k_begin, int K_real, int N_real,
-                                                      int N, int n_off, int N_tile, int K, uint8_t* tiles, int tid, int nthreads) {
+                                                      int N, int n_off, int N_tile, int K, uint8_t* tiles, int tid, int nthreads,
+                                                      int k_off = 0, int K_blk = -1) {
   const uint32_t part = tile_bytes(N_tile, K);
-  for (int i = tid; i < N * (K / 8); i += nthreads) {
+  if (K_blk < 0) K_blk = K;  // columns [k_off, k_off + K_blk) of the tile are written (K_blk % 8 == 0)
+  for (int i = tid; i < N * (K_blk / 8); i += nthreads) {
     const int k0 = (i / N) * 8, n = i - (i / N) * N;  // consecutive threads -> consecutive n (coalesced reads)
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (n < N_real && k0 + j < K_real) ? __ldg(w + (size_t)(k_begin + k0 + j) * ld + n) : 0.f;
-    store_split8(tiles, tiles + part, tiles + 2 * part, n_off + n, k0, K, v);
+    store_split8(tiles, tiles + part, tiles + 2 * part, n_off + n, k_off + k0, K, v);
   }
 }
 __device__ __forceinline__ void stage_weight_split(const float* __restrict__ w, int ld, int k_begin, int K_real, int N_real,
