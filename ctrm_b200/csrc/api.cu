@@ -36,22 +36,46 @@ int ctrm_fail_cuda(cudaError_t e, const char* what) {
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-struct DevArena {  // tracked device allocations
-  std::vector<void*> ptrs;
+struct DevArena {  // tracked device allocations with reuse: cudaMalloc / cudaFree of GB-sized buffers cost tens of
+                   // milliseconds and serialise the device, and successive batches of the same shape ask for the same sizes
+  struct Blk {
+    void* p;
+    size_t bytes;
+    bool used;
+  };
+  std::vector<Blk> blks;
   template <typename T>
   int alloc(T** out, size_t n) {
     *out = nullptr;
     if (n == 0) n = 1;
+    const size_t bytes = n * sizeof(T);
+    for (Blk& b : blks)
+      if (!b.used && b.bytes == bytes) {
+        b.used = true;
+        *out = reinterpret_cast<T*>(b.p);
+        return 0;
+      }
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) return ctrm_fail_cuda(e, "cudaMalloc");
-    ptrs.push_back(p);
+    blks.push_back({p, bytes, true});
     *out = reinterpret_cast<T*>(p);
     return 0;
   }
-  void release() {
-    for (void* p : ptrs) cudaFree(p);
-    ptrs.clear();
+  void release() {  // keep the memory for the next round of allocations
+    for (Blk& b : blks) b.used = false;
+  }
+  void trim() {  // free whatever the last round did not take again
+    size_t w = 0;
+    for (size_t i = 0; i < blks.size(); ++i) {
+      if (blks[i].used) blks[w++] = blks[i];
+      else cudaFree(blks[i].p);
+    }
+    blks.resize(w);
+  }
+  void destroy() {
+    for (Blk& b : blks) cudaFree(b.p);
+    blks.clear();
   }
 };
 
@@ -128,11 +152,11 @@ extern "C" void ctrm_ctx_destroy(ctrm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->w_arena.release();
-  c->b_arena.release();
-  c->r_arena.release();
-  c->t_arena.release();
-  c->c_arena.release();
+  c->w_arena.destroy();
+  c->b_arena.destroy();
+  c->r_arena.destroy();
+  c->t_arena.destroy();
+  c->c_arena.destroy();
   if (c->h_ndone) cudaFreeHost(c->h_ndone);
   for (int i = 0; i < 4; ++i)
     if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
@@ -253,7 +277,7 @@ static int cost_to_go_device(const uint8_t* d_occ, int M, const std::vector<uint
     cudaError_t e = cudaStreamSynchronize(st);  // the host vectors and temporaries die here
     if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "cost_to_go sync");
   } while (0);
-  tmp.release();
+  tmp.destroy();
   return rc;
 }
 
@@ -268,8 +292,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(sync_in(c, (cudaStream_t)user_stream));
   CTRM_CUDA_OK(cudaStreamSynchronize(st));
   c->b_arena.release();
-  c->r_arena.release();
-  c->r_L = c->r_S = 0;
+  const int prev_A = c->have_batch ? c->bt.A : -1;
   c->have_batch = false;
   c->have_result = false;
   const int M = c->model.desc.map_size, F = c->model.desc.fov_size;
@@ -317,6 +340,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   for (size_t i = 0; i < st_r.size(); ++i) disk_stencil(st_r[i], st_ld, stencils.data() + i * (size_t)st_ld * st_ld);
 
   Batch& bt = c->bt;
+  const Batch old_bt = bt;
   bt = Batch{};
   bt.B = B; bt.A = A; bt.O = O; bt.M = M; bt.F = F; bt.n_max = n_max;
   DevArena& ar = c->b_arena;
@@ -367,6 +391,16 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&c->d_agent_nv, (size_t)A));
   CHECK(ar.alloc(&c->d_agent_ne, (size_t)A));
   CHECK(ar.alloc(&c->d_totals, (size_t)4));
+  ar.trim();
+  if (A != prev_A) {  // the roadmap store is sized by the agent count: keep it across same-shaped batches
+    c->r_arena.destroy();
+    c->r_L = c->r_S = 0;
+  } else {
+    bt.L = old_bt.L; bt.S = old_bt.S; bt.W = old_bt.W; bt.K = old_bt.K;
+    bt.vpos = old_bt.vpos; bt.vcnt = old_bt.vcnt; bt.cmask = old_bt.cmask; bt.pmask = old_bt.pmask;
+    bt.samples = old_bt.samples;
+    bt.tr_samples = old_bt.tr_samples; bt.tr_loc_pred = old_bt.tr_loc_pred; bt.tr_loc_next = old_bt.tr_loc_next;
+  }
   CTRM_CUDA_OK(cudaMemsetAsync(bt.done, 0, (size_t)B, st));
   // occupancy raster + cost-to-go for every goal (Format2D_CTRM_Input.set_instance, format_input.py:200-210)
   {
@@ -379,7 +413,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "raster sync");
     }
-    tmp.release();
+    tmp.destroy();
     CHECK(rc);
   }
   CHECK(cost_to_go_device(d_occ, M, stencils, st_r, st_ld, pm_inst, pm_st, agent_pm, d_goals, A, d_ctg, st));
@@ -530,6 +564,7 @@ static int ensure_rollout_store(ctrm_ctx* c, const ctrm_params* p, int K) {
     CHECK(ar.alloc(&bt.tr_loc_pred, steps * bt.A * 2));
     CHECK(ar.alloc(&bt.tr_loc_next, steps * bt.A * 2));
   }
+  ar.trim();
   c->r_L = L; c->r_S = S; c->r_W = W; c->r_K = K; c->r_NT = p->N_traj; c->r_MT = p->max_T; c->r_att = p->max_attempt;
   c->r_trace = c->trace;
   return 0;
@@ -678,6 +713,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   }
   if (bt.tab_uniforms != nullptr)
     return ctrm_fail(CTRM_ERR_ARG, "per-step uniform tables are only supported through ctrm_cvae_sample (stage entry point)");
+  c->t_arena.trim();
   const bool nn = (bt.tab_teacher == nullptr) || c->trace;
   // reset the roadmap store and the roll-out state
   CTRM_CUDA_OK(cudaEventRecord(c->ev_t[0], st));
@@ -792,6 +828,7 @@ extern "C" int ctrm_export_csr(ctrm_ctx* c, int32_t* layer_ptr, double* pos, int
   if (!dst_is_device || !pos) CHECK(c->c_arena.alloc(&d_pos, (size_t)2 * nv));
   if (!dst_is_device || !eptr) CHECK(c->c_arena.alloc(&d_ep, (size_t)nv + 1));
   if (!dst_is_device || !eidx) CHECK(c->c_arena.alloc(&d_ei, (size_t)ne));
+  c->c_arena.trim();
   CHECK(launch_csr_fill(bt, c->d_agent_nv, c->d_agent_ne, c->d_totals, d_lp, d_pos, d_ep, d_ei, st));
   if (!dst_is_device) {
     if (layer_ptr) CTRM_CUDA_OK(cudaMemcpyAsync(layer_ptr, d_lp, nlp * sizeof(int32_t), kind, st));
@@ -897,7 +934,7 @@ extern "C" int ctrm_host_cost_to_go_2d(const double* goal, const int32_t* occ, i
     cudaError_t e = cudaMemcpy(h.data(), d_ctg, h.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "memcpy");
   }
-  ar.release();
+  ar.destroy();
   if (!rc)
     for (size_t i = 0; i < h.size(); ++i) out[i] = (int32_t)h[i];
   return rc;
@@ -931,7 +968,7 @@ extern "C" int ctrm_host_fov2d(const double* pos, const int32_t* occ, const int3
     cudaError_t e = cudaMemcpy(h.data(), d_fov, n * sizeof(float), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "memcpy");
   }
-  ar.release();
+  ar.destroy();
   if (!rc)
     for (size_t i = 0; i < n; ++i) out[i] = (int32_t)h[i];
   return rc;
