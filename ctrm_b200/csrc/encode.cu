@@ -12,7 +12,6 @@
 // pairwise features + agent encoder + neighbour attention, one warp per agent i
 // ------------------------------------------------------------------------------------------------
 #define AC_WARPS 4
-#define AC_ROW 45  // per-pair smem row: msg 32 | att 10 | dist 1, padded to an odd stride
 
 // get_normed_vec_mag (compiled.py:11-27) in float64, cast to float32 like `.float()` (format_input.py:327)
 __device__ __forceinline__ void nvm(double vx, double vy, float* o) {
@@ -40,13 +39,16 @@ __device__ __forceinline__ void dense_reg(const float* x, const float* __restric
   }
 }
 
+// Only the k nearest neighbours of an agent ever reach its communication vector (format_input.py:250-275), so the
+// 43->32->32->42 MLP runs for P = k + 1 pairs per agent (self + k nearest) instead of all N.  A warp serves G = 32 / P
+// agents (two for the trained k = 15): lane = (agent g, slot s), slot 0 = the agent itself, slot s = its s-th nearest.
 __global__ void __launch_bounds__(AC_WARPS * 32) agent_comm_kernel(Batch bt, const double* __restrict__ cur,
                                                                    const double* __restrict__ prev,
                                                                    const float* __restrict__ e_self,
                                                                    const float* __restrict__ vain_proj,
                                                                    const float* __restrict__ blob, ctrm_weight_offsets_t off,
                                                                    int num_neighbors, int use_k_neighbor, int include_self,
-                                                                   int n_max, float* __restrict__ X) {
+                                                                   int n_max, int P, int G, float* __restrict__ X) {
   extern __shared__ __align__(16) float smem[];
   // weights: w0i [11][32] | w1 [32][32] | w2 [32][44] | b1 [32] | b2 [44]
   float* Ww0 = smem;
@@ -54,8 +56,9 @@ __global__ void __launch_bounds__(AC_WARPS * 32) agent_comm_kernel(Batch bt, con
   float* Ww2 = Ww1 + 32 * 32;
   float* Wb1 = Ww2 + 32 * 44;
   float* Wb2 = Wb1 + 32;
-  float* pair_base = Wb2 + 44;  // [AC_WARPS][n_max][AC_ROW]
-  int* order_base = reinterpret_cast<int*>(pair_base + (size_t)AC_WARPS * n_max * AC_ROW);  // [AC_WARPS][n_max]
+  float* dist_base = Wb2 + 44;                                      // [AC_WARPS][G][n_max] fp32 distances
+  int* order_base = reinterpret_cast<int*>(dist_base + (size_t)AC_WARPS * G * n_max);  // [AC_WARPS][G][P]
+  float* msg_base = reinterpret_cast<float*>(order_base + (size_t)AC_WARPS * G * P);   // [AC_WARPS][G][P][33]: w*msg | w
   for (int i = threadIdx.x; i < 11 * 32; i += blockDim.x) Ww0[i] = __ldg(&blob[off.ag_w0i + i]);
   for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) Ww1[i] = __ldg(&blob[off.ag_w1 + i]);
   for (int i = threadIdx.x; i < 32 * 44; i += blockDim.x) Ww2[i] = __ldg(&blob[off.ag_w2 + i]);
@@ -63,23 +66,57 @@ __global__ void __launch_bounds__(AC_WARPS * 32) agent_comm_kernel(Batch bt, con
   for (int i = threadIdx.x; i < 44; i += blockDim.x) Wb2[i] = __ldg(&blob[off.ag_b2 + i]);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a = blockIdx.x * AC_WARPS + warp;
-  if (a >= bt.A) return;
-  const int b = bt.agent_inst[a];
-  if (bt.done != nullptr && bt.done[b]) return;
-  const int a0 = bt.agent_off[b], N = bt.agent_off[b + 1] - a0, il = a - a0;
-  float* prow = pair_base + (size_t)warp * n_max * AC_ROW;
-  int* order = order_base + (size_t)warp * n_max;
-  const double cix = cur[2 * a], ciy = cur[2 * a + 1];
-  for (int j = lane; j < N; j += 32) {
-    const int aj = a0 + j;
+  const int g = lane / P, s = lane - g * P;
+  const int a = (blockIdx.x * AC_WARPS + warp) * G + g;
+  bool active = g < G && a < bt.A;
+  int b = 0;
+  if (active) {
+    b = bt.agent_inst[a];
+    if (bt.done != nullptr && bt.done[b]) active = false;
+  }
+  if (!__any_sync(0xFFFFFFFFu, active)) return;
+  const int a0 = active ? bt.agent_off[b] : 0, N = active ? bt.agent_off[b + 1] - a0 : 0, il = a - a0;
+  float* dist = dist_base + (size_t)(warp * G + (g < G ? g : 0)) * n_max;
+  int* order = order_base + (size_t)(warp * G + (g < G ? g : 0)) * P;
+  float* mrow = msg_base + (size_t)(warp * G + (g < G ? g : 0)) * P * 33;
+  int k_nb = N - 1;
+  if (use_k_neighbor) k_nb = min(num_neighbors, k_nb);
+  const double cix = active ? cur[2 * a] : 0.0, ciy = active ? cur[2 * a + 1] : 0.0;
+  // ---- distances to every agent of the instance (column 2 of others_info, the fp32 value the reference argsorts)
+  if (active)
+    for (int j = s; j < N; j += P) {
+      const double dx = f64sub(cur[2 * (a0 + j)], cix), dy = f64sub(cur[2 * (a0 + j) + 1], ciy);
+      dist[j] = (float)sqrt(f64add(f64mul(dx, dx), f64mul(dy, dy)));
+    }
+  __syncwarp();
+  // ---- rank (argsort, format_input.py:239-243): self first, ties broken by index; keep ranks 0..k
+  if (active)
+    for (int j = s; j < N; j += P) {
+      int rank = 0;
+      if (j != il) {
+        const float dj = dist[j];
+        rank = 1;
+        for (int j2 = 0; j2 < N; ++j2) {
+          if (j2 == il || j2 == j) continue;
+          const float d2 = dist[j2];
+          rank += (d2 < dj || (d2 == dj && j2 < j)) ? 1 : 0;
+        }
+      }
+      if (rank <= k_nb) order[rank] = j;
+    }
+  __syncwarp();
+  // ---- pair MLP for slot s (pair i -> order[s])
+  const bool has_pair = active && s <= k_nb;
+  float o[44];
+  if (has_pair) {
+    const int aj = a0 + order[s];
     float info[CTRM_DIM_INFO];
     nvm(f64sub(cur[2 * aj], cix), f64sub(cur[2 * aj + 1], ciy), info + 0);
     nvm(f64sub(bt.goals[2 * aj], cix), f64sub(bt.goals[2 * aj + 1], ciy), info + 3);
     nvm(f64sub(prev[2 * aj], cix), f64sub(prev[2 * aj + 1], ciy), info + 6);
     info[9] = (float)bt.rads[aj];
     info[10] = (float)bt.speeds[aj];
-    float h1[32], h2[32], o[44];
+    float h1[32], h2[32];
     {
       const float4* vp = reinterpret_cast<const float4*>(vain_proj + (size_t)aj * 32);
 #pragma unroll
@@ -97,90 +134,76 @@ __global__ void __launch_bounds__(AC_WARPS * 32) agent_comm_kernel(Batch bt, con
 #pragma unroll
     for (int k = 0; k < 44; ++k) o[k] = Wb2[k];
     dense_reg<32, 42, 44>(h2, Ww2, o);
-    float* pr = prow + (size_t)j * AC_ROW;
-#pragma unroll
-    for (int k = 0; k < 42; ++k) pr[k] = o[k];
-    pr[42] = info[2];
-    if (j == il) {  // get_self_info (compiled.py:100-125): row (i,i), columns 3..10
+    if (s == 0) {  // get_self_info (compiled.py:100-125): row (i,i), columns 3..10
       float* xr = X + (size_t)a * CTRM_DIM_X;
 #pragma unroll
       for (int k = 0; k < 8; ++k) xr[k] = info[3 + k];
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 44; ++k) o[k] = 0.f;
   }
-  __syncwarp();
-  // rank neighbours by distance (argsort of column 2, format_input.py:239-243); self (distance 0) first,
-  // ties broken by index
-  int k_nb = N - 1;
-  if (use_k_neighbor) k_nb = min(num_neighbors, k_nb);
-  for (int j = lane; j < N; j += 32) {
-    float dj = prow[(size_t)j * AC_ROW + 42];
-    int rank = 0;
-    if (j != il) {
-      rank = 1;
-      for (int j2 = 0; j2 < N; ++j2) {
-        if (j2 == il || j2 == j) continue;
-        float d2 = prow[(size_t)j2 * AC_ROW + 42];
-        rank += (d2 < dj || (d2 == dj && j2 < j)) ? 1 : 0;
-      }
-    }
-    order[rank] = j;
-  }
-  __syncwarp();
-  // similarity to own attention vector, softmax over the k nearest (self excluded unless include_self_attention)
-  const float* self_row = prow + (size_t)il * AC_ROW;
-  const int first = include_self ? 0 : 1;
-  float mx = -INFINITY;
-  for (int r = first + lane; r <= k_nb; r += 32) {
-    const float* pr = prow + (size_t)order[r] * AC_ROW;
-    float s = 0.f;
+  // ---- similarity to the agent's own attention vector (slot 0 of the group), softmax over the neighbours
+  float sim = 0.f;
+  {
+    const int src = (g < G ? g : 0) * P;
 #pragma unroll
     for (int c = 0; c < 10; ++c) {
-      float d = pr[32 + c] - self_row[32 + c];
-      s += d * d;
+      const float self_att = __shfl_sync(0xFFFFFFFFu, o[32 + c], src);
+      const float d = o[32 + c] - self_att;
+      sim += d * d;
     }
-    s = -s;
-    pr = nullptr;
-    prow[(size_t)order[r] * AC_ROW + 43] = s;
-    mx = fmaxf(mx, s);
+    sim = -sim;
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
-  float sum = 0.f;
-  for (int r = first + lane; r <= k_nb; r += 32) {
-    float* pr = prow + (size_t)order[r] * AC_ROW;
-    float ev = expf(pr[43] - mx);
-    pr[43] = ev;
-    sum += ev;
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+  const int first = include_self ? 0 : 1;
+  const bool in_softmax = has_pair && s >= first;
+  if (has_pair) mrow[s * 33 + 32] = sim;
   __syncwarp();
-  // comm_i[c] = sum over the k neighbours (rank order) of w_j * msg_ij[c]; lane = channel c
-  float comm = 0.f;
-  for (int r = 1; r <= k_nb; ++r) {
-    const float* pr = prow + (size_t)order[r] * AC_ROW;
-    comm += pr[lane] * (pr[43] / sum);
+  float w = 0.f;
+  if (in_softmax) {
+    float mx = -INFINITY, sum = 0.f;
+    for (int r = first; r <= k_nb; ++r) mx = fmaxf(mx, mrow[r * 33 + 32]);
+    for (int r = first; r <= k_nb; ++r) sum += expf(mrow[r * 33 + 32] - mx);
+    w = expf(sim - mx) / sum;
   }
-  float* xr = X + (size_t)a * CTRM_DIM_X;
-  xr[8 + lane] = __ldg(&e_self[(size_t)a * 32 + lane]);
-  xr[40 + lane] = comm;
+  __syncwarp();
+  if (has_pair) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) mrow[s * 33 + c] = o[c] * w;
+  }
+  __syncwarp();
+  // ---- comm_i[c] = sum over the neighbours in rank order of w_j * msg_ij[c]; X row = [self_info | e_self | comm]
+  if (active) {
+    float* xr = X + (size_t)a * CTRM_DIM_X;
+    for (int c = s; c < 32; c += P) {
+      float comm = 0.f;
+      for (int r = 1; r <= k_nb; ++r) comm += mrow[r * 33 + c];
+      xr[40 + c] = comm;
+      xr[8 + c] = __ldg(&e_self[(size_t)a * 32 + c]);
+    }
+  }
 }
 
 int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, const double* d_prev, const float* d_e_self,
                       const float* d_vain_proj, float* d_X, cudaStream_t st) {
   if (bt.A <= 0) return 0;
   const int n_max = bt.n_max;
+  int P = (m.desc.use_k_neighbor ? (m.desc.num_neighbors < n_max - 1 ? m.desc.num_neighbors : n_max - 1) : n_max - 1) + 1;
+  if (P < 1) P = 1;
+  if (P > 32) return ctrm_fail(-1, "agent_comm: more than 31 neighbours per agent are not supported");
+  const int G = 32 / P;
   size_t smem = (size_t)(11 * 32 + 32 * 32 + 32 * 44 + 32 + 44) * sizeof(float) +
-                (size_t)AC_WARPS * n_max * AC_ROW * sizeof(float) + (size_t)AC_WARPS * n_max * sizeof(int);
+                (size_t)AC_WARPS * G * ((size_t)n_max * sizeof(float) + (size_t)P * sizeof(int) + (size_t)P * 33 * sizeof(float));
   if (smem > 200 * 1024) return ctrm_fail(-1, "instance too large for agent_comm shared memory");
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     CTRM_CUDA_OK(cudaFuncSetAttribute(agent_comm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  agent_comm_kernel<<<(bt.A + AC_WARPS - 1) / AC_WARPS, AC_WARPS * 32, smem, st>>>(
+  const int agents_per_block = AC_WARPS * G;
+  agent_comm_kernel<<<(bt.A + agents_per_block - 1) / agents_per_block, AC_WARPS * 32, smem, st>>>(
       bt, d_cur, d_prev, d_e_self, d_vain_proj, m.blob, m.off, m.desc.num_neighbors, m.desc.use_k_neighbor,
-      m.desc.include_self_attention, n_max, d_X);
+      m.desc.include_self_attention, n_max, P, G, d_X);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }
