@@ -167,8 +167,8 @@ class ClockSampler:
 def algorithmic_work(kernel, agent_steps, pair_steps, K, F=19):
     """ALGORITHMIC bytes / flops of one kernel over the counted units (DESIGN.md 'Kernels')"""
     FF = F * F
-    if kernel == "fov_raster":      # write 2F^2 f32, read F^2 (1 B occ + 2 B cost) + position
-        return dict(bound="hbm", work=agent_steps * (2 * FF * 4 + FF * 3 + 16), unit="GB/s")
+    if kernel == "fov_raster":      # write 2F^2 bf16 {0,1} operand-tile entries, read F^2 (1 B occ + 2 B cost) + position
+        return dict(bound="hbm", work=agent_steps * (2 * FF * 2 + FF * 3 + 16), unit="GB/s")
     if kernel == "fov_encode":      # 2 x (722->32->32->32) + the 32x32 vain projection
         return dict(bound="tensor", work=agent_steps * 2.0 * (2 * FF * 64 + 4 * 1024 + 1024), unit="TFLOP/s")
     if kernel == "agent_comm":      # per ordered pair: 11x32 + 32x32 + 32x42 MAC
@@ -177,11 +177,9 @@ def algorithmic_work(kernel, agent_steps, pair_steps, K, F=19):
         return dict(bound="tensor", work=agent_steps * 2.0 * (3424 + 5472 + 75 * 32), unit="TFLOP/s")
     if kernel == "cvae_decode":     # z-part of layer 0 + layers 1, 2 per (agent, copy) row
         return dict(bound="tensor", work=agent_steps * K * 2.0 * (64 * 32 + 1024 + 96), unit="TFLOP/s")
-    if kernel == "select":          # per agent-step: samples K*12 B + state 64 B + loc_pred 16 B
-        return dict(bound="hbm", work=agent_steps * (K * 12 + 80), unit="GB/s")
-    if kernel == "merge":           # per agent-step: <= 3 layers x 26 candidates x 16 B + masks
-        return dict(bound="hbm", work=agent_steps * (3 * 26 * 16 + 3 * 26 * 8 + 64), unit="GB/s")
-    return dict(bound="hbm", work=agent_steps * 16, unit="GB/s")
+    # step (select + merge + advance): per agent-step K samples x 12 B + state ~96 B + <= 3 layers x 26 candidates x
+    # (16 B position + 8 B masks) + the new vertex
+    return dict(bound="hbm", work=agent_steps * (K * 12 + 96 + 3 * 26 * 24 + 32), unit="GB/s")
 
 
 def gpu_arm(args):
@@ -294,7 +292,7 @@ def gpu_arm(args):
     kt = builder.kernel_times()
     builder.set_profile(False)
     agent_steps = float((steps_inst * n_ag).sum())
-    pair_steps = float((steps_inst * n_ag * n_ag).sum())
+    pair_steps = float((steps_inst * n_ag * (np.minimum(15, n_ag - 1) + 1)).sum())  # self + k nearest per agent
     total_kernel_ms = sum(v["ms"] for v in kt.values()) or 1.0
     kernels = {}
     for name, v in kt.items():

@@ -386,6 +386,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&bt.cnt_collide, (size_t)B));
   CHECK(ar.alloc(&bt.n_done, (size_t)1));
   CHECK(ar.alloc(&bt.steps_done, (size_t)B));
+  CHECK(ar.alloc(&bt.arrive_cnt, (size_t)B));
   CHECK(ar.alloc(&bt.nlayers, (size_t)A));
   CHECK(ar.alloc(&c->d_tfin, (size_t)B));
   CHECK(ar.alloc(&c->d_agent_nv, (size_t)A));
@@ -571,8 +572,7 @@ static int ensure_rollout_store(ctrm_ctx* c, const ctrm_params* p, int K) {
 }
 
 // kernel ids of the per-kernel timing table (ctrm_last_kernel_times)
-enum { KID_FOV_RASTER = 0, KID_FOV_ENCODE, KID_AGENT_COMM, KID_CVAE_PRIOR, KID_CVAE_DECODE, KID_SELECT, KID_MERGE, KID_ADVANCE,
-       KID_STEP_COUNT };
+enum { KID_FOV_RASTER = 0, KID_FOV_ENCODE, KID_AGENT_COMM, KID_CVAE_PRIOR, KID_CVAE_DECODE, KID_STEP, KID_STEP_COUNT };
 
 // profile mode: the step runs eagerly with a CUDA event after every kernel
 struct StepProfiler {
@@ -635,12 +635,8 @@ static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, 
     CHECK(launch_cvae_decode(c->model, bt, bt.cv_logits, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st));
     CHECK(mark(KID_CVAE_DECODE));
   }
-  CHECK(launch_select(bt, st));
-  CHECK(mark(KID_SELECT));
-  CHECK(launch_merge(bt, st));
-  CHECK(mark(KID_MERGE));
-  CHECK(launch_advance(bt, st));
-  CHECK(mark(KID_ADVANCE));
+  CHECK(launch_step(bt, st));
+  CHECK(mark(KID_STEP));
   *n_kernels = k;
   return 0;
 }
@@ -871,7 +867,7 @@ extern "C" int ctrm_set_profile(ctrm_ctx* c, int enable) {
 
 extern "C" int ctrm_last_kernel_times(ctrm_ctx* c, double ms[8], int64_t launches[8]) {
   if (!c || !ms || !launches) return ctrm_fail(CTRM_ERR_ARG, "NULL argument");
-  for (int k = 0; k < KID_STEP_COUNT; ++k) { ms[k] = c->kernel_ms[k]; launches[k] = c->kernel_n[k]; }
+  for (int k = 0; k < 8; ++k) { ms[k] = k < KID_STEP_COUNT ? c->kernel_ms[k] : 0.0; launches[k] = k < KID_STEP_COUNT ? c->kernel_n[k] : 0; }
   return 0;
 }
 

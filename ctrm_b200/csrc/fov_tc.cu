@@ -19,13 +19,14 @@
 #define FT_A_CHUNK 24576u   // tile_bytes(128, 96)
 #define FT_W_DIGIT 12288u   // tile_bytes(64, 96)
 #define FT_W_CHUNK 49152u   // four digits
+#define FT_STAGES 2
 #define FT_STAGE (FT_A_CHUNK + FT_W_CHUNK)
 #define FT_H_PART 16384u    // tile_bytes(128, 64)
 #define FT_H32_PART 8192u   // tile_bytes(128, 32)
 #define FT_W64_PART 8192u   // tile_bytes(64, 64)
 #define FT_W32_PART 2048u   // tile_bytes(32, 32)
 #define FT_NF 256
-#define FT_SMEM (2 * FT_STAGE + 2 * 3 * FT_W64_PART + 3 * FT_W32_PART + FT_NF * 4 + 64)
+#define FT_SMEM (FT_STAGES * FT_STAGE + 2 * 3 * FT_W64_PART + 3 * FT_W32_PART + FT_NF * 4 + 128)
 
 // ---- weight preparation (once per ctrm_load_weights): digit tiles of W0 in global memory, chunk-major ----
 __global__ void fov_w0_prep_kernel(const float* __restrict__ w0 /*[KD][64]*/, int KD, int n_chunks, float scale,
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t
                                                                    float* __restrict__ vain_proj, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage0 = smem;                              // stage s: A chunk | W chunk (4 digits)
-  uint8_t* W1c = smem + 2 * FT_STAGE;                  // blockdiag(self.mlp.2, vain.mlp.2)  [64 x 64] x 3
+  uint8_t* W1c = smem + FT_STAGES * FT_STAGE;                  // blockdiag(self.mlp.2, vain.mlp.2)  [64 x 64] x 3
   uint8_t* W2c = W1c + 3 * FT_W64_PART;                // blockdiag(self.mlp.4, vain.mlp.4)
   uint8_t* Wp = W2c + 3 * FT_W64_PART;                 // agent.mlp.0 rows 11..42  [32 x 32] x 3
   float* cf = reinterpret_cast<float*>(Wp + 3 * FT_W32_PART);
@@ -88,8 +89,8 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t
   float* b1 = cf + 64;     // 64
   float* b2 = cf + 128;    // 64
   float* bp = cf + 192;    // 32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cf + FT_NF);  // full[2], empty[2], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cf + FT_NF);  // full[FT_STAGES], empty[FT_STAGES], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FT_STAGES + 1);
   uint8_t* Ht = stage0;    // hidden tiles reuse the operand stages once layer 0 has completed
   const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -110,13 +111,14 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
   if (tid == 0)
-    for (int i = 0; i < 5; ++i) tc::mbar_init(tc::smem_u32(&bars[i]), 1);
+    for (int i = 0; i < 2 * FT_STAGES + 1; ++i) tc::mbar_init(tc::smem_u32(&bars[i]), 1);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = *tmem_slot;
-  const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[2]), done = tc::smem_u32(&bars[4]);
+  const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[FT_STAGES]),
+                 done = tc::smem_u32(&bars[2 * FT_STAGES]);
   const uint32_t sStage = tc::smem_u32(stage0), sH = tc::smem_u32(Ht), sW1 = tc::smem_u32(W1c), sW2 = tc::smem_u32(W2c),
                  sWp = tc::smem_u32(Wp);
   const uint32_t id64 = tc::idesc_bf16(128, 64);
@@ -149,16 +151,16 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t
     if (tid == 0) {  // producer
       const uint8_t* gA = fov_tiles + (size_t)tile * n_chunks * FT_A_CHUNK;
       for (int c = 0; c < n_chunks; ++c) {
-        const uint32_t u = it + c, s = u & 1u;
-        if (u >= 2) tc::mbar_wait(empty0 + 8 * s, ((u >> 1) - 1) & 1u);
+        const uint32_t u = it + c, s = u % FT_STAGES;
+        if (u >= FT_STAGES) tc::mbar_wait(empty0 + 8 * s, ((u / FT_STAGES) - 1) & 1u);
         tc::mbar_expect_tx(full0 + 8 * s, FT_STAGE);
         tc::tma_bulk_g2s(sStage + s * FT_STAGE, gA + (size_t)c * FT_A_CHUNK, FT_A_CHUNK, full0 + 8 * s);
         tc::tma_bulk_g2s(sStage + s * FT_STAGE + FT_A_CHUNK, w0_tiles + (size_t)c * FT_W_CHUNK, FT_W_CHUNK, full0 + 8 * s);
       }
     } else if (tid == 32) {  // MMA issuer
       for (int c = 0; c < n_chunks; ++c) {
-        const uint32_t u = it + c, s = u & 1u;
-        tc::mbar_wait(full0 + 8 * s, (u >> 1) & 1u);
+        const uint32_t u = it + c, s = u % FT_STAGES;
+        tc::mbar_wait(full0 + 8 * s, (u / FT_STAGES) & 1u);
         tc::fence_after_sync();
         const uint32_t sa = sStage + s * FT_STAGE, sw = sa + FT_A_CHUNK;
 #pragma unroll

@@ -38,6 +38,7 @@ struct Batch {
   unsigned long long* cnt_collide;      // [B]   StaticObjects.cnt_continuous_collide
   int32_t* n_done;                      // [1]
   int32_t* steps_done;                  // [B] executed roll-out steps (bench accounting)
+  int32_t* arrive_cnt;                  // [B] warps of the instance that finished the current step
   // per-step tensors
   uint8_t* fov_tiles;  // bf16 operand tiles [ceil(A/128)][n_chunks][128 x 96]
   float *e_self, *e_vain, *vain_proj, *X, *samples;
@@ -95,9 +96,7 @@ int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, floa
 int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits, const float* d_dec0, const float* d_uniforms,
                        int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st);
 
-int launch_select(const Batch& bt, cudaStream_t st);
-int launch_merge(const Batch& bt, cudaStream_t st);
-int launch_advance(const Batch& bt, cudaStream_t st);
+int launch_step(const Batch& bt, cudaStream_t st);
 int launch_rollout_init(const Batch& bt, cudaStream_t st);
 
 int launch_finalize(const Batch& bt, int32_t* d_tfin, cudaStream_t st);

@@ -37,6 +37,7 @@ __global__ void rollout_init_kernel(Batch bt) {
     bt.done[i] = (bt.N_traj <= 0) ? 1 : 0;
     bt.cnt_collide[i] = 0ULL;
     bt.steps_done[i] = 0;
+    bt.arrive_cnt[i] = 0;
   }
   if (i == 0) *bt.n_done = (bt.N_traj <= 0) ? bt.B : 0;
 }
@@ -44,12 +45,8 @@ __global__ void rollout_init_kernel(Batch bt) {
 // ------------------------------------------------------------------------------------------------
 // select: loc_pred for every agent
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RO_WARPS * 32) select_kernel(Batch bt) {
-  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (a >= bt.A) return;
-  const int b = bt.agent_inst[a];
-  if (bt.done[b]) return;
+__device__ __forceinline__ unsigned int select_agent(const Batch& bt, const int a, const int b, const int lane, double* out_x,
+                                                     double* out_y) {
   const int t = bt.t[b], kt = bt.k_traj[b];
   const int a0 = bt.agent_off[b], il = a - a0;
   const int N = bt.agent_off[b + 1] - a0;
@@ -136,91 +133,97 @@ __global__ void __launch_bounds__(RO_WARPS * 32) select_kernel(Batch bt) {
       count += __popc(pre_mask);
     }
   }
-  if (lane == 0) {
-    bt.loc_pred[2 * a] = lx;
-    bt.loc_pred[2 * a + 1] = ly;
-    if (count) atomicAdd(&bt.cnt_collide[b], (unsigned long long)count);
-    if (bt.tr_loc_pred != nullptr) {
-      bt.tr_loc_pred[2 * (si * bt.A + a)] = lx;
-      bt.tr_loc_pred[2 * (si * bt.A + a) + 1] = ly;
-    }
+  if (lane == 0 && bt.tr_loc_pred != nullptr) {
+    bt.tr_loc_pred[2 * (si * bt.A + a)] = lx;
+    bt.tr_loc_pred[2 * (si * bt.A + a) + 1] = ly;
   }
   if (bt.tr_samples != nullptr && bt.samples != nullptr) {
     for (int i = lane; i < bt.K * 3; i += 32)
       bt.tr_samples[(si * bt.A + a) * (size_t)bt.K * 3 + i] = bt.samples[(size_t)a * bt.K * 3 + i];
   }
+  *out_x = lx;
+  *out_y = ly;
+  return count;
 }
 
 // ------------------------------------------------------------------------------------------------
 // merge: insert loc_pred into the agent's timed roadmap or merge it with a compatible vertex
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RO_WARPS * 32) merge_kernel(Batch bt) {
-  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (a >= bt.A) return;
-  const int b = bt.agent_inst[a];
-  if (bt.done[b]) return;
-  const int t = bt.t[b], kt = bt.k_traj[b];
+// layer sizes and this lane's candidate positions of V[t-1], V[t], V[t+1], loaded BEFORE the candidate selection runs so
+// that their latency overlaps it (the kernel is bound by dependent global loads, not by arithmetic)
+template <int W>
+struct MergePrefetch {
+  int nl, n_prev, n_t, n_next;
+  double px[3][W], py[3][W];
+};
+template <int W>
+__device__ __forceinline__ void merge_prefetch(const Batch& bt, int a, int t, int lane, MergePrefetch<W>& pf) {
+  pf.nl = bt.nlayers[a];
+  const int32_t* vc = bt.vcnt + (size_t)a * bt.L;
+  pf.n_prev = vc[t - 1];
+  pf.n_t = (pf.nl > t) ? vc[t] : 0;
+  pf.n_next = (pf.nl > t + 1) ? vc[t + 1] : 0;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const int n = l == 0 ? pf.n_prev : (l == 1 ? pf.n_t : pf.n_next);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int sl = w * 32 + lane;
+      pf.px[l][w] = 0.0;
+      pf.py[l][w] = 0.0;
+      if (sl < n) {
+        const size_t v = vslot(bt, a, t - 1 + l, sl);
+        const double2 p = *reinterpret_cast<const double2*>(&bt.vpos[2 * v]);
+        pf.px[l][w] = p.x;
+        pf.py[l][w] = p.y;
+      }
+    }
+  }
+}
+
+template <int W>
+__device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const int a, const int b, const int lane, const int t,
+                                                    const int kt, const double lx, const double ly,
+                                                    const MergePrefetch<W>& pf) {
   const int o0 = bt.obs_off[b], o1 = bt.obs_off[b + 1];
-  const double lx = bt.loc_pred[2 * a], ly = bt.loc_pred[2 * a + 1];
   const double speed = bt.speeds[a], speed2 = bt.speeds2[a], merge2 = bt.merge2[a], rad = bt.rads[a];
   const double gx = bt.goals[2 * a], gy = bt.goals[2 * a + 1];
-  const int W = bt.W;
-  const int nl = bt.nlayers[a];
-  const bool has_t = nl > t, has_next = nl > t + 1;
+  const int nl = pf.nl;
+  const bool has_next = nl > t + 1;
   unsigned int count = 0;
-  uint32_t P[CTRM_MAX_W], Cm[CTRM_MAX_W], Mg[CTRM_MAX_W];
+  uint32_t P[W], Cm[W], Mg[W];
 #pragma unroll
-  for (int w = 0; w < CTRM_MAX_W; ++w) { P[w] = 0u; Cm[w] = 0u; Mg[w] = 0u; }
+  for (int w = 0; w < W; ++w) { P[w] = 0u; Cm[w] = 0u; Mg[w] = 0u; }
   // parents: V[t-1] within speed and collision free, tested as (parent -> loc)   utils.py:58-69
-  {
-    const int n = bt.vcnt[(size_t)a * bt.L + (t - 1)];
 #pragma unroll
-    for (int w = 0; w < CTRM_MAX_W; ++w) {
-      if (w < W && w * 32 < n) {
-        const int s = w * 32 + lane;
-        bool cand = false, ok = false;
-        if (s < n) {
-          const size_t v = vslot(bt, a, t - 1, s);
-          const double px = bt.vpos[2 * v], py = bt.vpos[2 * v + 1];
-          cand = dist2(px, py, lx, ly) <= speed2;
-          if (cand) ok = !any_obstacle_hit(px, py, lx, ly, rad, bt.obs_xyr, o0, o1);
-        }
-        count += __popc(__ballot_sync(0xFFFFFFFFu, cand));
-        P[w] = __ballot_sync(0xFFFFFFFFu, ok);
-      }
+  for (int w = 0; w < W; ++w) {
+    if (w * 32 < pf.n_prev) {
+      const bool in = w * 32 + lane < pf.n_prev;
+      const bool cand = in && dist2(pf.px[0][w], pf.py[0][w], lx, ly) <= speed2;
+      const bool ok = cand && !any_obstacle_hit(pf.px[0][w], pf.py[0][w], lx, ly, rad, bt.obs_xyr, o0, o1);
+      count += __popc(__ballot_sync(0xFFFFFFFFu, cand));
+      P[w] = __ballot_sync(0xFFFFFFFFu, ok);
     }
   }
   // children: V[t+1], tested as (child -> loc)   utils.py:72-84
   if (has_next) {
-    const int n = bt.vcnt[(size_t)a * bt.L + (t + 1)];
 #pragma unroll
-    for (int w = 0; w < CTRM_MAX_W; ++w) {
-      if (w < W && w * 32 < n) {
-        const int s = w * 32 + lane;
-        bool cand = false, ok = false;
-        if (s < n) {
-          const size_t v = vslot(bt, a, t + 1, s);
-          const double px = bt.vpos[2 * v], py = bt.vpos[2 * v + 1];
-          cand = dist2(px, py, lx, ly) <= speed2;
-          if (cand) ok = !any_obstacle_hit(px, py, lx, ly, rad, bt.obs_xyr, o0, o1);
-        }
+    for (int w = 0; w < W; ++w) {
+      if (w * 32 < pf.n_next) {
+        const bool in = w * 32 + lane < pf.n_next;
+        const bool cand = in && dist2(pf.px[2][w], pf.py[2][w], lx, ly) <= speed2;
+        const bool ok = cand && !any_obstacle_hit(pf.px[2][w], pf.py[2][w], lx, ly, rad, bt.obs_xyr, o0, o1);
         count += __popc(__ballot_sync(0xFFFFFFFFu, cand));
         Cm[w] = __ballot_sync(0xFFFFFFFFu, ok);
       }
     }
   }
-  const int n_t = has_t ? bt.vcnt[(size_t)a * bt.L + t] : 0;
+  const int n_t = pf.n_t;
   // merge candidates: V[t] within merge_distance   utils.py:86-89
 #pragma unroll
-  for (int w = 0; w < CTRM_MAX_W; ++w) {
-    if (w < W && w * 32 < n_t) {
-      const int s = w * 32 + lane;
-      bool cand = false;
-      if (s < n_t) {
-        const size_t v = vslot(bt, a, t, s);
-        cand = dist2(bt.vpos[2 * v], bt.vpos[2 * v + 1], lx, ly) <= merge2;
-      }
+  for (int w = 0; w < W; ++w) {
+    if (w * 32 < n_t) {
+      const bool cand = (w * 32 + lane < n_t) && dist2(pf.px[1][w], pf.py[1][w], lx, ly) <= merge2;
       Mg[w] = __ballot_sync(0xFFFFFFFFu, cand);
     }
   }
@@ -230,8 +233,8 @@ __global__ void __launch_bounds__(RO_WARPS * 32) merge_kernel(Batch bt) {
   bool add_edges = false, resolved = false;
   const double h_loc = dist2(lx, ly, gx, gy);
 #pragma unroll
-  for (int w = 0; w < CTRM_MAX_W; ++w) {
-    uint32_t m = (w < W) ? Mg[w] : 0u;
+  for (int w = 0; w < W; ++w) {
+    uint32_t m = Mg[w];
     while (m && !resolved) {
       const int u = w * 32 + __ffs(m) - 1;
       m &= m - 1;
@@ -277,8 +280,8 @@ __global__ void __launch_bounds__(RO_WARPS * 32) merge_kernel(Batch bt) {
       const uint32_t tbit = 1u << (target & 31);
       const int tw = target >> 5;
 #pragma unroll
-      for (int w = 0; w < CTRM_MAX_W; ++w) {
-        if (w < W) {
+      for (int w = 0; w < W; ++w) {
+        {
           const uint32_t pu = resolved ? bt.pmask[v * W + w] : 0u;
           const uint32_t cu = resolved ? bt.cmask[v * W + w] : 0u;
           const int s = w * 32 + lane;
@@ -309,26 +312,23 @@ __global__ void __launch_bounds__(RO_WARPS * 32) merge_kernel(Batch bt) {
     bt.nxt[2 * a] = rx;
     bt.nxt[2 * a + 1] = ry;
     if (arr) bt.arrived[a] = 1;
-    if (count) atomicAdd(&bt.cnt_collide[b], (unsigned long long)count);
     if (bt.tr_loc_next != nullptr) {
       const size_t si = step_index(bt, kt, t);
       bt.tr_loc_next[2 * (si * bt.A + a)] = rx;
       bt.tr_loc_next[2 * (si * bt.A + a) + 1] = ry;
     }
   }
+  return count;
 }
 
 // ------------------------------------------------------------------------------------------------
-// advance: one warp per instance
+// advance: roll-out bookkeeping of one instance, run by the last of its agents' warps to finish the step (the other
+// warps' writes are read with ld.global.cg after a __threadfence: L1 may hold stale lines of the same 128 bytes)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RO_WARPS * 32) advance_kernel(Batch bt) {
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (b >= bt.B) return;
-  if (bt.done[b]) return;
+__device__ __forceinline__ void advance_instance(const Batch& bt, const int b, const int lane) {
   const int a0 = bt.agent_off[b], N = bt.agent_off[b + 1] - a0;
   bool all = true;
-  for (int i = lane; i < N; i += 32) all = all && (bt.arrived[a0 + i] != 0);
+  for (int i = lane; i < N; i += 32) all = all && (__ldcg(&bt.arrived[a0 + i]) != 0);
   all = __all_sync(0xFFFFFFFFu, all);
   const int t = bt.t[b];
   if (lane == 0) bt.steps_done[b] += 1;
@@ -344,8 +344,8 @@ __global__ void __launch_bounds__(RO_WARPS * 32) advance_kernel(Batch bt) {
       const int a = a0 + i;
       bt.prev[2 * a] = bt.cur[2 * a];
       bt.prev[2 * a + 1] = bt.cur[2 * a + 1];
-      bt.cur[2 * a] = bt.nxt[2 * a];
-      bt.cur[2 * a + 1] = bt.nxt[2 * a + 1];
+      bt.cur[2 * a] = __ldcg(&bt.nxt[2 * a]);
+      bt.cur[2 * a + 1] = __ldcg(&bt.nxt[2 * a + 1]);
     }
     if (lane == 0) bt.t[b] = t + 1;
   } else {
@@ -379,21 +379,48 @@ int launch_rollout_init(const Batch& bt, cudaStream_t st) {
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int launch_select(const Batch& bt, cudaStream_t st) {
-  if (bt.A <= 0) return 0;
-  select_kernel<<<(bt.A + RO_WARPS - 1) / RO_WARPS, RO_WARPS * 32, 0, st>>>(bt);
-  CTRM_CUDA_OK(cudaGetLastError());
-  return 0;
+// ------------------------------------------------------------------------------------------------
+// step: select -> merge -> (last warp of the instance) advance, one warp per agent
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(RO_WARPS * 32) step_kernel(Batch bt) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= bt.A) return;
+  const int b = bt.agent_inst[a];
+  if (bt.done[b]) return;
+  const int t = bt.t[b], kt = bt.k_traj[b];
+  MergePrefetch<W> pf;
+  merge_prefetch<W>(bt, a, t, lane, pf);
+  double lx, ly;
+  unsigned int count = select_agent(bt, a, b, lane, &lx, &ly);
+  count += merge_agent<W>(bt, a, b, lane, t, kt, lx, ly, pf);
+  // publish this agent's state, then let the last warp of the instance do the roll-out bookkeeping
+  int last = 0;
+  if (lane == 0) {
+    if (count) atomicAdd(&bt.cnt_collide[b], (unsigned long long)count);
+    __threadfence();
+    const int n = bt.agent_off[b + 1] - bt.agent_off[b];
+    last = (atomicAdd(&bt.arrive_cnt[b], 1) == n - 1) ? 1 : 0;
+  }
+  last = __shfl_sync(0xFFFFFFFFu, last, 0);
+  if (last) {
+    __threadfence();
+    if (lane == 0) bt.arrive_cnt[b] = 0;
+    advance_instance(bt, b, lane);
+  }
 }
-int launch_merge(const Batch& bt, cudaStream_t st) {
+
+int launch_step(const Batch& bt, cudaStream_t st) {
   if (bt.A <= 0) return 0;
-  merge_kernel<<<(bt.A + RO_WARPS - 1) / RO_WARPS, RO_WARPS * 32, 0, st>>>(bt);
-  CTRM_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-int launch_advance(const Batch& bt, cudaStream_t st) {
-  if (bt.B <= 0) return 0;
-  advance_kernel<<<(bt.B + RO_WARPS - 1) / RO_WARPS, RO_WARPS * 32, 0, st>>>(bt);
+  const int blocks = (bt.A + RO_WARPS - 1) / RO_WARPS;
+  switch (bt.W) {
+    case 1: step_kernel<1><<<blocks, RO_WARPS * 32, 0, st>>>(bt); break;
+    case 2: step_kernel<2><<<blocks, RO_WARPS * 32, 0, st>>>(bt); break;
+    case 3: step_kernel<3><<<blocks, RO_WARPS * 32, 0, st>>>(bt); break;
+    case 4: step_kernel<4><<<blocks, RO_WARPS * 32, 0, st>>>(bt); break;
+    default: return ctrm_fail(-1, "unsupported adjacency mask width");
+  }
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }

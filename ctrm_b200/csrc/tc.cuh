@@ -39,8 +39,9 @@ __device__ __forceinline__ void split3(float x, uint32_t& p1, uint32_t& p2, uint
   p3 = (uint32_t)__bfloat16_as_ushort(b3);
 }
 // store 8 consecutive k (k0 % 8 == 0) of row r as three bf16 parts into the three operand tiles (one 16-byte store each)
-__device__ __forceinline__ void store_split8(uint8_t* t1, uint8_t* t2, uint8_t* t3, int r, int k0, int K, const float* v) {
-  const uint32_t off = elem_offset(r, k0, K);
+__device__ __forceinline__ void store_split8_body(uint8_t* t1, uint8_t* t2, uint8_t* t3, uint32_t off, float v0, float v1, float v2,
+                                               float v3, float v4, float v5, float v6, float v7) {
+  const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
   uint32_t w1[4], w2[4], w3[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -54,6 +55,9 @@ __device__ __forceinline__ void store_split8(uint8_t* t1, uint8_t* t2, uint8_t* 
   *reinterpret_cast<uint4*>(t1 + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
   *reinterpret_cast<uint4*>(t2 + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
   *reinterpret_cast<uint4*>(t3 + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+}
+__device__ __forceinline__ void store_split8(uint8_t* t1, uint8_t* t2, uint8_t* t3, int r, int k0, int K, const float* v) {
+  store_split8_body(t1, t2, t3, elem_offset(r, k0, K), v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
 }
 
 // ---- descriptors ----
@@ -87,7 +91,7 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
 //   tmem_d + n_cols    : a1*b2 + a2*b1              (2^-8 of the main term)
 //   tmem_d + 2*n_cols  : a2*b2 + a1*b3 + a3*b1      (2^-16)
 // and the epilogue adds them (tmem_ld32_sum3).
-__device__ __forceinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t n_cols, uint32_t a, uint32_t a_part, uint32_t b,
+static __device__ __noinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t n_cols, uint32_t a, uint32_t a_part, uint32_t b,
                                            uint32_t b_part, int K, int N) {
   const uint32_t id = idesc_bf16(128, N);
   uint32_t acc = 0u;
@@ -150,7 +154,7 @@ __device__ __forceinline__ void digits4_signed(float b, float scale, uint32_t* q
 }
 // 10 MMAs per 16-wide k-step into four accumulators (32-bit columns tmem_d + n_cols * (g - 2)); a / b point at four
 // consecutive digit tiles
-__device__ __forceinline__ void mma_digits4(uint32_t tmem_d, uint32_t n_cols, uint32_t a, uint32_t a_part, uint32_t b,
+static __device__ __noinline__ void mma_digits4(uint32_t tmem_d, uint32_t n_cols, uint32_t a, uint32_t a_part, uint32_t b,
                                             uint32_t b_part, int K, int N) {
   const uint32_t id = idesc_bf16(128, N);
   for (int s = 0; s < K / 16; ++s) {
@@ -239,7 +243,7 @@ __device__ __forceinline__ void tmem_ld32_sum3(uint32_t tbase, int warp, int col
 // copy rows [k_begin, k_begin + K_real) of a blob weight matrix stored [in][ld] (fp32, global) into three consecutive
 // bf16 B-operand tiles (N_tile x K, K-major, tile_bytes(N_tile, K) apart) at tile rows [n_off, n_off + N):
 // B[n_off + n][k] = w[(k_begin + k) * ld + n]; k >= K_real and n >= N_real are zero padding
-__device__ __forceinline__ void stage_weight_split_at(const float* __restrict__ w, int ld, int k_begin, int K_real, int N_real,
+static __device__ __noinline__ void stage_weight_split_at(const float* __restrict__ w, int ld, int k_begin, int K_real, int N_real,
                                                       int N, int n_off, int N_tile, int K, uint8_t* tiles, int tid, int nthreads,
                                                       int k_off = 0, int K_blk = -1) {
   const uint32_t part = tile_bytes(N_tile, K);
@@ -258,7 +262,7 @@ __device__ __forceinline__ void stage_weight_split(const float* __restrict__ w, 
 }
 
 // four signed fixed-point digit tiles of rows [k_begin, k_begin + K_real) of a blob weight matrix [in][ld]
-__device__ __forceinline__ void stage_weight_digits(const float* __restrict__ w, int ld, int k_begin, int K_real, int N_real,
+static __device__ __noinline__ void stage_weight_digits(const float* __restrict__ w, int ld, int k_begin, int K_real, int N_real,
                                                     int N, int K, float scale, uint8_t* tiles, int tid, int nthreads) {
   const uint32_t part = tile_bytes(N, K);
   for (int i = tid; i < N * (K / 8); i += nthreads) {
@@ -278,16 +282,20 @@ __device__ __forceinline__ void stage_weight_digits(const float* __restrict__ w,
   }
 }
 // row r, 8 consecutive k of an input in [0, 1] as four digit tiles
-__device__ __forceinline__ void store_digits8_unit(uint8_t* tiles, uint32_t part, int r, int k0, int K, const float* v) {
+__device__ __forceinline__ void store_digits8_unit_body(uint8_t* tiles, uint32_t part, uint32_t off, float v0, float v1, float v2,
+                                                     float v3, float v4, float v5, float v6, float v7) {
+  const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
   uint32_t dg[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) digits4_unit(v[j], dg[j]);
-  const uint32_t off = elem_offset(r, k0, K);
 #pragma unroll
   for (int d = 0; d < 4; ++d)
     *reinterpret_cast<uint4*>(tiles + d * part + off) =
         make_uint4(dg[0][d] | (dg[1][d] << 16), dg[2][d] | (dg[3][d] << 16), dg[4][d] | (dg[5][d] << 16),
                    dg[6][d] | (dg[7][d] << 16));
+}
+__device__ __forceinline__ void store_digits8_unit(uint8_t* tiles, uint32_t part, int r, int k0, int K, const float* v) {
+  store_digits8_unit_body(tiles, part, elem_offset(r, k0, K), v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
 }
 
 }  // namespace tc

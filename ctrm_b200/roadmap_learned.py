@@ -51,6 +51,8 @@ class RoadmapBuilder:
         self.device = int(device)
         self._uploaded = None
         self._prw_cache = {}
+        self._pinned = {}  # cached pinned host buffers of export(); a CSRRoadmaps returned with pinned=True is a view into
+        #                    them and stays valid until the next export() of this builder
 
     def close(self):
         if self.ctx:
@@ -158,27 +160,33 @@ class RoadmapBuilder:
         B = len(p["n_agents"])
         L = self._last["max_T"] + 2
 
-        def host(shape, dtype):
-            if pinned:
-                import torch
+        def host(name, shape, dtype):
+            """pinned staging buffers are cached and grown geometrically: cudaHostAlloc costs ~0.3 s per GB"""
+            if not pinned:
+                return np.empty(shape, dtype=dtype)
+            import torch
 
-                tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}[dtype]
-                return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
-            return np.empty(shape, dtype=dtype)
+            n = int(np.prod(shape))
+            tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}[dtype]
+            buf = self._pinned.get(name)
+            if buf is None or buf.numel() < n or buf.dtype != tdt:
+                buf = torch.empty(max(n + n // 8, 1), dtype=tdt, pin_memory=True)
+                self._pinned[name] = buf
+            return buf[:n].numpy().reshape(shape)
 
-        layer_ptr = host(A * L + 1, np.int32)
-        pos = host((nv, 2), np.float64)
-        eptr = host(nv + 1, np.int64)
-        eidx = host(max(ne, 1), np.int32)[:ne]
-        n_layers = host(A, np.int32)
-        cnt = host(B, np.int64)
+        layer_ptr = host("layer_ptr", A * L + 1, np.int32)
+        pos = host("pos", (nv, 2), np.float64)
+        eptr = host("eptr", nv + 1, np.int64)
+        eidx = host("eidx", max(ne, 1), np.int32)[:ne]
+        n_layers = host("n_layers", A, np.int32)
+        cnt = host("cnt", B, np.int64)
         _lib.check(self.lib.ctrm_export_csr(self.ctx, _lib.ptr(layer_ptr), _lib.ptr(pos), _lib.ptr(eptr),
                                             eidx.ctypes.data_as(C.c_void_p), _lib.ptr(n_layers), _lib.ptr(cnt), 0, stream),
                    "ctrm_export_csr")
         agent_off = np.concatenate([[0], np.cumsum(p["n_agents"])]).astype(np.int32)
         return CSRRoadmaps(agent_off, L, layer_ptr, pos, eptr, eidx, n_layers, cnt, self.timing())
 
-    KERNELS = ("fov_raster", "fov_encode", "agent_comm", "cvae_prior", "cvae_decode", "select", "merge", "advance")
+    KERNELS = ("fov_raster", "fov_encode", "agent_comm", "cvae_prior", "cvae_decode", "step")
 
     def set_profile(self, enable: bool):
         """eager launches with a CUDA event after every kernel (per-kernel device times, see kernel_times)"""
@@ -265,7 +273,7 @@ def get_timed_roadmaps_multiple_paths_with_learned_indicator(
     csr = builder.build([ins], prob_uniform_sampling_after_goal=prob_uniform_sampling_after_goal,
                         prob_uniform_bias=prob_uniform_bias, prob_uniform_gamma=prob_uniform_gamma, max_T=max_T,
                         N_traj=N_traj, max_attempt=max_attempt, randomize_indicator=randomize_indicator,
-                        merge_distance_rate=merge_distance_rate, seed=seed)
+                        merge_distance_rate=merge_distance_rate, seed=seed).copy()
     if hasattr(ins, "objs") and hasattr(ins.objs, "cnt_continuous_collide"):
         ins.objs.cnt_continuous_collide += int(csr.cnt_collide[0])
         ins.objs.time_continuous_collide += csr.timing.get("total_ms", 0.0) * 1e-3

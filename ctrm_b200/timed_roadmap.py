@@ -112,6 +112,11 @@ class CSRRoadmaps:
         self.cnt_collide = cnt_collide  # (B,) int64  StaticObjects.cnt_continuous_collide
         self.timing = timing or {}
 
+    def copy(self) -> "CSRRoadmaps":
+        """detach from the builder's cached pinned staging buffers"""
+        return CSRRoadmaps(self.agent_off.copy(), self.L, self.layer_ptr.copy(), self.pos.copy(), self.eptr.copy(), self.eidx.copy(),
+                           self.n_layers.copy(), self.cnt_collide.copy(), dict(self.timing))
+
     @property
     def num_instances(self) -> int:
         return len(self.agent_off) - 1

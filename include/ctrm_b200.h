@@ -212,8 +212,8 @@ int ctrm_last_timing(ctrm_ctx* ctx, float ms[3], int64_t* steps, int64_t* launch
 
 /* profile mode: the next ctrm_build_roadmaps calls launch every step kernel eagerly (no CUDA graph) with a CUDA event
  * after each kernel on the driver's stream; ctrm_last_kernel_times returns the summed device time (ms) and the
- * launch count per kernel, in the order fov_raster, fov_encode, agent_comm, cvae_prior, cvae_decode, select, merge,
- * advance.  Used by bench.py for the roofline of the dominant kernel. */
+ * launch count per kernel, in the order fov_raster, fov_encode, agent_comm, cvae_prior, cvae_decode, step (candidate
+ * selection + merge + roll-out bookkeeping); the remaining slots are zero.  Used by bench.py for the roofline of the dominant kernel. */
 /* executed roll-out steps per instance of the last build (sum over its N_traj roll-outs) */
 int ctrm_get_instance_steps(ctrm_ctx* ctx, int32_t* h_steps /*[B]*/);
 int ctrm_set_profile(ctrm_ctx* ctx, int enable);
