@@ -40,9 +40,11 @@ def prob_random_walk_table(max_T: int, gamma: float, bias: float) -> np.ndarray:
 class RoadmapBuilder:
     """owns one libctrm_b200 context (one GPU) with the networks resident"""
 
-    def __init__(self, pred_basename: str, device: int = 0):
+    def __init__(self, pred_basename: str, device: int = 0, map_size: Optional[int] = None):
         self.lib = _lib.load()
         self.bundle = load_bundle(pred_basename)
+        if map_size is not None:  # the networks only see F x F crops, so the grid resolution M is free (SURVEY §8d config 5)
+            self.bundle.map_size = int(map_size)
         self.desc, self.off, self.blob = pack_blob(self.bundle)
         self.ctx = C.c_void_p()
         _lib.check(self.lib.ctrm_ctx_create(int(device), C.byref(self.ctx)), "ctrm_ctx_create")

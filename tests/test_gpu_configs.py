@@ -1,0 +1,100 @@
+"""Teacher-forced end-to-end parity on instance shapes beyond the demo: more candidates than indicators (K != dim_ind),
+more roll-outs than one 32-bit adjacency word (N_traj > 31), hetero radii / speeds, dense and absent obstacles, a single
+agent, a larger crowd and a different grid resolution.  Topology, positions and the collision counter must equal the
+oracle's bit for bit; the GPU's own CVAE outputs must stay within 1e-5 relative at every executed step."""
+import numpy as np
+import pytest
+
+import ctrm_oracle as O
+from conftest import WEIGHTS
+from helpers import assert_same_roadmaps, csr_to_arrays, otrms_to_arrays, rel_err, teacher_table
+from rng_tables import PhiloxTables
+
+pytestmark = pytest.mark.gpu
+
+
+def _instance(seed, n_lo, n_hi, obs_num, speeds="0.03125", rads="0.015625"):
+    from ctrm_b200.environment import generate_ins_2d_with_obs_hetero_nonfix_agents as gen
+
+    return gen(n_lo, n_hi, speeds, rads, obs_num, 0.05, 0.08, rng=np.random.RandomState(seed))
+
+
+def _oins(ins):
+    s, g, sp, r, o = ins.arrays()
+    return O.OInstance.from_arrays(s, g, sp, r, o[:, :2], o[:, 2])
+
+
+CASES = [
+    # name,            instances (seed, n_lo, n_hi, obs, speeds, rads),                      N_traj, max_T, K, rate, M
+    ("k5",             [(1, 12, 13, 6, "0.03125", "0.015625")],                               2, 40, 5, 0.1, 160),
+    ("ntraj40_w2",     [(2, 5, 6, 4, "0.03125", "0.015625")],                                 40, 12, 3, 0.25, 160),
+    ("hetero",         [(3, 10, 11, 8, "0.03125,0.046875", "0.015625,0.0234375,0.01")],       2, 48, 3, 0.1, 160),
+    ("dense_and_none", [(4, 8, 9, 20, "0.03125", "0.015625"), (5, 7, 8, 0, "0.03125", "0.015625")], 2, 48, 3, 0.1, 160),
+    ("single_agent",   [(6, 1, 2, 3, "0.03125", "0.015625"), (7, 3, 4, 3, "0.03125", "0.015625")], 3, 32, 3, 0.1, 160),
+    ("crowd60",        [(8, 60, 61, 10, "0.03125", "0.0078125")],                             1, 24, 3, 0.1, 160),
+    ("map250_k4",      [(9, 9, 10, 6, "0.03125", "0.015625")],                                2, 40, 4, 0.1, 250),
+]
+
+
+@pytest.mark.parametrize("name,specs,NT,MT,K,rate,M", CASES, ids=[c[0] for c in CASES])
+def test_teacher_forced_parity(name, specs, NT, MT, K, rate, M):
+    from ctrm_b200 import RoadmapBuilder
+
+    w = O.OWeights.load(WEIGHTS)
+    w.map_size = M
+    instances = [_instance(*s) for s in specs]
+    oins = [_oins(i) for i in instances]
+    seed = 1000 + len(name)
+    p = O.OParams(N_traj=NT, max_T=MT, merge_distance_rate=rate, max_attempt=3, K=K)
+    recs_all, trms_all = [], []
+    for b, oi in enumerate(oins):
+        recs = []
+        trms_all.append(O.build_timed_roadmaps(oi, w, p, PhiloxTables(seed, 3 + b), recorder=recs))
+        recs_all.append(recs)
+    teacher = np.concatenate([teacher_table(r, oi.num_agents, K, NT, MT, key="SAMPLES_nn") for r, oi in zip(recs_all, oins)], axis=2)
+    builder = RoadmapBuilder(WEIGHTS, 0, map_size=M)
+    try:
+        builder.upload(instances)
+        csr = builder.run(N_traj=NT, max_T=MT, max_attempt=3, merge_distance_rate=rate, K=K, seed=seed, instance_id_base=3,
+                          tables=dict(teacher=teacher), trace=True)
+        samples, _, loc_next = builder.read_trace()
+        a0, worst = 0, 0.0
+        for b, oi in enumerate(oins):
+            assert_same_roadmaps(csr_to_arrays(csr, b), otrms_to_arrays(trms_all[b]))
+            assert int(csr.cnt_collide[b]) == oi.cnt_continuous_collide
+            N = oi.num_agents
+            for r in recs_all[b]:
+                k, t = r["k_traj"], r["t"] - 1
+                assert np.array_equal(loc_next[k, t, a0:a0 + N], np.array(r["loc_next"]))
+                worst = max(worst, rel_err(samples[k, t, a0:a0 + N], r["SAMPLES_nn"].reshape(K, N, 3).transpose(1, 0, 2)))
+            a0 += N
+        assert worst <= 1e-5, worst
+    finally:
+        builder.close()
+
+
+def test_api_error_paths():
+    """bad arguments come back as negative status codes with a message, never as exceptions from native code"""
+    import ctypes as C
+
+    from ctrm_b200 import RoadmapBuilder, _lib
+
+    lib = _lib.load()
+    assert lib.ctrm_collide_segments(None, None, None, None, 5, None, None, None, None, None, None) == -1
+    assert b"NULL" in lib.ctrm_last_error(None)
+    assert lib.ctrm_fov_raster(None, None, None, None, 0, 160, 19, None, None) == -1
+    b = RoadmapBuilder(WEIGHTS, 0)
+    try:
+        with pytest.raises(_lib.CtrmError):
+            b.run()  # nothing uploaded
+        b.upload([_instance(11, 4, 5, 2)])
+        with pytest.raises(_lib.CtrmError, match="N_traj"):
+            b.run(N_traj=500)
+        with pytest.raises(_lib.CtrmError, match="randomize_indicator"):
+            b.run(N_traj=1, randomize_indicator=True)
+        nv = C.c_int64()
+        assert lib.ctrm_result_sizes(b.ctx, C.byref(nv), None, None) == -3  # CTRM_ERR_STATE: no result yet
+        csr = b.run(N_traj=0, max_T=8)  # zero roll-outs: only the start layer, extended once, plus goals
+        assert csr.n_vertices > 0 and all(int(n) == 2 for n in csr.n_layers)
+    finally:
+        b.close()
