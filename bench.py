@@ -124,16 +124,51 @@ def reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled every 200 ms DURING the timed region, in-process through NVML (a polling
+    nvidia-smi subprocess was seen to perturb kernel launches); falls back to `nvidia-smi -lms` when NVML is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.sm, self.mx, self.reasons, self.proc, self.stop_flag, self.mode = gpu_index, [], [], set(), None, False, None
+
+    def _nvml_loop(self):
+        import pynvml as N
+
+        h = N.nvmlDeviceGetHandleByIndex(self._nvml_index)
+        bits = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        self.mx.append(float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
 
     def start(self):
         try:
+            import pynvml as N
+
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            self._nvml_index = int(vis.split(",")[self.gpu]) if vis and vis.replace(",", "").isdigit() else self.gpu
+            self.mode = "nvml"
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -141,26 +176,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 9 and r[1].replace(".", "").isdigit():
+                self.sm.append(float(r[1]))
+                if r[2].replace(".", "").isdigit():
+                    self.mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
-                        reasons.add(name)
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
-                    samples=len(sm))
+                        self.reasons.add(name)
+
+    def stop(self):
+        self.stop_flag = True
+        if self.mode is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock sampling unavailable"])
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        else:
+            self.th.join(timeout=1.0)
+        sm = sorted(self.sm)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(self.mx) if self.mx else None,
+                    reasons=sorted(self.reasons), samples=len(sm), source=self.mode)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm

@@ -226,6 +226,7 @@ extern "C" int ctrm_load_weights(ctrm_ctx* c, const ctrm_model_desc* d, const fl
     return e;
   };
   c->model.dec_w0z_exp = exp_bound(off.dec_w0, 64 * 32);
+  CHECK(upload_agent_constants(h_blob, off));  // AgentEncoder weights live in constant memory (encode.cu)
   {  // digit tiles of the FOV encoders' first layer for the tensor-core kernel
     const int F = d->fov_size;
     c->model.fov_w0_exp = exp_bound(off.fov_w0, 2 * F * F * 64);

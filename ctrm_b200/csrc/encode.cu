@@ -5,6 +5,8 @@
 //                (format_input.py:212-277), get_self_info (compiled.py:100-125) and the final concat
 //                (format_input.py:354-355), one warp per agent i, never materialising the N^2 tensors.
 // fp32 with FMA; the summation order differs from ATen's blocked sgemm, parity is 1e-5 relative (BASELINE.json).
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -22,21 +24,38 @@ __device__ __forceinline__ void nvm(double vx, double vy, float* o) {
   o[2] = (float)mag;
 }
 
-template <int IN, int OUT, int LDW>
-__device__ __forceinline__ void dense_reg(const float* x, const float* __restrict__ Ws, float* acc) {
-  // acc[OUT] += x[IN] . Ws[IN][LDW]; Ws in shared memory (warp-broadcast float4 reads)
+// AgentEncoder weights in constant memory: with fully unrolled loops every weight is an immediate constant-bank operand of
+// its FFMA (c[bank][offset]), so the MLP issues no load instructions at all — the shared-memory version spent its time
+// waiting on one broadcast LDS.128 per four FMAs (short-scoreboard stalls, profiles/r1_full_step_kernels_b1024_tc.md).
+// layout: w0i [11][32] | w1 [32][32] | w2 [32][44] | b1 [32] | b2 [44]
+#define AG_W0 0
+#define AG_W1 (11 * 32)
+#define AG_W2 (AG_W1 + 32 * 32)
+#define AG_B1 (AG_W2 + 32 * 44)
+#define AG_B2 (AG_B1 + 32)
+#define AG_TOTAL (AG_B2 + 44)
+__constant__ float c_ag[AG_TOTAL];
+
+template <int IN, int OUT, int LDW, int BASE>
+__device__ __forceinline__ void dense_const(const float* x, float* acc) {
+  // acc[OUT] += x[IN] . c_ag[BASE + k * LDW + j]
 #pragma unroll
   for (int k = 0; k < IN; ++k) {
-    float xv = x[k];
+    const float xv = x[k];
 #pragma unroll
-    for (int j4 = 0; j4 < (OUT + 3) / 4; ++j4) {
-      float4 w = *reinterpret_cast<const float4*>(&Ws[k * LDW + j4 * 4]);
-      acc[j4 * 4 + 0] = fmaf(xv, w.x, acc[j4 * 4 + 0]);
-      if (j4 * 4 + 1 < OUT) acc[j4 * 4 + 1] = fmaf(xv, w.y, acc[j4 * 4 + 1]);
-      if (j4 * 4 + 2 < OUT) acc[j4 * 4 + 2] = fmaf(xv, w.z, acc[j4 * 4 + 2]);
-      if (j4 * 4 + 3 < OUT) acc[j4 * 4 + 3] = fmaf(xv, w.w, acc[j4 * 4 + 3]);
-    }
+    for (int j = 0; j < OUT; ++j) acc[j] = fmaf(xv, c_ag[BASE + k * LDW + j], acc[j]);
   }
+}
+
+int upload_agent_constants(const float* h_blob, const ctrm_weight_offsets_t& off) {
+  float h[AG_TOTAL];
+  memcpy(h + AG_W0, h_blob + off.ag_w0i, 11 * 32 * sizeof(float));
+  memcpy(h + AG_W1, h_blob + off.ag_w1, 32 * 32 * sizeof(float));
+  memcpy(h + AG_W2, h_blob + off.ag_w2, 32 * 44 * sizeof(float));
+  memcpy(h + AG_B1, h_blob + off.ag_b1, 32 * sizeof(float));
+  memcpy(h + AG_B2, h_blob + off.ag_b2, 44 * sizeof(float));
+  CTRM_CUDA_OK(cudaMemcpyToSymbol(c_ag, h, sizeof(h)));
+  return 0;
 }
 
 // Only the k nearest neighbours of an agent ever reach its communication vector (format_input.py:250-275), so the
@@ -50,21 +69,9 @@ __global__ void __launch_bounds__(AC_WARPS * 32) agent_comm_kernel(Batch bt, con
                                                                    int num_neighbors, int use_k_neighbor, int include_self,
                                                                    int n_max, int P, int G, float* __restrict__ X) {
   extern __shared__ __align__(16) float smem[];
-  // weights: w0i [11][32] | w1 [32][32] | w2 [32][44] | b1 [32] | b2 [44]
-  float* Ww0 = smem;
-  float* Ww1 = Ww0 + 11 * 32;
-  float* Ww2 = Ww1 + 32 * 32;
-  float* Wb1 = Ww2 + 32 * 44;
-  float* Wb2 = Wb1 + 32;
-  float* dist_base = Wb2 + 44;                                      // [AC_WARPS][G][n_max] fp32 distances
+  float* dist_base = smem;                                          // [AC_WARPS][G][n_max] fp32 distances
   int* order_base = reinterpret_cast<int*>(dist_base + (size_t)AC_WARPS * G * n_max);  // [AC_WARPS][G][P]
   float* msg_base = reinterpret_cast<float*>(order_base + (size_t)AC_WARPS * G * P);   // [AC_WARPS][G][P][33]: w*msg | w
-  for (int i = threadIdx.x; i < 11 * 32; i += blockDim.x) Ww0[i] = __ldg(&blob[off.ag_w0i + i]);
-  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) Ww1[i] = __ldg(&blob[off.ag_w1 + i]);
-  for (int i = threadIdx.x; i < 32 * 44; i += blockDim.x) Ww2[i] = __ldg(&blob[off.ag_w2 + i]);
-  for (int i = threadIdx.x; i < 32; i += blockDim.x) Wb1[i] = __ldg(&blob[off.ag_b1 + i]);
-  for (int i = threadIdx.x; i < 44; i += blockDim.x) Wb2[i] = __ldg(&blob[off.ag_b2 + i]);
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / P, s = lane - g * P;
   const int a = (blockIdx.x * AC_WARPS + warp) * G + g;
@@ -125,15 +132,16 @@ __global__ void __launch_bounds__(AC_WARPS * 32) agent_comm_kernel(Batch bt, con
         h1[q * 4] = v.x; h1[q * 4 + 1] = v.y; h1[q * 4 + 2] = v.z; h1[q * 4 + 3] = v.w;
       }
     }
-    dense_reg<CTRM_DIM_INFO, 32, 32>(info, Ww0, h1);
+    dense_const<CTRM_DIM_INFO, 32, 32, AG_W0>(info, h1);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) { h1[k] = fmaxf(h1[k], 0.f); h2[k] = Wb1[k]; }
-    dense_reg<32, 32, 32>(h1, Ww1, h2);
+    for (int k = 0; k < 32; ++k) { h1[k] = fmaxf(h1[k], 0.f); h2[k] = c_ag[AG_B1 + k]; }
+    dense_const<32, 32, 32, AG_W1>(h1, h2);
 #pragma unroll
     for (int k = 0; k < 32; ++k) h2[k] = fmaxf(h2[k], 0.f);
 #pragma unroll
-    for (int k = 0; k < 44; ++k) o[k] = Wb2[k];
-    dense_reg<32, 42, 44>(h2, Ww2, o);
+    for (int k = 0; k < 42; ++k) o[k] = c_ag[AG_B2 + k];
+    o[42] = 0.f; o[43] = 0.f;
+    dense_const<32, 42, 44, AG_W2>(h2, o);
     if (s == 0) {  // get_self_info (compiled.py:100-125): row (i,i), columns 3..10
       float* xr = X + (size_t)a * CTRM_DIM_X;
 #pragma unroll
@@ -192,8 +200,7 @@ int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, c
   if (P < 1) P = 1;
   if (P > 32) return ctrm_fail(-1, "agent_comm: more than 31 neighbours per agent are not supported");
   const int G = 32 / P;
-  size_t smem = (size_t)(11 * 32 + 32 * 32 + 32 * 44 + 32 + 44) * sizeof(float) +
-                (size_t)AC_WARPS * G * ((size_t)n_max * sizeof(float) + (size_t)P * sizeof(int) + (size_t)P * 33 * sizeof(float));
+  size_t smem = (size_t)AC_WARPS * G * ((size_t)n_max * sizeof(float) + (size_t)P * sizeof(int) + (size_t)P * 33 * sizeof(float));
   if (smem > 200 * 1024) return ctrm_fail(-1, "instance too large for agent_comm shared memory");
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {

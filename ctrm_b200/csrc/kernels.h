@@ -89,6 +89,7 @@ int launch_fov_w0_prep(const float* d_w0, int F, int w0_exp, uint8_t* d_out, cud
 int launch_fov_f32_to_tiles(const float* d_fov, int A, int F, uint8_t* d_tiles, cudaStream_t st);
 int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32_t* d_agent_inst, const uint8_t* d_skip_inst,
                       int A, float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st);
+int upload_agent_constants(const float* h_blob, const ctrm_weight_offsets_t& off);
 int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, const double* d_prev, const float* d_e_self,
                       const float* d_vain_proj, float* d_X, cudaStream_t st);
 int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,
