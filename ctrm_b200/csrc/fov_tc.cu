@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t
         const uint32_t u = it + c, s = u % FT_STAGES;
         if (u >= FT_STAGES) tc::mbar_wait(empty0 + 8 * s, ((u / FT_STAGES) - 1) & 1u);
         tc::mbar_expect_tx(full0 + 8 * s, FT_STAGE);
-        tc::tma_bulk_g2s(sStage + s * FT_STAGE, gA + (size_t)c * FT_A_CHUNK, FT_A_CHUNK, full0 + 8 * s);
+        tc::tma_bulk_g2s_evict_first(sStage + s * FT_STAGE, gA + (size_t)c * FT_A_CHUNK, FT_A_CHUNK, full0 + 8 * s);
         tc::tma_bulk_g2s(sStage + s * FT_STAGE + FT_A_CHUNK, w0_tiles + (size_t)c * FT_W_CHUNK, FT_W_CHUNK, full0 + 8 * s);
       }
     } else if (tid == 32) {  // MMA issuer

@@ -261,13 +261,15 @@ __global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __r
 // ------------------------------------------------------------------------------------------------
 #define RT_APB 8
 #define RT_CHUNK 96
+template <int FT>  // FT > 0: compile-time fov_size (constant divisions, unrolled loads); 0: run-time F
 __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uint8_t* __restrict__ occ,
                                                                       const uint16_t* __restrict__ ctg,
                                                                       const int32_t* __restrict__ agent_inst,
                                                                       const double* __restrict__ pos,
-                                                                      const uint8_t* __restrict__ skip_inst, int A, int M, int F,
+                                                                      const uint8_t* __restrict__ skip_inst, int A, int M, int F_rt,
                                                                       int n_chunks, uint8_t* __restrict__ tiles) {
   extern __shared__ __align__(16) uint8_t rt_smem[];
+  const int F = FT > 0 ? FT : F_rt;
   const int FF = F * F, KD = 2 * FF, Kpad = n_chunks * RT_CHUNK;
   const int row_bytes = Kpad * 2 + 16;  // +16: rows land in different banks for the 16-byte read-out
   __shared__ int live_row[RT_APB];
@@ -286,13 +288,14 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
       const bool centre_in = cx < M && cy < M;
       const int cc = centre_in ? (int)c[cx * M + cy] : CTRM_UNREACH;
       const bool c_reach = cc != CTRM_UNREACH;
+#pragma unroll 4
       for (int i = lane; i < FF; i += 32) {
         const int xf = i / F, yf = i - xf * F;
         const int x = cx - buf + xf, y = cy - buf + yf;
         uint16_t v0 = 0, v1 = 0;
         if (centre_in && x >= 0 && x < M && y >= 0 && y < M) {
-          v0 = o[x * M + y] ? 0 : 0x3F80;  // bf16 1.0
-          const int _c = (int)c[x * M + y];
+          v0 = __ldg(&o[x * M + y]) ? 0 : 0x3F80;  // bf16 1.0
+          const int _c = (int)__ldg(&c[x * M + y]);
           v1 = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 0x3F80 : 0;
         }
         t[i] = v0;
@@ -312,7 +315,9 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
     const int r = ar & 127;
     const size_t off = ((size_t)(ar >> 7) * n_chunks + c) * (size_t)(128 * RT_CHUNK * 2) +
                        (size_t)(r >> 3) * (RT_CHUNK / 8) * 128 + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16;
-    *reinterpret_cast<uint4*>(tiles + off) = *reinterpret_cast<const uint4*>(rt_smem + (size_t)rr * row_bytes + (size_t)k8 * 16);
+    // streaming store: the tiles are read exactly once (by fov_encode); keeping them out of the way lets the cost-to-go
+    // crops, which overlap ~85% between consecutive steps, survive in L2
+    __stcs(reinterpret_cast<uint4*>(tiles + off), *reinterpret_cast<const uint4*>(rt_smem + (size_t)rr * row_bytes + (size_t)k8 * 16));
   }
 }
 
@@ -382,13 +387,19 @@ int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const i
                             const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, uint8_t* d_tiles, cudaStream_t st) {
   if (A <= 0) return 0;
   const size_t smem = (size_t)RT_APB * ((size_t)n_chunks * RT_CHUNK * 2 + 16);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    CTRM_CUDA_OK(cudaFuncSetAttribute(fov_raster_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+  const int blocks = (A + RT_APB - 1) / RT_APB;
+  if (F == 19) {  // the trained configuration
+    fov_raster_tiles_kernel<19><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
+                                                                 d_tiles);
+  } else {
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+      CTRM_CUDA_OK(cudaFuncSetAttribute(fov_raster_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = smem;
+    }
+    fov_raster_tiles_kernel<0><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
+                                                                d_tiles);
   }
-  fov_raster_tiles_kernel<<<(A + RT_APB - 1) / RT_APB, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A,
-                                                                             M, F, n_chunks, d_tiles);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -200,6 +200,16 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src,
                : "memory");
 }
 
+// same, with an L2 evict-first hint for data that is consumed exactly once
+__device__ __forceinline__ void tma_bulk_g2s_evict_first(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   dst_smem),
+               "l"(src), "r"(bytes), "r"(mbar), "l"(policy)
+               : "memory");
+}
+
 // ---- TMEM ----
 // whole warp executes; ncols power of two >= 32; the base address lands in *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
