@@ -388,6 +388,8 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&bt.n_done, (size_t)1));
   CHECK(ar.alloc(&bt.steps_done, (size_t)B));
   CHECK(ar.alloc(&bt.arrive_cnt, (size_t)B));
+  CHECK(ar.alloc(&bt.inst_pack, (size_t)8 * B));
+  CHECK(ar.alloc(&bt.agent_pack, (size_t)6 * A));
   CHECK(ar.alloc(&bt.nlayers, (size_t)A));
   CHECK(ar.alloc(&c->d_tfin, (size_t)B));
   CHECK(ar.alloc(&c->d_agent_nv, (size_t)A));

@@ -39,6 +39,8 @@ struct Batch {
   int32_t* n_done;                      // [1]
   int32_t* steps_done;                  // [B] executed roll-out steps (bench accounting)
   int32_t* arrive_cnt;                  // [B] warps of the instance that finished the current step
+  int32_t* inst_pack;                   // [B][8] {done, t, k_traj, makespan, agent_off, n_agents, obs_off, n_obs}
+  double* agent_pack;                   // [A][6] {goal x, goal y, speed, speed^2, merge_distance^2, rad}
   // per-step tensors
   uint8_t* fov_tiles;  // bf16 operand tiles [ceil(A/128)][n_chunks][128 x 96]
   float *e_self, *e_vain, *vain_proj, *X, *samples;

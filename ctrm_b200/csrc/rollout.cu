@@ -24,6 +24,9 @@ __global__ void rollout_init_kernel(Batch bt) {
     bt.prev[2 * i] = sx; bt.prev[2 * i + 1] = sy;
     bt.nxt[2 * i] = sx; bt.nxt[2 * i + 1] = sy;
     bt.arrived[i] = 0;
+    double* ap = bt.agent_pack + 6 * (size_t)i;  // {goal x, goal y, speed, speed^2, merge_distance^2, rad}
+    ap[0] = bt.goals[2 * i]; ap[1] = bt.goals[2 * i + 1]; ap[2] = bt.speeds[i]; ap[3] = bt.speeds2[i];
+    ap[4] = bt.merge2[i]; ap[5] = bt.rads[i];
     bt.nlayers[i] = 1;  // TimedRoadmap(start): V = [[start]], E = [[[]]]  (timed_roadmap.py:59-65)
     bt.vcnt[(size_t)i * bt.L] = 1;
     size_t s = vslot(bt, i, 0, 0);
@@ -38,26 +41,61 @@ __global__ void rollout_init_kernel(Batch bt) {
     bt.cnt_collide[i] = 0ULL;
     bt.steps_done[i] = 0;
     bt.arrive_cnt[i] = 0;
+    int* ip = bt.inst_pack + 8 * i;  // {done, t, k_traj, makespan, agent_off, n_agents, obs_off, n_obs}
+    ip[0] = (bt.N_traj <= 0) ? 1 : 0; ip[1] = 1; ip[2] = 0; ip[3] = 0;
+    ip[4] = bt.agent_off[i]; ip[5] = bt.agent_off[i + 1] - bt.agent_off[i];
+    ip[6] = bt.obs_off[i]; ip[7] = bt.obs_off[i + 1] - bt.obs_off[i];
   }
   if (i == 0) *bt.n_done = (bt.N_traj <= 0) ? bt.B : 0;
+}
+
+// Per-warp context of one agent-step: the instance state and the agent's constants arrive in a few wide loads
+// (inst_pack / agent_pack) instead of a chain of dependent scalar loads, and the instance's obstacles are staged once in
+// shared memory as (x, y, rad_agent + rad_obstacle) so that the swept-circle loops never wait on global memory.
+#define RO_OBS_MAX 64
+struct StepCtx {
+  int b, t, kt, makespan, a0, N, o0, nO;
+  double gx, gy, speed, speed2, merge2, rad;
+  const double* sobs;  // shared memory [nO][3] when nO <= RO_OBS_MAX, else nullptr (global fallback)
+};
+
+__device__ __forceinline__ void obstacle_at(const Batch& bt, const StepCtx& cx, int o, double* ox, double* oy, double* rs) {
+  if (cx.sobs != nullptr) {
+    *ox = cx.sobs[3 * o];
+    *oy = cx.sobs[3 * o + 1];
+    *rs = cx.sobs[3 * o + 2];
+  } else {
+    const double* g = bt.obs_xyr + 3 * (size_t)(cx.o0 + o);
+    *ox = __ldg(g);
+    *oy = __ldg(g + 1);
+    *rs = f64add(cx.rad, __ldg(g + 2));
+  }
+}
+// StaticObjects.collide_continuous_sphere: any over the instance's obstacles (no early exit: the loop pipelines)
+__device__ __forceinline__ bool hits_any(const Batch& bt, const StepCtx& cx, double fx, double fy, double tx, double ty) {
+  bool hit = false;
+#pragma unroll 2
+  for (int o = 0; o < cx.nO; ++o) {
+    double ox, oy, rs;
+    obstacle_at(bt, cx, o, &ox, &oy, &rs);
+    hit = hit || (!sweep_far(fx, fy, tx, ty, ox, oy, rs) && sweep_static(fx, fy, tx, ty, ox, oy, rs));
+  }
+  return hit;
 }
 
 // ------------------------------------------------------------------------------------------------
 // select: loc_pred for every agent
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int select_agent(const Batch& bt, const int a, const int b, const int lane, double* out_x,
+__device__ __forceinline__ unsigned int select_agent(const Batch& bt, const StepCtx& sc, const int a, const int lane,
+                                                     const double cx, const double cy, const bool arrived, double* out_x,
                                                      double* out_y) {
-  const int t = bt.t[b], kt = bt.k_traj[b];
-  const int a0 = bt.agent_off[b], il = a - a0;
-  const int N = bt.agent_off[b + 1] - a0;
-  const int o0 = bt.obs_off[b], nO = bt.obs_off[b + 1] - o0;
-  const double cx = bt.cur[2 * a], cy = bt.cur[2 * a + 1];
-  const double speed = bt.speeds[a], speed2 = bt.speeds2[a], rad = bt.rads[a];
-  const bool arrived = bt.arrived[a] != 0;
+  const int b = sc.b, t = sc.t, kt = sc.kt;
+  const int a0 = sc.a0, il = a - a0, N = sc.N, nO = sc.nO;
+  const double speed = sc.speed, speed2 = sc.speed2, rad = sc.rad;
   const size_t si = step_index(bt, kt, t);
   const uint32_t c0 = bt.inst_base + (uint32_t)b, c1 = rng_ctr1(kt, t);
   // prob_random_walk (learned_sampler.py:84-91), tabulated by the host over (t, makespan)
-  const int D = bt.makespan[b] ? bt.makespan[b] : bt.max_T;
+  const int D = sc.makespan ? sc.makespan : bt.max_T;
   const double p_rw = bt.p_rw[(size_t)t * (bt.max_T + 1) + D];
   double u_gate;
   if (bt.rng_mode == 1) {
@@ -115,9 +153,8 @@ __device__ __forceinline__ unsigned int select_agent(const Batch& bt, const int 
       const int src = act ? (__ffs(pm) - 1) : 0;
       const double tx = __shfl_sync(0xFFFFFFFFu, x, src), ty = __shfl_sync(0xFFFFFFFFu, y, src);
       if (act) {
-        const int o = o0 + (p - ci * nO);
-        const double ox = __ldg(&bt.obs_xyr[3 * o]), oy = __ldg(&bt.obs_xyr[3 * o + 1]);
-        const double rs = f64add(rad, __ldg(&bt.obs_xyr[3 * o + 2]));
+        double ox, oy, rs;
+        obstacle_at(bt, sc, p - ci * nO, &ox, &oy, &rs);
         if (!sweep_far(cx, cy, tx, ty, ox, oy, rs) && sweep_static(cx, cy, tx, ty, ox, oy, rs)) coll |= 1u << src;
       }
     }
@@ -182,12 +219,11 @@ __device__ __forceinline__ void merge_prefetch(const Batch& bt, int a, int t, in
 }
 
 template <int W>
-__device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const int a, const int b, const int lane, const int t,
-                                                    const int kt, const double lx, const double ly,
-                                                    const MergePrefetch<W>& pf) {
-  const int o0 = bt.obs_off[b], o1 = bt.obs_off[b + 1];
-  const double speed = bt.speeds[a], speed2 = bt.speeds2[a], merge2 = bt.merge2[a], rad = bt.rads[a];
-  const double gx = bt.goals[2 * a], gy = bt.goals[2 * a + 1];
+__device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const StepCtx& sc, const int a, const int lane,
+                                                    const double lx, const double ly, const MergePrefetch<W>& pf) {
+  const int t = sc.t, kt = sc.kt;
+  const double speed = sc.speed, speed2 = sc.speed2, merge2 = sc.merge2, rad = sc.rad;
+  const double gx = sc.gx, gy = sc.gy;
   const int nl = pf.nl;
   const bool has_next = nl > t + 1;
   unsigned int count = 0;
@@ -200,7 +236,7 @@ __device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const int a
     if (w * 32 < pf.n_prev) {
       const bool in = w * 32 + lane < pf.n_prev;
       const bool cand = in && dist2(pf.px[0][w], pf.py[0][w], lx, ly) <= speed2;
-      const bool ok = cand && !any_obstacle_hit(pf.px[0][w], pf.py[0][w], lx, ly, rad, bt.obs_xyr, o0, o1);
+      const bool ok = cand && !hits_any(bt, sc, pf.px[0][w], pf.py[0][w], lx, ly);
       count += __popc(__ballot_sync(0xFFFFFFFFu, cand));
       P[w] = __ballot_sync(0xFFFFFFFFu, ok);
     }
@@ -212,7 +248,7 @@ __device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const int a
       if (w * 32 < pf.n_next) {
         const bool in = w * 32 + lane < pf.n_next;
         const bool cand = in && dist2(pf.px[2][w], pf.py[2][w], lx, ly) <= speed2;
-        const bool ok = cand && !any_obstacle_hit(pf.px[2][w], pf.py[2][w], lx, ly, rad, bt.obs_xyr, o0, o1);
+        const bool ok = cand && !hits_any(bt, sc, pf.px[2][w], pf.py[2][w], lx, ly);
         count += __popc(__ballot_sync(0xFFFFFFFFu, cand));
         Cm[w] = __ballot_sync(0xFFFFFFFFu, ok);
       }
@@ -301,9 +337,9 @@ __device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const int a
   if (bounds_ok(gx, gy, rad) && speed_ok(rx, ry, gx, gy, speed, speed2)) {
     count += 1;
     bool hit = false;
-    for (int o = o0 + lane; o < o1; o += 32) {
-      const double ox = __ldg(&bt.obs_xyr[3 * o]), oy = __ldg(&bt.obs_xyr[3 * o + 1]);
-      const double rs = f64add(rad, __ldg(&bt.obs_xyr[3 * o + 2]));
+    for (int o = lane; o < sc.nO; o += 32) {
+      double ox, oy, rs;
+      obstacle_at(bt, sc, o, &ox, &oy, &rs);
       hit = hit || (!sweep_far(rx, ry, gx, gy, ox, oy, rs) && sweep_static(rx, ry, gx, gy, ox, oy, rs));
     }
     arr = !__any_sync(0xFFFFFFFFu, hit);
@@ -334,7 +370,10 @@ __device__ __forceinline__ void advance_instance(const Batch& bt, const int b, c
   if (lane == 0) bt.steps_done[b] += 1;
   bool end_roll = false;
   if (all) {  // learned_sampler.py:186-191
-    if (lane == 0) bt.makespan[b] = bt.makespan[b] ? max(bt.makespan[b], t) : t;
+    if (lane == 0) {
+      bt.makespan[b] = bt.makespan[b] ? max(bt.makespan[b], t) : t;
+      bt.inst_pack[8 * b + 3] = bt.makespan[b];
+    }
     end_roll = true;
   } else if (t >= bt.max_T) {
     end_roll = true;
@@ -347,13 +386,18 @@ __device__ __forceinline__ void advance_instance(const Batch& bt, const int b, c
       bt.cur[2 * a] = __ldcg(&bt.nxt[2 * a]);
       bt.cur[2 * a + 1] = __ldcg(&bt.nxt[2 * a + 1]);
     }
-    if (lane == 0) bt.t[b] = t + 1;
+    if (lane == 0) {
+      bt.t[b] = t + 1;
+      bt.inst_pack[8 * b + 1] = t + 1;
+    }
   } else {
     const int kt = bt.k_traj[b] + 1;
     if (kt >= bt.N_traj) {
       if (lane == 0) {
         bt.k_traj[b] = kt;
         bt.done[b] = 1;
+        bt.inst_pack[8 * b + 0] = 1;
+        bt.inst_pack[8 * b + 2] = kt;
         atomicAdd(bt.n_done, 1);
       }
     } else {  // next roll-out restarts from the starts (learned_sampler.py:68-73)
@@ -367,6 +411,8 @@ __device__ __forceinline__ void advance_instance(const Batch& bt, const int b, c
       if (lane == 0) {
         bt.k_traj[b] = kt;
         bt.t[b] = 1;
+        bt.inst_pack[8 * b + 1] = 1;
+        bt.inst_pack[8 * b + 2] = kt;
       }
     }
   }
@@ -384,30 +430,52 @@ int launch_rollout_init(const Batch& bt, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(RO_WARPS * 32) step_kernel(Batch bt) {
+  __shared__ double s_obs[RO_WARPS][3 * RO_OBS_MAX];
+  const int warp = threadIdx.x >> 5;
   const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (a >= bt.A) return;
-  const int b = bt.agent_inst[a];
-  if (bt.done[b]) return;
-  const int t = bt.t[b], kt = bt.k_traj[b];
+  StepCtx sc;
+  sc.b = bt.agent_inst[a];
+  const int4 p0 = *reinterpret_cast<const int4*>(bt.inst_pack + 8 * sc.b);
+  if (p0.x) return;  // instance finished
+  const int4 p1 = *reinterpret_cast<const int4*>(bt.inst_pack + 8 * sc.b + 4);
+  sc.t = p0.y; sc.kt = p0.z; sc.makespan = p0.w;
+  sc.a0 = p1.x; sc.N = p1.y; sc.o0 = p1.z; sc.nO = p1.w;
+  const double2 q0 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a);
+  const double2 q1 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a + 2);
+  const double2 q2 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a + 4);
+  const double2 cur = *reinterpret_cast<const double2*>(bt.cur + 2 * (size_t)a);
+  const bool arrived = bt.arrived[a] != 0;
+  sc.gx = q0.x; sc.gy = q0.y; sc.speed = q1.x; sc.speed2 = q1.y; sc.merge2 = q2.x; sc.rad = q2.y;
   MergePrefetch<W> pf;
-  merge_prefetch<W>(bt, a, t, lane, pf);
+  merge_prefetch<W>(bt, a, sc.t, lane, pf);
+  sc.sobs = nullptr;
+  if (sc.nO <= RO_OBS_MAX) {
+    for (int o = lane; o < sc.nO; o += 32) {
+      const double* g = bt.obs_xyr + 3 * (size_t)(sc.o0 + o);
+      s_obs[warp][3 * o] = __ldg(g);
+      s_obs[warp][3 * o + 1] = __ldg(g + 1);
+      s_obs[warp][3 * o + 2] = f64add(sc.rad, __ldg(g + 2));  // rad1 + rad2, rounded once (collision_check.cpp:56)
+    }
+    __syncwarp();
+    sc.sobs = s_obs[warp];
+  }
   double lx, ly;
-  unsigned int count = select_agent(bt, a, b, lane, &lx, &ly);
-  count += merge_agent<W>(bt, a, b, lane, t, kt, lx, ly, pf);
+  unsigned int count = select_agent(bt, sc, a, lane, cur.x, cur.y, arrived, &lx, &ly);
+  count += merge_agent<W>(bt, sc, a, lane, lx, ly, pf);
   // publish this agent's state, then let the last warp of the instance do the roll-out bookkeeping
   int last = 0;
   if (lane == 0) {
-    if (count) atomicAdd(&bt.cnt_collide[b], (unsigned long long)count);
+    if (count) atomicAdd(&bt.cnt_collide[sc.b], (unsigned long long)count);
     __threadfence();
-    const int n = bt.agent_off[b + 1] - bt.agent_off[b];
-    last = (atomicAdd(&bt.arrive_cnt[b], 1) == n - 1) ? 1 : 0;
+    last = (atomicAdd(&bt.arrive_cnt[sc.b], 1) == sc.N - 1) ? 1 : 0;
   }
   last = __shfl_sync(0xFFFFFFFFu, last, 0);
   if (last) {
     __threadfence();
-    if (lane == 0) bt.arrive_cnt[b] = 0;
-    advance_instance(bt, b, lane);
+    if (lane == 0) bt.arrive_cnt[sc.b] = 0;
+    advance_instance(bt, sc.b, lane);
   }
 }
 
