@@ -221,6 +221,13 @@ def algorithmic_work(kernel, agent_steps, pair_steps, K, F=19):
     return dict(bound="hbm", work=agent_steps * (K * 12 + 96 + 3 * 26 * 24 + 32), unit="GB/s")
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload at 1,024
+# instances (profiles/r1_full_step_kernels_b1024_final.md); scaled linearly with the instance count
+NCU_TRAFFIC_B1024 = dict(fov_raster=113.9e6, fov_encode=39.9e6, agent_comm=8.36e6, cvae_prior=7.62e6, cvae_decode=9.99e6,
+                         step=13.4e6)
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # FMA issue peak of the CUDA cores at the max SM clock
+
+
 def gpu_arm(args):
     import numpy as np
     import torch
@@ -341,14 +348,20 @@ def gpu_arm(args):
         achieved = w["work"] / (v["ms"] * 1e-3) / (1e9 if w["bound"] == "hbm" else 1e12)
         peak = hbm_peak if w["bound"] == "hbm" else tc_peak
         kernels[name] = dict(ms_per_launch=v["ms"] / v["launches"], share=v["ms"] / total_kernel_ms, bound=w["bound"],
-                             achieved=achieved, peak=peak, unit=w["unit"], frac=achieved / peak)
+                             achieved=achieved, peak=peak, unit=w["unit"], frac=achieved / peak,
+                             traffic=NCU_TRAFFIC_B1024.get(name, 0.0) * B / 1024.0 or None)
+        if w["bound"] == "tensor":
+            kernels[name]["frac_of_fp32_fma_peak"] = achieved / FP32_PEAK_TFLOPS
     dom = max(kernels, key=lambda k: kernels[k]["share"])
     roofline = dict(kernel=dom, bound=kernels[dom]["bound"], achieved=kernels[dom]["achieved"], peak=kernels[dom]["peak"],
-                    unit=kernels[dom]["unit"], frac=kernels[dom]["frac"], traffic=None, share_of_step=kernels[dom]["share"],
-                    peak_source=peak_src,
-                    note="achieved = algorithmic work of all launches / summed CUDA-event time of the kernel, eager pass over "
-                         "the same workload right after the timed region; fp32 CUDA-core kernels are reported against the "
-                         "dense bf16 tensor peak")
+                    unit=kernels[dom]["unit"], frac=kernels[dom]["frac"], traffic=kernels[dom]["traffic"],
+                    share_of_step=kernels[dom]["share"], peak_source=peak_src,
+                    frac_of_fp32_fma_peak=kernels[dom].get("frac_of_fp32_fma_peak"),
+                    note="achieved = algorithmic work of all launches / summed CUDA-event time of the kernel (eager pass over "
+                         "the same workload right after the timed region, one CUDA event after every kernel on the driver's "
+                         "stream); traffic = ncu dram bytes per launch at 1,024 instances scaled to this batch; exact-fp32 "
+                         "32-wide MLP kernels are issue-bound on the CUDA cores and are reported against the dense bf16 tensor "
+                         "peak as the contract asks, with the fp32 FMA peak beside it")
 
     if rank != 0:
         if world > 1:
@@ -385,7 +398,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("CTRM_BENCH_BATCH", "1024")), help="instances per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("CTRM_BENCH_BATCH", "2048")), help="instances per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-worker", action="store_true")
     ap.add_argument("--nproc", type=int, default=1)
