@@ -354,19 +354,25 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, in
         }
         park8(At, tid, q * 8, s);
       }
+      // z = softmax(s): e = exp(s - max) is computed once and parked; z = e / sum(e) (torch evaluates
+      // exp(s - logsumexp(s)); the two agree to an ulp and this one saves 64 expf per row)
       float se = 0.f;
       for (int q = 0; q < 8; ++q) {
         float s[8];
         unpark8(At, tid, q * 8, s);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) se += expf(s[j] - mx);
+        for (int j = 0; j < 8; ++j) {
+          s[j] = expf(s[j] - mx);
+          se += s[j];
+        }
+        park8(At, tid, q * 8, s);
       }
-      const float lse = mx + logf(se);  // torch: z = exp(scores - logsumexp(scores))
+      const float inv = 1.f / se;
       for (int q = 0; q < 8; ++q) {
         float s[8];
         unpark8(At, tid, q * 8, s);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[j] = fminf(expf(s[j] - lse), 1.f);
+        for (int j = 0; j < 8; ++j) s[j] = fminf(s[j] * inv, 1.f);
         tc::store_digits8_unit(At, DT_A_PART, tid, q * 8, 64, s);
       }
     } else {

@@ -15,13 +15,17 @@
 // ------------------------------------------------------------------------------------------------
 #define AC_WARPS 4
 
-// get_normed_vec_mag (compiled.py:11-27) in float64, cast to float32 like `.float()` (format_input.py:327)
+// get_normed_vec_mag (compiled.py:11-27).  The reference works in float64 and casts to float32 (format_input.py:327);
+// here the difference vector is formed in float64 (no cancellation error), rounded once to float32 and normalised in
+// float32 — within 2e-7 relative of the reference's values, far inside the 1e-5 bar.  Three fp64 sqrt + six fp64
+// divisions per pair were ~20% of this kernel's issue slots.
 __device__ __forceinline__ void nvm(double vx, double vy, float* o) {
-  double mag = sqrt(f64add(f64mul(vx, vx), f64mul(vy, vy)));
-  double d = (mag == 0.0) ? 1.0 : mag;
-  o[0] = (float)(vx / d);
-  o[1] = (float)(vy / d);
-  o[2] = (float)mag;
+  const float x = (float)vx, y = (float)vy;
+  const float mag = sqrtf(fmaf(x, x, y * y));
+  const float d = (mag == 0.f) ? 1.f : mag;
+  o[0] = x / d;
+  o[1] = y / d;
+  o[2] = mag;
 }
 
 // AgentEncoder weights in constant memory: with fully unrolled loops every weight is an immediate constant-bank operand of
@@ -61,7 +65,7 @@ int upload_agent_constants(const float* h_blob, const ctrm_weight_offsets_t& off
 // Only the k nearest neighbours of an agent ever reach its communication vector (format_input.py:250-275), so the
 // 43->32->32->42 MLP runs for P = k + 1 pairs per agent (self + k nearest) instead of all N.  A warp serves G = 32 / P
 // agents (two for the trained k = 15): lane = (agent g, slot s), slot 0 = the agent itself, slot s = its s-th nearest.
-__global__ void __launch_bounds__(AC_WARPS * 32) agent_comm_kernel(Batch bt, const double* __restrict__ cur,
+__global__ void __launch_bounds__(AC_WARPS * 32, 6) agent_comm_kernel(Batch bt, const double* __restrict__ cur,
                                                                    const double* __restrict__ prev,
                                                                    const float* __restrict__ e_self,
                                                                    const float* __restrict__ vain_proj,
@@ -92,8 +96,8 @@ __global__ void __launch_bounds__(AC_WARPS * 32) agent_comm_kernel(Batch bt, con
   // ---- distances to every agent of the instance (column 2 of others_info, the fp32 value the reference argsorts)
   if (active)
     for (int j = s; j < N; j += P) {
-      const double dx = f64sub(cur[2 * (a0 + j)], cix), dy = f64sub(cur[2 * (a0 + j) + 1], ciy);
-      dist[j] = (float)sqrt(f64add(f64mul(dx, dx), f64mul(dy, dy)));
+      const float dx = (float)f64sub(cur[2 * (a0 + j)], cix), dy = (float)f64sub(cur[2 * (a0 + j) + 1], ciy);
+      dist[j] = sqrtf(fmaf(dx, dx, dy * dy));
     }
   __syncwarp();
   // ---- rank (argsort, format_input.py:239-243): self first, ties broken by index; keep ranks 0..k
@@ -165,15 +169,20 @@ __global__ void __launch_bounds__(AC_WARPS * 32) agent_comm_kernel(Batch bt, con
   }
   const int first = include_self ? 0 : 1;
   const bool in_softmax = has_pair && s >= first;
-  if (has_pair) mrow[s * 33 + 32] = sim;
-  __syncwarp();
-  float w = 0.f;
-  if (in_softmax) {
-    float mx = -INFINITY, sum = 0.f;
-    for (int r = first; r <= k_nb; ++r) mx = fmaxf(mx, mrow[r * 33 + 32]);
-    for (int r = first; r <= k_nb; ++r) sum += expf(mrow[r * 33 + 32] - mx);
-    w = expf(sim - mx) / sum;
+  // softmax over the group's slots first..k_nb: max and sum by register shuffles (one expf per lane)
+  const int gbase = (g < G ? g : 0) * P;
+  float mx = -INFINITY;
+  for (int r = 0; r < P; ++r) {
+    const float v = __shfl_sync(0xFFFFFFFFu, sim, gbase + r);
+    if (r >= first && r <= k_nb) mx = fmaxf(mx, v);
   }
+  const float ev = in_softmax ? expf(sim - mx) : 0.f;
+  float sum = 0.f;
+  for (int r = 0; r < P; ++r) {
+    const float v = __shfl_sync(0xFFFFFFFFu, ev, gbase + r);
+    if (r >= first && r <= k_nb) sum += v;
+  }
+  const float w = in_softmax ? ev / sum : 0.f;
   __syncwarp();
   if (has_pair) {
 #pragma unroll

@@ -429,7 +429,7 @@ int launch_rollout_init(const Batch& bt, cudaStream_t st) {
 // step: select -> merge -> (last warp of the instance) advance, one warp per agent
 // ------------------------------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(RO_WARPS * 32) step_kernel(Batch bt) {
+__global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
   __shared__ double s_obs[RO_WARPS][3 * RO_OBS_MAX];
   const int warp = threadIdx.x >> 5;
   const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
