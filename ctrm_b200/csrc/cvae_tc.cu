@@ -1,7 +1,7 @@
 // CVAE decoder on the 5th-generation tensor cores (tcgen05 + TMEM), fused with the Gumbel-softmax that produces its
 // input.  reference: RelaxedOneHotCategorical(temp).rsample() + CTRMNet.decoder (learning/model/cvae.py:72-76, :133-137).
 //
-// One CTA = 128 threads = one 128-row tile at a time (row = (agent, copy)); thread r owns row r and TMEM lane r.
+// One CTA = 256 threads = one 128-row tile at a time (row = (agent, copy)); two threads share row r / TMEM lane r.
 //   1. thread r: Philox uniforms -> Gumbel noise -> z = softmax((logits + g)/temp)   (64 values, fp32)
 //      z is split exactly into three bf16 parts and written to shared memory in the UMMA K-major canonical layout
 //   2. one thread issues 4 k-steps x 6 tcgen05.mma (BF16x3): D0[128x32] = z[128x64] . W0z[64x32]  -> TMEM cols 0..31
@@ -228,7 +228,7 @@ int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, floa
   return 0;
 }
 
-#define DT_THREADS 128
+#define DT_THREADS 256
 // shared memory: z digit tiles 4 x 16 KB (K = 64; tiles 2 and 3 double as the fp32 scratch of the softmax, and the whole
 // region is reused for the three bf16 parts of h1, K = 32) | W0 digit tiles 4 x 4 KB | W1 parts 3 x 2 KB | W2, b1, b2 |
 // mbarrier, TMEM slot
@@ -236,7 +236,7 @@ int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, floa
 #define DT_H_PART 8192u
 #define DT_W0_PART 4096u
 #define DT_W1_PART 2048u
-#define DT_SMEM (4 * 16384 + 4 * 4096 + 3 * 2048 + (128 + 32 + 4) * 4 + 16)
+#define DT_SMEM (4 * 16384 + 4 * 4096 + 3 * 2048 + (128 + 32 + 4 + 256 + 512) * 4 + 16)
 #define DT_TMEM_COLS 256  // 4 x 32 layer-0 digit accumulators + 3 x 32 layer-1 magnitude classes
 
 // 8 fp32 values of row r, columns k0..k0+7, parked as two 16-byte halves in the slots of digit tiles 2 and 3
@@ -264,12 +264,16 @@ __device__ __forceinline__ void unpark8(const uint8_t* At, int r, int k0, float*
   }
 }
 
-__global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, int K, const float* __restrict__ logits,
-                                                                    const float* __restrict__ dec0,
-                                                                    const float* __restrict__ uniforms, int use_state_kt,
-                                                                    int kt_fixed, int t_fixed, float temp, int w0_exp,
-                                                                    const float* __restrict__ blob, ctrm_weight_offsets_t off,
-                                                                    float* __restrict__ samples, int n_tiles) {
+// Two threads per row: thread (row, half) owns latent columns [32 half, 32 half + 32) in the Gumbel-softmax phase and
+// hidden columns [16 half, 16 half + 16) in the epilogues; warps 0-3 and 4-7 address the same TMEM lanes (lane group =
+// warp % 4) at different columns.  The kernel is bound by the latency of the logf / expf chains, so twice the warps per
+// tile is worth more than anything else here.
+__global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt, int K, const float* __restrict__ logits,
+                                                                       const float* __restrict__ dec0,
+                                                                       const float* __restrict__ uniforms, int use_state_kt,
+                                                                       int kt_fixed, int t_fixed, float temp, int w0_exp,
+                                                                       const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                       float* __restrict__ samples, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* At = smem;                       // z digits 1..4, [128 x 64] bf16 each
   uint8_t* W0t = At + 4 * DT_A_PART;        // W0z digits 1..4, [32 x 64]
@@ -277,9 +281,12 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, in
   float* W2 = reinterpret_cast<float*>(W1t + 3 * DT_W1_PART);  // [32][4]
   float* B1 = W2 + 128;
   float* B2 = B1 + 32;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(B2 + 4);
+  float* red = B2 + 4;                      // [2][128] max / sum exchange between the two halves of a row
+  float* red3 = red + 256;                  // [128][4] partial outputs of half 1
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red3 + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;
 
   // |W0z| < 2^w0_exp (host): digit scale 2^(7 - w0_exp) puts every weight in [-128, 128]
   tc::stage_weight_digits(blob + off.dec_w0, 32, 0, 64, 32, 32, 64, exp2f((float)(7 - w0_exp)), W0t, tid, DT_THREADS);
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, in
   for (int g = 0; g < 4; ++g) acc_scale[g] = exp2((double)(w0_exp - 7 - 8 * (g + 1)));
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row = (long long)tile * 128 + tid;
+    const long long row = (long long)tile * 128 + r;
     bool live = row < n_rows;
     int a = 0, k = 0, b = 0;
     if (live) {
@@ -316,6 +323,7 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, in
     }
     // a tile whose rows all belong to finished instances is skipped entirely
     if (!__syncthreads_or(live)) continue;
+    float mx = -INFINITY;
     if (live) {
       const float* lg = logits + (size_t)a * 64;
       const float* urow = nullptr;
@@ -329,8 +337,7 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, in
         c1 = rng_ctr1(kt, tt);
         c2 = (uint32_t)(k * N + il);  // the reference's row order k*N + i (learned_sampler.py:82)
       }
-      float mx = -INFINITY;
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 4 * half; q < 4 * half + 4; ++q) {
         float u8[8], s[8];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -352,32 +359,43 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, in
           s[j] = (l[j] + g) / temp;
           mx = fmaxf(mx, s[j]);
         }
-        park8(At, tid, q * 8, s);
+        park8(At, r, q * 8, s);
       }
-      // z = softmax(s): e = exp(s - max) is computed once and parked; z = e / sum(e) (torch evaluates
-      // exp(s - logsumexp(s)); the two agree to an ulp and this one saves 64 expf per row)
-      float se = 0.f;
-      for (int q = 0; q < 8; ++q) {
+    }
+    red[half * 128 + r] = mx;
+    __syncthreads();
+    mx = fmaxf(red[r], red[128 + r]);
+    __syncthreads();
+    // z = softmax(s): e = exp(s - max) is computed once and parked; z = e / sum(e) (torch evaluates
+    // exp(s - logsumexp(s)); the two agree to an ulp and this one saves 64 expf per row)
+    float se = 0.f;
+    if (live) {
+      for (int q = 4 * half; q < 4 * half + 4; ++q) {
         float s[8];
-        unpark8(At, tid, q * 8, s);
+        unpark8(At, r, q * 8, s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s[j] = expf(s[j] - mx);
           se += s[j];
         }
-        park8(At, tid, q * 8, s);
+        park8(At, r, q * 8, s);
       }
+    }
+    red[half * 128 + r] = se;
+    __syncthreads();
+    se = red[r] + red[128 + r];
+    if (live) {
       const float inv = 1.f / se;
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 4 * half; q < 4 * half + 4; ++q) {
         float s[8];
-        unpark8(At, tid, q * 8, s);
+        unpark8(At, r, q * 8, s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] = fminf(s[j] * inv, 1.f);
-        tc::store_digits8_unit(At, DT_A_PART, tid, q * 8, 64, s);
+        tc::store_digits8_unit(At, DT_A_PART, r, q * 8, 64, s);
       }
     } else {
       const float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int q = 0; q < 8; ++q) tc::store_digits8_unit(At, DT_A_PART, tid, q * 8, 64, v);
+      for (int q = 4 * half; q < 4 * half + 4; ++q) tc::store_digits8_unit(At, DT_A_PART, r, q * 8, 64, v);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -389,29 +407,30 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, in
     tc::mbar_wait(mb, phase);
     phase ^= 1u;
     tc::fence_after_sync();
-    // combine the four exact digit accumulators in fp64, add the x-part / bias, round once to fp32
-    float h[32];
+    // combine the four exact digit accumulators in fp64, add the x-part / bias, round once to fp32 (16 columns per thread)
+    float h[16];
     {
-      double pre[32];
-      const float4* d0 = reinterpret_cast<const float4*>(dec0 + (size_t)a * 32);
+      double pre[16];
+      const float4* d0 = reinterpret_cast<const float4*>(dec0 + (size_t)a * 32 + 16 * half);
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
+      for (int j4 = 0; j4 < 4; ++j4) {
         const float4 v = live ? __ldg(&d0[j4]) : make_float4(0.f, 0.f, 0.f, 0.f);
         pre[j4 * 4 + 0] = (double)v.x; pre[j4 * 4 + 1] = (double)v.y; pre[j4 * 4 + 2] = (double)v.z; pre[j4 * 4 + 3] = (double)v.w;
       }
 #pragma unroll
       for (int g = 3; g >= 0; --g) {
-        tc::tmem_ld32(tbase, warp, 32 * g, h);
+        tc::tmem_ld16(tbase, warp, 32 * g + 16 * half, h);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pre[j] = fma((double)h[j], acc_scale[g], pre[j]);
+        for (int j = 0; j < 16; ++j) pre[j] = fma((double)h[j], acc_scale[g], pre[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) h[j] = fmaxf((float)pre[j], 0.f);
+      for (int j = 0; j < 16; ++j) h[j] = fmaxf((float)pre[j], 0.f);
     }
     // h1 becomes the A operand of layer 1 (K = 32), reusing the digit tiles (layer 0 has completed)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) tc::store_split8(At, At + DT_H_PART, At + 2 * DT_H_PART, tid, q * 8, 32, h + q * 8);
     tc::fence_before_sync();
+    __syncthreads();  // every thread has read its layer-0 accumulators before the tile memory is rewritten
+#pragma unroll
+    for (int q = 0; q < 2; ++q) tc::store_split8(At, At + DT_H_PART, At + 2 * DT_H_PART, r, 16 * half + q * 8, 32, h + q * 8);
     tc::fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -422,25 +441,32 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_tc_kernel(Batch bt, in
     tc::mbar_wait(mb, phase);
     phase ^= 1u;
     tc::fence_after_sync();
-    tc::tmem_ld32_sum3(tbase, warp, 128, 32, h);
-    if (live) {
-      float o0 = B2[0], o1 = B2[1], o2 = B2[2];
+    tc::tmem_ld16_sum3(tbase, warp, 128 + 16 * half, 32, h);
+    {
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = fmaxf(h[j] + B1[j], 0.f);
-        const float4 w = *reinterpret_cast<const float4*>(&W2[j * 4]);
+      for (int j = 0; j < 16; ++j) {
+        const float v = fmaxf(h[j] + B1[16 * half + j], 0.f);
+        const float4 w = *reinterpret_cast<const float4*>(&W2[(16 * half + j) * 4]);
         o0 = fmaf(v, w.x, o0);
         o1 = fmaf(v, w.y, o1);
         o2 = fmaf(v, w.z, o2);
       }
-      float* out = samples + (size_t)row * 3;
-      out[0] = o0;
-      out[1] = o1;
-      out[2] = o2;
+      if (half == 1) {
+        red3[r * 4 + 0] = o0;
+        red3[r * 4 + 1] = o1;
+        red3[r * 4 + 2] = o2;
+      }
+      tc::fence_before_sync();
+      __syncthreads();  // also: every TMEM / shared-memory read of this tile is done before the next tile overwrites them
+      tc::fence_after_sync();
+      if (half == 0 && live) {
+        float* out = samples + (size_t)row * 3;
+        out[0] = (B2[0] + o0) + red3[r * 4 + 0];
+        out[1] = (B2[1] + o1) + red3[r * 4 + 1];
+        out[2] = (B2[2] + o2) + red3[r * 4 + 2];
+      }
     }
-    tc::fence_before_sync();
-    __syncthreads();  // every TMEM / shared-memory read of this tile is done before the next tile overwrites them
-    tc::fence_after_sync();
   }
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tbase, DT_TMEM_COLS);

@@ -238,6 +238,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t tbase, int warp, int col, flo
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16-column variant
+__device__ __forceinline__ void tmem_ld16(uint32_t tbase, int warp, int col, float* v) {
+  const uint32_t addr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16_sum3(uint32_t tbase, int warp, int col, int n_cols, float* v) {
+  float t[16];
+  tmem_ld16(tbase, warp, col + 2 * n_cols, v);
+  tmem_ld16(tbase, warp, col + n_cols, t);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += t[i];
+  tmem_ld16(tbase, warp, col, t);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += t[i];
+}
+
 // v[32] = (acc_lo + acc_mid) + acc_main for the three accumulators of mma_bf16x3 (columns col, col+n_cols, col+2*n_cols)
 __device__ __forceinline__ void tmem_ld32_sum3(uint32_t tbase, int warp, int col, int n_cols, float* v) {
   float t[32];
