@@ -266,10 +266,17 @@ def gpu_arm(args):
 
         return gather_csr(res, rank, world)
 
+    phase_ms = []
+
     def device_step():
+        t0 = time.perf_counter()
         builder.upload(None, packed=packed)
+        t1 = time.perf_counter()
         builder.run(seed=seed, instance_id_base=rank * B, export=False, **PARAMS)
-        return gather_to_rank0(builder.export_device())
+        t2 = time.perf_counter()
+        out = gather_to_rank0(builder.export_device())
+        phase_ms.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2)))
+        return out
 
     def e2e_step():
         csr = builder.build(instances, seed=seed, instance_id_base=rank * B, **PARAMS)
@@ -296,6 +303,9 @@ def gpu_arm(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    if rank == 0:
+        sys.stderr.write("host ms per step (upload, build, export_device+gather): " + ", ".join(
+            "(%.0f %.0f %.0f)" % p for p in phase_ms[-args.steps:]) + "\n")
     clocks = sampler.stop() if rank == 0 else None
     nv, ne, _ = builder.result_sizes()
     steps_inst = builder.instance_steps().astype(np.int64)

@@ -99,6 +99,8 @@ struct ctrm_ctx {
   bool r_trace = false;
   // tables
   DevArena t_arena;
+  // scratch of ctrm_upload_instances (footprint stencils, passability masks): cached across batches
+  DevArena s_arena;
   // results
   DevArena c_arena;
   int32_t* d_tfin = nullptr;
@@ -156,6 +158,7 @@ extern "C" void ctrm_ctx_destroy(ctrm_ctx* c) {
   c->b_arena.destroy();
   c->r_arena.destroy();
   c->t_arena.destroy();
+  c->s_arena.destroy();
   c->c_arena.destroy();
   if (c->h_ndone) cudaFreeHost(c->h_ndone);
   for (int i = 0; i < 4; ++i)
@@ -259,8 +262,9 @@ static void disk_stencil(int r, int ld, uint8_t* out) {
 static int cost_to_go_device(const uint8_t* d_occ, int M, const std::vector<uint8_t>& stencils, const std::vector<int32_t>& st_r,
                              int st_ld, const std::vector<int32_t>& pm_inst, const std::vector<int32_t>& pm_st,
                              const std::vector<int32_t>& agent_pm, const double* d_goals, int A, uint16_t* d_ctg,
-                             cudaStream_t st) {
-  DevArena tmp;
+                             cudaStream_t st, DevArena* cache = nullptr) {
+  DevArena local;
+  DevArena& tmp = cache ? *cache : local;  // a context passes its scratch arena: no cudaMalloc / cudaFree per batch
   uint8_t* d_st = nullptr;
   int32_t *d_str = nullptr, *d_pmi = nullptr, *d_pms = nullptr, *d_apm = nullptr;
   uint32_t* d_pmask = nullptr;
@@ -278,7 +282,8 @@ static int cost_to_go_device(const uint8_t* d_occ, int M, const std::vector<uint
     cudaError_t e = cudaStreamSynchronize(st);  // the host vectors and temporaries die here
     if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "cost_to_go sync");
   } while (0);
-  tmp.destroy();
+  if (cache) cache->release();
+  else local.destroy();
   return rc;
 }
 
@@ -408,19 +413,18 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CTRM_CUDA_OK(cudaMemsetAsync(bt.done, 0, (size_t)B, st));
   // occupancy raster + cost-to-go for every goal (Format2D_CTRM_Input.set_instance, format_input.py:200-210)
   {
-    DevArena tmp;
     int4* d_cells = nullptr;
-    int rc = tmp.alloc(&d_cells, (size_t)O);
+    int rc = c->s_arena.alloc(&d_cells, (size_t)O);
     if (!rc) rc = launch_obs_to_cells(d_obs, O, M, d_cells, st);
     if (!rc) rc = launch_raster_occupancy(d_cells, d_ooff, B, M, d_occ, st);
     if (!rc) {
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "raster sync");
     }
-    tmp.destroy();
+    c->s_arena.release();
     CHECK(rc);
   }
-  CHECK(cost_to_go_device(d_occ, M, stencils, st_r, st_ld, pm_inst, pm_st, agent_pm, d_goals, A, d_ctg, st));
+  CHECK(cost_to_go_device(d_occ, M, stencils, st_r, st_ld, pm_inst, pm_st, agent_pm, d_goals, A, d_ctg, st, &c->s_arena));
   c->have_batch = true;
   CHECK(sync_out(c, (cudaStream_t)user_stream));
   return 0;
