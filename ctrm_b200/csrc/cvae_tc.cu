@@ -23,18 +23,18 @@
 // (TMEM columns 0..31 indicator, 32..63 encoder, 64..95 decoder, times three magnitude classes); the one-hot indicator columns are added as a weight row
 // in the epilogue.  outputs per agent: logits[64], dec0[32], ind.
 // ------------------------------------------------------------------------------------------------
-#define PR_THREADS 128
+#define PR_THREADS 256
 #define PR_K0 80                      // 72 padded to a multiple of 16
 #define PR_X_PART 20480u              // tile_bytes(128, 80)
 #define PR_H_PART 8192u               // tile_bytes(128, 32)
 #define PR_W0_PART 15360u             // tile_bytes(96, 80)
 #define PR_W1_PART 2048u              // tile_bytes(32, 32)
 #define PR_W2_PART 4096u              // tile_bytes(64, 32)
-#define PR_NF 608                     // fp32 constants
+#define PR_NF 1664                    // fp32 constants + the [2][128][4] exchange buffer of the two halves of a row
 #define PR_SMEM (3 * 20480 + 3 * 15360 + 2 * 3 * 2048 + 3 * 4096 + PR_NF * 4 + 16)
 #define PR_TMEM_COLS 512  // layer 0: 3 x 96 | head layers: 3 x 32 at 288 | encoder output 3 x 64 reuses 0..191
 
-__global__ void __launch_bounds__(PR_THREADS) cvae_prior_tc_kernel(Batch bt, const float* __restrict__ X,
+__global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, const float* __restrict__ X,
                                                                    const float* __restrict__ blob, ctrm_weight_offsets_t off,
                                                                    float* __restrict__ logits_out, float* __restrict__ dec0_out,
                                                                    int32_t* __restrict__ ind_out, int n_tiles) {
@@ -55,9 +55,11 @@ __global__ void __launch_bounds__(PR_THREADS) cvae_prior_tc_kernel(Batch bt, con
   float* dec_b0 = cf + 324;      // 32
   float* enc_oh = cf + 356;      // [3][32] rows 72..74 of enc_w0
   float* dec_oh = cf + 452;      // [3][32] rows 136..138 of dec_w0
+  float* red = cf + 608;         // [2][128][4]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(cf + PR_NF);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;  // two threads per row: TMEM lane group = warp % 4 for both halves
 
   tc::stage_weight_split_at(blob + off.ind_w0, 32, 0, 72, 32, 32, 0, 96, PR_K0, W0t, tid, PR_THREADS);
   tc::stage_weight_split_at(blob + off.enc_w0, 32, 0, 72, 32, 32, 32, 96, PR_K0, W0t, tid, PR_THREADS);
@@ -106,99 +108,122 @@ __global__ void __launch_bounds__(PR_THREADS) cvae_prior_tc_kernel(Batch bt, con
     phase ^= 1u;
     tc::fence_after_sync();
   };
-  auto store_hidden = [&](const float* h) {  // h[32] -> three bf16 parts of the [128 x 32] hidden tile
+  // thread (row r, half): hidden columns [16 half, 16 half + 16) -> three bf16 parts of the [128 x 32] hidden tile
+  auto store_hidden16 = [&](const float* h) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tc::store_split8(Xt, Xt + PR_H_PART, Xt + 2 * PR_H_PART, tid, q * 8, 32, h + q * 8);
+    for (int q = 0; q < 2; ++q) tc::store_split8(Xt, Xt + PR_H_PART, Xt + 2 * PR_H_PART, r, 16 * half + q * 8, 32, h + q * 8);
   };
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int a = tile * 128 + tid;
+    const int a = tile * 128 + r;
     bool live = a < bt.A;
     if (live) live = !(bt.done != nullptr && bt.done[bt.agent_inst[a]]);
     if (!__syncthreads_or(live)) continue;
-    {  // X row -> three bf16 parts (K padded 72 -> 80 with zeros)
+    {  // X row -> three bf16 parts (K padded 72 -> 80 with zeros); each half stages five of the ten 8-wide chunks
       const float4* xr = reinterpret_cast<const float4*>(X + (size_t)a * CTRM_DIM_X);
 #pragma unroll
-      for (int q = 0; q < 10; ++q) {
+      for (int qq = 0; qq < 5; ++qq) {
+        const int q = 5 * half + qq;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (live && q < 9) {
           const float4 p0 = __ldg(&xr[2 * q]), p1 = __ldg(&xr[2 * q + 1]);
           v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
         }
-        tc::store_split8(Xt, Xt + PR_X_PART, Xt + 2 * PR_X_PART, tid, q * 8, PR_K0, v);
+        tc::store_split8(Xt, Xt + PR_X_PART, Xt + 2 * PR_X_PART, r, q * 8, PR_K0, v);
       }
     }
     mma_round(0, sX, PR_X_PART, sW0, PR_W0_PART, PR_K0, 96);
-    float h[32];
+    float h[16];
     // ---- indicator: hidden 1 -> hidden 2 -> 3 logits -> argmax
-    tc::tmem_ld32_sum3(tbase, warp, 0, 96, h);
+    tc::tmem_ld16_sum3(tbase, warp, 16 * half, 96, h);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + ind_b0[j], 0.f);
-    store_hidden(h);
+    for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j] + ind_b0[16 * half + j], 0.f);
+    tc::fence_before_sync();
+    __syncthreads();  // the X tile is dead (layer 0 done) and every thread has issued its first TMEM reads
+    store_hidden16(h);
     mma_round(288, sX, PR_H_PART, sWi1, PR_W1_PART, 32, 32);
-    tc::tmem_ld32_sum3(tbase, warp, 288, 32, h);
+    tc::tmem_ld16_sum3(tbase, warp, 288 + 16 * half, 32, h);
     int ind = 0;
     {
-      float o0 = ind_b2[0], o1 = ind_b2[1], o2 = ind_b2[2];
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = fmaxf(h[j] + ind_b1[j], 0.f);
-        const float4 w = *reinterpret_cast<const float4*>(&ind_w2[j * 4]);
+      for (int j = 0; j < 16; ++j) {
+        const float v = fmaxf(h[j] + ind_b1[16 * half + j], 0.f);
+        const float4 w = *reinterpret_cast<const float4*>(&ind_w2[(16 * half + j) * 4]);
         o0 = fmaf(v, w.x, o0);
         o1 = fmaf(v, w.y, o1);
         o2 = fmaf(v, w.z, o2);
       }
+      red[(half * 128 + r) * 4 + 0] = o0;
+      red[(half * 128 + r) * 4 + 1] = o1;
+      red[(half * 128 + r) * 4 + 2] = o2;
+      __syncthreads();
+      // both halves form the same sums in the same order: identical argmax
+      o0 = (ind_b2[0] + red[r * 4 + 0]) + red[(128 + r) * 4 + 0];
+      o1 = (ind_b2[1] + red[r * 4 + 1]) + red[(128 + r) * 4 + 1];
+      o2 = (ind_b2[2] + red[r * 4 + 2]) + red[(128 + r) * 4 + 2];
       float best = o0;
       if (o1 > best) { best = o1; ind = 1; }
       if (o2 > best) { best = o2; ind = 2; }
-      if (live && ind_out != nullptr) ind_out[a] = ind;
+      if (live && half == 0 && ind_out != nullptr) ind_out[a] = ind;
     }
     // ---- decoder first layer, [X, onehot] part (TMEM columns 64..95 of the shared chain)
-    tc::tmem_ld32_sum3(tbase, warp, 64, 96, h);
+    tc::tmem_ld16_sum3(tbase, warp, 64 + 16 * half, 96, h);
     if (live) {
-      float4* d0 = reinterpret_cast<float4*>(dec0_out + (size_t)a * 32);
+      float4* d0 = reinterpret_cast<float4*>(dec0_out + (size_t)a * 32 + 16 * half);
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        d0[j4] = make_float4(h[j4 * 4 + 0] + dec_b0[j4 * 4 + 0] + dec_oh[ind * 32 + j4 * 4 + 0],
-                             h[j4 * 4 + 1] + dec_b0[j4 * 4 + 1] + dec_oh[ind * 32 + j4 * 4 + 1],
-                             h[j4 * 4 + 2] + dec_b0[j4 * 4 + 2] + dec_oh[ind * 32 + j4 * 4 + 2],
-                             h[j4 * 4 + 3] + dec_b0[j4 * 4 + 3] + dec_oh[ind * 32 + j4 * 4 + 3]);
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const int c0 = 16 * half + j4 * 4;
+        d0[j4] = make_float4(h[j4 * 4 + 0] + dec_b0[c0 + 0] + dec_oh[ind * 32 + c0 + 0],
+                             h[j4 * 4 + 1] + dec_b0[c0 + 1] + dec_oh[ind * 32 + c0 + 1],
+                             h[j4 * 4 + 2] + dec_b0[c0 + 2] + dec_oh[ind * 32 + c0 + 2],
+                             h[j4 * 4 + 3] + dec_b0[c0 + 3] + dec_oh[ind * 32 + c0 + 3]);
+      }
     }
     // ---- encoder_input: hidden 1 (+ one-hot row) -> hidden 2 -> 64 logits -> log_softmax -> clamped log-probs
-    tc::tmem_ld32_sum3(tbase, warp, 32, 96, h);
+    tc::tmem_ld16_sum3(tbase, warp, 32 + 16 * half, 96, h);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + enc_b0[j] + enc_oh[ind * 32 + j], 0.f);
-    store_hidden(h);
+    for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j] + enc_b0[16 * half + j] + enc_oh[ind * 32 + 16 * half + j], 0.f);
+    store_hidden16(h);  // the indicator's hidden tile was consumed by its MMA round (waited on above)
     mma_round(288, sX, PR_H_PART, sWe1, PR_W1_PART, 32, 32);
-    tc::tmem_ld32_sum3(tbase, warp, 288, 32, h);
+    tc::tmem_ld16_sum3(tbase, warp, 288 + 16 * half, 32, h);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + enc_b1[j], 0.f);
-    store_hidden(h);
+    for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j] + enc_b1[16 * half + j], 0.f);
+    store_hidden16(h);
     mma_round(0, sX, PR_H_PART, sWe2, PR_W2_PART, 32, 64);  // every layer-0 column has been consumed
     {
-      float lg[64];
-      tc::tmem_ld32_sum3(tbase, warp, 0, 64, lg);
-      tc::tmem_ld32_sum3(tbase, warp, 32, 64, lg + 32);
+      float lg[32];  // this half's 32 of the 64 logits
+      tc::tmem_ld32_sum3(tbase, warp, 32 * half, 64, lg);
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        lg[j] += enc_b2[j];
+      for (int j = 0; j < 32; ++j) {
+        lg[j] += enc_b2[32 * half + j];
         mx = fmaxf(mx, lg[j]);
       }
+      red[half * 128 + r] = mx;
+      __syncthreads();
+      mx = fmaxf(red[r], red[128 + r]);
+      __syncthreads();
       float se = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) se += expf(lg[j] - mx);
-      const float lse = logf(se);
+      for (int j = 0; j < 32; ++j) se += expf(lg[j] - mx);
+      red[half * 128 + r] = se;
+      __syncthreads();
+      const float lse = logf(red[r] + red[128 + r]);
+      __syncthreads();
       float ps = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
+      for (int j = 0; j < 32; ++j) {
         lg[j] = expf((lg[j] - mx) - lse);  // probs = exp(log_softmax)
         ps += lg[j];
       }
+      red[half * 128 + r] = ps;
+      __syncthreads();
+      ps = red[r] + red[128 + r];
       if (live) {
-        float4* lo = reinterpret_cast<float4*>(logits_out + (size_t)a * 64);
+        float4* lo = reinterpret_cast<float4*>(logits_out + (size_t)a * 64 + 32 * half);
 #pragma unroll
-        for (int j4 = 0; j4 < 16; ++j4)
+        for (int j4 = 0; j4 < 8; ++j4)
           lo[j4] = make_float4(logf(fminf(fmaxf(lg[j4 * 4 + 0] / ps, eps), 1.f - eps)),
                                logf(fminf(fmaxf(lg[j4 * 4 + 1] / ps, eps), 1.f - eps)),
                                logf(fminf(fmaxf(lg[j4 * 4 + 2] / ps, eps), 1.f - eps)),
