@@ -14,7 +14,7 @@
 #include "kernels.h"
 #include "tc.cuh"
 
-#define FT_THREADS 128
+#define FT_THREADS 256
 #define FT_CHUNK 96
 #define FT_A_CHUNK 24576u   // tile_bytes(128, 96)
 #define FT_W_DIGIT 12288u   // tile_bytes(64, 96)
@@ -72,7 +72,7 @@ __global__ void fov_f32_to_tiles_kernel(const float* __restrict__ fov, int A, in
   }
 }
 
-__global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t* __restrict__ fov_tiles,
+__global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint8_t* __restrict__ fov_tiles,
                                                                    const uint8_t* __restrict__ w0_tiles, int n_chunks, int w0_exp,
                                                                    const int32_t* __restrict__ agent_inst,
                                                                    const uint8_t* __restrict__ skip_inst, int A,
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FT_STAGES + 1);
   uint8_t* Ht = stage0;    // hidden tiles reuse the operand stages once layer 0 has completed
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;  // two threads per row; TMEM lane group = warp % 4 for both halves
 
   for (int i = tid; i < (int)(6 * FT_W64_PART) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(W1c)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t
   };
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int a = tile * 128 + tid;
+    const int a = tile * 128 + r;
     bool live = a < A;
     if (live && skip_inst != nullptr) live = skip_inst[agent_inst[a]] == 0;
     if (!__syncthreads_or(live)) continue;
@@ -179,10 +180,10 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t
     tc::mbar_wait(done, done_phase);
     done_phase ^= 1u;
     tc::fence_after_sync();
-    // ---- epilogue 0: combine digits in fp64, + bias, ReLU -> hidden tile [128 x 64]
+    // ---- epilogue 0: combine digits in fp64, + bias, ReLU -> hidden tile [128 x 64].  Thread (row r, half) owns the
+    //      32 columns of ONE encoder: half 0 = fov_encoder_self, half 1 = fov_encoder_vain
     float h[32];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    {
       double pre[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) pre[j] = 0.0;
@@ -195,47 +196,43 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_tc_kernel(const uint8_t
 #pragma unroll
       for (int j = 0; j < 32; ++j) h[j] = fmaxf((float)pre[j] + b0[32 * half + j], 0.f);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, tid, 32 * half + q * 8, 64, h + q * 8);
+      for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + q * 8, 64, h + q * 8);
     }
     // ---- tail 1
     mma_round(256, sH, FT_H_PART, sW1, FT_W64_PART, 64, 64);
+    tc::tmem_ld32_sum3(tbase, warp, 256 + 32 * half, 64, h);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      tc::tmem_ld32_sum3(tbase, warp, 256 + 32 * half, 64, h);
+    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + b1[32 * half + j], 0.f);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + b1[32 * half + j], 0.f);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, tid, 32 * half + q * 8, 64, h + q * 8);
-    }
-    // ---- tail 2 -> e_self | e_vain
+    for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + q * 8, 64, h + q * 8);
+    // ---- tail 2 -> e_self (half 0) | e_vain (half 1)
     mma_round(256, sH, FT_H_PART, sW2, FT_W64_PART, 64, 64);
-    tc::tmem_ld32_sum3(tbase, warp, 256, 64, h);
-    if (live) {
-      float4* dst = reinterpret_cast<float4*>(e_self + (size_t)a * 32);
+    tc::tmem_ld32_sum3(tbase, warp, 256 + 32 * half, 64, h);
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        dst[j4] = make_float4(h[j4 * 4] + b2[j4 * 4], h[j4 * 4 + 1] + b2[j4 * 4 + 1], h[j4 * 4 + 2] + b2[j4 * 4 + 2],
-                              h[j4 * 4 + 3] + b2[j4 * 4 + 3]);
-    }
-    tc::tmem_ld32_sum3(tbase, warp, 288, 64, h);
+    for (int j = 0; j < 32; ++j) h[j] += b2[32 * half + j];
+    {
+      float* dstp = half == 0 ? e_self : e_vain;
+      if (live && dstp != nullptr) {
+        float4* dst = reinterpret_cast<float4*>(dstp + (size_t)a * 32);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) h[j] += b2[32 + j];
-    if (live && e_vain != nullptr) {
-      float4* dst = reinterpret_cast<float4*>(e_vain + (size_t)a * 32);
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) dst[j4] = make_float4(h[j4 * 4], h[j4 * 4 + 1], h[j4 * 4 + 2], h[j4 * 4 + 3]);
+        for (int j4 = 0; j4 < 8; ++j4) dst[j4] = make_float4(h[j4 * 4], h[j4 * 4 + 1], h[j4 * 4 + 2], h[j4 * 4 + 3]);
+      }
     }
     // ---- fov_vain part of AgentEncoder layer 0: vain_proj = b0 + W0[11:43]^T e_vain, shared by every pair (i, j)
+    tc::fence_before_sync();
+    __syncthreads();  // tail-2 accumulators read by everyone before the hidden tile is rewritten
+    if (half == 1) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H32_PART, Ht + 2 * FT_H32_PART, tid, q * 8, 32, h + q * 8);
+      for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H32_PART, Ht + 2 * FT_H32_PART, r, q * 8, 32, h + q * 8);
+    }
     mma_round(0, sH, FT_H32_PART, sWp, FT_W32_PART, 32, 32);
-    tc::tmem_ld32_sum3(tbase, warp, 0, 32, h);
+    tc::tmem_ld16_sum3(tbase, warp, 16 * half, 32, h);
     if (live) {
-      float4* dst = reinterpret_cast<float4*>(vain_proj + (size_t)a * 32);
+      float4* dst = reinterpret_cast<float4*>(vain_proj + (size_t)a * 32 + 16 * half);
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        dst[j4] = make_float4(h[j4 * 4] + bp[j4 * 4], h[j4 * 4 + 1] + bp[j4 * 4 + 1], h[j4 * 4 + 2] + bp[j4 * 4 + 2],
-                              h[j4 * 4 + 3] + bp[j4 * 4 + 3]);
+      for (int j4 = 0; j4 < 4; ++j4)
+        dst[j4] = make_float4(h[j4 * 4] + bp[16 * half + j4 * 4], h[j4 * 4 + 1] + bp[16 * half + j4 * 4 + 1],
+                              h[j4 * 4 + 2] + bp[16 * half + j4 * 4 + 2], h[j4 * 4 + 3] + bp[16 * half + j4 * 4 + 3]);
     }
     tc::fence_before_sync();
     __syncthreads();
