@@ -54,7 +54,7 @@ class WeightOffsets(C.Structure):
 class DeviceView(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "A", "O", "M", "F", "L", "S", "W")] + [
         (n, C.c_void_p) for n in ("d_agent_off", "d_obs_off", "d_agent_inst", "d_starts", "d_goals", "d_speeds",
-                                  "d_speeds2", "d_rads", "d_obs_xyr", "d_occ", "d_ctg")]
+                                  "d_speeds2", "d_rads", "d_obs_xyr", "d_occ", "d_ctg")] + [("ctg_layout", C.c_int32)]
 
 
 # every symbol include/ctrm_b200.h declares: name -> (restype, argtypes)
@@ -71,7 +71,7 @@ SIGNATURES = {
     "ctrm_collide_sphere_pairs": (C.c_int, [V, V, V, V, V, V, C.c_int, C.c_int64, V, V]),
     "ctrm_raster_occupancy": (C.c_int, [V, V, C.c_int, C.c_int, V, V]),
     "ctrm_cost_to_go": (C.c_int, [V, V, V, V, C.c_int, C.c_int, V, V]),
-    "ctrm_fov_raster": (C.c_int, [V, V, V, V, C.c_int, C.c_int, C.c_int, V, V]),
+    "ctrm_fov_raster": (C.c_int, [V, V, C.c_int, V, V, C.c_int, C.c_int, C.c_int, V, V]),
     "ctrm_encode_features": (C.c_int, [V, V, V, V, V, V]),
     "ctrm_cvae_sample": (C.c_int, [V, V, V, C.c_int, C.c_uint64, C.c_int, C.c_int, V, V, V]),
     "ctrm_build_roadmaps": (C.c_int, [V, C.POINTER(Params), C.POINTER(Tables), V]),

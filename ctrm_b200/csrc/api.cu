@@ -262,7 +262,7 @@ static void disk_stencil(int r, int ld, uint8_t* out) {
 static int cost_to_go_device(const uint8_t* d_occ, int M, const std::vector<uint8_t>& stencils, const std::vector<int32_t>& st_r,
                              int st_ld, const std::vector<int32_t>& pm_inst, const std::vector<int32_t>& pm_st,
                              const std::vector<int32_t>& agent_pm, const double* d_goals, int A, uint16_t* d_ctg,
-                             cudaStream_t st, DevArena* cache = nullptr) {
+                             cudaStream_t st, DevArena* cache = nullptr, int layout = 0) {
   DevArena local;
   DevArena& tmp = cache ? *cache : local;  // a context passes its scratch arena: no cudaMalloc / cudaFree per batch
   uint8_t* d_st = nullptr;
@@ -278,7 +278,7 @@ static int cost_to_go_device(const uint8_t* d_occ, int M, const std::vector<uint
     if ((rc = upload(tmp, &d_apm, agent_pm.data(), agent_pm.size(), st))) break;
     if ((rc = tmp.alloc(&d_pmask, (size_t)P * M * MW))) break;
     if ((rc = launch_passable_masks(d_occ, M, d_st, d_str, st_ld, d_pmi, d_pms, P, d_pmask, st))) break;
-    if ((rc = launch_wavefront(d_pmask, d_apm, d_goals, A, M, d_ctg, st))) break;
+    if ((rc = launch_wavefront(d_pmask, d_apm, d_goals, A, M, layout, d_ctg, st))) break;
     cudaError_t e = cudaStreamSynchronize(st);  // the host vectors and temporaries die here
     if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "cost_to_go sync");
   } while (0);
@@ -368,7 +368,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   uint8_t* d_occ;
   uint16_t* d_ctg;
   CHECK(ar.alloc(&d_occ, (size_t)B * M * M + 16));
-  CHECK(ar.alloc(&d_ctg, (size_t)A * M * M));
+  CHECK(ar.alloc(&d_ctg, (size_t)A * ctg_field_elems(M, 1)));
   bt.occ = d_occ; bt.ctg = d_ctg;
   // per-step tensors (A-sized)
   CHECK(ar.alloc(&bt.fov_tiles, fov_tiles_bytes(A, F)));
@@ -424,7 +424,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
     c->s_arena.release();
     CHECK(rc);
   }
-  CHECK(cost_to_go_device(d_occ, M, stencils, st_r, st_ld, pm_inst, pm_st, agent_pm, d_goals, A, d_ctg, st, &c->s_arena));
+  CHECK(cost_to_go_device(d_occ, M, stencils, st_r, st_ld, pm_inst, pm_st, agent_pm, d_goals, A, d_ctg, st, &c->s_arena, 1));
   c->have_batch = true;
   CHECK(sync_out(c, (cudaStream_t)user_stream));
   return 0;
@@ -438,6 +438,7 @@ extern "C" int ctrm_get_device_view(ctrm_ctx* c, ctrm_device_view* v) {
   v->d_agent_off = bt.agent_off; v->d_obs_off = bt.obs_off; v->d_agent_inst = bt.agent_inst;
   v->d_starts = bt.starts; v->d_goals = bt.goals; v->d_speeds = bt.speeds; v->d_speeds2 = bt.speeds2; v->d_rads = bt.rads;
   v->d_obs_xyr = bt.obs_xyr; v->d_occ = bt.occ; v->d_ctg = bt.ctg;
+  v->ctg_layout = 1;
   return 0;
 }
 
@@ -503,12 +504,13 @@ extern "C" int ctrm_cost_to_go(const uint8_t* d_occ, const int32_t* d_agent_inst
   return cost_to_go_device(d_occ, M, stencils, st_r, st_ld, pm_inst, pm_st, agent_pm, d_goals, A, d_ctg, st);
 }
 
-extern "C" int ctrm_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
-                               int A, int M, int F, float* d_fov, void* stream) {
+extern "C" int ctrm_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, int ctg_layout, const int32_t* d_agent_inst,
+                               const double* d_pos, int A, int M, int F, float* d_fov, void* stream) {
   if (A <= 0 || M < 1 || M > 255 || F < 1 || (F & 1) == 0 || F > 63 || !d_occ || !d_ctg || !d_agent_inst || !d_pos || !d_fov)
     return ctrm_fail(CTRM_ERR_ARG, "ctrm_fov_raster: bad argument");
   if ((reinterpret_cast<uintptr_t>(d_fov) & 15) != 0) return ctrm_fail(CTRM_ERR_ARG, "ctrm_fov_raster: d_fov must be 16-byte aligned");
-  return launch_fov_raster(d_occ, d_ctg, d_agent_inst, d_pos, nullptr, A, M, F, d_fov, (cudaStream_t)stream);
+  if (ctg_layout != 0 && ctg_layout != 1) return ctrm_fail(CTRM_ERR_ARG, "ctrm_fov_raster: ctg_layout must be 0 or 1");
+  return launch_fov_raster(d_occ, d_ctg, d_agent_inst, d_pos, nullptr, A, M, F, ctg_layout, d_fov, (cudaStream_t)stream);
 }
 
 extern "C" int ctrm_encode_features(ctrm_ctx* c, const float* d_fov, const double* d_cur, const double* d_prev, float* d_X,
@@ -630,7 +632,7 @@ static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, 
   };
   if (prof) CTRM_CUDA_OK(cudaEventRecord(prof->at(pstep, 0), st));
   if (nn) {
-    CHECK(launch_fov_raster_tiles(bt.occ, bt.ctg, bt.agent_inst, bt.cur, bt.done, bt.A, bt.M, bt.F, fov_n_chunks(bt.F),
+    CHECK(launch_fov_raster_tiles(bt.occ, bt.ctg, bt.agent_inst, bt.cur, bt.done, bt.A, bt.M, bt.F, fov_n_chunks(bt.F), 1,
                                   bt.fov_tiles, st));
     CHECK(mark(KID_FOV_RASTER));
     CHECK(launch_fov_encode(c->model, bt.fov_tiles, bt.agent_inst, bt.done, bt.A, bt.e_self, nullptr, bt.vain_proj, st));
@@ -965,7 +967,7 @@ extern "C" int ctrm_host_fov2d(const double* pos, const int32_t* occ, const int3
   if (!rc) rc = upload(ar, &d_pos, pos, 2, (cudaStream_t) nullptr);
   if (!rc) rc = upload(ar, &d_inst, &zero, 1, (cudaStream_t) nullptr);
   if (!rc) rc = ar.alloc(&d_fov, n + 8);
-  if (!rc) rc = launch_fov_raster(d_occ, d_ctg, d_inst, d_pos, nullptr, 1, M, F, d_fov, nullptr);
+  if (!rc) rc = launch_fov_raster(d_occ, d_ctg, d_inst, d_pos, nullptr, 1, M, F, 0, d_fov, nullptr);
   std::vector<float> h(n);
   if (!rc) {
     cudaError_t e = cudaMemcpy(h.data(), d_fov, n * sizeof(float), cudaMemcpyDeviceToHost);

@@ -83,6 +83,17 @@ __device__ __forceinline__ double dist2(double cx, double cy, double lx, double 
   return f64add(f64add(0.0, f64mul(dx, dx)), f64mul(dy, dy));
 }
 
+// ---- cost-to-go field layouts ----
+// layout 0: row-major [x][y] (what getCostToGo2D returns, cost_to_go.cpp:105-106).
+// layout 1: 8 x 4 cell micro-tiles of 64 bytes (one DRAM burst): a 19 x 19 FOV crop then touches ~18 bursts (1.1 KB) instead
+//           of 19 row segments that each straddle 2-3 sectors (measured 3.7 KB of DRAM reads per crop with layout 0).
+__host__ __device__ __forceinline__ size_t ctg_field_elems(int M, int layout) {
+  return layout ? (size_t)((M + 7) >> 3) * ((M + 3) >> 2) * 32 : (size_t)M * M;
+}
+__device__ __forceinline__ int ctg_index(int x, int y, int M, int layout) {
+  return layout ? ((((x >> 3) * ((M + 3) >> 2) + (y >> 2)) << 5) + ((x & 7) << 2) + (y & 3)) : (x * M + y);
+}
+
 // ---- Philox4x32-10, counter layout of oracle/rng_tables.py ----
 #define PHILOX_M0 0xD2511F53u
 #define PHILOX_M1 0xCD9E8D57u

@@ -29,7 +29,7 @@ struct Batch {
   const int32_t *agent_off, *obs_off, *agent_inst;
   const double *starts, *goals, *speeds, *speeds2, *merge2, *rads, *obs_xyr;
   const uint8_t* occ;   // [B][M][M]
-  const uint16_t* ctg;  // [A][M][M]
+  const uint16_t* ctg;  // [A][field]: cost-to-go in the 8 x 4 micro-tiled layout (common.cuh ctg_index, layout 1)
   // roll-out state
   double *cur, *prev, *nxt, *loc_pred;  // [A][2]
   uint8_t* arrived;                     // [A]
@@ -71,10 +71,10 @@ int launch_obs_to_cells(const double* d_obs_xyr, int O, int M, int4* d_cells, cu
 int launch_raster_occupancy(const int4* d_cells, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, cudaStream_t st);
 int launch_passable_masks(const uint8_t* d_occ, int M, const uint8_t* d_stencils, const int32_t* d_stencil_r, int st_ld,
                           const int32_t* d_pm_inst, const int32_t* d_pm_stencil, int P, uint32_t* d_pmask, cudaStream_t st);
-int launch_wavefront(const uint32_t* d_pmask, const int32_t* d_agent_pm, const double* d_goals, int A, int M,
+int launch_wavefront(const uint32_t* d_pmask, const int32_t* d_agent_pm, const double* d_goals, int A, int M, int layout,
                      uint16_t* d_ctg, cudaStream_t st);
 int launch_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
-                      const uint8_t* d_skip_inst, int A, int M, int F, float* d_fov, cudaStream_t st);
+                      const uint8_t* d_skip_inst, int A, int M, int F, int layout, float* d_fov, cudaStream_t st);
 
 int launch_collide_segments(const double* d_from, const double* d_to, const double* d_rad, const int32_t* d_seg_inst,
                             int64_t n, const double* d_obs_xyr, const int32_t* d_obs_off, uint8_t* d_verdict,
@@ -83,7 +83,8 @@ int launch_collide_pairs(const double* f1, const double* t1, const double* r1, c
                          const double* r2, int dim, int64_t n, uint8_t* verdict, cudaStream_t st);
 
 int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
-                            const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, uint8_t* d_tiles, cudaStream_t st);
+                            const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, int layout, uint8_t* d_tiles,
+                            cudaStream_t st);
 int fov_n_chunks(int F);
 size_t fov_tiles_bytes(int A, int F);
 size_t fov_w0_tiles_bytes(int F);

@@ -117,13 +117,13 @@ template <int RPL, int MW>
 __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restrict__ pmask,
                                                         const int32_t* __restrict__ agent_pm,
                                                         const double* __restrict__ goals, int A, int M,
-                                                        uint16_t* __restrict__ ctg) {
+                                                        int layout, uint16_t* __restrict__ ctg) {
   int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (a >= A) return;
   const int mw = (M + 31) >> 5;  // words per row of the mask as written by passable_mask_kernel
   const uint32_t* pm = pmask + (size_t)agent_pm[a] * M * mw;
-  uint16_t* out = ctg + (size_t)a * M * M;
+  uint16_t* out = ctg + (size_t)a * ctg_field_elems(M, layout);
   uint32_t pass[RPL][MW], vis[RPL][MW], fr[RPL][MW];
 #pragma unroll
   for (int r = 0; r < RPL; ++r) {
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restri
       }
     }
   }
-  if (lane == gx / RPL) out[gx * M + gy] = 0;
+  if (lane == gx / RPL) out[ctg_index(gx, gy, M, layout)] = 0;
   for (int level = 1; level < 65535; ++level) {
     uint32_t nw[RPL][MW];
     uint32_t any = 0u;
@@ -183,11 +183,10 @@ __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restri
         uint32_t n = nw[r][w];
         vis[r][w] |= n;
         fr[r][w] = n;
-        uint16_t* row = out + (size_t)(lane * RPL + r) * M + w * 32;
         while (n) {
           int bit = __ffs(n) - 1;
           n &= n - 1;
-          row[bit] = (uint16_t)level;
+          out[ctg_index(lane * RPL + r, w * 32 + bit, M, layout)] = (uint16_t)level;
         }
       }
     }
@@ -206,7 +205,7 @@ __global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __r
                                                               const int32_t* __restrict__ agent_inst,
                                                               const double* __restrict__ pos,
                                                               const uint8_t* __restrict__ skip_inst, int A, int M,
-                                                              int F, float* __restrict__ fov) {
+                                                              int F, int layout, float* __restrict__ fov) {
   extern __shared__ __align__(16) float tile[];  // [APB][2F^2]
   const int FF = F * F, ROW = 2 * FF;
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,12 +218,12 @@ __global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __r
     float* t = tile + warp * ROW;
     if (live) {
       const uint8_t* o = occ + (size_t)b * M * M;
-      const uint16_t* c = ctg + (size_t)a * M * M;
+      const uint16_t* c = ctg + (size_t)a * ctg_field_elems(M, layout);
       int cx = grid_cell(pos[2 * a + 0], M), cy = grid_cell(pos[2 * a + 1], M);
       int buf = (F - 1) / 2;
       // a position outside [0,1] wraps through uint16 in the reference; such crops are entirely outside the map
       bool centre_in = cx < M && cy < M;
-      int cc = centre_in ? (int)c[cx * M + cy] : CTRM_UNREACH;
+      int cc = centre_in ? (int)c[ctg_index(cx, cy, M, layout)] : CTRM_UNREACH;
       bool c_reach = cc != CTRM_UNREACH;
       for (int i = lane; i < FF; i += 32) {
         int xf = i / F, yf = i - xf * F;
@@ -232,7 +231,7 @@ __global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __r
         float v0 = 0.f, v1 = 0.f;
         if (centre_in && x >= 0 && x < M && y >= 0 && y < M) {
           v0 = (float)(1 - (int)o[x * M + y]);
-          int _c = (int)c[x * M + y];
+          int _c = (int)c[ctg_index(x, y, M, layout)];
           v1 = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 1.f : 0.f;
         }
         t[i] = v0;
@@ -267,7 +266,7 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
                                                                       const int32_t* __restrict__ agent_inst,
                                                                       const double* __restrict__ pos,
                                                                       const uint8_t* __restrict__ skip_inst, int A, int M, int F_rt,
-                                                                      int n_chunks, uint8_t* __restrict__ tiles) {
+                                                                      int n_chunks, int layout, uint8_t* __restrict__ tiles) {
   extern __shared__ __align__(16) uint8_t rt_smem[];
   const int F = FT > 0 ? FT : F_rt;
   const int FF = F * F, KD = 2 * FF, Kpad = n_chunks * RT_CHUNK;
@@ -282,11 +281,11 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
     live = (skip_inst == nullptr) || (skip_inst[b] == 0);
     if (live) {
       const uint8_t* o = occ + (size_t)b * M * M;
-      const uint16_t* c = ctg + (size_t)a * M * M;
+      const uint16_t* c = ctg + (size_t)a * ctg_field_elems(M, layout);
       const int cx = grid_cell(pos[2 * a + 0], M), cy = grid_cell(pos[2 * a + 1], M);
       const int buf = (F - 1) / 2;
       const bool centre_in = cx < M && cy < M;
-      const int cc = centre_in ? (int)c[cx * M + cy] : CTRM_UNREACH;
+      const int cc = centre_in ? (int)c[ctg_index(cx, cy, M, layout)] : CTRM_UNREACH;
       const bool c_reach = cc != CTRM_UNREACH;
 #pragma unroll 4
       for (int i = lane; i < FF; i += 32) {
@@ -295,7 +294,7 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
         uint16_t v0 = 0, v1 = 0;
         if (centre_in && x >= 0 && x < M && y >= 0 && y < M) {
           v0 = __ldg(&o[x * M + y]) ? 0 : 0x3F80;  // bf16 1.0
-          const int _c = (int)__ldg(&c[x * M + y]);
+          const int _c = (int)__ldg(&c[ctg_index(x, y, M, layout)]);
           v1 = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 0x3F80 : 0;
         }
         t[i] = v0;
@@ -352,13 +351,13 @@ int launch_passable_masks(const uint8_t* d_occ, int M, const uint8_t* d_stencils
   return 0;
 }
 
-int launch_wavefront(const uint32_t* d_pmask, const int32_t* d_agent_pm, const double* d_goals, int A, int M,
+int launch_wavefront(const uint32_t* d_pmask, const int32_t* d_agent_pm, const double* d_goals, int A, int M, int layout,
                      uint16_t* d_ctg, cudaStream_t st) {
   if (A <= 0) return 0;
-  CTRM_CUDA_OK(cudaMemsetAsync(d_ctg, 0xFF, (size_t)A * M * M * sizeof(uint16_t), st));
+  CTRM_CUDA_OK(cudaMemsetAsync(d_ctg, 0xFF, (size_t)A * ctg_field_elems(M, layout) * sizeof(uint16_t), st));
   int blocks = (A + 3) / 4;
-  if (M <= 160) wavefront_kernel<5, 5><<<blocks, 128, 0, st>>>(d_pmask, d_agent_pm, d_goals, A, M, d_ctg);
-  else if (M <= 256) wavefront_kernel<8, 8><<<blocks, 128, 0, st>>>(d_pmask, d_agent_pm, d_goals, A, M, d_ctg);
+  if (M <= 160) wavefront_kernel<5, 5><<<blocks, 128, 0, st>>>(d_pmask, d_agent_pm, d_goals, A, M, layout, d_ctg);
+  else if (M <= 256) wavefront_kernel<8, 8><<<blocks, 128, 0, st>>>(d_pmask, d_agent_pm, d_goals, A, M, layout, d_ctg);
   else return ctrm_fail(-1, "map_size > 255 unsupported (reference limit, cost_to_go.cpp:47)");
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
@@ -366,31 +365,32 @@ int launch_wavefront(const uint32_t* d_pmask, const int32_t* d_agent_pm, const d
 
 template <int APB>
 static int launch_fov_raster_t(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
-                               const uint8_t* d_skip_inst, int A, int M, int F, float* d_fov, cudaStream_t st) {
+                               const uint8_t* d_skip_inst, int A, int M, int F, int layout, float* d_fov, cudaStream_t st) {
   size_t smem = (size_t)APB * 2 * F * F * sizeof(float);
   if (smem > 48 * 1024)
     CTRM_CUDA_OK(cudaFuncSetAttribute(fov_raster_kernel<APB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fov_raster_kernel<APB><<<(A + APB - 1) / APB, APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F,
-                                                                   d_fov);
+                                                                   layout, d_fov);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int launch_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
-                      const uint8_t* d_skip_inst, int A, int M, int F, float* d_fov, cudaStream_t st) {
+                      const uint8_t* d_skip_inst, int A, int M, int F, int layout, float* d_fov, cudaStream_t st) {
   if (A <= 0) return 0;
-  if (F <= 27) return launch_fov_raster_t<8>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, d_fov, st);
-  return launch_fov_raster_t<2>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, d_fov, st);
+  if (F <= 27) return launch_fov_raster_t<8>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, layout, d_fov, st);
+  return launch_fov_raster_t<2>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, layout, d_fov, st);
 }
 
 int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
-                            const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, uint8_t* d_tiles, cudaStream_t st) {
+                            const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, int layout, uint8_t* d_tiles,
+                            cudaStream_t st) {
   if (A <= 0) return 0;
   const size_t smem = (size_t)RT_APB * ((size_t)n_chunks * RT_CHUNK * 2 + 16);
   const int blocks = (A + RT_APB - 1) / RT_APB;
   if (F == 19) {  // the trained configuration
     fov_raster_tiles_kernel<19><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
-                                                                 d_tiles);
+                                                                 layout, d_tiles);
   } else {
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -398,7 +398,7 @@ int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const i
       attr = smem;
     }
     fov_raster_tiles_kernel<0><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
-                                                                d_tiles);
+                                                                layout, d_tiles);
   }
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;

@@ -161,9 +161,11 @@ int ctrm_cost_to_go(const uint8_t* d_occ /*[B][M][M]*/, const int32_t* d_agent_i
                     uint16_t* d_ctg /*[A][M][M]*/, void* stream);
 
 /* replaces getFov2dOccupancyCost (cost_to_go.cpp:109-186) + torch.tensor(...).float() (format_input.py:299-308)
- * for all agents at once: fov[a][0..2F^2) float32 {0,1}, flatten layout idx = x_fov*F + y_fov, channel 1 at F^2. */
-int ctrm_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos /*[A][2]*/,
-                    int A, int M, int F, float* d_fov /*[A][2F^2]*/, void* stream);
+ * for all agents at once: fov[a][0..2F^2) float32 {0,1}, flatten layout idx = x_fov*F + y_fov, channel 1 at F^2.
+ * ctg_layout 0 = row-major [A][M][M] as ctrm_cost_to_go / the reference return it; 1 = the context's own 8 x 4 micro-tiled
+ * fields (ctrm_device_view.d_ctg), which keep a crop's DRAM traffic near its algorithmic size. */
+int ctrm_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, int ctg_layout, const int32_t* d_agent_inst,
+                    const double* d_pos /*[A][2]*/, int A, int M, int F, float* d_fov /*[A][2F^2]*/, void* stream);
 
 /* replaces Format2D_CTRM_Input.get_feature_one_step after the FOV crop (format_input.py:311-357):
  * FOV encoders, numba get_arr_others_info (compiled.py:30-97), AgentEncoder, get_comm (format_input.py:212-277),
@@ -226,6 +228,7 @@ typedef struct {
   const double *d_starts, *d_goals, *d_speeds, *d_speeds2, *d_rads, *d_obs_xyr;
   const uint8_t* d_occ;
   const uint16_t* d_ctg;
+  int32_t ctg_layout; /* layout of d_ctg, to be passed to ctrm_fov_raster */
 } ctrm_device_view;
 int ctrm_get_device_view(ctrm_ctx* ctx, ctrm_device_view* out);
 

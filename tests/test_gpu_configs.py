@@ -82,7 +82,7 @@ def test_api_error_paths():
     lib = _lib.load()
     assert lib.ctrm_collide_segments(None, None, None, None, 5, None, None, None, None, None, None) == -1
     assert b"NULL" in lib.ctrm_last_error(None)
-    assert lib.ctrm_fov_raster(None, None, None, None, 0, 160, 19, None, None) == -1
+    assert lib.ctrm_fov_raster(None, None, 0, None, None, 0, 160, 19, None, None) == -1
     b = RoadmapBuilder(WEIGHTS, 0)
     try:
         with pytest.raises(_lib.CtrmError):

@@ -153,7 +153,7 @@ def test_occupancy_ctg_fov_golden(stage_gold):
     ctg_rep = ctg.view(N, M * M).repeat_interleave(P, dim=0).contiguous()
     inst2 = torch.zeros(N * P, dtype=torch.int32, device="cuda")
     fov = torch.zeros(N * P * 2 * F * F + 8, dtype=torch.float32, device="cuda")
-    L.check(lib.ctrm_fov_raster(occ.data_ptr(), ctg_rep.data_ptr(), inst2.data_ptr(), pos.data_ptr(), N * P, M, F,
+    L.check(lib.ctrm_fov_raster(occ.data_ptr(), ctg_rep.data_ptr(), 0, inst2.data_ptr(), pos.data_ptr(), N * P, M, F,
                                 fov.data_ptr(), _stream()))
     got = fov[:N * P * 2 * F * F].cpu().numpy().reshape(N, P, 2 * F * F)
     assert np.array_equal(got, z["s1.fov"].astype(np.float32))
@@ -223,7 +223,7 @@ def test_set_instance_matches_oracle(builder, trace_gold, oracle_weights):
     M, F = v.M, v.F
     for pts, dptr in ((oi.starts, v.d_starts), (oi.goals, v.d_goals)):
         fov = torch.zeros(v.A * 2 * F * F + 8, dtype=torch.float32, device="cuda")
-        L.check(lib.ctrm_fov_raster(v.d_occ, v.d_ctg, v.d_agent_inst, dptr, v.A, M, F, fov.data_ptr(), _stream()))
+        L.check(lib.ctrm_fov_raster(v.d_occ, v.d_ctg, v.ctg_layout, v.d_agent_inst, dptr, v.A, M, F, fov.data_ptr(), _stream()))
         want = O.fov_crop_batch(pts, occ, ctgs, F).astype(np.float32)
         assert np.array_equal(fov[:v.A * 2 * F * F].cpu().numpy().reshape(v.A, -1), want)
 
@@ -240,7 +240,7 @@ def test_encode_features_vs_reference(builder, trace_gold):
         cur, prev = _dev(z["cur"][s]), _dev(z["prev"][s])
         fov = torch.zeros(A * 2 * F * F + 8, dtype=torch.float32, device="cuda")
         X = torch.zeros(A * 72, dtype=torch.float32, device="cuda")
-        L.check(lib.ctrm_fov_raster(v.d_occ, v.d_ctg, v.d_agent_inst, cur.data_ptr(), A, M, F, fov.data_ptr(), _stream()))
+        L.check(lib.ctrm_fov_raster(v.d_occ, v.d_ctg, v.ctg_layout, v.d_agent_inst, cur.data_ptr(), A, M, F, fov.data_ptr(), _stream()))
         L.check(lib.ctrm_encode_features(builder.ctx, fov.data_ptr(), cur.data_ptr(), prev.data_ptr(), X.data_ptr(), _stream()))
         got = X.cpu().numpy().reshape(A, 72)
         ref = z["nn_X"][j]

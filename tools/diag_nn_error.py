@@ -27,7 +27,7 @@ for r in recs:
     cur, prev = torch.from_numpy(r["cur"]).cuda(), torch.from_numpy(r["prev"]).cuda()
     fov = torch.zeros(A * 2 * F * F + 8, dtype=torch.float32, device="cuda")
     X = torch.zeros(A * 72, dtype=torch.float32, device="cuda")
-    lib.ctrm_fov_raster(v.d_occ, v.d_ctg, v.d_agent_inst, cur.data_ptr(), A, M, F, fov.data_ptr(), st)
+    lib.ctrm_fov_raster(v.d_occ, v.d_ctg, v.ctg_layout, v.d_agent_inst, cur.data_ptr(), A, M, F, fov.data_ptr(), st)
     lib.ctrm_encode_features(b.ctx, fov.data_ptr(), cur.data_ptr(), prev.data_ptr(), X.data_ptr(), st)
     Xg = X.cpu().numpy().reshape(A, 72)
     ex.append([rel_err(Xg[:, lo:hi], r["X"][:, lo:hi]) for lo, hi in ((0, 8), (8, 40), (40, 72))])
