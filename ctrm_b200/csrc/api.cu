@@ -229,7 +229,6 @@ extern "C" int ctrm_load_weights(ctrm_ctx* c, const ctrm_model_desc* d, const fl
     return e;
   };
   c->model.dec_w0z_exp = exp_bound(off.dec_w0, 64 * 32);
-  CHECK(upload_agent_constants(h_blob, off));  // AgentEncoder weights live in constant memory (encode.cu)
   {  // digit tiles of the FOV encoders' first layer for the tensor-core kernel
     const int F = d->fov_size;
     c->model.fov_w0_exp = exp_bound(off.fov_w0, 2 * F * F * 64);
@@ -238,6 +237,17 @@ extern "C" int ctrm_load_weights(ctrm_ctx* c, const ctrm_model_desc* d, const fl
     CHECK(launch_fov_w0_prep(blob + off.fov_w0, F, c->model.fov_w0_exp, tiles, c->stream));
     CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
     c->model.fov_w0_tiles = tiles;
+  }
+  {  // shared-memory weight images of the other tensor-core kernels
+    uint8_t *pi = nullptr, *di = nullptr, *ai = nullptr;
+    CHECK(c->w_arena.alloc(&pi, cvae_prior_image_bytes()));
+    CHECK(c->w_arena.alloc(&di, cvae_decode_image_bytes()));
+    CHECK(c->w_arena.alloc(&ai, agent_comm_image_bytes()));
+    CHECK(launch_cvae_prior_image(blob, off, pi, c->stream));
+    CHECK(launch_cvae_decode_image(blob, off, c->model.dec_w0z_exp, di, c->stream));
+    CHECK(launch_agent_comm_image(blob, off, ai, c->stream));
+    CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->model.prior_img = pi; c->model.decode_img = di; c->model.agent_img = ai;
   }
   c->have_weights = true;
   return 0;

@@ -30,12 +30,51 @@
 #define PR_W0_PART 15360u             // tile_bytes(96, 80)
 #define PR_W1_PART 2048u              // tile_bytes(32, 32)
 #define PR_W2_PART 4096u              // tile_bytes(64, 32)
+#define PR_NW 608                     // fp32 constants (biases, output layer, one-hot rows) that follow the weight tiles
+#define PR_W_BYTES (3 * 15360 + 2 * 3 * 2048 + 3 * 4096 + PR_NW * 4)  // the prebuilt weight image
 #define PR_NF 1664                    // fp32 constants + the [2][128][4] exchange buffer of the two halves of a row
 #define PR_SMEM (3 * 20480 + 3 * 15360 + 2 * 3 * 2048 + 3 * 4096 + PR_NF * 4 + 16)
 #define PR_TMEM_COLS 512  // layer 0: 3 x 96 | head layers: 3 x 32 at 288 | encoder output 3 x 64 reuses 0..191
 
+// weight operands of cvae_prior exactly as they sit in its shared memory from W0t on: split bf16 tiles, then fp32 constants
+__device__ __forceinline__ void prior_stage_weights(uint8_t* W0t, const float* __restrict__ blob, const ctrm_weight_offsets_t& off,
+                                                    int tid, int nthreads) {
+  uint8_t* Wi1 = W0t + 3 * PR_W0_PART;
+  uint8_t* We1 = Wi1 + 3 * PR_W1_PART;
+  uint8_t* We2 = We1 + 3 * PR_W1_PART;
+  float* cf = reinterpret_cast<float*>(We2 + 3 * PR_W2_PART);
+  tc::stage_weight_split_at(blob + off.ind_w0, 32, 0, 72, 32, 32, 0, 96, PR_K0, W0t, tid, nthreads);
+  tc::stage_weight_split_at(blob + off.enc_w0, 32, 0, 72, 32, 32, 32, 96, PR_K0, W0t, tid, nthreads);
+  tc::stage_weight_split_at(blob + off.dec_w0, 32, 64, 72, 32, 32, 64, 96, PR_K0, W0t, tid, nthreads);
+  tc::stage_weight_split(blob + off.ind_w1, 32, 0, 32, 32, 32, 32, Wi1, tid, nthreads);
+  tc::stage_weight_split(blob + off.enc_w1, 32, 0, 32, 32, 32, 32, We1, tid, nthreads);
+  tc::stage_weight_split(blob + off.enc_w2, 64, 0, 32, 64, 64, 32, We2, tid, nthreads);
+  for (int i = tid; i < 32; i += nthreads) {
+    cf[i] = __ldg(&blob[off.ind_b0 + i]);
+    cf[32 + i] = __ldg(&blob[off.ind_b1 + i]);
+    cf[196 + i] = __ldg(&blob[off.enc_b0 + i]);
+    cf[228 + i] = __ldg(&blob[off.enc_b1 + i]);
+    cf[324 + i] = __ldg(&blob[off.dec_b0 + i]);
+  }
+  for (int i = tid; i < 64; i += nthreads) cf[260 + i] = __ldg(&blob[off.enc_b2 + i]);
+  for (int i = tid; i < 4; i += nthreads) cf[192 + i] = __ldg(&blob[off.ind_b2 + i]);
+  for (int i = tid; i < 128; i += nthreads) cf[64 + i] = __ldg(&blob[off.ind_w2 + i]);
+  for (int i = tid; i < 96; i += nthreads) {
+    cf[356 + i] = __ldg(&blob[off.enc_w0 + CTRM_DIM_X * 32 + i]);
+    cf[452 + i] = __ldg(&blob[off.dec_w0 + (64 + CTRM_DIM_X) * 32 + i]);
+  }
+  for (int i = 548 + tid; i < PR_NW; i += nthreads) cf[i] = 0.f;
+}
+__global__ void __launch_bounds__(PR_THREADS) cvae_prior_image_kernel(const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                    uint8_t* __restrict__ image) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  prior_stage_weights(smem, blob, off, threadIdx.x, PR_THREADS);
+  __syncthreads();
+  tc::dump_image(smem, image, PR_W_BYTES, threadIdx.x, PR_THREADS);
+}
+
 __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, const float* __restrict__ X,
-                                                                   const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                   const uint8_t* __restrict__ w_image,
                                                                    float* __restrict__ logits_out, float* __restrict__ dec0_out,
                                                                    int32_t* __restrict__ ind_out, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -61,37 +100,20 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;  // two threads per row: TMEM lane group = warp % 4 for both halves
 
-  tc::stage_weight_split_at(blob + off.ind_w0, 32, 0, 72, 32, 32, 0, 96, PR_K0, W0t, tid, PR_THREADS);
-  tc::stage_weight_split_at(blob + off.enc_w0, 32, 0, 72, 32, 32, 32, 96, PR_K0, W0t, tid, PR_THREADS);
-  tc::stage_weight_split_at(blob + off.dec_w0, 32, 64, 72, 32, 32, 64, 96, PR_K0, W0t, tid, PR_THREADS);
-  tc::stage_weight_split(blob + off.ind_w1, 32, 0, 32, 32, 32, 32, Wi1, tid, PR_THREADS);
-  tc::stage_weight_split(blob + off.enc_w1, 32, 0, 32, 32, 32, 32, We1, tid, PR_THREADS);
-  tc::stage_weight_split(blob + off.enc_w2, 64, 0, 32, 64, 64, 32, We2, tid, PR_THREADS);
-  if (tid < 32) {
-    ind_b0[tid] = __ldg(&blob[off.ind_b0 + tid]);
-    ind_b1[tid] = __ldg(&blob[off.ind_b1 + tid]);
-    enc_b0[tid] = __ldg(&blob[off.enc_b0 + tid]);
-    enc_b1[tid] = __ldg(&blob[off.enc_b1 + tid]);
-    dec_b0[tid] = __ldg(&blob[off.dec_b0 + tid]);
-  }
-  if (tid < 64) enc_b2[tid] = __ldg(&blob[off.enc_b2 + tid]);
-  if (tid < 4) ind_b2[tid] = __ldg(&blob[off.ind_b2 + tid]);
-  for (int i = tid; i < 128; i += PR_THREADS) ind_w2[i] = __ldg(&blob[off.ind_w2 + i]);
-  for (int i = tid; i < 96; i += PR_THREADS) {
-    enc_oh[i] = __ldg(&blob[off.enc_w0 + CTRM_DIM_X * 32 + i]);
-    dec_oh[i] = __ldg(&blob[off.dec_w0 + (64 + CTRM_DIM_X) * 32 + i]);
+  if (tid == 0) {  // the weight operands arrive as one prebuilt image (cvae_prior_image_kernel), through the TMA engine
+    tc::mbar_init(tc::smem_u32(mbar), 1);
+    tc::tma_load_image(W0t, w_image, PR_W_BYTES, tc::smem_u32(mbar));
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, PR_TMEM_COLS);
-  if (tid == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
-  tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = *tmem_slot;
   const uint32_t mb = tc::smem_u32(mbar);
+  tc::mbar_wait(mb, 0);  // weights have landed; the MMA rounds continue on the same barrier with phase 1
   const uint32_t sX = tc::smem_u32(Xt), sW0 = tc::smem_u32(W0t), sWi1 = tc::smem_u32(Wi1), sWe1 = tc::smem_u32(We1),
                  sWe2 = tc::smem_u32(We2);
-  uint32_t phase = 0;
+  uint32_t phase = 1;
   const float eps = 1.1920928955078125e-07f;
 
   // one MMA round: the A tile in shared memory is complete -> issue, commit, wait
@@ -238,6 +260,14 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
   if (warp == 0) tc::tmem_dealloc(tbase, PR_TMEM_COLS);
 }
 
+size_t cvae_prior_image_bytes() { return PR_W_BYTES; }
+int launch_cvae_prior_image(const float* d_blob, const ctrm_weight_offsets_t& off, uint8_t* d_image, cudaStream_t st) {
+  CTRM_CUDA_OK(cudaFuncSetAttribute(cvae_prior_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_W_BYTES));
+  cvae_prior_image_kernel<<<1, PR_THREADS, PR_W_BYTES, st>>>(d_blob, off, d_image);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,
                       cudaStream_t st) {
   if (bt.A <= 0) return 0;
@@ -248,7 +278,7 @@ int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, floa
     attr = true;
   }
   const int grid = n_tiles < 148 ? n_tiles : 148;  // persistent, one CTA per SM (135 KB of shared memory each)
-  cvae_prior_tc_kernel<<<grid, PR_THREADS, PR_SMEM, st>>>(bt, d_X, m.blob, m.off, d_logits, d_dec0, d_ind, n_tiles);
+  cvae_prior_tc_kernel<<<grid, PR_THREADS, PR_SMEM, st>>>(bt, d_X, m.prior_img, d_logits, d_dec0, d_ind, n_tiles);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -293,11 +323,32 @@ __device__ __forceinline__ void unpark8(const uint8_t* At, int r, int k0, float*
 // hidden columns [16 half, 16 half + 16) in the epilogues; warps 0-3 and 4-7 address the same TMEM lanes (lane group =
 // warp % 4) at different columns.  The kernel is bound by the latency of the logf / expf chains, so twice the warps per
 // tile is worth more than anything else here.
+// weight operands of cvae_decode exactly as they sit in its shared memory from W0t on
+#define DT_W_BYTES (4 * DT_W0_PART + 3 * DT_W1_PART + (128 + 32 + 4) * 4)
+__global__ void __launch_bounds__(DT_THREADS) cvae_decode_image_kernel(const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                     int w0_exp, uint8_t* __restrict__ image) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* W0t = smem;
+  uint8_t* W1t = W0t + 4 * DT_W0_PART;
+  float* W2 = reinterpret_cast<float*>(W1t + 3 * DT_W1_PART);
+  float* B1 = W2 + 128;
+  float* B2 = B1 + 32;
+  const int tid = threadIdx.x;
+  // |W0z| < 2^w0_exp (host): digit scale 2^(7 - w0_exp) puts every weight in [-128, 128]
+  tc::stage_weight_digits(blob + off.dec_w0, 32, 0, 64, 32, 32, 64, exp2f((float)(7 - w0_exp)), W0t, tid, DT_THREADS);
+  tc::stage_weight_split(blob + off.dec_w1, 32, 0, 32, 32, 32, 32, W1t, tid, DT_THREADS);
+  for (int i = tid; i < 128; i += DT_THREADS) W2[i] = __ldg(&blob[off.dec_w2 + i]);
+  if (tid < 32) B1[tid] = __ldg(&blob[off.dec_b1 + tid]);
+  if (tid < 4) B2[tid] = __ldg(&blob[off.dec_b2 + tid]);
+  __syncthreads();
+  tc::dump_image(smem, image, DT_W_BYTES, tid, DT_THREADS);
+}
+
 __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt, int K, const float* __restrict__ logits,
                                                                        const float* __restrict__ dec0,
                                                                        const float* __restrict__ uniforms, int use_state_kt,
                                                                        int kt_fixed, int t_fixed, float temp, int w0_exp,
-                                                                       const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                       const uint8_t* __restrict__ w_image,
                                                                        float* __restrict__ samples, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* At = smem;                       // z digits 1..4, [128 x 64] bf16 each
@@ -313,22 +364,19 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;
 
-  // |W0z| < 2^w0_exp (host): digit scale 2^(7 - w0_exp) puts every weight in [-128, 128]
-  tc::stage_weight_digits(blob + off.dec_w0, 32, 0, 64, 32, 32, 64, exp2f((float)(7 - w0_exp)), W0t, tid, DT_THREADS);
-  tc::stage_weight_split(blob + off.dec_w1, 32, 0, 32, 32, 32, 32, W1t, tid, DT_THREADS);
-  for (int i = tid; i < 128; i += DT_THREADS) W2[i] = __ldg(&blob[off.dec_w2 + i]);
-  if (tid < 32) B1[tid] = __ldg(&blob[off.dec_b1 + tid]);
-  if (tid < 4) B2[tid] = __ldg(&blob[off.dec_b2 + tid]);
+  if (tid == 0) {  // the weight operands arrive as one prebuilt image (cvae_decode_image_kernel), through the TMA engine
+    tc::mbar_init(tc::smem_u32(mbar), 1);
+    tc::tma_load_image(W0t, w_image, DT_W_BYTES, tc::smem_u32(mbar));
+  }
   if (warp == 0) tc::tmem_alloc(tmem_slot, DT_TMEM_COLS);
-  if (tid == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
-  tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = *tmem_slot;
   const uint32_t mb = tc::smem_u32(mbar);
+  tc::mbar_wait(mb, 0);  // weights have landed; the MMA rounds continue on the same barrier with phase 1
   const uint32_t sA = tc::smem_u32(At), sW0 = tc::smem_u32(W0t), sW1 = tc::smem_u32(W1t);
-  uint32_t phase = 0;
+  uint32_t phase = 1;
   const float eps = 1.1920928955078125e-07f;
   const long long n_rows = (long long)bt.A * K;
   // accumulator g (digit index sum, 0-based) carries weight 256^-(g+1) * 2^(w0_exp - 7)
@@ -497,6 +545,13 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
   if (warp == 0) tc::tmem_dealloc(tbase, DT_TMEM_COLS);
 }
 
+size_t cvae_decode_image_bytes() { return DT_W_BYTES; }
+int launch_cvae_decode_image(const float* d_blob, const ctrm_weight_offsets_t& off, int w0_exp, uint8_t* d_image, cudaStream_t st) {
+  cvae_decode_image_kernel<<<1, DT_THREADS, DT_W_BYTES, st>>>(d_blob, off, w0_exp, d_image);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits, const float* d_dec0, const float* d_uniforms,
                        int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st) {
   if (bt.A <= 0) return 0;
@@ -510,7 +565,7 @@ int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits
   }
   const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent: two CTAs per SM
   cvae_decode_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(bt, K, d_logits, d_dec0, d_uniforms, use_state_kt, kt_fixed, t_fixed,
-                                                          m.desc.temp, m.dec_w0z_exp, m.blob, m.off, d_samples, n_tiles);
+                                                          m.desc.temp, m.dec_w0z_exp, m.decode_img, d_samples, n_tiles);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -18,7 +18,18 @@ struct DevModel {
   const uint8_t* fov_w0_tiles;  // digit tiles of the FOV encoders' first layer (fov_tc.cu), chunk-major
   int fov_w0_exp;               // |fov W0| < 2^fov_w0_exp
   int dec_w0z_exp;  // |decoder W0[0:64]| < 2^dec_w0z_exp (digit scale of the exact tensor-core product, tc.cuh)
+  // prebuilt shared-memory images of the tensor-core kernels' weight operands (split / digit tiles + fp32 constants), built once
+  // at ctrm_load_weights and bulk-copied by every CTA
+  const uint8_t* prior_img;
+  const uint8_t* decode_img;
+  const uint8_t* agent_img;
 };
+size_t cvae_prior_image_bytes();
+int launch_cvae_prior_image(const float* d_blob, const ctrm_weight_offsets_t& off, uint8_t* d_image, cudaStream_t st);
+size_t cvae_decode_image_bytes();
+int launch_cvae_decode_image(const float* d_blob, const ctrm_weight_offsets_t& off, int w0_exp, uint8_t* d_image, cudaStream_t st);
+size_t agent_comm_image_bytes();
+int launch_agent_comm_image(const float* d_blob, const ctrm_weight_offsets_t& off, uint8_t* d_image, cudaStream_t st);
 
 // device-side view of one uploaded batch and its roll-out state; passed to kernels by value
 struct Batch {
@@ -92,7 +103,6 @@ int launch_fov_w0_prep(const float* d_w0, int F, int w0_exp, uint8_t* d_out, cud
 int launch_fov_f32_to_tiles(const float* d_fov, int A, int F, uint8_t* d_tiles, cudaStream_t st);
 int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32_t* d_agent_inst, const uint8_t* d_skip_inst,
                       int A, float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st);
-int upload_agent_constants(const float* h_blob, const ctrm_weight_offsets_t& off);
 int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, const double* d_prev, const float* d_e_self,
                       const float* d_vain_proj, float* d_X, cudaStream_t st);
 int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,

@@ -108,6 +108,26 @@ static __device__ __noinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t n_cols,
     acc = 1u;
   }
 }
+// Two-accumulator variant: the main term alone at tmem_d, every correction term (2^-8 and 2^-16 classes) at tmem_d + n_cols.
+// What matters for the truncating accumulate is that nothing small is ever added to the full-magnitude sum inside the tensor
+// core; mixing the two correction classes costs 2^-24 * 2^-8 relative, and saves a third of the TMEM columns and loads.
+static __device__ __noinline__ void mma_bf16x3_c2(uint32_t tmem_d, uint32_t n_cols, uint32_t a, uint32_t a_part, uint32_t b,
+                                              uint32_t b_part, int K, int N) {
+  const uint32_t id = idesc_bf16(128, N);
+  uint32_t acc = 0u;
+  for (int s = 0; s < K / 16; ++s) {
+    const uint32_t o = 256u * s;
+    const uint64_t a1 = smem_desc(a + o, K), a2 = smem_desc(a + a_part + o, K), a3 = smem_desc(a + 2 * a_part + o, K);
+    const uint64_t b1 = smem_desc(b + o, K), b2 = smem_desc(b + b_part + o, K), b3 = smem_desc(b + 2 * b_part + o, K);
+    mma_bf16(tmem_d + n_cols, a1, b3, id, acc);
+    mma_bf16(tmem_d + n_cols, a3, b1, id, 1u);
+    mma_bf16(tmem_d + n_cols, a2, b2, id, 1u);
+    mma_bf16(tmem_d + n_cols, a1, b2, id, 1u);
+    mma_bf16(tmem_d + n_cols, a2, b1, id, 1u);
+    mma_bf16(tmem_d, a1, b1, id, acc);
+    acc = 1u;
+  }
+}
 // A exactly representable in bf16 (e.g. {0,1} inputs): only B is split (3 MMAs per k-step)
 __device__ __forceinline__ void mma_bf16_exactA(uint32_t tmem_d, uint32_t a, uint32_t b, uint32_t b_part, int K, int N,
                                                 bool accumulate) {
@@ -200,6 +220,19 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src,
                : "memory");
 }
 
+// one thread: bulk-copy a prebuilt operand image (16-byte aligned, size % 16 == 0) into shared memory; completion is counted on
+// `mbar` (initialised with count 1: this call is its one arrival)
+__device__ __forceinline__ void tma_load_image(void* dst, const uint8_t* src, uint32_t bytes, uint32_t mbar) {
+  mbar_expect_tx(mbar, bytes);
+  for (uint32_t o = 0; o < bytes; o += 32768u)
+    tma_bulk_g2s(smem_u32(reinterpret_cast<uint8_t*>(dst) + o), src + o, bytes - o < 32768u ? bytes - o : 32768u, mbar);
+}
+// the reverse, for the one-off kernels that build such an image in their own shared memory
+__device__ __forceinline__ void dump_image(const uint8_t* smem_src, uint8_t* __restrict__ dst, uint32_t bytes, int tid, int nthreads) {
+  for (uint32_t i = (uint32_t)tid * 16u; i < bytes; i += (uint32_t)nthreads * 16u)
+    *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(smem_src + i);
+}
+
 // same, with an L2 evict-first hint for data that is consumed exactly once
 __device__ __forceinline__ void tma_bulk_g2s_evict_first(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
   uint64_t policy;
@@ -259,6 +292,22 @@ __device__ __forceinline__ void tmem_ld16_sum3(uint32_t tbase, int warp, int col
   tmem_ld16(tbase, warp, col + n_cols, t);
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] += t[i];
+  tmem_ld16(tbase, warp, col, t);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += t[i];
+}
+
+// two-accumulator epilogues of mma_bf16x3_c2: v = corrections + main
+__device__ __forceinline__ void tmem_ld32_sum2(uint32_t tbase, int warp, int col, int n_cols, float* v) {
+  float t[32];
+  tmem_ld32(tbase, warp, col + n_cols, v);
+  tmem_ld32(tbase, warp, col, t);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] += t[i];
+}
+__device__ __forceinline__ void tmem_ld16_sum2(uint32_t tbase, int warp, int col, int n_cols, float* v) {
+  float t[16];
+  tmem_ld16(tbase, warp, col + n_cols, v);
   tmem_ld16(tbase, warp, col, t);
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] += t[i];
