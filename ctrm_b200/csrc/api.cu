@@ -239,15 +239,17 @@ extern "C" int ctrm_load_weights(ctrm_ctx* c, const ctrm_model_desc* d, const fl
     c->model.fov_w0_tiles = tiles;
   }
   {  // shared-memory weight images of the other tensor-core kernels
-    uint8_t *pi = nullptr, *di = nullptr, *ai = nullptr;
+    uint8_t *pi = nullptr, *di = nullptr, *ai = nullptr, *fi = nullptr;
     CHECK(c->w_arena.alloc(&pi, cvae_prior_image_bytes()));
     CHECK(c->w_arena.alloc(&di, cvae_decode_image_bytes()));
     CHECK(c->w_arena.alloc(&ai, agent_comm_image_bytes()));
+    CHECK(c->w_arena.alloc(&fi, fov_encode_image_bytes()));
+    CHECK(launch_fov_encode_image(blob, off, fi, c->stream));
     CHECK(launch_cvae_prior_image(blob, off, pi, c->stream));
     CHECK(launch_cvae_decode_image(blob, off, c->model.dec_w0z_exp, di, c->stream));
     CHECK(launch_agent_comm_image(blob, off, ai, c->stream));
     CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
-    c->model.prior_img = pi; c->model.decode_img = di; c->model.agent_img = ai;
+    c->model.prior_img = pi; c->model.decode_img = di; c->model.agent_img = ai; c->model.fov_img = fi;
   }
   c->have_weights = true;
   return 0;

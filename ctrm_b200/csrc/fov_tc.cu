@@ -72,11 +72,41 @@ __global__ void fov_f32_to_tiles_kernel(const float* __restrict__ fov, int A, in
   }
 }
 
+// tail-layer weight operands of fov_encode exactly as they sit in its shared memory from W1c on
+#define FT_W_BYTES (2 * 3 * FT_W64_PART + 3 * FT_W32_PART + 224 * 4)
+__global__ void __launch_bounds__(FT_THREADS) fov_encode_image_kernel(const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                    uint8_t* __restrict__ image) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* W1c = smem;
+  uint8_t* W2c = W1c + 3 * FT_W64_PART;
+  uint8_t* Wp = W2c + 3 * FT_W64_PART;
+  float* cf = reinterpret_cast<float*>(Wp + 3 * FT_W32_PART);
+  float *b0 = cf, *b1 = cf + 64, *b2 = cf + 128, *bp = cf + 192;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (int)(6 * FT_W64_PART) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(W1c)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  tc::stage_weight_split_at(blob + off.fovs_w1, 32, 0, 32, 32, 32, 0, 64, 64, W1c, tid, FT_THREADS, 0, 32);
+  tc::stage_weight_split_at(blob + off.fovv_w1, 32, 0, 32, 32, 32, 32, 64, 64, W1c, tid, FT_THREADS, 32, 32);
+  tc::stage_weight_split_at(blob + off.fovs_w2, 32, 0, 32, 32, 32, 0, 64, 64, W2c, tid, FT_THREADS, 0, 32);
+  tc::stage_weight_split_at(blob + off.fovv_w2, 32, 0, 32, 32, 32, 32, 64, 64, W2c, tid, FT_THREADS, 32, 32);
+  tc::stage_weight_split(blob + off.ag_w0v, 32, 0, 32, 32, 32, 32, Wp, tid, FT_THREADS);
+  if (tid < 64) b0[tid] = __ldg(&blob[off.fov_b0 + tid]);
+  if (tid < 32) {
+    b1[tid] = __ldg(&blob[off.fovs_b1 + tid]);
+    b1[32 + tid] = __ldg(&blob[off.fovv_b1 + tid]);
+    b2[tid] = __ldg(&blob[off.fovs_b2 + tid]);
+    b2[32 + tid] = __ldg(&blob[off.fovv_b2 + tid]);
+    bp[tid] = __ldg(&blob[off.ag_b0 + tid]);
+  }
+  __syncthreads();
+  tc::dump_image(smem, image, FT_W_BYTES, tid, FT_THREADS);
+}
+
 __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint8_t* __restrict__ fov_tiles,
                                                                    const uint8_t* __restrict__ w0_tiles, int n_chunks, int w0_exp,
                                                                    const int32_t* __restrict__ agent_inst,
                                                                    const uint8_t* __restrict__ skip_inst, int A,
-                                                                   const float* __restrict__ blob, ctrm_weight_offsets_t off,
+                                                                   const uint8_t* __restrict__ w_image,
                                                                    float* __restrict__ e_self, float* __restrict__ e_vain,
                                                                    float* __restrict__ vain_proj, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -95,36 +125,24 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;  // two threads per row; TMEM lane group = warp % 4 for both halves
 
-  for (int i = tid; i < (int)(6 * FT_W64_PART) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(W1c)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  tc::stage_weight_split_at(blob + off.fovs_w1, 32, 0, 32, 32, 32, 0, 64, 64, W1c, tid, FT_THREADS, 0, 32);
-  tc::stage_weight_split_at(blob + off.fovv_w1, 32, 0, 32, 32, 32, 32, 64, 64, W1c, tid, FT_THREADS, 32, 32);
-  tc::stage_weight_split_at(blob + off.fovs_w2, 32, 0, 32, 32, 32, 0, 64, 64, W2c, tid, FT_THREADS, 0, 32);
-  tc::stage_weight_split_at(blob + off.fovv_w2, 32, 0, 32, 32, 32, 32, 64, 64, W2c, tid, FT_THREADS, 32, 32);
-  tc::stage_weight_split(blob + off.ag_w0v, 32, 0, 32, 32, 32, 32, Wp, tid, FT_THREADS);
-  if (tid < 64) b0[tid] = __ldg(&blob[off.fov_b0 + tid]);
-  if (tid < 32) {
-    b1[tid] = __ldg(&blob[off.fovs_b1 + tid]);
-    b1[32 + tid] = __ldg(&blob[off.fovv_b1 + tid]);
-    b2[tid] = __ldg(&blob[off.fovs_b2 + tid]);
-    b2[32 + tid] = __ldg(&blob[off.fovv_b2 + tid]);
-    bp[tid] = __ldg(&blob[off.ag_b0 + tid]);
-  }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-  if (tid == 0)
+  if (tid == 0) {
     for (int i = 0; i < 2 * FT_STAGES + 1; ++i) tc::mbar_init(tc::smem_u32(&bars[i]), 1);
-  tc::fence_async_smem();
+    // the tail-layer weight operands arrive as one prebuilt image (fov_encode_image_kernel), through the TMA engine
+    tc::tma_load_image(W1c, w_image, FT_W_BYTES, tc::smem_u32(&bars[2 * FT_STAGES]));
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = *tmem_slot;
   const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[FT_STAGES]),
                  done = tc::smem_u32(&bars[2 * FT_STAGES]);
+  tc::mbar_wait(done, 0);  // weights have landed; the tail MMA rounds continue on the same barrier with phase 1
   const uint32_t sStage = tc::smem_u32(stage0), sH = tc::smem_u32(Ht), sW1 = tc::smem_u32(W1c), sW2 = tc::smem_u32(W2c),
                  sWp = tc::smem_u32(Wp);
   const uint32_t id64 = tc::idesc_bf16(128, 64);
   uint32_t it = 0;          // chunks processed so far by this CTA (ring position)
-  uint32_t done_phase = 0;
+  uint32_t done_phase = 1;
   double dscale[4];         // digit j (0-based) weighs 2^(w0_exp - 7 - 8 j)
 #pragma unroll
   for (int d = 0; d < 4; ++d) dscale[d] = exp2((double)(w0_exp - 7 - 8 * d));
@@ -261,6 +279,14 @@ int launch_fov_f32_to_tiles(const float* d_fov, int A, int F, uint8_t* d_tiles, 
   return 0;
 }
 
+size_t fov_encode_image_bytes() { return FT_W_BYTES; }
+int launch_fov_encode_image(const float* d_blob, const ctrm_weight_offsets_t& off, uint8_t* d_image, cudaStream_t st) {
+  CTRM_CUDA_OK(cudaFuncSetAttribute(fov_encode_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W_BYTES));
+  fov_encode_image_kernel<<<1, FT_THREADS, FT_W_BYTES, st>>>(d_blob, off, d_image);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32_t* d_agent_inst, const uint8_t* d_skip_inst, int A,
                       float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st) {
   if (A <= 0) return 0;
@@ -272,7 +298,7 @@ int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32
   }
   const int grid = n_tiles < 148 ? n_tiles : 148;
   fov_encode_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(d_fov_tiles, m.fov_w0_tiles, fov_n_chunks(m.desc.fov_size), m.fov_w0_exp,
-                                                         d_agent_inst, d_skip_inst, A, m.blob, m.off, d_e_self, d_e_vain,
+                                                         d_agent_inst, d_skip_inst, A, m.fov_img, d_e_self, d_e_vain,
                                                          d_vain_proj, n_tiles);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;

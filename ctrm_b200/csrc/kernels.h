@@ -23,7 +23,10 @@ struct DevModel {
   const uint8_t* prior_img;
   const uint8_t* decode_img;
   const uint8_t* agent_img;
+  const uint8_t* fov_img;
 };
+size_t fov_encode_image_bytes();
+int launch_fov_encode_image(const float* d_blob, const ctrm_weight_offsets_t& off, uint8_t* d_image, cudaStream_t st);
 size_t cvae_prior_image_bytes();
 int launch_cvae_prior_image(const float* d_blob, const ctrm_weight_offsets_t& off, uint8_t* d_image, cudaStream_t st);
 size_t cvae_decode_image_bytes();
