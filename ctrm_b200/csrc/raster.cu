@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
                                                                       const int32_t* __restrict__ agent_inst,
                                                                       const double* __restrict__ pos,
                                                                       const uint8_t* __restrict__ skip_inst, int A, int M, int F_rt,
-                                                                      int n_chunks, int layout, uint8_t* __restrict__ tiles) {
+                                                                      int n_chunks, uint8_t* __restrict__ tiles) {
   extern __shared__ __align__(16) uint8_t rt_smem[];
   const int F = FT > 0 ? FT : F_rt;
   const int FF = F * F, KD = 2 * FF, Kpad = n_chunks * RT_CHUNK;
@@ -281,26 +281,48 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
     live = (skip_inst == nullptr) || (skip_inst[b] == 0);
     if (live) {
       const uint8_t* o = occ + (size_t)b * M * M;
-      const uint16_t* c = ctg + (size_t)a * ctg_field_elems(M, layout);
+      const uint16_t* c = ctg + (size_t)a * ctg_field_elems(M, 1);
       const int cx = grid_cell(pos[2 * a + 0], M), cy = grid_cell(pos[2 * a + 1], M);
       const int buf = (F - 1) / 2;
       const bool centre_in = cx < M && cy < M;
-      const int cc = centre_in ? (int)c[ctg_index(cx, cy, M, layout)] : CTRM_UNREACH;
+      const int cc = centre_in ? (int)c[ctg_index(cx, cy, M, 1)] : CTRM_UNREACH;
       const bool c_reach = cc != CTRM_UNREACH;
-#pragma unroll 4
-      for (int i = lane; i < FF; i += 32) {
-        const int xf = i / F, yf = i - xf * F;
-        const int x = cx - buf + xf, y = cy - buf + yf;
-        uint16_t v0 = 0, v1 = 0;
-        if (centre_in && x >= 0 && x < M && y >= 0 && y < M) {
-          v0 = __ldg(&o[x * M + y]) ? 0 : 0x3F80;  // bf16 1.0
-          const int _c = (int)__ldg(&c[ctg_index(x, y, M, layout)]);
-          v1 = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 0x3F80 : 0;
+      // zero the row (cells outside the map stay 0 in both channels), then visit the crop as (row xf, aligned group of four
+      // y cells): one 8-byte load of the micro-tiled cost field and one 4-byte load of the occupancy row per work item
+      for (int i = lane; i < Kpad / 8; i += 32) reinterpret_cast<uint4*>(t)[i] = make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();
+      if (centre_in) {
+        const int ylo = cy - buf;
+        const int g0 = ylo >> 2;                          // floor(ylo / 4), also for negative ylo
+        const int NG = ((cy + buf) >> 2) - g0 + 1;        // groups per crop row
+        const unsigned inv = 65536u / (unsigned)NG + 1u;  // it / NG == (it * inv) >> 16 for it < F * NG <= 1071
+        const bool occ_vec = (M & 3) == 0;
+        for (int it = lane; it < F * NG; it += 32) {
+          const int xf = (int)(((unsigned)it * inv) >> 16), gy = it - xf * NG;
+          const int x = cx - buf + xf, yb = (g0 + gy) << 2;
+          if (x < 0 || x >= M || yb < 0 || yb >= M) continue;  // yb is a multiple of 4: negative groups are entirely outside
+          const uint2 cw = __ldg(reinterpret_cast<const uint2*>(&c[ctg_index(x, yb, M, 1)]));
+          uint32_t ow;
+          if (occ_vec) {
+            ow = __ldg(reinterpret_cast<const uint32_t*>(&o[x * M + yb]));
+          } else {
+            ow = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (yb + j < M) ow |= (uint32_t)__ldg(&o[x * M + yb + j]) << (8 * j);
+          }
+          const uint32_t cv[4] = {cw.x & 0xFFFFu, cw.x >> 16, cw.y & 0xFFFFu, cw.y >> 16};
+          uint16_t* t0 = t + xf * F + (yb - ylo);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int yf = yb - ylo + j;
+            if (yf < 0 || yf >= F || yb + j >= M) continue;
+            const int _c = (int)cv[j];
+            t0[j] = ((ow >> (8 * j)) & 0xFFu) ? 0 : 0x3F80;  // bf16 1.0
+            t0[FF + j] = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 0x3F80 : 0;
+          }
         }
-        t[i] = v0;
-        t[FF + i] = v1;
       }
-      for (int i = KD + lane; i < Kpad; i += 32) t[i] = 0;
     }
   }
   if (lane == 0) live_row[warp] = live ? 1 : 0;
@@ -385,12 +407,13 @@ int launch_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t
 int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
                             const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, int layout, uint8_t* d_tiles,
                             cudaStream_t st) {
+  if (layout != 1) return ctrm_fail(-1, "fov_raster_tiles reads the micro-tiled cost-to-go layout only");
   if (A <= 0) return 0;
   const size_t smem = (size_t)RT_APB * ((size_t)n_chunks * RT_CHUNK * 2 + 16);
   const int blocks = (A + RT_APB - 1) / RT_APB;
   if (F == 19) {  // the trained configuration
     fov_raster_tiles_kernel<19><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
-                                                                 layout, d_tiles);
+                                                                 d_tiles);
   } else {
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -398,7 +421,7 @@ int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const i
       attr = smem;
     }
     fov_raster_tiles_kernel<0><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
-                                                                layout, d_tiles);
+                                                                d_tiles);
   }
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
