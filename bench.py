@@ -223,8 +223,8 @@ def algorithmic_work(kernel, agent_steps, pair_steps, K, F=19):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload at 1,024
 # instances (profiles/r1_full_step_kernels_b1024_final.md); scaled linearly with the instance count
-NCU_TRAFFIC_B1024 = dict(fov_raster=113.9e6, fov_encode=39.9e6, agent_comm=8.36e6, cvae_prior=7.62e6, cvae_decode=9.99e6,
-                         step=13.4e6)
+NCU_TRAFFIC_B1024 = dict(fov_raster=61.3e6, fov_encode=39.9e6, agent_comm=8.32e6, cvae_prior=7.59e6, cvae_decode=9.98e6,
+                         step=14.6e6)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # FMA issue peak of the CUDA cores at the max SM clock
 
 
@@ -369,9 +369,10 @@ def gpu_arm(args):
                     frac_of_fp32_fma_peak=kernels[dom].get("frac_of_fp32_fma_peak"),
                     note="achieved = algorithmic work of all launches / summed CUDA-event time of the kernel (eager pass over "
                          "the same workload right after the timed region, one CUDA event after every kernel on the driver's "
-                         "stream); traffic = ncu dram bytes per launch at 1,024 instances scaled to this batch; exact-fp32 "
-                         "32-wide MLP kernels are issue-bound on the CUDA cores and are reported against the dense bf16 tensor "
-                         "peak as the contract asks, with the fp32 FMA peak beside it")
+                         "stream); traffic = ncu dram bytes per launch at 1,024 instances scaled to this batch; the MLP kernels run "
+                         "fp32-exact BF16x3 / fixed-point digit products on tcgen05 (6-10 MMAs per useful one) and are bound by "
+                         "their epilogues and load latency, not by the tensor pipe; they are reported against the dense bf16 "
+                         "tensor peak as the contract asks, with the fp32 FMA peak beside it")
 
     if rank != 0:
         if world > 1:
