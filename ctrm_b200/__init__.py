@@ -9,10 +9,10 @@ Everything computes on the GPU through libctrm_b200.so (include/ctrm_b200.h); im
 a GPU, calling it does.
 """
 from .environment import Instance, ObstacleSphere, StaticObjects, continuous_collide_spheres, load_instance  # noqa: F401
-from .roadmap_learned import (RoadmapBuilder, get_builder,  # noqa: F401
+from .roadmap_learned import (PipelinedBuilder, RoadmapBuilder, get_builder,  # noqa: F401
                               get_timed_roadmaps_multiple_paths_with_learned_indicator)
 from .timed_roadmap import CSRRoadmaps, LazyTimedRoadmap, TimedNode, TimedRoadmap  # noqa: F401
 
-__all__ = ["Instance", "ObstacleSphere", "StaticObjects", "continuous_collide_spheres", "load_instance", "RoadmapBuilder",
+__all__ = ["Instance", "ObstacleSphere", "StaticObjects", "continuous_collide_spheres", "load_instance", "RoadmapBuilder", "PipelinedBuilder",
            "get_builder", "get_timed_roadmaps_multiple_paths_with_learned_indicator", "CSRRoadmaps", "LazyTimedRoadmap",
            "TimedNode", "TimedRoadmap"]

@@ -244,6 +244,40 @@ class RoadmapBuilder:
         return self.run(**kw)
 
 
+class PipelinedBuilder:
+    """Roadmaps for a STREAM of instance batches (what scripts/eval.py's joblib loop over instances is, `eval.py:108-111`).
+
+    Two RoadmapBuilder contexts on one GPU take the batches alternately, each from its own host thread (the C-ABI calls
+    release the GIL), so the host packing, the host->device upload and the device->host export of one batch overlap the
+    roll-out kernels of the other; the kernels of the two contexts share the GPU without gain or loss.  Results come back
+    in order.  A yielded CSRRoadmaps is a view of its context's pinned staging buffers: it stays valid until that context
+    finishes its next batch, i.e. while the following batch is being consumed; `.copy()` it to keep it longer."""
+
+    def __init__(self, pred_basename: str, device: int = 0, map_size: Optional[int] = None, depth: int = 2):
+        self.builders = [RoadmapBuilder(pred_basename, device, map_size=map_size) for _ in range(max(1, int(depth)))]
+
+    def close(self):
+        for b in self.builders:
+            b.close()
+
+    def map(self, batches, **kw):
+        """yield one CSRRoadmaps per batch of `batches` (an iterable of sequences of Instance), in order; `kw` as
+        RoadmapBuilder.run.  `instance_id_base` advances by the batch sizes so every instance keeps its own RNG key."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        base = int(kw.pop("instance_id_base", 0))
+        n = len(self.builders)
+        with ThreadPoolExecutor(max_workers=n) as pool:
+            pending = []
+            for i, batch in enumerate(batches):
+                if len(pending) == n:  # the context about to be reused must have delivered its previous result
+                    yield pending.pop(0).result()
+                pending.append(pool.submit(self.builders[i % n].build, batch, instance_id_base=base, **kw))
+                base += len(batch)
+            for f in pending:
+                yield f.result()
+
+
 def get_builder(pred_basename: str, device: int = 0) -> RoadmapBuilder:
     """one cached builder per (weights, device): the reference re-reads the model files on every call
     (learned_sampler.py:53, inside the timed region of scripts/eval.py:57-61); here they stay resident"""

@@ -120,3 +120,25 @@ def test_stress_shape_properties():
         assert np.all(steps > 0) and np.all(steps <= 3 * 96)
     finally:
         bld.close()
+
+
+def test_pipelined_builder_matches_sequential():
+    """PipelinedBuilder.map over three batches == RoadmapBuilder.build batch by batch with the same instance ids"""
+    from ctrm_b200 import PipelinedBuilder, RoadmapBuilder
+
+    prm = dict(N_traj=3, max_T=32, max_attempt=3, merge_distance_rate=0.1)
+    batches = [[_gen(300 + 10 * k + i, 8, 14, 6) for i in range(3 + k)] for k in range(3)]
+    pipe = PipelinedBuilder(WEIGHTS, 0)
+    seq = RoadmapBuilder(WEIGHTS, 0)
+    try:
+        got = [c.copy() for c in pipe.map(batches, seed=5, instance_id_base=100, **prm)]
+        base = 100
+        for k, batch in enumerate(batches):
+            want = seq.build(batch, seed=5, instance_id_base=base, **prm)
+            base += len(batch)
+            assert np.array_equal(got[k].pos.view(np.uint64), want.pos.view(np.uint64))
+            for f in ("layer_ptr", "eptr", "eidx", "n_layers", "cnt_collide"):
+                assert np.array_equal(getattr(got[k], f), getattr(want, f)), (k, f)
+    finally:
+        pipe.close()
+        seq.close()
