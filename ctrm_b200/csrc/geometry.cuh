@@ -15,11 +15,16 @@ __device__ __forceinline__ bool sweep_far(double fx, double fy, double tx, doubl
 __device__ __forceinline__ bool any_obstacle_hit(double fx, double fy, double tx, double ty, double rad,
                                                  const double* __restrict__ obs_xyr, int o0, int o1) {
   bool hit = false;
-  for (int o = o0; o < o1 && !hit; ++o) {
-    double ox = __ldg(&obs_xyr[3 * o + 0]), oy = __ldg(&obs_xyr[3 * o + 1]), orad = __ldg(&obs_xyr[3 * o + 2]);
-    double rs = f64add(rad, orad);
-    if (sweep_far(fx, fy, tx, ty, ox, oy, rs)) continue;
-    hit = sweep_static(fx, fy, tx, ty, ox, oy, rs);
+  // the segment's bounding box once; no early exit, so the obstacle loads of the following iterations are already in
+  // flight while one is tested
+  const double lox = fmin(fx, tx), hix = fmax(fx, tx), loy = fmin(fy, ty), hiy = fmax(fy, ty);
+#pragma unroll 2
+  for (int o = o0; o < o1; ++o) {
+    const double ox = __ldg(&obs_xyr[3 * o + 0]), oy = __ldg(&obs_xyr[3 * o + 1]), orad = __ldg(&obs_xyr[3 * o + 2]);
+    const double rs = f64add(rad, orad);
+    const double R = rs + 1e-9;  // sweep_far, with the box hoisted
+    if (ox < lox - R || ox > hix + R || oy < loy - R || oy > hiy + R) continue;
+    hit = hit || sweep_static(fx, fy, tx, ty, ox, oy, rs);
   }
   return hit;
 }
