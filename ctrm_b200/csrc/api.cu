@@ -903,6 +903,22 @@ extern "C" int ctrm_last_timing(ctrm_ctx* c, float ms[3], int64_t* steps, int64_
 // ------------------------------------------------------------------------------------------------
 // host-buffer wrappers with the pybind11 helpers' call shapes (B = 1); GPU only
 // ------------------------------------------------------------------------------------------------
+// planner
+// ------------------------------------------------------------------------------------------------
+extern "C" int ctrm_plan_prioritized(int B, int A, int L, const int32_t* d_agent_off, const int32_t* d_n_layers,
+                                     const int32_t* d_layer_ptr, const double* d_pos, const int64_t* d_eptr,
+                                     const int32_t* d_eidx, const double* d_goals, const double* d_speeds, const double* d_rads,
+                                     int max_agent_vertices, int32_t* d_paths, double* d_path_pos, int32_t* d_solved,
+                                     int32_t* d_failed_agent, int64_t* d_counters, void* stream) {
+  if (B <= 0 || A <= 0 || L < 2 || !d_agent_off || !d_n_layers || !d_layer_ptr || !d_pos || !d_eptr || !d_eidx || !d_goals ||
+      !d_speeds || !d_rads || max_agent_vertices < 1 || !d_paths || !d_path_pos || !d_solved || !d_failed_agent || !d_counters)
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_plan_prioritized: bad argument");
+  return launch_plan_prioritized(B, L, d_agent_off, d_n_layers, d_layer_ptr, d_pos, d_eptr, d_eidx, d_goals, d_speeds, d_rads,
+                                 max_agent_vertices, A, d_paths, d_solved, d_failed_agent,
+                                 reinterpret_cast<long long*>(d_counters), d_path_pos, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
 extern "C" int ctrm_host_continuous_collide_spheres(const double* from1, const double* to1, double rad1, const double* from2,
                                                     const double* to2, double rad2, int dim, int* out) {
   if (!from1 || !to1 || !from2 || !to2 || !out || (dim != 2 && dim != 3)) return ctrm_fail(CTRM_ERR_ARG, "bad argument");

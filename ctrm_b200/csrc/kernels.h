@@ -120,3 +120,9 @@ int launch_finalize(const Batch& bt, int32_t* d_tfin, cudaStream_t st);
 int launch_csr_count(const Batch& bt, int64_t* d_agent_nv, int64_t* d_agent_ne, int64_t* d_totals, cudaStream_t st);
 int launch_csr_fill(const Batch& bt, const int64_t* d_agent_v0, const int64_t* d_agent_e0, const int64_t* d_totals,
                     int32_t* d_layer_ptr, double* d_pos, int64_t* d_eptr, int32_t* d_eidx, cudaStream_t st);
+
+// prioritized planning over exported CSR roadmaps (plan.cu)
+int launch_plan_prioritized(int B, int L, const int32_t* d_agent_off, const int32_t* d_n_layers, const int32_t* d_layer_ptr,
+                            const double* d_pos, const int64_t* d_eptr, const int32_t* d_eidx, const double* d_goals,
+                            const double* d_speeds, const double* d_rads, int max_nv, int A, int32_t* d_paths, int32_t* d_solved,
+                            int32_t* d_failed_agent, long long* d_counters, double* d_sol_pos, cudaStream_t st);

@@ -228,6 +228,23 @@ class RoadmapBuilder:
         out["eidx"] = out["eidx"][:ne]
         return out
 
+    def plan(self, csr_device: Optional[dict] = None) -> dict:
+        """prioritized planning (planner/prioritized_planning.py:40-101) for every instance of the batch just built, on the
+        device-resident CSR roadmaps: no roadmap ever visits the host.  Returns CUDA tensors: paths [A][L] (vertex index per
+        time step), path_pos [A][L][2], solved [B], failed_agent [B], counters [B][3], and elapsed_ms."""
+        import torch
+
+        from .planner import plan_prioritized_device
+
+        p = self._uploaded
+        d = csr_device if csr_device is not None else self.export_device()
+        dev = d["pos"].device
+        A, B, L = int(p["n_agents"].sum()), len(p["n_agents"]), self._last["max_T"] + 2
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)  # noqa: E731
+        agent_off = up(np.concatenate([[0], np.cumsum(p["n_agents"])]), np.int32)
+        return plan_prioritized_device(B, A, L, agent_off, d["n_layers"], d["layer_ptr"], d["pos"], d["eptr"], d["eidx"],
+                                       up(p["goals"], np.float64), up(p["speeds"], np.float64), up(p["rads"], np.float64))
+
     def read_trace(self):
         """(samples [N_traj][max_T][A][K][3] f32, loc_pred, loc_next [N_traj][max_T][A][2] f64); NaN = not executed"""
         p = self._uploaded

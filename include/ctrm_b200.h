@@ -236,6 +236,23 @@ int ctrm_get_device_view(ctrm_ctx* ctx, ctrm_device_view* out);
  * host-buffer convenience wrappers with the pybind11 modules' exact call shapes (B = 1); they copy in,
  * launch the kernels above on the GPU and copy out.
  * ---------------------------------------------------------------------------------------------- */
+/* ------------------------------------------------------------------------------------------------
+ * Consumer of the roadmaps: replaces PrioritizedPlanning._solve
+ * (planner/prioritized_planning.py:40-101) with its space-time A* (Planner.get_single_agent_path, planner/planner.py:311-384)
+ * and its collision test against earlier agents (collide_dynamic_agents, planner.py:216-263 -> continuousCollideSpheres),
+ * batched over B instances.  All pointers are DEVICE pointers; the roadmaps come in the CSR layout of ctrm_export_csr
+ * (layer_ptr with a fixed stride of L slots per agent).  paths[a][t] = index within V[t] of the vertex agent a occupies at
+ * time t (the goal vertex once arrived; -1 beyond the instance's horizon or when the instance is unsolved, as the reference
+ * clears its solution); path_pos[a][t] the matching coordinates; solved[b] 0/1; failed_agent[b] = first agent without a
+ * path or -1; counters[b] = {cnt_continuous_collide, lowlevel_expanded, lowlevel_explored} of the reference's Result.
+ * max_agent_vertices = largest number of vertices of one agent's roadmap (sizes the per-CTA shared memory). */
+int ctrm_plan_prioritized(int B, int A, int L, const int32_t* d_agent_off /*[B+1]*/, const int32_t* d_n_layers /*[A]*/,
+                          const int32_t* d_layer_ptr /*[A*L+1]*/, const double* d_pos /*[nv][2]*/,
+                          const int64_t* d_eptr /*[nv+1]*/, const int32_t* d_eidx /*[ne]*/, const double* d_goals /*[A][2]*/,
+                          const double* d_speeds /*[A]*/, const double* d_rads /*[A]*/, int max_agent_vertices,
+                          int32_t* d_paths /*[A][L]*/, double* d_path_pos /*[A][L][2]*/, int32_t* d_solved /*[B]*/,
+                          int32_t* d_failed_agent /*[B]*/, int64_t* d_counters /*[B][3]*/, void* stream);
+
 /* sphere_collision_check_wrapper.continuousCollideSpheres(from1,to1,rad1,from2,to2,rad2) -> bool
  * (collision_check.cpp:16-24, :60-67) */
 int ctrm_host_continuous_collide_spheres(const double* from1, const double* to1, double rad1, const double* from2,

@@ -1,0 +1,130 @@
+"""Prioritized planning over timed roadmaps.
+
+CPU: the oracle restatement (oracle/pp_oracle.py) against the fixture written by the UNMODIFIED reference planner
+(oracle/gen_golden_pp.py): an unsolvable case on the reference's own roadmaps and a solved case on N_traj = 25 roadmaps.
+GPU: ctrm_plan_prioritized against the same fixture and, on synthetic batches, against the oracle — chosen vertices,
+solved flags and the planner's counters (collision checks, expanded, explored) must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+import pp_oracle as P
+from conftest import GOLD as GOLDEN, WEIGHTS
+
+KEYS = ("nlayers", "layer_ptr", "pos", "eptr", "eidx")
+
+
+@pytest.fixture(scope="module")
+def pp_gold():
+    return np.load(os.path.join(GOLDEN, "ref_pp_demo.npz"))
+
+
+@pytest.fixture(scope="module")
+def demo():
+    return np.load(os.path.join(GOLDEN, "ref_trace_demo.npz"))
+
+
+def _arrays(z, prefix):
+    return tuple(z[prefix + k] for k in KEYS)
+
+
+def _check(got, z, tag):
+    assert bool(got["solved"]) == bool(z[tag + ".solved"])
+    for i, k in enumerate(("cnt_continuous_collide", "lowlevel_expanded", "lowlevel_explored")):
+        assert int(got[k]) == int(z[f"{tag}.{k}"]), k
+    if bool(z[tag + ".solved"]):
+        assert np.array_equal(np.asarray(got["paths"]), z[tag + ".paths"])
+
+
+def test_oracle_matches_reference_planner_unsolved(pp_gold, demo):
+    got = P.prioritized_planning(demo["starts"], demo["goals"], demo["max_speeds"], demo["rads"], P.FlatRoadmaps(*_arrays(demo, "trm.")))
+    _check(got, pp_gold, "a")
+    assert got["failed_agent"] >= 0 and got["paths"] is None
+
+
+def test_oracle_matches_reference_planner_solved(pp_gold, demo):
+    trms = P.FlatRoadmaps(*_arrays(pp_gold, "b.trm."))
+    got = P.prioritized_planning(demo["starts"], demo["goals"], demo["max_speeds"], demo["rads"], trms)
+    _check(got, pp_gold, "b")
+    pos = P.path_positions(trms, got["paths"])
+    costs = [P.get_cost(pos[a], demo["goals"][a], float(pp_gold["goal_rads"][a])) for a in range(len(pos))]
+    assert sum(costs) == int(pp_gold["b.sum_of_costs"]) and max(costs) == int(pp_gold["b.maximum_costs"])
+    assert abs(sum(P.get_travel_dist(q) for q in pos) - float(pp_gold["b.sum_of_travel_dists"])) < 1e-9
+
+
+def _strided(arrays):
+    """oracle/golden layout (layer_ptr over existing layers only) -> the C-ABI's fixed stride of L slots per agent"""
+    nlayers, layer_ptr, pos, eptr, eidx = arrays
+    L = int(np.max(nlayers)) + 1
+    lp = np.zeros(len(nlayers) * L + 1, dtype=np.int32)
+    k = 0
+    for a, n in enumerate(nlayers):
+        n = int(n)
+        lp[a * L:a * L + n + 1] = layer_ptr[k:k + n + 1]
+        lp[a * L + n + 1:(a + 1) * L + 1] = layer_ptr[k + n]
+        k += n
+    return L, lp
+
+
+def _gpu_solve(arrays, starts, goals, speeds, rads, agent_off=None):
+    from ctrm_b200.planner import plan_prioritized_arrays
+
+    L, lp = _strided(arrays)
+    N = len(arrays[0])
+    off = np.array([0, N], dtype=np.int32) if agent_off is None else agent_off
+    return plan_prioritized_arrays(off, L, arrays[0], lp, arrays[2], arrays[3], arrays[4], goals, speeds, rads), L
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,src", [("a", "demo"), ("b", "gold")])
+def test_gpu_planner_matches_reference(pp_gold, demo, tag, src):
+    arrays = _arrays(demo, "trm.") if src == "demo" else _arrays(pp_gold, "b.trm.")
+    r, L = _gpu_solve(arrays, demo["starts"], demo["goals"], demo["max_speeds"], demo["rads"])
+    T = int(arrays[0][0]) - 1
+    got = dict(solved=r["solved"][0], cnt_continuous_collide=r["counters"][0, 0], lowlevel_expanded=r["counters"][0, 1],
+               lowlevel_explored=r["counters"][0, 2], paths=r["paths"][:, :T + 1])
+    _check(got, pp_gold, tag)
+    if not got["solved"]:
+        assert r["failed_agent"][0] >= 0 and np.all(r["paths"] == -1)
+
+
+@pytest.mark.gpu
+def test_gpu_planner_batch_vs_oracle_and_drop_in_class():
+    """roadmaps built by the GPU for a mixed batch, planned on the device, checked instance by instance against the oracle;
+    then the reference-shaped class on one instance"""
+    from ctrm_b200 import PrioritizedPlanning, RoadmapBuilder
+    from ctrm_b200.environment import generate_ins_2d_with_obs_hetero_nonfix_agents as gen
+    from helpers import csr_to_arrays
+
+    specs = [(71, 6, 9, 4), (72, 10, 14, 8), (73, 3, 4, 0), (74, 18, 20, 10)]
+    instances = [gen(lo, hi, "0.03125", "0.015625", o, 0.05, 0.08, rng=np.random.RandomState(s)) for s, lo, hi, o in specs]
+    bld = RoadmapBuilder(WEIGHTS, 0)
+    try:
+        csr = bld.build(instances, seed=9, N_traj=8, max_T=48, max_attempt=3, merge_distance_rate=0.1).copy()
+        r = bld.plan()
+        paths, solved, counters = r["paths"].cpu().numpy(), r["solved"].cpu().numpy(), r["counters"].cpu().numpy()
+        a0 = 0
+        for b, ins in enumerate(instances):
+            starts, goals, speeds, rads, _ = ins.arrays()
+            N = ins.num_agents
+            want = P.prioritized_planning(starts, goals, speeds, rads, P.FlatRoadmaps(*csr_to_arrays(csr, b)))
+            assert bool(solved[b]) == want["solved"], b
+            assert [int(x) for x in counters[b]] == [want["cnt_continuous_collide"], want["lowlevel_expanded"],
+                                                      want["lowlevel_explored"]], b
+            if want["solved"]:
+                T = want["paths"].shape[1] - 1
+                assert np.array_equal(paths[a0:a0 + N, :T + 1], want["paths"]), b
+            a0 += N
+        assert solved.sum() >= 2
+        # the reference-shaped class, fed with the lazy TimedRoadmap views of instance 1
+        b = int(np.nonzero(solved)[0][0])
+        res = PrioritizedPlanning(instances[b], csr.timed_roadmaps(b)).solve()
+        assert res.solved and len(res.paths) == instances[b].num_agents
+        for i, path in enumerate(res.paths):
+            assert np.array_equal(path[0].pos, instances[b].starts[i]) and np.array_equal(path[-1].pos, instances[b].goals[i])
+            d = np.diff(np.stack([v.pos for v in path]), axis=0)
+            assert np.all(np.linalg.norm(d, axis=1) <= instances[b].max_speeds[i] * (1 + 1e-12))
+        assert res.lowlevel_explored == int(counters[b][2]) and res.sum_of_costs > 0
+    finally:
+        bld.close()
