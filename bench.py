@@ -386,6 +386,26 @@ def gpu_arm(args):
                          "their epilogues and load latency, not by the tensor pipe; they are reported against the dense bf16 "
                          "tensor peak as the contract asks, with the fp32 FMA peak beside it")
 
+    # ---- the roadmaps' consumer: prioritized planning of the whole batch on the device-resident CSR
+    csr_dev = builder.export_device()
+    builder.plan(csr_dev)
+    pr = builder.plan(csr_dev)
+    planner = dict(ms_per_batch=pr["elapsed_ms"], instances=B, instances_per_s=B / (pr["elapsed_ms"] * 1e-3),
+                   solved_frac=float(pr["solved"].float().mean().item()),
+                   collision_checks=int(pr["counters"][:, 0].sum().item()), explored=int(pr["counters"][:, 2].sum().item()),
+                   note="ctrm_plan_prioritized on this rank's last batch, CUDA events; not part of `value`")
+    pp_host = None
+    if rank == 0 and world == 1 and not args.no_cpu:  # one SOLVED instance of that batch, kept for the planner's CPU leg
+        from ctrm_b200.planner import _flatten_trms
+
+        sol = pr["solved"].cpu().numpy()
+        pp_b = int(np.nonzero(sol)[0][0]) if sol.any() else 0
+        host_csr = builder.export()
+        pp_host = [np.array(x) for x in _flatten_trms(host_csr.timed_roadmaps(pp_b))[1:]]
+        pp_L = host_csr.L
+        planner["cpu_port_instance_explored"] = int(pr["counters"][pp_b, 2].item())
+        del host_csr
+    del csr_dev, pr
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -398,6 +418,17 @@ def gpu_arm(args):
                    sample=f"{cores} instances of the same workload at full N_traj=25, one process per core, oracle port "
                           f"(numpy + torch-CPU, 1 thread each), {r['seconds']:.1f} s wall",
                    instances_per_s=r["instances"] / r["seconds"])
+        # planner, CPU port (oracle/pp_oracle.py), one instance of the same workload on one core
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pp_oracle
+
+        n_layers, lp, pos, eptr, eidx = pp_host
+        lp_flat = np.concatenate([lp[a * pp_L:a * pp_L + int(n)] for a, n in enumerate(n_layers)] + [lp[-1:]])
+        ins0 = instances[pp_b].arrays()
+        t0 = time.perf_counter()
+        got = pp_oracle.prioritized_planning(ins0[0], ins0[1], ins0[2], ins0[3], pp_oracle.FlatRoadmaps(n_layers, lp_flat, pos, eptr, eidx))
+        planner["cpu_port_s_per_instance"] = time.perf_counter() - t0
+        planner["cpu_port_solved"] = bool(got["solved"])
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64+f32",
                 data="synthetic",
@@ -410,7 +441,7 @@ def gpu_arm(args):
                 clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                         ms_per_step=e2e_t[0].item(), steps=e2e_steps,
                                         api="PipelinedBuilder.map (2 contexts, copies of one batch overlap the other's kernels)"),
-                gpu_launches=int(launches_all), roofline=roofline, kernels=kernels, cpu_baseline=cpu)
+                gpu_launches=int(launches_all), roofline=roofline, kernels=kernels, cpu_baseline=cpu, planner=planner)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
