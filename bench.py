@@ -238,6 +238,11 @@ def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the JSON result: anything a library prints there meanwhile (NCCL's version banner)
+    # is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: ctrm_b200 has no CPU fallback")
     torch.cuda.set_device(local)
@@ -442,7 +447,10 @@ def gpu_arm(args):
                                         ms_per_step=e2e_t[0].item(), steps=e2e_steps,
                                         api="PipelinedBuilder.map (2 contexts, copies of one batch overlap the other's kernels)"),
                 gpu_launches=int(launches_all), roofline=roofline, kernels=kernels, cpu_baseline=cpu, planner=planner)
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
