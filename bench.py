@@ -461,7 +461,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("CTRM_BENCH_BATCH", "2048")), help="instances per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("CTRM_BENCH_BATCH", "2960")), help="instances per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-worker", action="store_true")
     ap.add_argument("--nproc", type=int, default=1)

@@ -114,9 +114,12 @@ __global__ void __launch_bounds__(AT_THREADS, 4) agent_comm_tc_kernel(Batch bt, 
   float* mrow = msg_base + (size_t)(wq * G + gg) * P * 33;
   const bool p_pow2 = (P & (P - 1)) == 0;
 
+  const int n_rows = bt.live_agent != nullptr ? *bt.n_live : bt.A;  // agents of the unfinished instances, or all
+  n_tiles = min(n_tiles, (n_rows + 4 * G - 1) / (4 * G));
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int a = (tile * 4 + wq) * G + g;
-    bool active = g < G && a < bt.A;
+    const int arow = (tile * 4 + wq) * G + g;
+    bool active = g < G && arow < n_rows;
+    const int a = active ? (bt.live_agent != nullptr ? bt.live_agent[arow] : arow) : 0;
     int b = 0;
     if (active) {
       b = bt.agent_inst[a];

@@ -406,6 +406,9 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&bt.steps_done, (size_t)B));
   CHECK(ar.alloc(&bt.arrive_cnt, (size_t)B));
   CHECK(ar.alloc(&bt.inst_pack, (size_t)8 * B));
+  CHECK(ar.alloc(&bt.live_agent, (size_t)A));
+  CHECK(ar.alloc(&bt.n_live, (size_t)1));
+  CHECK(ar.alloc(&bt.live_off, (size_t)B));
   CHECK(ar.alloc(&bt.agent_pack, (size_t)6 * A));
   CHECK(ar.alloc(&bt.nlayers, (size_t)A));
   CHECK(ar.alloc(&c->d_tfin, (size_t)B));
@@ -532,8 +535,10 @@ extern "C" int ctrm_encode_features(ctrm_ctx* c, const float* d_fov, const doubl
   cudaStream_t st = (cudaStream_t)stream;
   Batch bt = c->bt;
   bt.done = nullptr;
+  bt.live_agent = nullptr;
   CHECK(launch_fov_f32_to_tiles(d_fov, bt.A, bt.F, bt.fov_tiles, st));
-  CHECK(launch_fov_encode(c->model, bt.fov_tiles, bt.agent_inst, nullptr, bt.A, bt.e_self, bt.e_vain, bt.vain_proj, st));
+  CHECK(launch_fov_encode(c->model, bt.fov_tiles, bt.agent_inst, nullptr, bt.A, bt.e_self, bt.e_vain, bt.vain_proj, nullptr, nullptr,
+                          st));
   CHECK(launch_agent_comm(c->model, bt, d_cur, d_prev, bt.e_self, bt.vain_proj, d_X, st));
   return 0;
 }
@@ -544,6 +549,7 @@ extern "C" int ctrm_cvae_sample(ctrm_ctx* c, const float* d_X, const float* d_un
   if (!c->have_weights || !c->have_batch) return ctrm_fail(CTRM_ERR_STATE, "ctrm_cvae_sample: weights and instances first");
   Batch bt = c->bt;
   bt.done = nullptr;
+  bt.live_agent = nullptr;
   bt.K = K;
   bt.dim_ind = c->model.desc.dim_ind;
   bt.seed_lo = (uint32_t)(seed & 0xFFFFFFFFu);
@@ -645,9 +651,10 @@ static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, 
   if (prof) CTRM_CUDA_OK(cudaEventRecord(prof->at(pstep, 0), st));
   if (nn) {
     CHECK(launch_fov_raster_tiles(bt.occ, bt.ctg, bt.agent_inst, bt.cur, bt.done, bt.A, bt.M, bt.F, fov_n_chunks(bt.F), 1,
-                                  bt.fov_tiles, st));
+                                  bt.fov_tiles, bt.live_agent, bt.n_live, st));
     CHECK(mark(KID_FOV_RASTER));
-    CHECK(launch_fov_encode(c->model, bt.fov_tiles, bt.agent_inst, bt.done, bt.A, bt.e_self, nullptr, bt.vain_proj, st));
+    CHECK(launch_fov_encode(c->model, bt.fov_tiles, bt.agent_inst, bt.done, bt.A, bt.e_self, nullptr, bt.vain_proj,
+                            bt.live_agent, bt.n_live, st));
     CHECK(mark(KID_FOV_ENCODE));
     CHECK(launch_agent_comm(c->model, bt, bt.cur, bt.prev, bt.e_self, bt.vain_proj, bt.X, st));
     CHECK(mark(KID_AGENT_COMM));
@@ -748,6 +755,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   // capture one step as a CUDA graph, then replay it; n_done is polled every `chunk` replays.
   // profile mode runs the same kernels eagerly with an event after each one (per-kernel durations).
   const int chunk = 32;
+  int last_done = 0;
   int per_step = 0;
   int64_t steps = 0;
   int rc = 0;
@@ -775,6 +783,11 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
       if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
       if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "roll-out step loop"); break; }
       if (*c->h_ndone >= bt.B) break;
+      if (*c->h_ndone > last_done) {  // instances finished during this chunk: drop their rows
+        last_done = *c->h_ndone;
+        if ((rc = launch_compact_live(bt, st))) break;
+        launches += 2;
+      }
     }
     cudaGraphExecDestroy(gexec);
     cudaGraphDestroy(graph);
@@ -793,6 +806,11 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
       if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "roll-out step loop (profile)"); break; }
       rc = prof.flush(n, ran);
       if (*c->h_ndone >= bt.B) break;
+      if (!rc && *c->h_ndone > last_done) {
+        last_done = *c->h_ndone;
+        rc = launch_compact_live(bt, st);
+        launches += 2;
+      }
     }
     for (int k = 0; k < KID_STEP_COUNT; ++k) { c->kernel_ms[k] = prof.ms[k]; c->kernel_n[k] = prof.n[k]; }
     prof.destroy();

@@ -136,9 +136,12 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
     for (int q = 0; q < 2; ++q) tc::store_split8(Xt, Xt + PR_H_PART, Xt + 2 * PR_H_PART, r, 16 * half + q * 8, 32, h + q * 8);
   };
 
+  const int n_arows = bt.live_agent != nullptr ? *bt.n_live : bt.A;  // agents of the unfinished instances, or all
+  n_tiles = min(n_tiles, (n_arows + 127) >> 7);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int a = tile * 128 + r;
-    bool live = a < bt.A;
+    const int arow = tile * 128 + r;
+    bool live = arow < n_arows;
+    const int a = live ? (bt.live_agent != nullptr ? bt.live_agent[arow] : arow) : 0;
     if (live) live = !(bt.done != nullptr && bt.done[bt.agent_inst[a]]);
     if (!__syncthreads_or(live)) continue;
     {  // X row -> three bf16 parts (K padded 72 -> 80 with zeros); each half stages five of the ten 8-wide chunks
@@ -378,7 +381,9 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
   const uint32_t sA = tc::smem_u32(At), sW0 = tc::smem_u32(W0t), sW1 = tc::smem_u32(W1t);
   uint32_t phase = 1;
   const float eps = 1.1920928955078125e-07f;
-  const long long n_rows = (long long)bt.A * K;
+  const int n_arows = bt.live_agent != nullptr ? *bt.n_live : bt.A;  // agents of the unfinished instances, or all
+  const long long n_rows = (long long)n_arows * K;
+  n_tiles = (int)min((long long)n_tiles, (n_rows + 127) >> 7);
   // accumulator g (digit index sum, 0-based) carries weight 256^-(g+1) * 2^(w0_exp - 7)
   double acc_scale[4];
 #pragma unroll
@@ -388,9 +393,12 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     const long long row = (long long)tile * 128 + r;
     bool live = row < n_rows;
     int a = 0, k = 0, b = 0;
+    long long orow = 0;  // row of this (agent, copy) in the agent-major output / uniform tables
     if (live) {
-      a = (int)(row / K);
-      k = (int)(row - (long long)a * K);
+      const int arow = (int)(row / K);
+      k = (int)(row - (long long)arow * K);
+      a = bt.live_agent != nullptr ? bt.live_agent[arow] : arow;
+      orow = (long long)a * K + k;
       b = bt.agent_inst[a];
       live = !(bt.done != nullptr && bt.done[b]);
     }
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
       const float* urow = nullptr;
       uint32_t c0 = 0, c1 = 0, c2 = 0;
       if (uniforms != nullptr) {
-        urow = uniforms + (size_t)row * 64;
+        urow = uniforms + (size_t)orow * 64;
       } else {
         const int N = bt.agent_off[b + 1] - bt.agent_off[b], il = a - bt.agent_off[b];
         const int kt = use_state_kt ? bt.k_traj[b] : kt_fixed, tt = use_state_kt ? bt.t[b] : t_fixed;
@@ -534,7 +542,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
       __syncthreads();  // also: every TMEM / shared-memory read of this tile is done before the next tile overwrites them
       tc::fence_after_sync();
       if (half == 0 && live) {
-        float* out = samples + (size_t)row * 3;
+        float* out = samples + (size_t)orow * 3;
         out[0] = (B2[0] + o0) + red3[r * 4 + 0];
         out[1] = (B2[1] + o1) + red3[r * 4 + 1];
         out[2] = (B2[2] + o2) + red3[r * 4 + 2];

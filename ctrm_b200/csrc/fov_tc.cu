@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
                                                                    const uint8_t* __restrict__ skip_inst, int A,
                                                                    const uint8_t* __restrict__ w_image,
                                                                    float* __restrict__ e_self, float* __restrict__ e_vain,
-                                                                   float* __restrict__ vain_proj, int n_tiles) {
+                                                                   float* __restrict__ vain_proj, int n_tiles,
+                                                                   const int32_t* __restrict__ live_agent,
+                                                                   const int32_t* __restrict__ n_live) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage0 = smem;                              // stage s: A chunk | W chunk (4 digits)
   uint8_t* W1c = smem + FT_STAGES * FT_STAGE;                  // blockdiag(self.mlp.2, vain.mlp.2)  [64 x 64] x 3
@@ -161,9 +163,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
     tc::fence_after_sync();
   };
 
+  const int n_rows = live_agent != nullptr ? *n_live : A;
+  n_tiles = min(n_tiles, (n_rows + 127) >> 7);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int a = tile * 128 + r;
-    bool live = a < A;
+    const int row = tile * 128 + r;  // row of the operand tile; its agent comes from the live list when there is one
+    bool live = row < n_rows;
+    const int a = live ? (live_agent != nullptr ? live_agent[row] : row) : 0;
     if (live && skip_inst != nullptr) live = skip_inst[agent_inst[a]] == 0;
     if (!__syncthreads_or(live)) continue;
     // ---- layer 0: streamed exact digit products
@@ -288,7 +293,8 @@ int launch_fov_encode_image(const float* d_blob, const ctrm_weight_offsets_t& of
 }
 
 int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32_t* d_agent_inst, const uint8_t* d_skip_inst, int A,
-                      float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st) {
+                      float* d_e_self, float* d_e_vain, float* d_vain_proj, const int32_t* d_live_agent,
+                      const int32_t* d_n_live, cudaStream_t st) {
   if (A <= 0) return 0;
   const int n_tiles = (A + 127) / 128;
   static bool attr = false;
@@ -299,7 +305,7 @@ int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32
   const int grid = n_tiles < 148 ? n_tiles : 148;
   fov_encode_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(d_fov_tiles, m.fov_w0_tiles, fov_n_chunks(m.desc.fov_size), m.fov_w0_exp,
                                                          d_agent_inst, d_skip_inst, A, m.fov_img, d_e_self, d_e_vain,
-                                                         d_vain_proj, n_tiles);
+                                                         d_vain_proj, n_tiles, d_live_agent, d_n_live);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -54,6 +54,11 @@ struct Batch {
   int32_t* steps_done;                  // [B] executed roll-out steps (bench accounting)
   int32_t* arrive_cnt;                  // [B] warps of the instance that finished the current step
   int32_t* inst_pack;                   // [B][8] {done, t, k_traj, makespan, agent_off, n_agents, obs_off, n_obs}
+  // rows of the per-step kernels: agents of the UNFINISHED instances, instance-contiguous, rebuilt between graph chunks so that
+  // the tile kernels do not drag the dead rows of a lock-step batch's tail along (nullptr = identity over all A agents)
+  int32_t* live_agent;                  // [A]
+  int32_t* n_live;                      // [1] number of rows
+  int32_t* live_off;                    // [B] scratch: first row of an unfinished instance
   double* agent_pack;                   // [A][6] {goal x, goal y, speed, speed^2, merge_distance^2, rad}
   // per-step tensors
   uint8_t* fov_tiles;  // bf16 operand tiles [ceil(A/128)][n_chunks][128 x 96]
@@ -98,14 +103,17 @@ int launch_collide_pairs(const double* f1, const double* t1, const double* r1, c
 
 int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
                             const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, int layout, uint8_t* d_tiles,
-                            cudaStream_t st);
+                            const int32_t* d_live_agent, const int32_t* d_n_live, cudaStream_t st);
 int fov_n_chunks(int F);
 size_t fov_tiles_bytes(int A, int F);
 size_t fov_w0_tiles_bytes(int F);
 int launch_fov_w0_prep(const float* d_w0, int F, int w0_exp, uint8_t* d_out, cudaStream_t st);
 int launch_fov_f32_to_tiles(const float* d_fov, int A, int F, uint8_t* d_tiles, cudaStream_t st);
 int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32_t* d_agent_inst, const uint8_t* d_skip_inst,
-                      int A, float* d_e_self, float* d_e_vain, float* d_vain_proj, cudaStream_t st);
+                      int A, float* d_e_self, float* d_e_vain, float* d_vain_proj, const int32_t* d_live_agent,
+                      const int32_t* d_n_live, cudaStream_t st);
+// rebuild Batch::live_agent / n_live from the instances' done flags (rollout.cu)
+int launch_compact_live(const Batch& bt, cudaStream_t st);
 int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, const double* d_prev, const float* d_e_self,
                       const float* d_vain_proj, float* d_X, cudaStream_t st);
 int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,

@@ -281,14 +281,21 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
                                                                       const int32_t* __restrict__ agent_inst,
                                                                       const double* __restrict__ pos,
                                                                       const uint8_t* __restrict__ skip_inst, int A, int M, int F_rt,
-                                                                      int n_chunks, uint8_t* __restrict__ tiles) {
+                                                                      int n_chunks, uint8_t* __restrict__ tiles,
+                                                                      const int32_t* __restrict__ live_agent,
+                                                                      const int32_t* __restrict__ n_live) {
   extern __shared__ __align__(16) uint8_t rt_smem[];
   const int F = FT > 0 ? FT : F_rt;
   const int FF = F * F, KD = 2 * FF, Kpad = n_chunks * RT_CHUNK;
   const int row_bytes = Kpad * 2 + 16;  // +16: rows land in different banks for the 16-byte read-out
   __shared__ int live_row[RT_APB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a0 = blockIdx.x * RT_APB, a = a0 + warp;
+  // rows: agents of the unfinished instances (live_agent, rebuilt between graph chunks) or all agents
+  const int n_rows = live_agent != nullptr ? *n_live : A;
+  const int a0 = blockIdx.x * RT_APB;  // first ROW of this block
+  if (a0 >= n_rows) return;
+  const int row = a0 + warp;
+  const int a = row < n_rows ? (live_agent != nullptr ? live_agent[row] : row) : A;
   uint16_t* t = reinterpret_cast<uint16_t*>(rt_smem + (size_t)warp * row_bytes);
   bool live = false;
   if (a < A) {
@@ -421,14 +428,14 @@ int launch_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t
 
 int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,
                             const uint8_t* d_skip_inst, int A, int M, int F, int n_chunks, int layout, uint8_t* d_tiles,
-                            cudaStream_t st) {
+                            const int32_t* d_live_agent, const int32_t* d_n_live, cudaStream_t st) {
   if (layout != 1) return ctrm_fail(-1, "fov_raster_tiles reads the micro-tiled cost-to-go layout only");
   if (A <= 0) return 0;
   const size_t smem = (size_t)RT_APB * ((size_t)n_chunks * RT_CHUNK * 2 + 16);
   const int blocks = (A + RT_APB - 1) / RT_APB;
   if (F == 19) {  // the trained configuration
     fov_raster_tiles_kernel<19><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
-                                                                 d_tiles);
+                                                                 d_tiles, d_live_agent, d_n_live);
   } else {
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -436,7 +443,7 @@ int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const i
       attr = smem;
     }
     fov_raster_tiles_kernel<0><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
-                                                                d_tiles);
+                                                                d_tiles, d_live_agent, d_n_live);
   }
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;

@@ -24,6 +24,7 @@ __global__ void rollout_init_kernel(Batch bt) {
     bt.prev[2 * i] = sx; bt.prev[2 * i + 1] = sy;
     bt.nxt[2 * i] = sx; bt.nxt[2 * i + 1] = sy;
     bt.arrived[i] = 0;
+    if (bt.live_agent != nullptr) bt.live_agent[i] = i;
     double* ap = bt.agent_pack + 6 * (size_t)i;  // {goal x, goal y, speed, speed^2, merge_distance^2, rad}
     ap[0] = bt.goals[2 * i]; ap[1] = bt.goals[2 * i + 1]; ap[2] = bt.speeds[i]; ap[3] = bt.speeds2[i];
     ap[4] = bt.merge2[i]; ap[5] = bt.rads[i];
@@ -46,7 +47,65 @@ __global__ void rollout_init_kernel(Batch bt) {
     ip[4] = bt.agent_off[i]; ip[5] = bt.agent_off[i + 1] - bt.agent_off[i];
     ip[6] = bt.obs_off[i]; ip[7] = bt.obs_off[i + 1] - bt.obs_off[i];
   }
-  if (i == 0) *bt.n_done = (bt.N_traj <= 0) ? bt.B : 0;
+  if (i == 0) {
+    *bt.n_done = (bt.N_traj <= 0) ? bt.B : 0;
+    if (bt.n_live != nullptr) *bt.n_live = bt.A;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// live rows: the agents of the unfinished instances, in instance order.  Every roll-out ends at its own time, so from
+// about two thirds of the way a lock-step batch is a thinning, scattered set of instances; the per-step kernels index
+// their rows through this list, which keeps their tiles full.  Rebuilt between graph chunks (two tiny launches).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) live_scan_kernel(Batch bt) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < bt.B; base += 1024) {
+    const int b = base + threadIdx.x;
+    const int n = (b < bt.B && !bt.done[b]) ? bt.agent_off[b + 1] - bt.agent_off[b] : 0;
+    int x = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+        if (lane >= d) w += y;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const int excl = x - n + (warp > 0 ? wsum[warp - 1] : 0) + carry;
+    if (b < bt.B) bt.live_off[b] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + n;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *bt.n_live = carry;
+}
+__global__ void live_scatter_kernel(Batch bt) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= bt.A) return;
+  const int b = bt.agent_inst[a];
+  if (!bt.done[b]) bt.live_agent[bt.live_off[b] + (a - bt.agent_off[b])] = a;
+}
+int launch_compact_live(const Batch& bt, cudaStream_t st) {
+  if (bt.A <= 0 || bt.live_agent == nullptr) return 0;
+  live_scan_kernel<<<1, 1024, 0, st>>>(bt);
+  CTRM_CUDA_OK(cudaGetLastError());
+  live_scatter_kernel<<<(bt.A + 255) / 256, 256, 0, st>>>(bt);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 // Per-warp context of one agent-step: the instance state and the agent's constants arrive in a few wide loads
@@ -432,9 +491,10 @@ template <int W>
 __global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
   __shared__ double s_obs[RO_WARPS][3 * RO_OBS_MAX];
   const int warp = threadIdx.x >> 5;
-  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (a >= bt.A) return;
+  if (row >= (bt.live_agent != nullptr ? *bt.n_live : bt.A)) return;
+  const int a = bt.live_agent != nullptr ? bt.live_agent[row] : row;
   StepCtx sc;
   sc.b = bt.agent_inst[a];
   const int4 p0 = *reinterpret_cast<const int4*>(bt.inst_pack + 8 * sc.b);
