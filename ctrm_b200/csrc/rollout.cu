@@ -170,11 +170,16 @@ __device__ __forceinline__ unsigned int select_agent(const Batch& bt, const Step
   bool found = false;
   double lx = cx, ly = cy;  // fallback of sample_uniform_i: stay (learned_sampler.py:145)
   unsigned int count = 0;
-  for (int g0 = 0; g0 < C && !found; g0 += 32) {
+  // the reference scans the candidates in order and stops at the first valid one: the learned candidates are evaluated
+  // first and the random-walk ones (Philox + sin/cos in fp64) only when none of them survives — the draws are keyed, not
+  // streamed, so skipping them changes nothing
+  for (int phase = 0; phase < 2 && !found; ++phase) {
+   const int c_lo = phase == 0 ? 0 : nL, c_hi = phase == 0 ? nL : C;
+   for (int g0 = c_lo; g0 < c_hi && !found; g0 += 32) {
     const int c = g0 + lane;
     double x = cx, y = cy;
     bool pre = false;
-    if (c < C) {
+    if (c < c_hi) {
       if (c < nL) {
         const float* s3 = (bt.tab_teacher != nullptr) ? bt.tab_teacher + ((si * bt.A + a) * (size_t)bt.K + c) * 3
                                                       : bt.samples + ((size_t)a * bt.K + c) * 3;
@@ -228,6 +233,7 @@ __device__ __forceinline__ unsigned int select_agent(const Batch& bt, const Step
     } else {
       count += __popc(pre_mask);
     }
+   }
   }
   if (lane == 0 && bt.tr_loc_pred != nullptr) {
     bt.tr_loc_pred[2 * (si * bt.A + a)] = lx;
