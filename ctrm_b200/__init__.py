@@ -5,6 +5,7 @@ Public surface (mirrors the reference's names for this path):
   ctrm_b200.environment.Instance / ObstacleSphere / StaticObjects / continuous_collide_spheres
   ctrm_b200.timed_roadmap.TimedNode / TimedRoadmap / CSRRoadmaps
   ctrm_b200.planner.PrioritizedPlanning / Result   (the roadmaps' consumer)
+  ctrm_b200.dataset.demonstration_features          (training-time input features)
   ctrm_b200.shims.{sphere_collision_check_wrapper, cost_to_go_wrapper}   pybind11-compatible modules
 Everything computes on the GPU through libctrm_b200.so (include/ctrm_b200.h); importing the package does not need
 a GPU, calling it does.

@@ -921,6 +921,16 @@ extern "C" int ctrm_last_timing(ctrm_ctx* c, float ms[3], int64_t* steps, int64_
 // ------------------------------------------------------------------------------------------------
 // host-buffer wrappers with the pybind11 helpers' call shapes (B = 1); GPU only
 // ------------------------------------------------------------------------------------------------
+// training-time features
+// ------------------------------------------------------------------------------------------------
+extern "C" int ctrm_others_info(const double* d_cur, const double* d_goals, const double* d_prev, const double* d_rads,
+                                const double* d_speeds, int T, int N, float* d_info, float* d_self_info, void* stream) {
+  if (T <= 0 || N <= 0 || !d_cur || !d_goals || !d_prev || !d_rads || !d_speeds || !d_info)
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_others_info: bad argument");
+  return launch_others_info(d_cur, d_goals, d_prev, d_rads, d_speeds, T, N, d_info, d_self_info, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
 // planner
 // ------------------------------------------------------------------------------------------------
 extern "C" int ctrm_plan_prioritized(int B, int A, int L, const int32_t* d_agent_off, const int32_t* d_n_layers,

@@ -134,3 +134,7 @@ int launch_plan_prioritized(int B, int L, const int32_t* d_agent_off, const int3
                             const double* d_pos, const int64_t* d_eptr, const int32_t* d_eidx, const double* d_goals,
                             const double* d_speeds, const double* d_rads, int max_nv, int A, int32_t* d_paths, int32_t* d_solved,
                             int32_t* d_failed_agent, long long* d_counters, double* d_sol_pos, cudaStream_t st);
+
+// training-time pairwise features for T time steps (features.cu)
+int launch_others_info(const double* d_cur, const double* d_goals, const double* d_prev, const double* d_rads,
+                       const double* d_speeds, int T, int N, float* d_info, float* d_self, cudaStream_t st);

@@ -236,6 +236,14 @@ int ctrm_get_device_view(ctrm_ctx* ctx, ctrm_device_view* out);
  * host-buffer convenience wrappers with the pybind11 modules' exact call shapes (B = 1); they copy in,
  * launch the kernels above on the GPU and copy out.
  * ---------------------------------------------------------------------------------------------- */
+/* Training-time pairwise features: replaces numba get_arr_others_info (learning/compiled.py:30-97)
+ * and get_self_info (compiled.py:100-125) as Dataset.map_instance_to_tensor calls them (learning/dataset.py:135-160) for all T
+ * time steps of a demonstration: info[t][i*N + j][0:11] float32 (float64 arithmetic, one final cast, bit-exact),
+ * self_info[t][i][0:8] (optional) = columns 3..10 of row (i, i).  The FOV half of that function is ctrm_fov_raster. */
+int ctrm_others_info(const double* d_cur /*[T][N][2]*/, const double* d_goals /*[N][2]*/, const double* d_prev /*[T][N][2]*/,
+                     const double* d_rads /*[N]*/, const double* d_speeds /*[N]*/, int T, int N,
+                     float* d_info /*[T][N*N][11]*/, float* d_self_info /*[T][N][8] or NULL*/, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Consumer of the roadmaps: replaces PrioritizedPlanning._solve
  * (planner/prioritized_planning.py:40-101) with its space-time A* (Planner.get_single_agent_path, planner/planner.py:311-384)

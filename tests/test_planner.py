@@ -128,3 +128,35 @@ def test_gpu_planner_batch_vs_oracle_and_drop_in_class():
         assert res.lowlevel_explored == int(counters[b][2]) and res.sum_of_costs > 0
     finally:
         bld.close()
+
+
+@pytest.mark.gpu
+def test_demonstration_features_vs_oracle():
+    """FOV / others_info / self_info of a planned demonstration == the oracle's, bit for bit"""
+    import ctrm_oracle as O
+    from ctrm_b200 import PrioritizedPlanning, RoadmapBuilder
+    from ctrm_b200.dataset import demonstration_features
+    from ctrm_b200.environment import generate_ins_2d_with_obs_hetero_nonfix_agents as gen
+
+    ins = gen(7, 9, "0.03125,0.046875", "0.015625,0.0234375", 6, 0.05, 0.08, rng=np.random.RandomState(123))
+    bld = RoadmapBuilder(WEIGHTS, 0)
+    try:
+        csr = bld.build([ins], seed=4, N_traj=10, max_T=48, max_attempt=3, merge_distance_rate=0.1).copy()
+    finally:
+        bld.close()
+    pp = PrioritizedPlanning(ins, csr.timed_roadmaps(0))
+    res = pp.solve()
+    assert res.solved
+    T = int(res.maximum_costs)
+    got = demonstration_features(ins, pp.path_pos, T=T)
+    starts, goals, speeds, rads, obs = ins.arrays()
+    N, M, F = ins.num_agents, 160, 19
+    occ = O.draw_occupancy(obs[:, :2], obs[:, 2], M)
+    ctgs = np.stack([O.cost_to_go(goals[i], occ, float(rads[i])) for i in range(N)])
+    for t in range(T):
+        cur = pp.path_pos[:, t]
+        prev = pp.path_pos[:, max(0, t - 1)]
+        assert np.array_equal(got["fovs"][t], O.fov_crop_batch(cur, occ, ctgs, F).astype(np.float32)), t
+        want = O.others_info(cur, goals, prev, rads, speeds).astype(np.float32)
+        assert np.array_equal(got["others_info"][t], want), t
+        assert np.array_equal(got["self_info"][t], want.reshape(N, N, 11)[np.arange(N), np.arange(N), 3:]), t
