@@ -1,5 +1,5 @@
 """Short single-GPU run of the hot path for ncu: one batch of synthetic aamas22 instances, a few roll-outs.
-    python tools/ncu_target.py [batch] [n_traj]
+    python tools/ncu_target.py [batch] [n_traj] [plan]
 """
 import os
 import sys
@@ -16,3 +16,6 @@ b = RoadmapBuilder(WEIGHTS, 0)
 prm = dict(PARAMS, N_traj=NT)
 csr = b.build(make_instances(B, 0), seed=1, **prm)
 print("vertices", csr.n_vertices, "edges", csr.n_edges, csr.timing)
+if len(sys.argv) > 3 and sys.argv[3] == "plan":  # also run the planner on the device-resident roadmaps
+    r = b.plan()
+    print("planner ms", r["elapsed_ms"], "solved", float(r["solved"].float().mean()))
