@@ -33,6 +33,9 @@ CASES = [
     ("single_agent",   [(6, 1, 2, 3, "0.03125", "0.015625"), (7, 3, 4, 3, "0.03125", "0.015625")], 3, 32, 3, 0.1, 160),
     ("crowd60",        [(8, 60, 61, 10, "0.03125", "0.0078125")],                             1, 24, 3, 0.1, 160),
     ("map250_k4",      [(9, 9, 10, 6, "0.03125", "0.015625")],                                2, 40, 4, 0.1, 250),
+    # more obstacles than the step kernel stages in shared memory (global-memory fallback), and the widest adjacency mask
+    ("obs70",          [(10, 6, 7, 70, "0.03125", "0.0078125")],                              2, 32, 3, 0.1, 160),
+    ("ntraj100_w4",    [(11, 3, 4, 3, "0.03125", "0.015625")],                                100, 8, 3, 0.25, 160),
     # BASELINE configs[1] at its real roll-out sizes: one benchmark instance, every one of its ~1,400 steps compared
     ("full_size",      [(46, 21, 30, 10, "0.03125", "0.015625")],                             25, 64, 3, 0.1, 160),
 ]
