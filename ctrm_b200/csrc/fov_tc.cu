@@ -2,13 +2,14 @@
 // learning/formats/format_input.py:311-312) + the fov_vain rows of the AgentEncoder's first layer
 // (learning/model/agent_encoder.py:57-60; format_input.py:328-331).
 //
-// The FOV tensor is binary, so it is EXACT in bf16 and travels as bf16 operand tiles: [tile of 128 agents][chunk of 96
-// inputs][128 x 96 canonical UMMA tile] (24,576 B each, written in that form by the raster kernel, raster.cu).
-// First layers of both encoders side by side: D[128 x 64] = FOV[128 x 2F^2] . W0[2F^2 x 64] with the weights cut into four
-// signed fixed-point digits (tc.cuh): every digit product is an integer, all partial sums stay below 2^24, the fp32
-// accumulators are exact and the truncating tensor-core accumulate loses nothing; the four digit accumulators are combined
-// in fp64.  Operand chunks stream through a 2-stage TMA (cp.async.bulk) + mbarrier pipeline: one thread produces, one
-// thread issues the MMAs, tcgen05.commit releases the stage.
+// The FOV tensor is binary, so it travels as UNSIGNED 8-BIT operand tiles: [tile of 128 agents][chunk of 96 inputs]
+// [128 x 96 canonical UMMA tile] (12,288 B each, written in that form by the raster kernel, raster.cu).
+// First layers of both encoders side by side: D[128 x 64] = FOV[128 x 2F^2] . W0[2F^2 x 64] on the INTEGER tensor cores
+// (tcgen05.mma kind::i8): the weights are cut into four signed base-128 fixed-point digits (tc.cuh), every digit product
+// is an integer and the int32 accumulators are exact; the four digit accumulators are combined in fp64.  One byte per
+// operand element instead of two halves the bytes a tile pulls through its TMA (cp.async.bulk) + mbarrier pipeline, which
+// is what bounds this kernel (one CTA per SM waiting on L2 round trips), and lets the ring hold four stages instead of two:
+// one thread produces, one thread issues the MMAs, tcgen05.commit releases the stage.
 // Tails (32->32->32 per encoder as block-diagonal 64x64, then the 32x32 vain projection) are BF16x3 rounds on the same tile.
 #include "common.cuh"
 #include "kernels.h"
@@ -16,10 +17,10 @@
 
 #define FT_THREADS 256
 #define FT_CHUNK 96
-#define FT_A_CHUNK 24576u   // tile_bytes(128, 96)
-#define FT_W_DIGIT 12288u   // tile_bytes(64, 96)
-#define FT_W_CHUNK 49152u   // four digits
-#define FT_STAGES 2
+#define FT_A_CHUNK 12288u   // tile_bytes8(128, 96)
+#define FT_W_DIGIT 6144u    // tile_bytes8(64, 96)
+#define FT_W_CHUNK 24576u   // four digits
+#define FT_STAGES 4
 #define FT_STAGE (FT_A_CHUNK + FT_W_CHUNK)
 #define FT_H_PART 16384u    // tile_bytes(128, 64)
 #define FT_H32_PART 8192u   // tile_bytes(128, 32)
@@ -31,43 +32,44 @@
 // ---- weight preparation (once per ctrm_load_weights): digit tiles of W0 in global memory, chunk-major ----
 __global__ void fov_w0_prep_kernel(const float* __restrict__ w0 /*[KD][64]*/, int KD, int n_chunks, float scale,
                                    uint8_t* __restrict__ out /*[n_chunks][4][12288]*/) {
-  const int total = n_chunks * 64 * (FT_CHUNK / 8);
+  const int total = n_chunks * 64 * (FT_CHUNK / 16);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i / (64 * (FT_CHUNK / 8));
-    const int rem = i - c * 64 * (FT_CHUNK / 8);
-    const int k0 = (rem / 64) * 8, n = rem % 64;
-    uint32_t dg[8][4];
+    const int c = i / (64 * (FT_CHUNK / 16));
+    const int rem = i - c * 64 * (FT_CHUNK / 16);
+    const int k0 = (rem / 64) * 16, n = rem % 64;
+    uint32_t w[4][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 16; ++j) {
       const int k = c * FT_CHUNK + k0 + j;
-      tc::digits4_signed(k < KD ? w0[(size_t)k * 64 + n] : 0.f, scale, dg[j]);
+      int q[4];
+      tc::digits4_s7(k < KD ? w0[(size_t)k * 64 + n] : 0.f, scale, q);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) w[d][j >> 2] |= ((uint32_t)q[d] & 0xFFu) << (8 * (j & 3));
     }
-    const uint32_t off = tc::elem_offset(n, k0, FT_CHUNK);
+    const uint32_t off = tc::elem_offset8(n, k0, FT_CHUNK);
 #pragma unroll
     for (int d = 0; d < 4; ++d)
-      *reinterpret_cast<uint4*>(out + (size_t)c * FT_W_CHUNK + d * FT_W_DIGIT + off) =
-          make_uint4(dg[0][d] | (dg[1][d] << 16), dg[2][d] | (dg[3][d] << 16), dg[4][d] | (dg[5][d] << 16),
-                     dg[6][d] | (dg[7][d] << 16));
+      *reinterpret_cast<uint4*>(out + (size_t)c * FT_W_CHUNK + d * FT_W_DIGIT + off) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
   }
 }
 
 // ---- f32 FOV tensor [A][KD] -> bf16 operand tiles (stage entry point ctrm_encode_features only) ----
 __global__ void fov_f32_to_tiles_kernel(const float* __restrict__ fov, int A, int KD, int n_chunks, uint8_t* __restrict__ tiles) {
-  const long long total = (long long)((A + 127) / 128) * 128 * n_chunks * (FT_CHUNK / 8);
+  const long long total = (long long)((A + 127) / 128) * 128 * n_chunks * (FT_CHUNK / 16);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int per_row = n_chunks * (FT_CHUNK / 8);
-    const int a = (int)(i / per_row), k8 = (int)(i - (long long)a * per_row);
+    const int per_row = n_chunks * (FT_CHUNK / 16);
+    const int a = (int)(i / per_row), k16 = (int)(i - (long long)a * per_row);
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     if (a < A) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = k8 * 8 + j;
+      for (int j = 0; j < 16; ++j) {
+        const int k = k16 * 16 + j;
         const float v = (k < KD) ? fov[(size_t)a * KD + k] : 0.f;
-        w[j >> 1] |= (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)) << (16 * (j & 1));
+        w[j >> 2] |= (v != 0.f ? 1u : 0u) << (8 * (j & 3));  // the FOV tensor is {0, 1}
       }
     }
-    const int c = k8 / (FT_CHUNK / 8), kk = (k8 - c * (FT_CHUNK / 8)) * 8;
-    uint8_t* dst = tiles + ((size_t)(a >> 7) * n_chunks + c) * FT_A_CHUNK + tc::elem_offset(a & 127, kk, FT_CHUNK);
+    const int c = k16 / (FT_CHUNK / 16), kk = (k16 - c * (FT_CHUNK / 16)) * 16;
+    uint8_t* dst = tiles + ((size_t)(a >> 7) * n_chunks + c) * FT_A_CHUNK + tc::elem_offset8(a & 127, kk, FT_CHUNK);
     *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
@@ -142,12 +144,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
   tc::mbar_wait(done, 0);  // weights have landed; the tail MMA rounds continue on the same barrier with phase 1
   const uint32_t sStage = tc::smem_u32(stage0), sH = tc::smem_u32(Ht), sW1 = tc::smem_u32(W1c), sW2 = tc::smem_u32(W2c),
                  sWp = tc::smem_u32(Wp);
-  const uint32_t id64 = tc::idesc_bf16(128, 64);
+  const uint32_t id64 = tc::idesc_u8s8(128, 64);
   uint32_t it = 0;          // chunks processed so far by this CTA (ring position)
   uint32_t done_phase = 1;
-  double dscale[4];         // digit j (0-based) weighs 2^(w0_exp - 7 - 8 j)
+  double dscale[4];         // digit j (0-based) weighs 2^(w0_exp - 6 - 7 j)
 #pragma unroll
-  for (int d = 0; d < 4; ++d) dscale[d] = exp2((double)(w0_exp - 7 - 8 * d));
+  for (int d = 0; d < 4; ++d) dscale[d] = exp2((double)(w0_exp - 6 - 7 * d));
 
   auto mma_round = [&](uint32_t tcol, uint32_t a, uint32_t a_part, uint32_t b, uint32_t b_part, int Kk, int Nn) {
     tc::fence_before_sync();
@@ -188,12 +190,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
         tc::fence_after_sync();
         const uint32_t sa = sStage + s * FT_STAGE, sw = sa + FT_A_CHUNK;
 #pragma unroll
-        for (int ks = 0; ks < FT_CHUNK / 16; ++ks) {
-          const uint64_t ad = tc::smem_desc(sa + 256u * ks, FT_CHUNK);
+        for (int ks = 0; ks < FT_CHUNK / 32; ++ks) {
+          const uint64_t ad = tc::smem_desc8(sa + 256u * ks, FT_CHUNK);
           const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
 #pragma unroll
           for (int d = 0; d < 4; ++d)
-            tc::mma_bf16(tbase + 64 * d, ad, tc::smem_desc(sw + d * FT_W_DIGIT + 256u * ks, FT_CHUNK), id64, acc);
+            tc::mma_i8(tbase + 64 * d, ad, tc::smem_desc8(sw + d * FT_W_DIGIT + 256u * ks, FT_CHUNK), id64, acc);
         }
         tc::commit(empty0 + 8 * s);
       }
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
       for (int d = 3; d >= 0; --d) {
         tc::tmem_ld32(tbase, warp, 64 * d + 32 * half, h);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pre[j] = fma((double)h[j], dscale[d], pre[j]);
+        for (int j = 0; j < 32; ++j) pre[j] = fma((double)__float_as_int(h[j]), dscale[d], pre[j]);  // int32 accumulators
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) h[j] = fmaxf((float)pre[j] + b0[32 * half + j], 0.f);
@@ -272,7 +274,7 @@ size_t fov_w0_tiles_bytes(int F) { return (size_t)fov_n_chunks(F) * FT_W_CHUNK; 
 
 int launch_fov_w0_prep(const float* d_w0, int F, int w0_exp, uint8_t* d_out, cudaStream_t st) {
   const int n_chunks = fov_n_chunks(F);
-  fov_w0_prep_kernel<<<64, 256, 0, st>>>(d_w0, 2 * F * F, n_chunks, exp2f((float)(7 - w0_exp)), d_out);
+  fov_w0_prep_kernel<<<64, 256, 0, st>>>(d_w0, 2 * F * F, n_chunks, exp2f((float)(6 - w0_exp)), d_out);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }

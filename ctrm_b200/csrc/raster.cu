@@ -269,9 +269,9 @@ __global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// FOV raster, operand-tile output for the tensor-core encoders (fov_tc.cu): the same crop, written as bf16 {0, 1} into
-// [tile of 128 agents][chunk of 96 inputs][128 x 96 canonical UMMA tile].  A block rasterises 8 consecutive agents into
-// shared memory; 8 rows x 16 bytes are one 128-byte line of a core matrix, so every global store is a full line.
+// FOV raster, operand-tile output for the tensor-core encoders (fov_tc.cu): the same crop, written as unsigned bytes {0, 1}
+// into [tile of 128 rows][chunk of 96 inputs][128 x 96 canonical 8-bit UMMA tile].  A block rasterises 8 consecutive rows
+// into shared memory; 8 rows x 16 bytes are one 128-byte line of a core matrix, so every global store is a full line.
 // ------------------------------------------------------------------------------------------------
 #define RT_APB 8
 #define RT_CHUNK 96
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
   extern __shared__ __align__(16) uint8_t rt_smem[];
   const int F = FT > 0 ? FT : F_rt;
   const int FF = F * F, KD = 2 * FF, Kpad = n_chunks * RT_CHUNK;
-  const int row_bytes = Kpad * 2 + 16;  // +16: rows land in different banks for the 16-byte read-out
+  const int row_bytes = Kpad + 16;  // one byte per input; +16: rows land in different banks for the 16-byte read-out
   __shared__ int live_row[RT_APB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // rows: agents of the unfinished instances (live_agent, rebuilt between graph chunks) or all agents
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
   if (a0 >= n_rows) return;
   const int row = a0 + warp;
   const int a = row < n_rows ? (live_agent != nullptr ? live_agent[row] : row) : A;
-  uint16_t* t = reinterpret_cast<uint16_t*>(rt_smem + (size_t)warp * row_bytes);
+  uint8_t* t = rt_smem + (size_t)warp * row_bytes;
   bool live = false;
   if (a < A) {
     const int b = agent_inst[a];
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
       const bool c_reach = cc != CTRM_UNREACH;
       // zero the row (cells outside the map stay 0 in both channels), then visit the crop as (row xf, aligned group of four
       // y cells): one 8-byte load of the micro-tiled cost field and one 4-byte load of the occupancy row per work item
-      for (int i = lane; i < Kpad / 8; i += 32) reinterpret_cast<uint4*>(t)[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = lane; i < Kpad / 16; i += 32) reinterpret_cast<uint4*>(t)[i] = make_uint4(0u, 0u, 0u, 0u);
       __syncwarp();
       if (centre_in) {
         const int ylo = cy - buf;
@@ -334,14 +334,14 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
               if (yb + j < M) ow |= (uint32_t)__ldg(&o[x * M + yb + j]) << (8 * j);
           }
           const uint32_t cv[4] = {cw.x & 0xFFFFu, cw.x >> 16, cw.y & 0xFFFFu, cw.y >> 16};
-          uint16_t* t0 = t + xf * F + (yb - ylo);
+          uint8_t* t0 = t + xf * F + (yb - ylo);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int yf = yb - ylo + j;
             if (yf < 0 || yf >= F || yb + j >= M) continue;
             const int _c = (int)cv[j];
-            t0[j] = ((ow >> (8 * j)) & 0xFFu) ? 0 : 0x3F80;  // bf16 1.0
-            t0[FF + j] = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 0x3F80 : 0;
+            t0[j] = ((ow >> (8 * j)) & 0xFFu) ? 0 : 1;
+            t0[FF + j] = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 1 : 0;
           }
         }
       }
@@ -349,18 +349,18 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
   }
   if (lane == 0) live_row[warp] = live ? 1 : 0;
   if (!__syncthreads_or(live)) return;
-  const int n16 = RT_APB * (Kpad / 8);
+  const int n16 = RT_APB * (Kpad / 16);
   for (int idx = threadIdx.x; idx < n16; idx += blockDim.x) {
-    const int rr = idx & (RT_APB - 1), k8 = idx >> 3;
+    const int rr = idx & (RT_APB - 1), k16 = idx >> 3;
     if (!live_row[rr]) continue;  // finished instance (or beyond A: zero-filled at upload): nothing to write
     const int ar = a0 + rr;
-    const int c = k8 / (RT_CHUNK / 8), kk = (k8 - c * (RT_CHUNK / 8)) * 8;
+    const int c = k16 / (RT_CHUNK / 16), kk = (k16 - c * (RT_CHUNK / 16)) * 16;
     const int r = ar & 127;
-    const size_t off = ((size_t)(ar >> 7) * n_chunks + c) * (size_t)(128 * RT_CHUNK * 2) +
-                       (size_t)(r >> 3) * (RT_CHUNK / 8) * 128 + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16;
+    const size_t off = ((size_t)(ar >> 7) * n_chunks + c) * (size_t)(128 * RT_CHUNK) +
+                       (size_t)(r >> 3) * (RT_CHUNK / 16) * 128 + (size_t)(kk >> 4) * 128 + (size_t)(r & 7) * 16;
     // streaming store: the tiles are read exactly once (by fov_encode); keeping them out of the way lets the cost-to-go
     // crops, which overlap ~85% between consecutive steps, survive in L2
-    __stcs(reinterpret_cast<uint4*>(tiles + off), *reinterpret_cast<const uint4*>(rt_smem + (size_t)rr * row_bytes + (size_t)k8 * 16));
+    __stcs(reinterpret_cast<uint4*>(tiles + off), *reinterpret_cast<const uint4*>(rt_smem + (size_t)rr * row_bytes + (size_t)k16 * 16));
   }
 }
 
@@ -431,7 +431,7 @@ int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const i
                             const int32_t* d_live_agent, const int32_t* d_n_live, cudaStream_t st) {
   if (layout != 1) return ctrm_fail(-1, "fov_raster_tiles reads the micro-tiled cost-to-go layout only");
   if (A <= 0) return 0;
-  const size_t smem = (size_t)RT_APB * ((size_t)n_chunks * RT_CHUNK * 2 + 16);
+  const size_t smem = (size_t)RT_APB * ((size_t)n_chunks * RT_CHUNK + 16);
   const int blocks = (A + RT_APB - 1) / RT_APB;
   if (F == 19) {  // the trained configuration
     fov_raster_tiles_kernel<19><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,

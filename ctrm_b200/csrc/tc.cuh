@@ -142,6 +142,46 @@ __device__ __forceinline__ void mma_bf16_exactA(uint32_t tmem_d, uint32_t a, uin
     acc = 1u;
   }
 }
+// ---- 8-bit integer operands (kind::i8; sm_100a has it, sm_103a does not) ----
+// Same canonical K-major layout with 16 elements per 16-byte row of a core matrix:
+//     byte_offset(r, k) = (r / 8) * SBO + (k / 16) * 128 + (r % 8) * 16 + (k % 16),   SBO = (K / 16) * 128
+// one MMA consumes K = 32 (two core matrices, 256 bytes further per k-step); accumulators are int32, exact.
+__host__ __device__ constexpr uint32_t sbo_bytes8(int K) { return (uint32_t)(K / 16) * 128u; }
+__host__ __device__ constexpr uint32_t tile_bytes8(int rows, int K) { return (uint32_t)rows * (uint32_t)K; }
+__host__ __device__ __forceinline__ uint32_t elem_offset8(int r, int k, int K) {
+  return (uint32_t)(r >> 3) * sbo_bytes8(K) + (uint32_t)(k >> 4) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 15);
+}
+__device__ __forceinline__ uint64_t smem_desc8(uint32_t saddr, int K) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((128u >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes8(K) >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// A unsigned 8-bit (a_format 0), B signed 8-bit (b_format 1), int32 accumulate (c_format 2)
+__host__ __device__ constexpr uint32_t idesc_u8s8(int M, int N) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// four signed base-128 digits: b * scale in [-64, 64] (scale a power of two), b = sum_j q_j 2^(-7 j) / scale up to
+// 2^-28 / scale; every q_j is an integer in [-64, 64]
+__device__ __forceinline__ void digits4_s7(float b, float scale, int* q) {
+  float t = b * scale;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float d = rintf(t);
+    q[j] = (int)d;
+    t = (t - d) * 128.f;  // exact
+  }
+}
+
 __device__ __forceinline__ void commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
