@@ -223,8 +223,8 @@ def algorithmic_work(kernel, agent_steps, pair_steps, K, F=19):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload at 1,024
 # instances (profiles/r1_full_step_kernels_b1024_final.md); scaled linearly with the instance count
-NCU_TRAFFIC_B1024 = dict(fov_raster=61.3e6, fov_encode=39.9e6, agent_comm=8.32e6, cvae_prior=7.59e6, cvae_decode=9.98e6,
-                         step=14.6e6)
+NCU_TRAFFIC_B1024 = dict(fov_raster=59.7e6, fov_encode=20.2e6, agent_comm=8.42e6, cvae_prior=7.69e6, cvae_decode=10.1e6,
+                         step=14.7e6)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # FMA issue peak of the CUDA cores at the max SM clock
 
 
