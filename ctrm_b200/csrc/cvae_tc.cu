@@ -20,7 +20,7 @@
 //   LogSoftmax + Categorical normalisation + logits = log(clamp(p)) (learning/model/cvae.py:57-68, :132-136;
 //   torch.distributions probs_to_logits), and the [X, onehot] rows of the decoder's first layer (cvae.py:72-76, :137).
 // The three first layers share the A operand X[128 x 72]: ONE N = 96 MMA chain computes them side by side
-// (TMEM columns 0..31 indicator, 32..63 encoder, 64..95 decoder, times three magnitude classes); the one-hot indicator columns are added as a weight row
+// (TMEM columns 0..31 indicator, 32..63 encoder, 64..95 decoder, times two accumulator classes); the one-hot indicator columns are added as a weight row
 // in the epilogue.  outputs per agent: logits[64], dec0[32], ind.
 // ------------------------------------------------------------------------------------------------
 #define PR_THREADS 256
@@ -34,7 +34,7 @@
 #define PR_W_BYTES (3 * 15360 + 2 * 3 * 2048 + 3 * 4096 + PR_NW * 4)  // the prebuilt weight image
 #define PR_NF 1664                    // fp32 constants + the [2][128][4] exchange buffer of the two halves of a row
 #define PR_SMEM (3 * 20480 + 3 * 15360 + 2 * 3 * 2048 + 3 * 4096 + PR_NF * 4 + 16)
-#define PR_TMEM_COLS 512  // layer 0: 3 x 96 | head layers: 3 x 32 at 288 | encoder output 3 x 64 reuses 0..191
+#define PR_TMEM_COLS 512  // layer 0: 2 x 96 at 0 | head layers: 2 x 32 at 288 | encoder output 2 x 64 reuses 0..127
 
 // weight operands of cvae_prior exactly as they sit in its shared memory from W0t on: split bf16 tiles, then fp32 constants
 __device__ __forceinline__ void prior_stage_weights(uint8_t* W0t, const float* __restrict__ blob, const ctrm_weight_offsets_t& off,
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
     __syncthreads();
     if (tid == 0) {
       tc::fence_after_sync();
-      tc::mma_bf16x3(tbase + tcol, (uint32_t)Nn, a, a_part, b, b_part, Kk, Nn);
+      tc::mma_bf16x3_c2(tbase + tcol, (uint32_t)Nn, a, a_part, b, b_part, Kk, Nn);
       tc::commit(mb);
     }
     tc::mbar_wait(mb, phase);
@@ -160,14 +160,14 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
     mma_round(0, sX, PR_X_PART, sW0, PR_W0_PART, PR_K0, 96);
     float h[16];
     // ---- indicator: hidden 1 -> hidden 2 -> 3 logits -> argmax
-    tc::tmem_ld16_sum3(tbase, warp, 16 * half, 96, h);
+    tc::tmem_ld16_sum2(tbase, warp, 16 * half, 96, h);
 #pragma unroll
     for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j] + ind_b0[16 * half + j], 0.f);
     tc::fence_before_sync();
     __syncthreads();  // the X tile is dead (layer 0 done) and every thread has issued its first TMEM reads
     store_hidden16(h);
     mma_round(288, sX, PR_H_PART, sWi1, PR_W1_PART, 32, 32);
-    tc::tmem_ld16_sum3(tbase, warp, 288 + 16 * half, 32, h);
+    tc::tmem_ld16_sum2(tbase, warp, 288 + 16 * half, 32, h);
     int ind = 0;
     {
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
       if (live && half == 0 && ind_out != nullptr) ind_out[a] = ind;
     }
     // ---- decoder first layer, [X, onehot] part (TMEM columns 64..95 of the shared chain)
-    tc::tmem_ld16_sum3(tbase, warp, 64 + 16 * half, 96, h);
+    tc::tmem_ld16_sum2(tbase, warp, 64 + 16 * half, 96, h);
     if (live) {
       float4* d0 = reinterpret_cast<float4*>(dec0_out + (size_t)a * 32 + 16 * half);
 #pragma unroll
@@ -206,19 +206,19 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
       }
     }
     // ---- encoder_input: hidden 1 (+ one-hot row) -> hidden 2 -> 64 logits -> log_softmax -> clamped log-probs
-    tc::tmem_ld16_sum3(tbase, warp, 32 + 16 * half, 96, h);
+    tc::tmem_ld16_sum2(tbase, warp, 32 + 16 * half, 96, h);
 #pragma unroll
     for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j] + enc_b0[16 * half + j] + enc_oh[ind * 32 + 16 * half + j], 0.f);
     store_hidden16(h);  // the indicator's hidden tile was consumed by its MMA round (waited on above)
     mma_round(288, sX, PR_H_PART, sWe1, PR_W1_PART, 32, 32);
-    tc::tmem_ld16_sum3(tbase, warp, 288 + 16 * half, 32, h);
+    tc::tmem_ld16_sum2(tbase, warp, 288 + 16 * half, 32, h);
 #pragma unroll
     for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j] + enc_b1[16 * half + j], 0.f);
     store_hidden16(h);
     mma_round(0, sX, PR_H_PART, sWe2, PR_W2_PART, 32, 64);  // every layer-0 column has been consumed
     {
       float lg[32];  // this half's 32 of the 64 logits
-      tc::tmem_ld32_sum3(tbase, warp, 32 * half, 64, lg);
+      tc::tmem_ld32_sum2(tbase, warp, 32 * half, 64, lg);
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -295,7 +295,7 @@ int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, floa
 #define DT_W0_PART 4096u
 #define DT_W1_PART 2048u
 #define DT_SMEM (4 * 16384 + 4 * 4096 + 3 * 2048 + (128 + 32 + 4 + 256 + 512) * 4 + 16)
-#define DT_TMEM_COLS 256  // 4 x 32 layer-0 digit accumulators + 3 x 32 layer-1 magnitude classes
+#define DT_TMEM_COLS 256  // 4 x 32 layer-0 digit accumulators + 2 x 32 layer-1 accumulator classes at 128
 
 // 8 fp32 values of row r, columns k0..k0+7, parked as two 16-byte halves in the slots of digit tiles 2 and 3
 __device__ __forceinline__ void park8(uint8_t* At, int r, int k0, const float* v) {
@@ -516,13 +516,13 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     __syncthreads();
     if (tid == 0) {
       tc::fence_after_sync();
-      tc::mma_bf16x3(tbase + 128, 32, sA, DT_H_PART, sW1, DT_W1_PART, 32, 32);
+      tc::mma_bf16x3_c2(tbase + 128, 32, sA, DT_H_PART, sW1, DT_W1_PART, 32, 32);
       tc::commit(mb);
     }
     tc::mbar_wait(mb, phase);
     phase ^= 1u;
     tc::fence_after_sync();
-    tc::tmem_ld16_sum3(tbase, warp, 128 + 16 * half, 32, h);
+    tc::tmem_ld16_sum2(tbase, warp, 128 + 16 * half, 32, h);
     {
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll

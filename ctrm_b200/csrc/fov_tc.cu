@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
     __syncthreads();
     if (tid == 0) {
       tc::fence_after_sync();
-      tc::mma_bf16x3(tbase + tcol, (uint32_t)Nn, a, a_part, b, b_part, Kk, Nn);
+      tc::mma_bf16x3_c2(tbase + tcol, (uint32_t)Nn, a, a_part, b, b_part, Kk, Nn);
       tc::commit(done);
     }
     tc::mbar_wait(done, done_phase);
@@ -225,14 +225,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
     }
     // ---- tail 1
     mma_round(256, sH, FT_H_PART, sW1, FT_W64_PART, 64, 64);
-    tc::tmem_ld32_sum3(tbase, warp, 256 + 32 * half, 64, h);
+    tc::tmem_ld32_sum2(tbase, warp, 256 + 32 * half, 64, h);
 #pragma unroll
     for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + b1[32 * half + j], 0.f);
 #pragma unroll
     for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + q * 8, 64, h + q * 8);
     // ---- tail 2 -> e_self (half 0) | e_vain (half 1)
     mma_round(256, sH, FT_H_PART, sW2, FT_W64_PART, 64, 64);
-    tc::tmem_ld32_sum3(tbase, warp, 256 + 32 * half, 64, h);
+    tc::tmem_ld32_sum2(tbase, warp, 256 + 32 * half, 64, h);
 #pragma unroll
     for (int j = 0; j < 32; ++j) h[j] += b2[32 * half + j];
     {
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
       for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H32_PART, Ht + 2 * FT_H32_PART, r, q * 8, 32, h + q * 8);
     }
     mma_round(0, sH, FT_H32_PART, sWp, FT_W32_PART, 32, 32);
-    tc::tmem_ld16_sum3(tbase, warp, 16 * half, 32, h);
+    tc::tmem_ld16_sum2(tbase, warp, 16 * half, 32, h);
     if (live) {
       float4* dst = reinterpret_cast<float4*>(vain_proj + (size_t)a * 32 + 16 * half);
 #pragma unroll

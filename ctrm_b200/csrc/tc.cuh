@@ -85,32 +85,12 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
 }
 // D[128 x N] = A[128 x K] * B[N x K]^T, fp32-exact products (BF16x3, 6 MMAs per 16-wide k-step); one thread issues.
 // a / b are shared-memory byte addresses of the first of three consecutive operand tiles (parts 1, 2, 3), a_part / b_part
-// bytes apart.  The tensor core TRUNCATES when it adds into the fp32 accumulator, so the number of accumulations that see the
-// full-magnitude partial sum is kept minimal: the three magnitude classes go to THREE accumulators, n_cols TMEM columns apart
-//   tmem_d             : a1*b1                      (K/16 accumulations)
-//   tmem_d + n_cols    : a1*b2 + a2*b1              (2^-8 of the main term)
-//   tmem_d + 2*n_cols  : a2*b2 + a1*b3 + a3*b1      (2^-16)
-// and the epilogue adds them (tmem_ld32_sum3).
-static __device__ __noinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t n_cols, uint32_t a, uint32_t a_part, uint32_t b,
-                                           uint32_t b_part, int K, int N) {
-  const uint32_t id = idesc_bf16(128, N);
-  uint32_t acc = 0u;
-  for (int s = 0; s < K / 16; ++s) {
-    const uint32_t o = 256u * s;
-    const uint64_t a1 = smem_desc(a + o, K), a2 = smem_desc(a + a_part + o, K), a3 = smem_desc(a + 2 * a_part + o, K);
-    const uint64_t b1 = smem_desc(b + o, K), b2 = smem_desc(b + b_part + o, K), b3 = smem_desc(b + 2 * b_part + o, K);
-    mma_bf16(tmem_d + 2 * n_cols, a1, b3, id, acc);
-    mma_bf16(tmem_d + 2 * n_cols, a3, b1, id, 1u);
-    mma_bf16(tmem_d + 2 * n_cols, a2, b2, id, 1u);
-    mma_bf16(tmem_d + n_cols, a1, b2, id, acc);
-    mma_bf16(tmem_d + n_cols, a2, b1, id, 1u);
-    mma_bf16(tmem_d, a1, b1, id, acc);
-    acc = 1u;
-  }
-}
-// Two-accumulator variant: the main term alone at tmem_d, every correction term (2^-8 and 2^-16 classes) at tmem_d + n_cols.
-// What matters for the truncating accumulate is that nothing small is ever added to the full-magnitude sum inside the tensor
-// core; mixing the two correction classes costs 2^-24 * 2^-8 relative, and saves a third of the TMEM columns and loads.
+// bytes apart.  The tensor core TRUNCATES when it adds into the fp32 accumulator: with all six partial products in one
+// accumulator (30 accumulations for K = 80) the CVAE output showed outliers of 2.3e-5.  The main term a1*b1 therefore gets
+// an accumulator of its own (K/16 accumulations), every correction term goes to a second one n_cols TMEM columns further,
+// and the epilogue adds the two (tmem_ld*_sum2).
+// What matters is that nothing small is ever added to the full-magnitude sum inside the tensor core; mixing the 2^-8 and
+// 2^-16 correction classes in one accumulator costs 2^-24 * 2^-8 relative (three separate accumulators measured the same).
 static __device__ __noinline__ void mma_bf16x3_c2(uint32_t tmem_d, uint32_t n_cols, uint32_t a, uint32_t a_part, uint32_t b,
                                               uint32_t b_part, int K, int N) {
   const uint32_t id = idesc_bf16(128, N);
@@ -326,16 +306,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t tbase, int warp, int col, flo
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld16_sum3(uint32_t tbase, int warp, int col, int n_cols, float* v) {
-  float t[16];
-  tmem_ld16(tbase, warp, col + 2 * n_cols, v);
-  tmem_ld16(tbase, warp, col + n_cols, t);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += t[i];
-  tmem_ld16(tbase, warp, col, t);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += t[i];
-}
 
 // two-accumulator epilogues of mma_bf16x3_c2: v = corrections + main
 __device__ __forceinline__ void tmem_ld32_sum2(uint32_t tbase, int warp, int col, int n_cols, float* v) {
@@ -353,17 +323,6 @@ __device__ __forceinline__ void tmem_ld16_sum2(uint32_t tbase, int warp, int col
   for (int i = 0; i < 16; ++i) v[i] += t[i];
 }
 
-// v[32] = (acc_lo + acc_mid) + acc_main for the three accumulators of mma_bf16x3 (columns col, col+n_cols, col+2*n_cols)
-__device__ __forceinline__ void tmem_ld32_sum3(uint32_t tbase, int warp, int col, int n_cols, float* v) {
-  float t[32];
-  tmem_ld32(tbase, warp, col + 2 * n_cols, v);
-  tmem_ld32(tbase, warp, col + n_cols, t);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] += t[i];
-  tmem_ld32(tbase, warp, col, t);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] += t[i];
-}
 
 // copy rows [k_begin, k_begin + K_real) of a blob weight matrix stored [in][ld] (fp32, global) into three consecutive
 // bf16 B-operand tiles (N_tile x K, K-major, tile_bytes(N_tile, K) apart) at tile rows [n_off, n_off + N):
