@@ -30,19 +30,25 @@
 #define PR_W0_PART 15360u             // tile_bytes(96, 80)
 #define PR_W1_PART 2048u              // tile_bytes(32, 32)
 #define PR_W2_PART 4096u              // tile_bytes(64, 32)
-#define PR_NW 608                     // fp32 constants (biases, output layer, one-hot rows) that follow the weight tiles
-#define PR_W_BYTES (3 * 15360 + 2 * 3 * 2048 + 3 * 4096 + PR_NW * 4)  // the prebuilt weight image
+#define PR_NW 608                     // fp32 constants (biases, output layer, one-hot rows) that follow the W0 tiles
+#define PR_W0_BYTES (3 * 15360 + PR_NW * 4)         // resident part of the weight image: W0 tiles | constants
+#define PR_HEAD_BYTES (2 * 3 * 2048 + 3 * 4096)     // per-tile part: ind_w1 | enc_w1 | enc_w2 tiles
+#define PR_W_BYTES (PR_W0_BYTES + PR_HEAD_BYTES)    // the prebuilt weight image
+#define PR_HEAD_OFF 24576u            // the head-layer weights live in the X tile's memory behind the hidden tiles
 #define PR_NF 1664                    // fp32 constants + the [2][128][4] exchange buffer of the two halves of a row
-#define PR_SMEM (3 * 20480 + 3 * 15360 + 2 * 3 * 2048 + 3 * 4096 + PR_NF * 4 + 16)
-#define PR_TMEM_COLS 512  // layer 0: 2 x 96 at 0 | head layers: 2 x 32 at 288 | encoder output 2 x 64 reuses 0..127
+// 114 KB: TWO CTAs per SM.  The kernel is a chain of seven dependent MMA round trips per tile, so a second resident CTA
+// nearly doubles what an SM gets done; to fit, only W0 stays resident and the 24 KB of head-layer weights are pulled
+// again (TMA, from L2) for every tile into the part of the X tile that is dead once layer 0 has completed.
+#define PR_SMEM (3 * 20480 + 3 * 15360 + PR_NF * 4 + 32)
+#define PR_TMEM_COLS 256  // layer 0: 2 x 96 at 0 | head layers: 2 x 32 at 192 | encoder output 2 x 64 reuses 0..127
 
 // weight operands of cvae_prior exactly as they sit in its shared memory from W0t on: split bf16 tiles, then fp32 constants
 __device__ __forceinline__ void prior_stage_weights(uint8_t* W0t, const float* __restrict__ blob, const ctrm_weight_offsets_t& off,
                                                     int tid, int nthreads) {
-  uint8_t* Wi1 = W0t + 3 * PR_W0_PART;
+  float* cf = reinterpret_cast<float*>(W0t + 3 * PR_W0_PART);
+  uint8_t* Wi1 = W0t + PR_W0_BYTES;
   uint8_t* We1 = Wi1 + 3 * PR_W1_PART;
   uint8_t* We2 = We1 + 3 * PR_W1_PART;
-  float* cf = reinterpret_cast<float*>(We2 + 3 * PR_W2_PART);
   tc::stage_weight_split_at(blob + off.ind_w0, 32, 0, 72, 32, 32, 0, 96, PR_K0, W0t, tid, nthreads);
   tc::stage_weight_split_at(blob + off.enc_w0, 32, 0, 72, 32, 32, 32, 96, PR_K0, W0t, tid, nthreads);
   tc::stage_weight_split_at(blob + off.dec_w0, 32, 64, 72, 32, 32, 64, 96, PR_K0, W0t, tid, nthreads);
@@ -73,17 +79,17 @@ __global__ void __launch_bounds__(PR_THREADS) cvae_prior_image_kernel(const floa
   tc::dump_image(smem, image, PR_W_BYTES, threadIdx.x, PR_THREADS);
 }
 
-__global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, const float* __restrict__ X,
+__global__ void __launch_bounds__(PR_THREADS, 2) cvae_prior_tc_kernel(Batch bt, const float* __restrict__ X,
                                                                    const uint8_t* __restrict__ w_image,
                                                                    float* __restrict__ logits_out, float* __restrict__ dec0_out,
                                                                    int32_t* __restrict__ ind_out, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* Xt = smem;                        // X parts 1..3 [128 x 80]; reused for hidden tiles [128 x 32] x 3
+  uint8_t* Xt = smem;                        // X parts 1..3 [128 x 80]; after layer 0: hidden tiles [128 x 32] x 3 | head weights
   uint8_t* W0t = Xt + 3 * PR_X_PART;         // [96 x 80] x 3 : ind_w0 | enc_w0 | dec_w0 rows 64..135
-  uint8_t* Wi1 = W0t + 3 * PR_W0_PART;       // ind_w1 [32 x 32] x 3
+  uint8_t* Wi1 = Xt + PR_HEAD_OFF;           // ind_w1 [32 x 32] x 3   (re-loaded for every tile)
   uint8_t* We1 = Wi1 + 3 * PR_W1_PART;       // enc_w1 [32 x 32] x 3
   uint8_t* We2 = We1 + 3 * PR_W1_PART;       // enc_w2 [64 x 32] x 3
-  float* cf = reinterpret_cast<float*>(We2 + 3 * PR_W2_PART);
+  float* cf = reinterpret_cast<float*>(W0t + 3 * PR_W0_PART);
   float* ind_b0 = cf;            // 32
   float* ind_b1 = cf + 32;       // 32
   float* ind_w2 = cf + 64;       // [32][4]
@@ -96,13 +102,15 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
   float* dec_oh = cf + 452;      // [3][32] rows 136..138 of dec_w0
   float* red = cf + 608;         // [2][128][4]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(cf + PR_NF);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  uint64_t* hbar = mbar + 1;                 // head weights of the current tile have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hbar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;  // two threads per row: TMEM lane group = warp % 4 for both halves
 
-  if (tid == 0) {  // the weight operands arrive as one prebuilt image (cvae_prior_image_kernel), through the TMA engine
+  if (tid == 0) {  // the weight operands arrive as a prebuilt image (cvae_prior_image_kernel), through the TMA engine
     tc::mbar_init(tc::smem_u32(mbar), 1);
-    tc::tma_load_image(W0t, w_image, PR_W_BYTES, tc::smem_u32(mbar));
+    tc::mbar_init(tc::smem_u32(hbar), 1);
+    tc::tma_load_image(W0t, w_image, PR_W0_BYTES, tc::smem_u32(mbar));
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, PR_TMEM_COLS);
   tc::fence_before_sync();
@@ -113,15 +121,18 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
   tc::mbar_wait(mb, 0);  // weights have landed; the MMA rounds continue on the same barrier with phase 1
   const uint32_t sX = tc::smem_u32(Xt), sW0 = tc::smem_u32(W0t), sWi1 = tc::smem_u32(Wi1), sWe1 = tc::smem_u32(We1),
                  sWe2 = tc::smem_u32(We2);
-  uint32_t phase = 1;
+  uint32_t phase = 1, hphase = 0;
+  const uint32_t hb = tc::smem_u32(hbar);
   const float eps = 1.1920928955078125e-07f;
 
-  // one MMA round: the A tile in shared memory is complete -> issue, commit, wait
-  auto mma_round = [&](uint32_t tcol, uint32_t a, uint32_t a_part, uint32_t b, uint32_t b_part, int Kk, int Nn) {
+  // one MMA round: the A tile in shared memory is complete -> issue, commit, wait.  heads = the round reads the per-tile
+  // head weights, whose TMA must have landed (only the issuing thread needs to know)
+  auto mma_round = [&](uint32_t tcol, uint32_t a, uint32_t a_part, uint32_t b, uint32_t b_part, int Kk, int Nn, bool heads) {
     tc::fence_before_sync();
     tc::fence_async_smem();
     __syncthreads();
     if (tid == 0) {
+      if (heads) tc::mbar_wait(hb, hphase);
       tc::fence_after_sync();
       tc::mma_bf16x3_c2(tbase + tcol, (uint32_t)Nn, a, a_part, b, b_part, Kk, Nn);
       tc::commit(mb);
@@ -157,7 +168,10 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
         tc::store_split8(Xt, Xt + PR_X_PART, Xt + 2 * PR_X_PART, r, q * 8, PR_K0, v);
       }
     }
-    mma_round(0, sX, PR_X_PART, sW0, PR_W0_PART, PR_K0, 96);
+    mma_round(0, sX, PR_X_PART, sW0, PR_W0_PART, PR_K0, 96, false);
+    // layer 0 has completed: nothing reads the X tile any more.  Its tail receives this tile's head-layer weights while the
+    // first epilogue runs (the generic-proxy writes of the X staging were fenced before the MMA that consumed them)
+    if (tid == 0) tc::tma_load_image(Wi1, w_image + PR_W0_BYTES, PR_HEAD_BYTES, hb);
     float h[16];
     // ---- indicator: hidden 1 -> hidden 2 -> 3 logits -> argmax
     tc::tmem_ld16_sum2(tbase, warp, 16 * half, 96, h);
@@ -166,8 +180,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
     tc::fence_before_sync();
     __syncthreads();  // the X tile is dead (layer 0 done) and every thread has issued its first TMEM reads
     store_hidden16(h);
-    mma_round(288, sX, PR_H_PART, sWi1, PR_W1_PART, 32, 32);
-    tc::tmem_ld16_sum2(tbase, warp, 288 + 16 * half, 32, h);
+    mma_round(192, sX, PR_H_PART, sWi1, PR_W1_PART, 32, 32, true);
+    tc::tmem_ld16_sum2(tbase, warp, 192 + 16 * half, 32, h);
     int ind = 0;
     {
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
@@ -210,12 +224,12 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
 #pragma unroll
     for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j] + enc_b0[16 * half + j] + enc_oh[ind * 32 + 16 * half + j], 0.f);
     store_hidden16(h);  // the indicator's hidden tile was consumed by its MMA round (waited on above)
-    mma_round(288, sX, PR_H_PART, sWe1, PR_W1_PART, 32, 32);
-    tc::tmem_ld16_sum2(tbase, warp, 288 + 16 * half, 32, h);
+    mma_round(192, sX, PR_H_PART, sWe1, PR_W1_PART, 32, 32, true);
+    tc::tmem_ld16_sum2(tbase, warp, 192 + 16 * half, 32, h);
 #pragma unroll
     for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j] + enc_b1[16 * half + j], 0.f);
     store_hidden16(h);
-    mma_round(0, sX, PR_H_PART, sWe2, PR_W2_PART, 32, 64);  // every layer-0 column has been consumed
+    mma_round(0, sX, PR_H_PART, sWe2, PR_W2_PART, 32, 64, true);  // every layer-0 column has been consumed
     {
       float lg[32];  // this half's 32 of the 64 logits
       tc::tmem_ld32_sum2(tbase, warp, 32 * half, 64, lg);
@@ -255,6 +269,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) cvae_prior_tc_kernel(Batch bt, 
                                logf(fminf(fmaxf(lg[j4 * 4 + 3] / ps, eps), 1.f - eps)));
       }
     }
+    hphase ^= 1u;
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -280,7 +295,7 @@ int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, floa
     CTRM_CUDA_OK(cudaFuncSetAttribute(cvae_prior_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM));
     attr = true;
   }
-  const int grid = n_tiles < 148 ? n_tiles : 148;  // persistent, one CTA per SM (135 KB of shared memory each)
+  const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent, two CTAs per SM (114 KB of shared memory each)
   cvae_prior_tc_kernel<<<grid, PR_THREADS, PR_SMEM, st>>>(bt, d_X, m.prior_img, d_logits, d_dec0, d_ind, n_tiles);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
