@@ -20,14 +20,19 @@
 #define FT_A_CHUNK 12288u   // tile_bytes8(128, 96)
 #define FT_W_DIGIT 6144u    // tile_bytes8(64, 96)
 #define FT_W_CHUNK 24576u   // four digits
-#define FT_STAGES 4
+#define FT_STAGES 3
 #define FT_STAGE (FT_A_CHUNK + FT_W_CHUNK)
 #define FT_H_PART 16384u    // tile_bytes(128, 64)
 #define FT_H32_PART 8192u   // tile_bytes(128, 32)
 #define FT_W64_PART 8192u   // tile_bytes(64, 64)
 #define FT_W32_PART 2048u   // tile_bytes(32, 32)
 #define FT_NF 256
-#define FT_SMEM (FT_STAGES * FT_STAGE + 2 * 3 * FT_W64_PART + 3 * FT_W32_PART + FT_NF * 4 + 128)
+#define FT_TAIL_OFF 49152u  // after layer 0 the ring memory holds the hidden tiles [0, 48 KB) and the tail-layer weights behind them
+#define FT_TAILW_BYTES (2 * 3 * FT_W64_PART + 3 * FT_W32_PART)
+// 109 KB: TWO CTAs per SM.  The kernel waits on L2 round trips (operand ring) and on its three dependent tail rounds, so a
+// second resident CTA nearly doubles what an SM gets done; to fit, the 54 KB of tail-layer weights are not resident but
+// pulled again (TMA, from L2) for every tile into ring memory that is dead once layer 0 has completed.
+#define FT_SMEM (FT_STAGES * FT_STAGE + FT_NF * 4 + 128)
 
 // ---- weight preparation (once per ctrm_load_weights): digit tiles of W0 in global memory, chunk-major ----
 __global__ void fov_w0_prep_kernel(const float* __restrict__ w0 /*[KD][64]*/, int KD, int n_chunks, float scale,
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(FT_THREADS) fov_encode_image_kernel(const floa
   tc::dump_image(smem, image, FT_W_BYTES, tid, FT_THREADS);
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint8_t* __restrict__ fov_tiles,
+__global__ void __launch_bounds__(FT_THREADS, 2) fov_encode_tc_kernel(const uint8_t* __restrict__ fov_tiles,
                                                                    const uint8_t* __restrict__ w0_tiles, int n_chunks, int w0_exp,
                                                                    const int32_t* __restrict__ agent_inst,
                                                                    const uint8_t* __restrict__ skip_inst, int A,
@@ -115,25 +120,25 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
                                                                    const int32_t* __restrict__ n_live) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage0 = smem;                              // stage s: A chunk | W chunk (4 digits)
-  uint8_t* W1c = smem + FT_STAGES * FT_STAGE;                  // blockdiag(self.mlp.2, vain.mlp.2)  [64 x 64] x 3
+  uint8_t* W1c = smem + FT_TAIL_OFF;                   // blockdiag(self.mlp.2, vain.mlp.2)  [64 x 64] x 3   (per tile)
   uint8_t* W2c = W1c + 3 * FT_W64_PART;                // blockdiag(self.mlp.4, vain.mlp.4)
   uint8_t* Wp = W2c + 3 * FT_W64_PART;                 // agent.mlp.0 rows 11..42  [32 x 32] x 3
-  float* cf = reinterpret_cast<float*>(Wp + 3 * FT_W32_PART);
+  float* cf = reinterpret_cast<float*>(smem + FT_STAGES * FT_STAGE);
   float* b0 = cf;          // 64
   float* b1 = cf + 64;     // 64
   float* b2 = cf + 128;    // 64
   float* bp = cf + 192;    // 32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cf + FT_NF);  // full[FT_STAGES], empty[FT_STAGES], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FT_STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cf + FT_NF);  // full[FT_STAGES], empty[FT_STAGES], done, tail weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FT_STAGES + 2);
   uint8_t* Ht = stage0;    // hidden tiles reuse the operand stages once layer 0 has completed
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;  // two threads per row; TMEM lane group = warp % 4 for both halves
 
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
   if (tid == 0) {
-    for (int i = 0; i < 2 * FT_STAGES + 1; ++i) tc::mbar_init(tc::smem_u32(&bars[i]), 1);
-    // the tail-layer weight operands arrive as one prebuilt image (fov_encode_image_kernel), through the TMA engine
-    tc::tma_load_image(W1c, w_image, FT_W_BYTES, tc::smem_u32(&bars[2 * FT_STAGES]));
+    for (int i = 0; i < 2 * FT_STAGES + 2; ++i) tc::mbar_init(tc::smem_u32(&bars[i]), 1);
+    // biases: the constant tail of the prebuilt image (fov_encode_image_kernel), through the TMA engine
+    tc::tma_load_image(cf, w_image + FT_TAILW_BYTES, 224 * 4, tc::smem_u32(&bars[2 * FT_STAGES]));
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -141,7 +146,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
   const uint32_t tbase = *tmem_slot;
   const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[FT_STAGES]),
                  done = tc::smem_u32(&bars[2 * FT_STAGES]);
-  tc::mbar_wait(done, 0);  // weights have landed; the tail MMA rounds continue on the same barrier with phase 1
+  const uint32_t hb = tc::smem_u32(&bars[2 * FT_STAGES + 1]);
+  uint32_t hphase = 0;
+  tc::mbar_wait(done, 0);  // biases have landed; the tail MMA rounds continue on the same barrier with phase 1
   const uint32_t sStage = tc::smem_u32(stage0), sH = tc::smem_u32(Ht), sW1 = tc::smem_u32(W1c), sW2 = tc::smem_u32(W2c),
                  sWp = tc::smem_u32(Wp);
   const uint32_t id64 = tc::idesc_u8s8(128, 64);
@@ -156,6 +163,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
     tc::fence_async_smem();
     __syncthreads();
     if (tid == 0) {
+      tc::mbar_wait(hb, hphase);  // this tile's tail weights (only the issuing thread needs to know)
       tc::fence_after_sync();
       tc::mma_bf16x3_c2(tbase + tcol, (uint32_t)Nn, a, a_part, b, b_part, Kk, Nn);
       tc::commit(done);
@@ -205,34 +213,41 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
     tc::mbar_wait(done, done_phase);
     done_phase ^= 1u;
     tc::fence_after_sync();
+    // layer 0 has completed: nothing reads the ring any more.  This tile's tail-layer weights go behind the hidden tiles
+    // while the first epilogue runs.
+    if (tid == 0) tc::tma_load_image(W1c, w_image, FT_TAILW_BYTES, hb);
     // ---- epilogue 0: combine digits in fp64, + bias, ReLU -> hidden tile [128 x 64].  Thread (row r, half) owns the
-    //      32 columns of ONE encoder: half 0 = fov_encoder_self, half 1 = fov_encoder_vain
+    //      32 columns of ONE encoder: half 0 = fov_encoder_self, half 1 = fov_encoder_vain (16 columns at a time)
     float h[32];
-    {
-      double pre[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) pre[j] = 0.0;
+    for (int p16 = 0; p16 < 2; ++p16) {
+      double pre[16];
+      float hv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pre[j] = 0.0;
 #pragma unroll
       for (int d = 3; d >= 0; --d) {
-        tc::tmem_ld32(tbase, warp, 64 * d + 32 * half, h);
+        tc::tmem_ld16(tbase, warp, 64 * d + 32 * half + 16 * p16, hv);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pre[j] = fma((double)__float_as_int(h[j]), dscale[d], pre[j]);  // int32 accumulators
+        for (int j = 0; j < 16; ++j) pre[j] = fma((double)__float_as_int(hv[j]), dscale[d], pre[j]);  // int32 accumulators
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) h[j] = fmaxf((float)pre[j] + b0[32 * half + j], 0.f);
+      for (int j = 0; j < 16; ++j) hv[j] = fmaxf((float)pre[j] + b0[32 * half + 16 * p16 + j], 0.f);
+      // the hidden tile lies in ring memory that layer 0 has finished with (waited on above)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + q * 8, 64, h + q * 8);
+      for (int q = 0; q < 2; ++q)
+        tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + 16 * p16 + q * 8, 64, hv + q * 8);
     }
-    // ---- tail 1
-    mma_round(256, sH, FT_H_PART, sW1, FT_W64_PART, 64, 64);
-    tc::tmem_ld32_sum2(tbase, warp, 256 + 32 * half, 64, h);
+    // ---- tail 1 (the layer-0 accumulators have been read by everyone before the round's barrier)
+    mma_round(0, sH, FT_H_PART, sW1, FT_W64_PART, 64, 64);
+    tc::tmem_ld32_sum2(tbase, warp, 0 + 32 * half, 64, h);
 #pragma unroll
     for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + b1[32 * half + j], 0.f);
 #pragma unroll
     for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + q * 8, 64, h + q * 8);
     // ---- tail 2 -> e_self (half 0) | e_vain (half 1)
-    mma_round(256, sH, FT_H_PART, sW2, FT_W64_PART, 64, 64);
-    tc::tmem_ld32_sum2(tbase, warp, 256 + 32 * half, 64, h);
+    mma_round(128, sH, FT_H_PART, sW2, FT_W64_PART, 64, 64);
+    tc::tmem_ld32_sum2(tbase, warp, 128 + 32 * half, 64, h);
 #pragma unroll
     for (int j = 0; j < 32; ++j) h[j] += b2[32 * half + j];
     {
@@ -259,12 +274,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fov_encode_tc_kernel(const uint
         dst[j4] = make_float4(h[j4 * 4] + bp[16 * half + j4 * 4], h[j4 * 4 + 1] + bp[16 * half + j4 * 4 + 1],
                               h[j4 * 4 + 2] + bp[16 * half + j4 * 4 + 2], h[j4 * 4 + 3] + bp[16 * half + j4 * 4 + 3]);
     }
+    hphase ^= 1u;
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
   }
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tbase, 512);
+  if (warp == 0) tc::tmem_dealloc(tbase, 256);
 }
 
 // ---- host side ----
@@ -304,7 +320,7 @@ int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32
     CTRM_CUDA_OK(cudaFuncSetAttribute(fov_encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
     attr = true;
   }
-  const int grid = n_tiles < 148 ? n_tiles : 148;
+  const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent, two CTAs per SM
   fov_encode_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(d_fov_tiles, m.fov_w0_tiles, fov_n_chunks(m.desc.fov_size), m.fov_w0_exp,
                                                          d_agent_inst, d_skip_inst, A, m.fov_img, d_e_self, d_e_vain,
                                                          d_vain_proj, n_tiles, d_live_agent, d_n_live);
