@@ -244,7 +244,7 @@ def test_encode_features_vs_reference(builder, trace_gold):
         L.check(lib.ctrm_encode_features(builder.ctx, fov.data_ptr(), cur.data_ptr(), prev.data_ptr(), X.data_ptr(), _stream()))
         got = X.cpu().numpy().reshape(A, 72)
         ref = z["nn_X"][j]
-        assert rel_err(got[:, :8], ref[:, :8]) < 1e-6  # fp64 differences, fp32 normalisation (encode.cu nvm)
+        assert rel_err(got[:, :8], ref[:, :8]) < 1e-6  # fp64 differences, fp32 normalisation (agent_tc.cu nvm)
         for lo, hi in ((0, 8), (8, 40), (40, 72)):
             worst = max(worst, rel_err(got[:, lo:hi], ref[:, lo:hi]))
     assert worst <= TOL, worst
