@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
   const uint32_t sA = tc::smem_u32(At), sW0 = tc::smem_u32(W0t), sW1 = tc::smem_u32(W1t);
   uint32_t phase = 1;
   const float eps = 1.1920928955078125e-07f;
+  int temp_exp;
+  const float inv_temp = (frexpf(temp, &temp_exp) == 0.5f && temp_exp > -100 && temp_exp < 100) ? 1.f / temp : 0.f;
   const int n_arows = bt.live_agent != nullptr ? *bt.n_live : bt.A;  // agents of the unfinished instances, or all
   const long long n_rows = (long long)n_arows * K;
   n_tiles = (int)min((long long)n_tiles, (n_rows + 127) >> 7);
@@ -452,7 +454,9 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
         for (int j = 0; j < 8; ++j) {
           const float u = fminf(fmaxf(u8[j], eps), 1.f - eps);
           const float g = -logf(-logf(u));
-          s[j] = (l[j] + g) / temp;
+          // torch divides by the temperature; for a power of two (the trained 2.0) the reciprocal multiply is the same
+          // float and saves an IEEE division per latent
+          s[j] = inv_temp != 0.f ? (l[j] + g) * inv_temp : (l[j] + g) / temp;
           mx = fmaxf(mx, s[j]);
         }
         park8(At, r, q * 8, s);
