@@ -478,6 +478,19 @@ extern "C" int ctrm_collide_sphere_pairs(const double* f1, const double* t1, con
   return launch_collide_pairs(f1, t1, r1, f2, t2, r2, dim, n, verdict, (cudaStream_t)stream);
 }
 
+int keep_async_pool_warm() {
+  static bool done[64] = {false};
+  int dev = 0;
+  CTRM_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || done[dev]) return 0;
+  cudaMemPool_t pool;
+  CTRM_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t keep = 256ull << 20;  // scratch of these entry points is a few MB; cap what the pool may hold back
+  CTRM_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  done[dev] = true;
+  return 0;
+}
+
 extern "C" int ctrm_raster_occupancy(const double* d_obs_xyr, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, void* stream) {
   if (B <= 0 || M < 1 || M > 255 || !d_obs_off || !d_occ) return ctrm_fail(CTRM_ERR_ARG, "ctrm_raster_occupancy: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -485,6 +498,7 @@ extern "C" int ctrm_raster_occupancy(const double* d_obs_xyr, const int32_t* d_o
   CTRM_CUDA_OK(cudaMemcpyAsync(&O, d_obs_off + B, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CTRM_CUDA_OK(cudaStreamSynchronize(st));
   int4* d_cells = nullptr;
+  CHECK(keep_async_pool_warm());
   CTRM_CUDA_OK(cudaMallocAsync(&d_cells, sizeof(int4) * (size_t)(O > 0 ? O : 1), st));
   int rc = launch_obs_to_cells(d_obs_xyr, O, M, d_cells, st);
   if (!rc) rc = launch_raster_occupancy(d_cells, d_obs_off, B, M, d_occ, st);

@@ -112,6 +112,7 @@ int launch_collide_segments(const double* d_from, const double* d_to, const doub
   long long nb = (n + 255) / 256;
   if (nb > 0x7FFFFFFFLL) return ctrm_fail(-1, "too many segments");
   int32_t* d_block_cnt = nullptr;
+  if (d_survivors && keep_async_pool_warm()) return -2;
   if (d_survivors) CTRM_CUDA_OK(cudaMallocAsync(&d_block_cnt, (size_t)nb * sizeof(int32_t), st));
   collide_segments_kernel<<<(unsigned)nb, 256, 0, st>>>(reinterpret_cast<const double2*>(d_from),
                                                        reinterpret_cast<const double2*>(d_to), d_rad, d_seg_inst, n,

@@ -129,6 +129,10 @@ int launch_csr_count(const Batch& bt, int64_t* d_agent_nv, int64_t* d_agent_ne, 
 int launch_csr_fill(const Batch& bt, const int64_t* d_agent_v0, const int64_t* d_agent_e0, const int64_t* d_totals,
                     int32_t* d_layer_ptr, double* d_pos, int64_t* d_eptr, int32_t* d_eidx, cudaStream_t st);
 
+// stream-ordered scratch of the context-free stage entry points: keep freed blocks in the device's default pool instead of
+// returning them to the driver at every synchronisation (the default), which made each call pay a fresh allocation
+int keep_async_pool_warm();
+
 // prioritized planning over exported CSR roadmaps (plan.cu)
 int launch_plan_prioritized(int B, int L, const int32_t* d_agent_off, const int32_t* d_n_layers, const int32_t* d_layer_ptr,
                             const double* d_pos, const int64_t* d_eptr, const int32_t* d_eidx, const double* d_goals,
