@@ -118,6 +118,11 @@ __global__ void __launch_bounds__(PL_THREADS) plan_prioritized_kernel(PlanArgs p
       const size_t gv = (size_t)first + v;
       const long long e0 = p.eptr[gv];
       const int deg = (int)(p.eptr[gv + 1] - e0);
+      if (deg > PL_MAXDEG) {  // roadmaps built here have at most 128 slots per layer; a foreign CSR may not: report, do not overrun
+        if (tid == 0) p.failed_agent[b] = -2;
+        fin_v = -1;
+        break;
+      }
       const int nfirst = lp[t + 1] - first;  // local id of (t + 1, 0)
       const double vx = p.pos[2 * gv], vy = p.pos[2 * gv + 1];
       // ---- valid_successor for all (successor, earlier agent) pairs at once
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(PL_THREADS) plan_prioritized_kernel(PlanArgs p
       ok_all = false;
       if (tid == 0) {
         p.solved[b] = 0;
-        p.failed_agent[b] = ag;
+        if (p.failed_agent[b] != -2) p.failed_agent[b] = ag;
       }
       break;
     }

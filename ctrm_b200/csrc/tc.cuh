@@ -224,9 +224,9 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
       "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" ::"r"(mbar),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)  // suspend-time hint: the waiting warp sleeps in hardware instead of polling
       : "memory");
 }
 

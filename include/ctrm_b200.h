@@ -252,7 +252,7 @@ int ctrm_others_info(const double* d_cur /*[T][N][2]*/, const double* d_goals /*
  * (layer_ptr with a fixed stride of L slots per agent).  paths[a][t] = index within V[t] of the vertex agent a occupies at
  * time t (the goal vertex once arrived; -1 beyond the instance's horizon or when the instance is unsolved, as the reference
  * clears its solution); path_pos[a][t] the matching coordinates; solved[b] 0/1; failed_agent[b] = first agent without a
- * path or -1; counters[b] = {cnt_continuous_collide, lowlevel_expanded, lowlevel_explored} of the reference's Result.
+ * path, -1 if solved, -2 if a vertex has more than 128 successors (unsupported); counters[b] = {cnt_continuous_collide, lowlevel_expanded, lowlevel_explored} of the reference's Result.
  * max_agent_vertices = largest number of vertices of one agent's roadmap (sizes the per-CTA shared memory). */
 int ctrm_plan_prioritized(int B, int A, int L, const int32_t* d_agent_off /*[B+1]*/, const int32_t* d_n_layers /*[A]*/,
                           const int32_t* d_layer_ptr /*[A*L+1]*/, const double* d_pos /*[nv][2]*/,
