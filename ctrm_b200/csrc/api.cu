@@ -678,6 +678,7 @@ static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, 
     CHECK(mark(KID_CVAE_DECODE));
   }
   CHECK(launch_step(bt, st));
+  ++k;  // launch_step is two kernels: step, then advance
   CHECK(mark(KID_STEP));
   *n_kernels = k;
   return 0;

@@ -423,8 +423,7 @@ __device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const StepC
 }
 
 // ------------------------------------------------------------------------------------------------
-// advance: roll-out bookkeeping of one instance, run by the last of its agents' warps to finish the step (the other
-// warps' writes are read with ld.global.cg after a __threadfence: L1 may hold stale lines of the same 128 bytes)
+// advance: roll-out bookkeeping of one instance (advance_kernel, one warp per instance, after the step kernel)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void advance_instance(const Batch& bt, const int b, const int lane) {
   const int a0 = bt.agent_off[b], N = bt.agent_off[b + 1] - a0;
@@ -491,7 +490,7 @@ int launch_rollout_init(const Batch& bt, cudaStream_t st) {
   return 0;
 }
 // ------------------------------------------------------------------------------------------------
-// step: select -> merge -> (last warp of the instance) advance, one warp per agent
+// step: select -> merge, one warp per agent; then advance, one warp per instance
 // ------------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
@@ -530,19 +529,16 @@ __global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
   double lx, ly;
   unsigned int count = select_agent(bt, sc, a, lane, cur.x, cur.y, arrived, &lx, &ly);
   count += merge_agent<W>(bt, sc, a, lane, lx, ly, pf);
-  // publish this agent's state, then let the last warp of the instance do the roll-out bookkeeping
-  int last = 0;
-  if (lane == 0) {
-    if (count) atomicAdd(&bt.cnt_collide[sc.b], (unsigned long long)count);
-    __threadfence();
-    last = (atomicAdd(&bt.arrive_cnt[sc.b], 1) == sc.N - 1) ? 1 : 0;
-  }
-  last = __shfl_sync(0xFFFFFFFFu, last, 0);
-  if (last) {
-    __threadfence();
-    if (lane == 0) bt.arrive_cnt[sc.b] = 0;
-    advance_instance(bt, sc.b, lane);
-  }
+  if (lane == 0 && count) atomicAdd(&bt.cnt_collide[sc.b], (unsigned long long)count);
+}
+
+// roll-out bookkeeping, one warp per instance, after every agent of the step has been processed (a kernel boundary is
+// cheaper than electing the instance's last warp with __threadfence + atomics, which was 12% of the step kernel's stalls)
+__global__ void __launch_bounds__(RO_WARPS * 32) advance_kernel(Batch bt) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= bt.B || bt.done[b]) return;
+  advance_instance(bt, b, lane);
 }
 
 int launch_step(const Batch& bt, cudaStream_t st) {
@@ -555,6 +551,8 @@ int launch_step(const Batch& bt, cudaStream_t st) {
     case 4: step_kernel<4><<<blocks, RO_WARPS * 32, 0, st>>>(bt); break;
     default: return ctrm_fail(-1, "unsupported adjacency mask width");
   }
+  CTRM_CUDA_OK(cudaGetLastError());
+  advance_kernel<<<(bt.B + RO_WARPS - 1) / RO_WARPS, RO_WARPS * 32, 0, st>>>(bt);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }
