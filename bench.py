@@ -422,7 +422,8 @@ def gpu_arm(args):
         cpu = dict(value=r["vertices"] / r["seconds"], unit=UNIT, cores=cores, kind="port",
                    sample=f"{cores} instances of the same workload at full N_traj=25, one process per core, oracle port "
                           f"(numpy + torch-CPU, 1 thread each), {r['seconds']:.1f} s wall",
-                   instances_per_s=r["instances"] / r["seconds"])
+                   instances_per_s=r["instances"] / r["seconds"],
+                   single_core_s_per_instance=r["seconds"] * cores / r["instances"])  # one instance per process: its latency
         # planner, CPU port (oracle/pp_oracle.py), one instance of the same workload on one core
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import pp_oracle
