@@ -139,14 +139,14 @@ __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restri
   const int mw = (M + 31) >> 5;  // words per row of the mask as written by passable_mask_kernel
   const uint32_t* pm = pmask + (size_t)agent_pm[a] * M * mw;
   uint16_t* out = ctg + (size_t)a * ctg_field_elems(M, layout);
-  uint32_t pass[RPL][MW], vis[RPL][MW], fr[RPL][MW];
+  // open[r][w] = passable and not yet visited (one bit grid instead of two: the kernel is bound by registers -> occupancy)
+  uint32_t open[RPL][MW], fr[RPL][MW];
 #pragma unroll
   for (int r = 0; r < RPL; ++r) {
     int x = lane * RPL + r;
 #pragma unroll
     for (int w = 0; w < MW; ++w) {
-      pass[r][w] = (x < M && w < mw) ? __ldg(&pm[x * mw + w]) : 0u;
-      vis[r][w] = 0u;
+      open[r][w] = (x < M && w < mw) ? __ldg(&pm[x * mw + w]) : 0u;
       fr[r][w] = 0u;
     }
   }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restri
     for (int w = 0; w < MW; ++w) {
       if (lane * RPL + r == gx && w == (gy >> 5)) {
         fr[r][w] = 1u << (gy & 31);
-        vis[r][w] = fr[r][w];
+        open[r][w] &= ~fr[r][w];
       }
     }
   }
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restri
         uint32_t nb = (f << 1) | (lo >> 31) | (f >> 1) | (hi << 31);
         nb |= (r > 0) ? fr[r - 1][w] : up_in[w];
         nb |= (r < RPL - 1) ? fr[r + 1][w] : dn_in[w];
-        uint32_t n = nb & pass[r][w] & ~vis[r][w];
+        uint32_t n = nb & open[r][w];
         nw[r][w] = n;
         any |= n;
       }
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restri
 #pragma unroll
       for (int w = 0; w < MW; ++w) {
         uint32_t n = nw[r][w];
-        vis[r][w] |= n;
+        open[r][w] &= ~n;
         fr[r][w] = n;
         while (n) {
           int bit = __ffs(n) - 1;
