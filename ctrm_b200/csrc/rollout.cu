@@ -114,6 +114,7 @@ int launch_compact_live(const Batch& bt, cudaStream_t st) {
 #define RO_OBS_MAX 64
 struct StepCtx {
   int b, t, kt, makespan, a0, N, o0, nO;
+  uint32_t inv_nO;  // 2^20 / nO + 1 for nO in 1..128, else 0
   double gx, gy, speed, speed2, merge2, rad;
   const double* sobs;  // shared memory [nO][3] when nO <= RO_OBS_MAX, else nullptr (global fallback)
 };
@@ -130,16 +131,34 @@ __device__ __forceinline__ void obstacle_at(const Batch& bt, const StepCtx& cx, 
     *rs = f64add(cx.rad, __ldg(g + 2));
   }
 }
-// StaticObjects.collide_continuous_sphere: any over the instance's obstacles (no early exit: the loop pipelines)
-__device__ __forceinline__ bool hits_any(const Batch& bt, const StepCtx& cx, double fx, double fy, double tx, double ty) {
-  bool hit = false;
-#pragma unroll 2
-  for (int o = 0; o < cx.nO; ++o) {
-    double ox, oy, rs;
-    obstacle_at(bt, cx, o, &ox, &oy, &rs);
-    hit = hit || (!sweep_far(fx, fy, tx, ty, ox, oy, rs) && sweep_static(fx, fy, tx, ty, ox, oy, rs));
+// p / nO for pair indices p <= 32 * nO (exact: 32 * nO^2 < 2^20 for nO <= 128) without an integer division
+__device__ __forceinline__ int pair_div(const StepCtx& cx, int p) {
+  return cx.inv_nO ? (int)(((uint32_t)p * cx.inv_nO) >> 20) : p / cx.nO;
+}
+
+// StaticObjects.collide_continuous_sphere (any over the instance's obstacles) for the lanes set in `cand` at once (lane l
+// holds the segment start (vx, vy), the end (tx, ty) is uniform): the (candidate lane, obstacle) pairs are flattened over the warp, so a handful of candidates costs
+// ceil(candidates * nO / 32) passes instead of nO passes with most lanes idle.  Returns the lanes whose segment collides.
+__device__ __forceinline__ uint32_t hits_any_flat(const Batch& bt, const StepCtx& cx, uint32_t cand, double vx, double vy,
+                                                  double tx, double ty, int lane) {
+  const int nO = cx.nO;
+  const int npairs = __popc(cand) * nO;
+  uint32_t coll = 0u;
+  for (int p0 = 0; p0 < npairs; p0 += 32) {
+    const int p = p0 + lane;
+    const bool act = p < npairs;
+    const int ci = act ? pair_div(cx, p) : 0;
+    uint32_t pm = cand;
+    for (int q = 0; q < ci; ++q) pm &= pm - 1;  // drop the ci lowest set bits
+    const int src = act ? (__ffs(pm) - 1) : 0;
+    const double fx = __shfl_sync(0xFFFFFFFFu, vx, src), fy = __shfl_sync(0xFFFFFFFFu, vy, src);
+    if (act) {
+      double ox, oy, rs;
+      obstacle_at(bt, cx, p - ci * nO, &ox, &oy, &rs);
+      if (!sweep_far(fx, fy, tx, ty, ox, oy, rs) && sweep_static(fx, fy, tx, ty, ox, oy, rs)) coll |= 1u << src;
+    }
   }
-  return hit;
+  return __reduce_or_sync(0xFFFFFFFFu, coll);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -211,7 +230,7 @@ __device__ __forceinline__ unsigned int select_agent(const Batch& bt, const Step
     for (int p0 = 0; p0 < npairs; p0 += 32) {
       const int p = p0 + lane;
       const bool act = p < npairs;
-      const int ci = act ? p / nO : 0;
+      const int ci = act ? pair_div(sc, p) : 0;
       uint32_t pm = pre_mask;
       for (int q = 0; q < ci; ++q) pm &= pm - 1;  // drop the ci lowest set bits
       const int src = act ? (__ffs(pm) - 1) : 0;
@@ -301,9 +320,9 @@ __device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const StepC
     if (w * 32 < pf.n_prev) {
       const bool in = w * 32 + lane < pf.n_prev;
       const bool cand = in && dist2(pf.px[0][w], pf.py[0][w], lx, ly) <= speed2;
-      const bool ok = cand && !hits_any(bt, sc, pf.px[0][w], pf.py[0][w], lx, ly);
-      count += __popc(__ballot_sync(0xFFFFFFFFu, cand));
-      P[w] = __ballot_sync(0xFFFFFFFFu, ok);
+      const uint32_t cm = __ballot_sync(0xFFFFFFFFu, cand);
+      count += __popc(cm);
+      P[w] = cm & ~hits_any_flat(bt, sc, cm, pf.px[0][w], pf.py[0][w], lx, ly, lane);
     }
   }
   // children: V[t+1], tested as (child -> loc)   utils.py:72-84
@@ -313,9 +332,9 @@ __device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const StepC
       if (w * 32 < pf.n_next) {
         const bool in = w * 32 + lane < pf.n_next;
         const bool cand = in && dist2(pf.px[2][w], pf.py[2][w], lx, ly) <= speed2;
-        const bool ok = cand && !hits_any(bt, sc, pf.px[2][w], pf.py[2][w], lx, ly);
-        count += __popc(__ballot_sync(0xFFFFFFFFu, cand));
-        Cm[w] = __ballot_sync(0xFFFFFFFFu, ok);
+        const uint32_t cm = __ballot_sync(0xFFFFFFFFu, cand);
+        count += __popc(cm);
+        Cm[w] = cm & ~hits_any_flat(bt, sc, cm, pf.px[2][w], pf.py[2][w], lx, ly, lane);
       }
     }
   }
@@ -507,6 +526,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
   const int4 p1 = *reinterpret_cast<const int4*>(bt.inst_pack + 8 * sc.b + 4);
   sc.t = p0.y; sc.kt = p0.z; sc.makespan = p0.w;
   sc.a0 = p1.x; sc.N = p1.y; sc.o0 = p1.z; sc.nO = p1.w;
+  sc.inv_nO = (sc.nO >= 1 && sc.nO <= 128) ? (1u << 20) / (uint32_t)sc.nO + 1u : 0u;
   const double2 q0 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a);
   const double2 q1 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a + 2);
   const double2 q2 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a + 4);
