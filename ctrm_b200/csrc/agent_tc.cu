@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(AT_THREADS, 4) agent_comm_tc_kernel(Batch bt, 
     const int a = active ? (bt.live_agent != nullptr ? bt.live_agent[arow] : arow) : 0;
     int b = 0;
     if (active) {
-      b = bt.agent_inst[a];
+      b = bt.live_agent != nullptr ? bt.live_inst[arow] : bt.agent_inst[a];
       if (bt.done != nullptr && bt.done[b]) active = false;
     }
     // also: every shared-memory / TMEM read of the previous tile is done before this one overwrites them

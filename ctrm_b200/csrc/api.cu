@@ -407,6 +407,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&bt.arrive_cnt, (size_t)B));
   CHECK(ar.alloc(&bt.inst_pack, (size_t)8 * B));
   CHECK(ar.alloc(&bt.live_agent, (size_t)A));
+  CHECK(ar.alloc(&bt.live_inst, (size_t)A));
   CHECK(ar.alloc(&bt.n_live, (size_t)1));
   CHECK(ar.alloc(&bt.live_off, (size_t)B));
   CHECK(ar.alloc(&bt.agent_pack, (size_t)6 * A));

@@ -57,6 +57,7 @@ struct Batch {
   // rows of the per-step kernels: agents of the UNFINISHED instances, instance-contiguous, rebuilt between graph chunks so that
   // the tile kernels do not drag the dead rows of a lock-step batch's tail along (nullptr = identity over all A agents)
   int32_t* live_agent;                  // [A]
+  int32_t* live_inst;                   // [A] instance of live_agent[row]: read side by side, not after it
   int32_t* n_live;                      // [1] number of rows
   int32_t* live_off;                    // [B] scratch: first row of an unfinished instance
   double* agent_pack;                   // [A][6] {goal x, goal y, speed, speed^2, merge_distance^2, rad}

@@ -24,7 +24,10 @@ __global__ void rollout_init_kernel(Batch bt) {
     bt.prev[2 * i] = sx; bt.prev[2 * i + 1] = sy;
     bt.nxt[2 * i] = sx; bt.nxt[2 * i + 1] = sy;
     bt.arrived[i] = 0;
-    if (bt.live_agent != nullptr) bt.live_agent[i] = i;
+    if (bt.live_agent != nullptr) {
+      bt.live_agent[i] = i;
+      bt.live_inst[i] = bt.agent_inst[i];
+    }
     double* ap = bt.agent_pack + 6 * (size_t)i;  // {goal x, goal y, speed, speed^2, merge_distance^2, rad}
     ap[0] = bt.goals[2 * i]; ap[1] = bt.goals[2 * i + 1]; ap[2] = bt.speeds[i]; ap[3] = bt.speeds2[i];
     ap[4] = bt.merge2[i]; ap[5] = bt.rads[i];
@@ -97,7 +100,11 @@ __global__ void live_scatter_kernel(Batch bt) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= bt.A) return;
   const int b = bt.agent_inst[a];
-  if (!bt.done[b]) bt.live_agent[bt.live_off[b] + (a - bt.agent_off[b])] = a;
+  if (!bt.done[b]) {
+    const int row = bt.live_off[b] + (a - bt.agent_off[b]);
+    bt.live_agent[row] = a;
+    bt.live_inst[row] = b;
+  }
 }
 int launch_compact_live(const Batch& bt, cudaStream_t st) {
   if (bt.A <= 0 || bt.live_agent == nullptr) return 0;
@@ -131,6 +138,16 @@ __device__ __forceinline__ void obstacle_at(const Batch& bt, const StepCtx& cx, 
     *rs = f64add(cx.rad, __ldg(g + 2));
   }
 }
+// 2^20 / n + 1 for n = 1..128 (entry 0 unused): reciprocal table of pair_div, in constant memory
+struct PairInvTable {
+  uint32_t v[129];
+  constexpr PairInvTable() : v() {
+    v[0] = 0u;
+    for (int i = 1; i < 129; ++i) v[i] = (1u << 20) / (uint32_t)i + 1u;
+  }
+};
+__constant__ PairInvTable c_pair_inv = PairInvTable();
+
 // p / nO for pair indices p <= 32 * nO (exact: 32 * nO^2 < 2^20 for nO <= 128) without an integer division
 __device__ __forceinline__ int pair_div(const StepCtx& cx, int p) {
   return cx.inv_nO ? (int)(((uint32_t)p * cx.inv_nO) >> 20) : p / cx.nO;
@@ -520,13 +537,13 @@ __global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
   if (row >= (bt.live_agent != nullptr ? *bt.n_live : bt.A)) return;
   const int a = bt.live_agent != nullptr ? bt.live_agent[row] : row;
   StepCtx sc;
-  sc.b = bt.agent_inst[a];
+  sc.b = bt.live_agent != nullptr ? bt.live_inst[row] : bt.agent_inst[a];
   const int4 p0 = *reinterpret_cast<const int4*>(bt.inst_pack + 8 * sc.b);
   if (p0.x) return;  // instance finished
   const int4 p1 = *reinterpret_cast<const int4*>(bt.inst_pack + 8 * sc.b + 4);
   sc.t = p0.y; sc.kt = p0.z; sc.makespan = p0.w;
   sc.a0 = p1.x; sc.N = p1.y; sc.o0 = p1.z; sc.nO = p1.w;
-  sc.inv_nO = (sc.nO >= 1 && sc.nO <= 128) ? (1u << 20) / (uint32_t)sc.nO + 1u : 0u;
+  sc.inv_nO = (sc.nO >= 1 && sc.nO <= 128) ? c_pair_inv.v[sc.nO] : 0u;
   const double2 q0 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a);
   const double2 q1 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a + 2);
   const double2 q2 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a + 4);
