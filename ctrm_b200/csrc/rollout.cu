@@ -422,8 +422,9 @@ __device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const StepC
           const uint32_t pu = resolved ? bt.pmask[v * W + w] : 0u;
           const uint32_t cu = resolved ? bt.cmask[v * W + w] : 0u;
           const int s = w * 32 + lane;
-          if ((P[w] & ~pu) >> lane & 1u) bt.cmask[vslot(bt, a, t - 1, s) * W + tw] |= tbit;   // E[t-1][p].append(u)
-          if ((Cm[w] & ~cu) >> lane & 1u) bt.pmask[vslot(bt, a, t + 1, s) * W + tw] |= tbit;  // mirror of E[t][u] += ...
+          // reductions without a return value: the warp does not wait for the old word (it is the only writer of its roadmap)
+          if ((P[w] & ~pu) >> lane & 1u) atomicOr(&bt.cmask[vslot(bt, a, t - 1, s) * W + tw], tbit);   // E[t-1][p].append(u)
+          if ((Cm[w] & ~cu) >> lane & 1u) atomicOr(&bt.pmask[vslot(bt, a, t + 1, s) * W + tw], tbit);  // mirror of E[t][u] += ...
           __syncwarp();
           if (lane == 0) {
             bt.pmask[v * W + w] = pu | P[w];
