@@ -152,14 +152,16 @@ __global__ void __launch_bounds__(128) wavefront_kernel(const uint32_t* __restri
   }
   int gx = grid_cell(goals[2 * a + 0], M), gy = grid_cell(goals[2 * a + 1], M);
   if (gx >= M || gy >= M) return;  // asserts are compiled out in the reference; field stays unreachable
+  // selects, not an indexed store: a run-time index would push both bit grids into local memory for the whole kernel
+  const int g_r = gx - lane * RPL, g_w = gy >> 5;
+  const uint32_t g_bit = 1u << (gy & 31);
 #pragma unroll
   for (int r = 0; r < RPL; ++r) {
 #pragma unroll
     for (int w = 0; w < MW; ++w) {
-      if (lane * RPL + r == gx && w == (gy >> 5)) {
-        fr[r][w] = 1u << (gy & 31);
-        open[r][w] &= ~fr[r][w];
-      }
+      const uint32_t m = (g_r == r && g_w == w) ? g_bit : 0u;
+      fr[r][w] = m;
+      open[r][w] &= ~m;
     }
   }
   if (lane == gx / RPL) out[ctg_index(gx, gy, M, layout)] = 0;
