@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(AT_THREADS, 4) agent_comm_tc_kernel(Batch bt, 
           }
         }
       }
-      tc::store_split8(At, At + AT_A0_PART, At + 2 * AT_A0_PART, row, 8 * half, 16, info);
+      tc::store_act8(At, At + AT_A0_PART, At + 2 * AT_A0_PART, row, 8 * half, 16, info);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(AT_THREADS, 4) agent_comm_tc_kernel(Batch bt, 
 #pragma unroll
     for (int k = 0; k < 16; ++k) h[k] = fmaxf(h[k] + acc[k], 0.f);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) tc::store_split8(At, At + AT_A_PART, At + 2 * AT_A_PART, row, 16 * half + q * 8, 32, h + q * 8);
+    for (int q = 0; q < 2; ++q) tc::store_act8(At, At + AT_A_PART, At + 2 * AT_A_PART, row, 16 * half + q * 8, 32, h + q * 8);
     tc::fence_before_sync();
     tc::fence_async_smem();
     __syncthreads();
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(AT_THREADS, 4) agent_comm_tc_kernel(Batch bt, 
 #pragma unroll
     for (int k = 0; k < 16; ++k) h[k] = fmaxf(acc[k] + B1[16 * half + k], 0.f);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) tc::store_split8(At, At + AT_A_PART, At + 2 * AT_A_PART, row, 16 * half + q * 8, 32, h + q * 8);
+    for (int q = 0; q < 2; ++q) tc::store_act8(At, At + AT_A_PART, At + 2 * AT_A_PART, row, 16 * half + q * 8, 32, h + q * 8);
     tc::fence_before_sync();
     tc::fence_async_smem();
     __syncthreads();

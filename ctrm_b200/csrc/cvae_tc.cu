@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(PR_THREADS, 2) cvae_prior_tc_kernel(Batch bt, 
   // thread (row r, half): hidden columns [16 half, 16 half + 16) -> three bf16 parts of the [128 x 32] hidden tile
   auto store_hidden16 = [&](const float* h) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) tc::store_split8(Xt, Xt + PR_H_PART, Xt + 2 * PR_H_PART, r, 16 * half + q * 8, 32, h + q * 8);
+    for (int q = 0; q < 2; ++q) tc::store_act8(Xt, Xt + PR_H_PART, Xt + 2 * PR_H_PART, r, 16 * half + q * 8, 32, h + q * 8);
   };
 
   const int n_arows = bt.live_agent != nullptr ? *bt.n_live : bt.A;  // agents of the unfinished instances, or all
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(PR_THREADS, 2) cvae_prior_tc_kernel(Batch bt, 
           const float4 p0 = __ldg(&xr[2 * q]), p1 = __ldg(&xr[2 * q + 1]);
           v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
         }
-        tc::store_split8(Xt, Xt + PR_X_PART, Xt + 2 * PR_X_PART, r, q * 8, PR_K0, v);
+        tc::store_act8(Xt, Xt + PR_X_PART, Xt + 2 * PR_X_PART, r, q * 8, PR_K0, v);
       }
     }
     mma_round(0, sX, PR_X_PART, sW0, PR_W0_PART, PR_K0, 96, false);
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     tc::fence_before_sync();
     __syncthreads();  // every thread has read its layer-0 accumulators before the tile memory is rewritten
 #pragma unroll
-    for (int q = 0; q < 2; ++q) tc::store_split8(At, At + DT_H_PART, At + 2 * DT_H_PART, r, 16 * half + q * 8, 32, h + q * 8);
+    for (int q = 0; q < 2; ++q) tc::store_act8(At, At + DT_H_PART, At + 2 * DT_H_PART, r, 16 * half + q * 8, 32, h + q * 8);
     tc::fence_async_smem();
     __syncthreads();
     if (tid == 0) {

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fov_encode_tc_kernel(const uint
       // the hidden tile lies in ring memory that layer 0 has finished with (waited on above)
 #pragma unroll
       for (int q = 0; q < 2; ++q)
-        tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + 16 * p16 + q * 8, 64, hv + q * 8);
+        tc::store_act8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + 16 * p16 + q * 8, 64, hv + q * 8);
     }
     // ---- tail 1 (the layer-0 accumulators have been read by everyone before the round's barrier)
     mma_round(0, sH, FT_H_PART, sW1, FT_W64_PART, 64, 64);
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fov_encode_tc_kernel(const uint
 #pragma unroll
     for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j] + b1[32 * half + j], 0.f);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + q * 8, 64, h + q * 8);
+    for (int q = 0; q < 4; ++q) tc::store_act8(Ht, Ht + FT_H_PART, Ht + 2 * FT_H_PART, r, 32 * half + q * 8, 64, h + q * 8);
     // ---- tail 2 -> e_self (half 0) | e_vain (half 1)
     mma_round(128, sH, FT_H_PART, sW2, FT_W64_PART, 64, 64);
     tc::tmem_ld32_sum2(tbase, warp, 128 + 32 * half, 64, h);
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fov_encode_tc_kernel(const uint
     __syncthreads();  // tail-2 accumulators read by everyone before the hidden tile is rewritten
     if (half == 1) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tc::store_split8(Ht, Ht + FT_H32_PART, Ht + 2 * FT_H32_PART, r, q * 8, 32, h + q * 8);
+      for (int q = 0; q < 4; ++q) tc::store_act8(Ht, Ht + FT_H32_PART, Ht + 2 * FT_H32_PART, r, q * 8, 32, h + q * 8);
     }
     mma_round(0, sH, FT_H32_PART, sWp, FT_W32_PART, 32, 32);
     tc::tmem_ld16_sum2(tbase, warp, 16 * half, 32, h);

@@ -60,6 +60,29 @@ __device__ __forceinline__ void store_split8(uint8_t* t1, uint8_t* t2, uint8_t* 
   store_split8_body(t1, t2, t3, elem_offset(r, k0, K), v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
 }
 
+// The same exact three-way split for ACTIVATIONS, by truncation instead of rounding: each part keeps the next 8 significant
+// bits (x = x1 + x2 + x3 still holds exactly: 3 x 8 = 24), the packed words come straight out of the fp32 registers with
+// one byte permute per pair and part, and the residuals cost an AND and a subtraction instead of two conversions.  With the
+// weights split by rounding (|b2| <= 2^-9 |b|, |b3| <= 2^-17 |b|) the dropped products a2*b3, a3*b2 stay <= 2^-24 |a||b|.
+__device__ __forceinline__ void store_act8(uint8_t* t1, uint8_t* t2, uint8_t* t3, int r, int k0, int K, const float* v) {
+  uint32_t w1[4], w2[4], w3[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = v[2 * j], b = v[2 * j + 1];
+    const uint32_t ab = __float_as_uint(a), bb = __float_as_uint(b);
+    w1[j] = __byte_perm(ab, bb, 0x7632);
+    const float ra = a - __uint_as_float(ab & 0xFFFF0000u), rb = b - __uint_as_float(bb & 0xFFFF0000u);
+    const uint32_t rab = __float_as_uint(ra), rbb = __float_as_uint(rb);
+    w2[j] = __byte_perm(rab, rbb, 0x7632);
+    const float sa = ra - __uint_as_float(rab & 0xFFFF0000u), sb = rb - __uint_as_float(rbb & 0xFFFF0000u);
+    w3[j] = __byte_perm(__float_as_uint(sa), __float_as_uint(sb), 0x7632);
+  }
+  const uint32_t off = elem_offset(r, k0, K);
+  *reinterpret_cast<uint4*>(t1 + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+  *reinterpret_cast<uint4*>(t2 + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+  *reinterpret_cast<uint4*>(t3 + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+}
+
 // ---- descriptors ----
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int K) {
   uint64_t d = 0;
