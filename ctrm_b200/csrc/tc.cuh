@@ -392,14 +392,25 @@ static __device__ __noinline__ void stage_weight_digits(const float* __restrict_
 __device__ __forceinline__ void store_digits8_unit_body(uint8_t* tiles, uint32_t part, uint32_t off, float v0, float v1, float v2,
                                                      float v3, float v4, float v5, float v6, float v7) {
   const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
-  uint32_t dg[8][4];
+  // a digit is an integer in [0, 256]: at most 8 significant bits, so the upper half of its fp32 pattern IS its bf16 pattern
+  // and two digits pack with one byte permute (no conversion instruction)
+  float t[8];
+  uint32_t w[4][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) digits4_unit(v[j], dg[j]);
+  for (int j = 0; j < 8; ++j) t[j] = v[j] * 256.f;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float da = floorf(t[2 * j]), db = floorf(t[2 * j + 1]);
+      w[d][j] = __byte_perm(__float_as_uint(da), __float_as_uint(db), 0x7632);
+      t[2 * j] = (t[2 * j] - da) * 256.f;        // exact
+      t[2 * j + 1] = (t[2 * j + 1] - db) * 256.f;
+    }
+  }
 #pragma unroll
   for (int d = 0; d < 4; ++d)
-    *reinterpret_cast<uint4*>(tiles + d * part + off) =
-        make_uint4(dg[0][d] | (dg[1][d] << 16), dg[2][d] | (dg[3][d] << 16), dg[4][d] | (dg[5][d] << 16),
-                   dg[6][d] | (dg[7][d] << 16));
+    *reinterpret_cast<uint4*>(tiles + d * part + off) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
 }
 __device__ __forceinline__ void store_digits8_unit(uint8_t* tiles, uint32_t part, int r, int k0, int K, const float* v) {
   store_digits8_unit_body(tiles, part, elem_offset(r, k0, K), v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
