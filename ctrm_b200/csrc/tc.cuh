@@ -197,15 +197,6 @@ __device__ __forceinline__ void commit(uint32_t mbar) {
 // Every digit product is an integer below 2^15; a K <= 64 dot product of up to four digit pairs stays below 2^24, so the
 // fp32 accumulator holds it EXACTLY.  Pairs with equal i + j share one accumulator g = i + j in {2, 3, 4, 5} with scale
 // 2^(e + 1 - 8 g); the epilogue combines the four accumulators in fp64.  Truncation: 2^-32 absolute in a, 2^(e-32) in b.
-__device__ __forceinline__ void digits4_unit(float a, uint32_t* q) {  // a in [0, 1]
-  float t = a * 256.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float d = floorf(t);
-    q[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(d));  // integer <= 256: exact
-    t = (t - d) * 256.f;                                            // exact
-  }
-}
 __device__ __forceinline__ void digits4_signed(float b, float scale, uint32_t* q) {  // |b * scale| <= 128
   float t = b * scale;  // power-of-two scale: exact
 #pragma unroll
