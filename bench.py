@@ -263,13 +263,27 @@ def gpu_arm(args):
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     seed = 2022
 
+    pending = []  # (works, keepalive) of the previous step's gather
+
+    def drain_gather():
+        while pending:
+            works, keep = pending.pop()
+            for w in works:
+                w.wait()
+            del keep
+
     def gather_to_rank0(res):
-        """the only collective of the path: NCCL gather of the variable-length CSR payload over NVLink"""
+        """the only collective of the path: NCCL gather of the variable-length CSR payload over NVLink.  It is enqueued
+        asynchronously: the transfer of step i overlaps the kernels of step i + 1 and is waited for before the next gather
+        starts (and, for the last step, before the timed region closes)"""
         if world == 1:
             return res
         from ctrm_b200.parallel import gather_csr
 
-        return gather_csr(res, rank, world)
+        drain_gather()
+        out, works, keep = gather_csr(res, rank, world, async_op=True)
+        pending.append((works, (keep, res)))
+        return out
 
     phase_ms = []
 
@@ -295,6 +309,7 @@ def gpu_arm(args):
     # ---- device-resident timing
     for _ in range(args.warmup):
         device_step()
+    drain_gather()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -305,6 +320,7 @@ def gpu_arm(args):
     for _ in range(args.steps):
         device_step()
         launches += builder.timing()["launches"] + 5  # + occupancy (2), passability, wavefront, csr fill
+    drain_gather()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
