@@ -160,3 +160,28 @@ def test_demonstration_features_vs_oracle():
         want = O.others_info(cur, goals, prev, rads, speeds).astype(np.float32)
         assert np.array_equal(got["others_info"][t], want), t
         assert np.array_equal(got["self_info"][t], want.reshape(N, N, 11)[np.arange(N), np.arange(N), 3:]), t
+
+
+def test_flatten_trms_lazy_views_equal_plain_lists(pp_gold):
+    """host logic of the planner mirror (no GPU): the CSR fast path over lazy views and the generic path over plain
+    TimedRoadmap lists describe the same layered graph"""
+    from ctrm_b200.planner import _flatten_trms
+    from ctrm_b200.timed_roadmap import CSRRoadmaps
+
+    nlayers, layer_ptr, pos, eptr, eidx = _arrays(pp_gold, "b.trm.")
+    N = 6  # the first six agents are enough
+    L, lp = _strided((nlayers[:N], layer_ptr, pos, eptr, eidx))
+    nv = int(lp[-1])
+    csr = CSRRoadmaps(np.array([0, N], dtype=np.int32), L, lp, pos[:nv], eptr[:nv + 1], eidx[:int(eptr[nv])],
+                      nlayers[:N].astype(np.int32), np.zeros(1, dtype=np.int64))
+    lazy = csr.timed_roadmaps(0, lazy=True)
+    plain = csr.timed_roadmaps(0, lazy=False)
+    a = _flatten_trms(lazy)
+    b = _flatten_trms(plain)
+    assert a[0] >= int(nlayers[0]) + 1 and b[0] == int(nlayers[0]) + 1
+    assert np.array_equal(a[1], b[1])                      # n_layers
+    assert np.array_equal(a[3], b[3])                      # positions
+    assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])   # CSR adjacency
+    for ag in range(N):                                    # layer starts agree wherever a layer exists
+        n = int(a[1][ag])
+        assert np.array_equal(a[2][ag * a[0]:ag * a[0] + n + 1], b[2][ag * b[0]:ag * b[0] + n + 1])
