@@ -26,6 +26,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.ctrm_abi_version() == _lib.ABI_VERSION
 
 
+def test_ctypes_signatures_have_the_declared_arity():
+    """the Python binding (ctrm_b200/_lib.py) passes exactly as many arguments as include/ctrm_b200.h declares for every
+    entry point: a parameter added on one side only would otherwise shift every later argument silently"""
+    from ctrm_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "ctrm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)      # comments carry commas and parentheses
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(", hdr)
+        assert m, name
+        depth, i = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(hdr[i], 0)
+            i += 1
+        params = hdr[m.end():i - 1].strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(argtypes), f"{name}: header declares {n} parameters, _lib.SIGNATURES passes {len(argtypes)}"
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
 
