@@ -305,11 +305,9 @@ int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, c
   const int G = 32 / P;
   const size_t smem = (size_t)AT_FIXED_SMEM + (size_t)4 * G * ((size_t)n_max * sizeof(unsigned long long) + (size_t)P * sizeof(int));
   if (smem > 200 * 1024) return ctrm_fail(-1, "instance too large for agent_comm shared memory");
-  static size_t attr = 0;
-  if (smem > attr) {
+  static SmemAttrCache attr;
+  if (attr.need(smem))
     CTRM_CUDA_OK(cudaFuncSetAttribute(agent_comm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
   const int agents_per_tile = 4 * G;
   const int n_tiles = (bt.A + agents_per_tile - 1) / agents_per_tile;
   const int grid = n_tiles < 4 * 148 ? n_tiles : 4 * 148;  // persistent: four CTAs per SM (128 TMEM columns each)

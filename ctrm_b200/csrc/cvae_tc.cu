@@ -290,11 +290,9 @@ int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, floa
                       cudaStream_t st) {
   if (bt.A <= 0) return 0;
   const int n_tiles = (bt.A + 127) / 128;
-  static bool attr = false;
-  if (!attr) {
+  static SmemAttrCache attr;
+  if (attr.need(PR_SMEM))
     CTRM_CUDA_OK(cudaFuncSetAttribute(cvae_prior_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM));
-    attr = true;
-  }
   const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent, two CTAs per SM (114 KB of shared memory each)
   cvae_prior_tc_kernel<<<grid, PR_THREADS, PR_SMEM, st>>>(bt, d_X, m.prior_img, d_logits, d_dec0, d_ind, n_tiles);
   CTRM_CUDA_OK(cudaGetLastError());
@@ -585,11 +583,9 @@ int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits
   const int K = bt.K;
   const long long rows = (long long)bt.A * K;
   const int n_tiles = (int)((rows + 127) / 128);
-  static bool attr = false;
-  if (!attr) {
+  static SmemAttrCache attr;
+  if (attr.need(DT_SMEM))
     CTRM_CUDA_OK(cudaFuncSetAttribute(cvae_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
-    attr = true;
-  }
   const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent: two CTAs per SM
   cvae_decode_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(bt, K, d_logits, d_dec0, d_uniforms, use_state_kt, kt_fixed, t_fixed,
                                                           m.desc.temp, m.dec_w0z_exp, m.decode_img, d_samples, n_tiles);

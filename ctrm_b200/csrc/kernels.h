@@ -130,6 +130,19 @@ int launch_csr_count(const Batch& bt, int64_t* d_agent_nv, int64_t* d_agent_ne, 
 int launch_csr_fill(const Batch& bt, const int64_t* d_agent_v0, const int64_t* d_agent_e0, const int64_t* d_totals,
                     int32_t* d_layer_ptr, double* d_pos, int64_t* d_eptr, int32_t* d_eidx, cudaStream_t st);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: remember what has been granted on each device
+// (a process may hold contexts on several GPUs), not once per process
+struct SmemAttrCache {
+  size_t granted[64] = {0};
+  bool need(size_t smem) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (smem <= granted[d]) return false;
+    granted[d] = smem;
+    return true;
+  }
+};
+
 // stream-ordered scratch of the context-free stage entry points: keep freed blocks in the device's default pool instead of
 // returning them to the driver at every synchronisation (the default), which made each call pay a fresh allocation
 int keep_async_pool_warm();

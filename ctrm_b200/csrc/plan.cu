@@ -220,11 +220,9 @@ int launch_plan_prioritized(int B, int L, const int32_t* d_agent_off, const int3
   if (max_nv > 32767 * 4) return ctrm_fail(-1, "plan_prioritized: roadmap of one agent too large");
   const size_t smem = (size_t)max_nv * (sizeof(double) + sizeof(int16_t) + 1) + 16;
   if (smem > 200 * 1024) return ctrm_fail(-1, "plan_prioritized: roadmap of one agent does not fit shared memory");
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+  static SmemAttrCache attr;
+  if (smem > 48 * 1024 && attr.need(smem))
     CTRM_CUDA_OK(cudaFuncSetAttribute(plan_prioritized_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
   CTRM_CUDA_OK(cudaMemsetAsync(d_paths, 0xFF, (size_t)A * L * sizeof(int32_t), st));
   PlanArgs p;
   p.B = B; p.L = L; p.agent_off = d_agent_off; p.n_layers = d_n_layers; p.layer_ptr = d_layer_ptr; p.pos = d_pos;
