@@ -24,8 +24,16 @@ def _worker(rank, world, port, q):
                eptr=torch.arange(nv + 1, dtype=torch.int64) * 2, eidx=torch.full((2 * nv,), rank, dtype=torch.int32),
                n_layers=torch.full((hi - lo,), 66, dtype=torch.int32), cnt_collide=torch.arange(lo, hi, dtype=torch.int64))
     out = gather_csr(res, rank, world)
+    # the asynchronous form used by bench.py (transfer overlaps the next step): same result once the works are waited for
+    out2, works, keep = gather_csr(res, rank, world, async_op=True)
+    for w in works:
+        w.wait()
+    del keep
     if rank == 0:
-        ok = len(out) == world
+        ok = len(out) == world and len(out2) == world
+        for r in range(world):
+            for k in out[r]:
+                ok &= bool(torch.equal(out[r][k], out2[r][k]))
         cover = []
         for r in range(world):
             l, h = shard_range(7, r, world)
@@ -36,7 +44,7 @@ def _worker(rank, world, port, q):
         ok &= cover == list(range(7))
         q.put(ok)
     else:
-        assert out is None
+        assert out is None and out2 is None
     dist.barrier()
     dist.destroy_process_group()
 
