@@ -185,3 +185,53 @@ def test_flatten_trms_lazy_views_equal_plain_lists(pp_gold):
     for ag in range(N):                                    # layer starts agree wherever a layer exists
         n = int(a[1][ag])
         assert np.array_equal(a[2][ag * a[0]:ag * a[0] + n + 1], b[2][ag * b[0]:ag * b[0] + n + 1])
+
+
+def _random_layered_roadmaps(rng, N, T, width):
+    """small random timed roadmaps in the flat layout: V[0] = [start], V[t][-1] = goal, random forward edges"""
+    starts, goals = rng.rand(N, 2), rng.rand(N, 2)
+    nlayers, layer_ptr, pos, eptr, eidx = [], [0], [], [0], []
+    for a in range(N):
+        layers = [[starts[a]]] + [[rng.rand(2) for _ in range(width - 1)] + [goals[a]] for _ in range(T)]
+        nlayers.append(len(layers))
+        for t, layer in enumerate(layers):
+            for _ in layer:
+                nxt = len(layers[t + 1]) if t + 1 < len(layers) else 0
+                adj = sorted(set(rng.randint(0, nxt, size=rng.randint(1, 4)).tolist())) if nxt else []
+                eidx.extend(adj)
+                eptr.append(len(eidx))
+            pos.extend(layer)
+            layer_ptr.append(len(pos))
+    return starts, goals, (np.array(nlayers), np.array(layer_ptr), np.array(pos), np.array(eptr), np.array(eidx, dtype=np.int64))
+
+
+@pytest.mark.parametrize("seed", [0, 3, 6, 7])  # 3 and 7 are solved, 0 and 6 fail at a late agent
+def test_oracle_planner_solutions_are_valid(seed):
+    """self-consistency of the planner restatement on random layered graphs: every returned path follows edges from the
+    start to the goal vertex, waits at the goal afterwards, and no two agents collide on any step"""
+    rng = np.random.RandomState(seed)
+    N, T, width = 5, 9, 6
+    starts, goals, arrays = _random_layered_roadmaps(rng, N, T, width)
+    speeds, rads = np.full(N, 10.0), np.full(N, 0.03)
+    trms = P.FlatRoadmaps(*arrays)
+    got = P.prioritized_planning(starts, goals, speeds, rads, trms)
+    assert got["lowlevel_explored"] >= 1
+    if not got["solved"]:
+        assert 0 <= got["failed_agent"] < N
+        return
+    paths = got["paths"]
+    assert paths.shape == (N, T + 1)
+    xy = P.path_positions(trms, paths)
+    for a in range(N):
+        assert paths[a, 0] == 0 and np.array_equal(xy[a, 0], starts[a])
+        assert np.array_equal(xy[a, -1], goals[a]) and paths[a, -1] == trms.width(a, T) - 1
+        arrived = False
+        for t in range(T):
+            if paths[a, t] == trms.width(a, t) - 1 and t >= 1:
+                arrived = arrived or all(paths[a, u] == trms.width(a, u) - 1 for u in range(t, T + 1))
+            if not arrived:
+                assert paths[a, t + 1] in trms.succ(a, t, int(paths[a, t])), (a, t)
+    for t in range(T):
+        for i in range(N):
+            for j in range(i):
+                assert not P.sweep_pair(xy[i, t], xy[i, t + 1], rads[i], xy[j, t], xy[j, t + 1], rads[j]), (t, i, j)
