@@ -235,3 +235,69 @@ def test_oracle_planner_solutions_are_valid(seed):
         for i in range(N):
             for j in range(i):
                 assert not P.sweep_pair(xy[i, t], xy[i, t + 1], rads[i], xy[j, t], xy[j, t + 1], rads[j]), (t, i, j)
+
+
+def _batch_layout(insts, L):
+    """several instances' flat roadmaps -> one batch in the strided layout of the C-ABI"""
+    n_layers, lps, poss, eptrs, eidxs, goals_all, off = [], [], [], [], [], [], [0]
+    v_base = e_base = 0
+    for starts, goals, arrays in insts:
+        nl, lp_flat, pos, eptr, eidx = arrays
+        Li, lp = _strided((nl, lp_flat, pos, eptr, eidx))
+        assert Li == L
+        lps.append(lp[:-1].astype(np.int64) + v_base)
+        n_layers.append(nl)
+        poss.append(pos)
+        eptrs.append(eptr[1:].astype(np.int64) + e_base)
+        eidxs.append(eidx)
+        goals_all.append(goals)
+        v_base += len(pos)
+        e_base += len(eidx)
+        off.append(off[-1] + len(nl))
+    return (np.array(off, dtype=np.int32), np.concatenate(n_layers).astype(np.int32),
+            np.concatenate(lps + [np.array([v_base])]).astype(np.int32), np.concatenate(poss),
+            np.concatenate([np.zeros(1, dtype=np.int64)] + eptrs), np.concatenate(eidxs).astype(np.int32), np.concatenate(goals_all))
+
+
+def _random_insts():
+    insts = []
+    for seed in (0, 3, 6, 7, 11):
+        rng = np.random.RandomState(seed)
+        insts.append(_random_layered_roadmaps(rng, 3 + seed % 4, 9, 6))
+    return insts
+
+
+def test_batch_layout_round_trip():
+    """host side of the batched planner call (no GPU): slicing the concatenated strided layout gives each instance back"""
+    insts = _random_insts()
+    off, n_layers, lp, pos, eptr, eidx, goals = _batch_layout(insts, 11)
+    assert lp[-1] == len(pos) and eptr[-1] == len(eidx) and len(eptr) == len(pos) + 1
+    for b, (starts, g, arrays) in enumerate(insts):
+        a0, a1 = int(off[b]), int(off[b + 1])
+        v0, v1 = int(lp[a0 * 11]), int(lp[a1 * 11])
+        assert np.array_equal(pos[v0:v1], arrays[2]) and np.array_equal(goals[a0:a1], g)
+        assert np.array_equal(eptr[v0:v1 + 1] - eptr[v0], arrays[3]) and np.array_equal(eidx[eptr[v0]:eptr[v1]], arrays[4])
+        for a in range(a0, a1):
+            n = int(n_layers[a])
+            assert n == 10 and lp[a * 11] - v0 == arrays[1][(a - a0) * 10]
+            assert lp[a * 11 + n] == (lp[(a + 1) * 11] if a + 1 < len(n_layers) else len(pos))
+
+
+@pytest.mark.gpu
+def test_gpu_planner_random_layered_graphs_vs_oracle():
+    """foreign roadmaps (not built by this package): sparse random edges, several instances of different sizes per call"""
+    from ctrm_b200.planner import plan_prioritized_arrays
+
+    insts = _random_insts()
+    off, n_layers, lp, pos, eptr, eidx, goals = _batch_layout(insts, 11)
+    A = int(off[-1])
+    r = plan_prioritized_arrays(off, 11, n_layers, lp, pos, eptr, eidx, goals, np.full(A, 10.0), np.full(A, 0.03))
+    for b, (starts, g, arrays) in enumerate(insts):
+        N = len(starts)
+        want = P.prioritized_planning(starts, g, np.full(N, 10.0), np.full(N, 0.03), P.FlatRoadmaps(*arrays))
+        assert bool(r["solved"][b]) == want["solved"], b
+        assert [int(x) for x in r["counters"][b]] == [want["cnt_continuous_collide"], want["lowlevel_expanded"],
+                                                      want["lowlevel_explored"]], b
+        assert int(r["failed_agent"][b]) == want["failed_agent"], b
+        if want["solved"]:
+            assert np.array_equal(r["paths"][off[b]:off[b + 1], :10], want["paths"]), b
