@@ -136,8 +136,10 @@ __global__ void __launch_bounds__(AT_THREADS, 4) agent_comm_tc_kernel(Batch bt, 
     //      sort keys (distance bits + 1, index); the agent itself gets key 0: self first, ties broken by index
     if (active)
       for (int j = s + P * half; j < N; j += 2 * P) {
-        const float dx = (float)f64sub(cur[2 * (a0 + j)], cix), dy = (float)f64sub(cur[2 * (a0 + j) + 1], ciy);
-        const float d = sqrtf(fmaf(dx, dx, dy * dy));
+        // exactly the value the reference argsorts: float32(sqrt_f64(dx^2 + dy^2)) (compiled.py:24, format_input.py:327) —
+        // an fp32 evaluation can swap two neighbours whose distances differ by an fp32 ulp on the k-th boundary
+        const double dx = f64sub(cur[2 * (a0 + j)], cix), dy = f64sub(cur[2 * (a0 + j) + 1], ciy);
+        const float d = __double2float_rn(__dsqrt_rn(f64add(f64mul(dx, dx), f64mul(dy, dy))));
         key[j] = (j == il) ? 0ull : (((unsigned long long)(__float_as_uint(d) + 1u) << 32) | (unsigned)j);
       }
     pair_sync(wq);
@@ -306,8 +308,7 @@ int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, c
   const size_t smem = (size_t)AT_FIXED_SMEM + (size_t)4 * G * ((size_t)n_max * sizeof(unsigned long long) + (size_t)P * sizeof(int));
   if (smem > 200 * 1024) return ctrm_fail(-1, "instance too large for agent_comm shared memory");
   static SmemAttrCache attr;
-  if (attr.need(smem))
-    CTRM_CUDA_OK(cudaFuncSetAttribute(agent_comm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CTRM_CUDA_OK(attr.ensure(agent_comm_tc_kernel, smem));
   const int agents_per_tile = 4 * G;
   const int n_tiles = (bt.A + agents_per_tile - 1) / agents_per_tile;
   const int grid = n_tiles < 4 * 148 ? n_tiles : 4 * 148;  // persistent: four CTAs per SM (128 TMEM columns each)

@@ -389,7 +389,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&bt.e_vain, (size_t)A * 32));
   CHECK(ar.alloc(&bt.vain_proj, (size_t)A * 32));
   CHECK(ar.alloc(&bt.X, (size_t)A * CTRM_DIM_X));
-  CHECK(ar.alloc(&bt.cv_logits, (size_t)A * 64));
+  CHECK(ar.alloc(&bt.cv_sqrtp, (size_t)A * 64));
   CHECK(ar.alloc(&bt.cv_dec0, (size_t)A * 32));
   CHECK(ar.alloc(&bt.ind, (size_t)A));
   CHECK(ar.alloc(&bt.cur, (size_t)2 * A));
@@ -461,9 +461,20 @@ extern "C" int ctrm_get_device_view(ctrm_ctx* c, ctrm_device_view* v) {
 // ------------------------------------------------------------------------------------------------
 // stage entry points
 // ------------------------------------------------------------------------------------------------
+// The context-free entry points take bare device pointers: make the device that owns them current, so that a caller whose
+// current device is another GPU does not launch on a foreign stream (and the per-device caches key on the right device).
+static int use_device_of(const void* p) {
+  if (!p) return 0;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }  // not a CUDA pointer: the kernels will report it
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) CTRM_CUDA_OK(cudaSetDevice(at.device));
+  return 0;
+}
 extern "C" int ctrm_collide_segments(const double* d_from, const double* d_to, const double* d_rad, const int32_t* d_seg_inst,
                                      int64_t n_seg, const double* d_obs_xyr, const int32_t* d_obs_off, uint8_t* d_verdict,
                                      int32_t* d_survivors, int32_t* d_n_survivors, void* stream) {
+  CHECK(use_device_of(d_verdict));
   if (n_seg < 0 || (n_seg > 0 && (!d_from || !d_to || !d_rad || !d_obs_off || !d_verdict)))
     return ctrm_fail(CTRM_ERR_ARG, "ctrm_collide_segments: NULL argument");
   if ((d_survivors == nullptr) != (d_n_survivors == nullptr))
@@ -474,6 +485,7 @@ extern "C" int ctrm_collide_segments(const double* d_from, const double* d_to, c
 
 extern "C" int ctrm_collide_sphere_pairs(const double* f1, const double* t1, const double* r1, const double* f2, const double* t2,
                                          const double* r2, int dim, int64_t n, uint8_t* verdict, void* stream) {
+  CHECK(use_device_of(verdict));
   if (n < 0 || (n > 0 && (!f1 || !t1 || !r1 || !f2 || !t2 || !r2 || !verdict)))
     return ctrm_fail(CTRM_ERR_ARG, "ctrm_collide_sphere_pairs: NULL argument");
   return launch_collide_pairs(f1, t1, r1, f2, t2, r2, dim, n, verdict, (cudaStream_t)stream);
@@ -493,6 +505,7 @@ int keep_async_pool_warm() {
 }
 
 extern "C" int ctrm_raster_occupancy(const double* d_obs_xyr, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, void* stream) {
+  CHECK(use_device_of(d_occ));
   if (B <= 0 || M < 1 || M > 255 || !d_obs_off || !d_occ) return ctrm_fail(CTRM_ERR_ARG, "ctrm_raster_occupancy: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   int32_t O = 0;
@@ -509,6 +522,7 @@ extern "C" int ctrm_raster_occupancy(const double* d_obs_xyr, const int32_t* d_o
 
 extern "C" int ctrm_cost_to_go(const uint8_t* d_occ, const int32_t* d_agent_inst, const double* d_goals,
                                const int32_t* d_stencil_r, int A, int M, uint16_t* d_ctg, void* stream) {
+  CHECK(use_device_of(d_ctg));
   if (A <= 0 || M < 1 || M > 255 || !d_occ || !d_agent_inst || !d_goals || !d_stencil_r || !d_ctg)
     return ctrm_fail(CTRM_ERR_ARG, "ctrm_cost_to_go: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -536,6 +550,7 @@ extern "C" int ctrm_cost_to_go(const uint8_t* d_occ, const int32_t* d_agent_inst
 
 extern "C" int ctrm_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, int ctg_layout, const int32_t* d_agent_inst,
                                const double* d_pos, int A, int M, int F, float* d_fov, void* stream) {
+  CHECK(use_device_of(d_fov));
   if (A <= 0 || M < 1 || M > 255 || F < 1 || (F & 1) == 0 || F > 63 || !d_occ || !d_ctg || !d_agent_inst || !d_pos || !d_fov)
     return ctrm_fail(CTRM_ERR_ARG, "ctrm_fov_raster: bad argument");
   if ((reinterpret_cast<uintptr_t>(d_fov) & 15) != 0) return ctrm_fail(CTRM_ERR_ARG, "ctrm_fov_raster: d_fov must be 16-byte aligned");
@@ -570,8 +585,8 @@ extern "C" int ctrm_cvae_sample(ctrm_ctx* c, const float* d_X, const float* d_un
   bt.seed_lo = (uint32_t)(seed & 0xFFFFFFFFu);
   bt.seed_hi = (uint32_t)(seed >> 32);
   bt.inst_base = 0;
-  CHECK(launch_cvae_prior(c->model, bt, d_X, bt.cv_logits, bt.cv_dec0, d_ind, (cudaStream_t)stream));
-  return launch_cvae_decode(c->model, bt, bt.cv_logits, bt.cv_dec0, d_uniforms, 0, k_traj, t, d_samples, (cudaStream_t)stream);
+  CHECK(launch_cvae_prior(c->model, bt, d_X, bt.cv_sqrtp, bt.cv_dec0, d_ind, (cudaStream_t)stream));
+  return launch_cvae_decode(c->model, bt, bt.cv_sqrtp, bt.cv_dec0, d_uniforms, 0, k_traj, t, d_samples, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -673,9 +688,9 @@ static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, 
     CHECK(mark(KID_FOV_ENCODE));
     CHECK(launch_agent_comm(c->model, bt, bt.cur, bt.prev, bt.e_self, bt.vain_proj, bt.X, st));
     CHECK(mark(KID_AGENT_COMM));
-    CHECK(launch_cvae_prior(c->model, bt, bt.X, bt.cv_logits, bt.cv_dec0, bt.ind, st));
+    CHECK(launch_cvae_prior(c->model, bt, bt.X, bt.cv_sqrtp, bt.cv_dec0, bt.ind, st));
     CHECK(mark(KID_CVAE_PRIOR));
-    CHECK(launch_cvae_decode(c->model, bt, bt.cv_logits, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st));
+    CHECK(launch_cvae_decode(c->model, bt, bt.cv_sqrtp, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st));
     CHECK(mark(KID_CVAE_DECODE));
   }
   CHECK(launch_step(bt, st));
@@ -941,6 +956,7 @@ extern "C" int ctrm_last_timing(ctrm_ctx* c, float ms[3], int64_t* steps, int64_
 // ------------------------------------------------------------------------------------------------
 extern "C" int ctrm_others_info(const double* d_cur, const double* d_goals, const double* d_prev, const double* d_rads,
                                 const double* d_speeds, int T, int N, float* d_info, float* d_self_info, void* stream) {
+  CHECK(use_device_of(d_info));
   if (T <= 0 || N <= 0 || !d_cur || !d_goals || !d_prev || !d_rads || !d_speeds || !d_info)
     return ctrm_fail(CTRM_ERR_ARG, "ctrm_others_info: bad argument");
   return launch_others_info(d_cur, d_goals, d_prev, d_rads, d_speeds, T, N, d_info, d_self_info, (cudaStream_t)stream);
@@ -954,6 +970,7 @@ extern "C" int ctrm_plan_prioritized(int B, int A, int L, const int32_t* d_agent
                                      const int32_t* d_eidx, const double* d_goals, const double* d_speeds, const double* d_rads,
                                      int max_agent_vertices, int32_t* d_paths, double* d_path_pos, int32_t* d_solved,
                                      int32_t* d_failed_agent, int64_t* d_counters, void* stream) {
+  CHECK(use_device_of(d_paths));
   if (B <= 0 || A <= 0 || L < 2 || !d_agent_off || !d_n_layers || !d_layer_ptr || !d_pos || !d_eptr || !d_eidx || !d_goals ||
       !d_speeds || !d_rads || max_agent_vertices < 1 || !d_paths || !d_path_pos || !d_solved || !d_failed_agent || !d_counters)
     return ctrm_fail(CTRM_ERR_ARG, "ctrm_plan_prioritized: bad argument");

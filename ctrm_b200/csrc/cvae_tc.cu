@@ -17,11 +17,11 @@
 // ------------------------------------------------------------------------------------------------
 // cvae_prior: everything the K copies of an agent share, one 128-agent tile per CTA, all dense layers on tcgen05 (BF16x3):
 //   indicator 72->32->32->3 + argmax (roadmap_learned/learned_sampler.py:99-104), encoder_input [X, onehot] 75->32->32->64 +
-//   LogSoftmax + Categorical normalisation + logits = log(clamp(p)) (learning/model/cvae.py:57-68, :132-136;
-//   torch.distributions probs_to_logits), and the [X, onehot] rows of the decoder's first layer (cvae.py:72-76, :137).
+//   LogSoftmax + Categorical normalisation + clamp(p) of torch.distributions' probs_to_logits (learning/model/cvae.py:57-68,
+//   :132-136; emitted as sqrt(clamp(p)), see cvae_decode), and the [X, onehot] rows of the decoder's first layer (cvae.py:72-76, :137).
 // The three first layers share the A operand X[128 x 72]: ONE N = 96 MMA chain computes them side by side
 // (TMEM columns 0..31 indicator, 32..63 encoder, 64..95 decoder, times two accumulator classes); the one-hot indicator columns are added as a weight row
-// in the epilogue.  outputs per agent: logits[64], dec0[32], ind.
+// in the epilogue.  outputs per agent: sqrtp[64], dec0[32], ind.
 // ------------------------------------------------------------------------------------------------
 #define PR_THREADS 256
 #define PR_K0 80                      // 72 padded to a multiple of 16
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(PR_THREADS) cvae_prior_image_kernel(const floa
 
 __global__ void __launch_bounds__(PR_THREADS, 2) cvae_prior_tc_kernel(Batch bt, const float* __restrict__ X,
                                                                    const uint8_t* __restrict__ w_image,
-                                                                   float* __restrict__ logits_out, float* __restrict__ dec0_out,
+                                                                   float* __restrict__ sqrtp_out, float* __restrict__ dec0_out,
                                                                    int32_t* __restrict__ ind_out, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Xt = smem;                        // X parts 1..3 [128 x 80]; after layer 0: hidden tiles [128 x 32] x 3 | head weights
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(PR_THREADS, 2) cvae_prior_tc_kernel(Batch bt, 
                              h[j4 * 4 + 3] + dec_b0[c0 + 3] + dec_oh[ind * 32 + c0 + 3]);
       }
     }
-    // ---- encoder_input: hidden 1 (+ one-hot row) -> hidden 2 -> 64 logits -> log_softmax -> clamped log-probs
+    // ---- encoder_input: hidden 1 (+ one-hot row) -> hidden 2 -> 64 logits -> log_softmax -> sqrt of the clamped probabilities
     tc::tmem_ld16_sum2(tbase, warp, 32 + 16 * half, 96, h);
 #pragma unroll
     for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j] + enc_b0[16 * half + j] + enc_oh[ind * 32 + 16 * half + j], 0.f);
@@ -260,13 +260,15 @@ __global__ void __launch_bounds__(PR_THREADS, 2) cvae_prior_tc_kernel(Batch bt, 
       __syncthreads();
       ps = red[r] + red[128 + r];
       if (live) {
-        float4* lo = reinterpret_cast<float4*>(logits_out + (size_t)a * 64 + 32 * half);
+        // sqrt of the clamped, renormalised probabilities (see cvae_decode: for the trained temperature 2 the relaxed one-hot
+        // sample is z_i = sqrt(p_i / E_i) / sum_j sqrt(p_j / E_j) with E = -log u; the K copies share sqrt(p))
+        float4* lo = reinterpret_cast<float4*>(sqrtp_out + (size_t)a * 64 + 32 * half);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
-          lo[j4] = make_float4(logf(fminf(fmaxf(lg[j4 * 4 + 0] / ps, eps), 1.f - eps)),
-                               logf(fminf(fmaxf(lg[j4 * 4 + 1] / ps, eps), 1.f - eps)),
-                               logf(fminf(fmaxf(lg[j4 * 4 + 2] / ps, eps), 1.f - eps)),
-                               logf(fminf(fmaxf(lg[j4 * 4 + 3] / ps, eps), 1.f - eps)));
+          lo[j4] = make_float4(sqrtf(fminf(fmaxf(lg[j4 * 4 + 0] / ps, eps), 1.f - eps)),
+                               sqrtf(fminf(fmaxf(lg[j4 * 4 + 1] / ps, eps), 1.f - eps)),
+                               sqrtf(fminf(fmaxf(lg[j4 * 4 + 2] / ps, eps), 1.f - eps)),
+                               sqrtf(fminf(fmaxf(lg[j4 * 4 + 3] / ps, eps), 1.f - eps)));
       }
     }
     hphase ^= 1u;
@@ -286,15 +288,14 @@ int launch_cvae_prior_image(const float* d_blob, const ctrm_weight_offsets_t& of
   return 0;
 }
 
-int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,
+int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_sqrtp, float* d_dec0, int32_t* d_ind,
                       cudaStream_t st) {
   if (bt.A <= 0) return 0;
   const int n_tiles = (bt.A + 127) / 128;
   static SmemAttrCache attr;
-  if (attr.need(PR_SMEM))
-    CTRM_CUDA_OK(cudaFuncSetAttribute(cvae_prior_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM));
+  CTRM_CUDA_OK(attr.ensure(cvae_prior_tc_kernel, PR_SMEM));
   const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent, two CTAs per SM (114 KB of shared memory each)
-  cvae_prior_tc_kernel<<<grid, PR_THREADS, PR_SMEM, st>>>(bt, d_X, m.prior_img, d_logits, d_dec0, d_ind, n_tiles);
+  cvae_prior_tc_kernel<<<grid, PR_THREADS, PR_SMEM, st>>>(bt, d_X, m.prior_img, d_sqrtp, d_dec0, d_ind, n_tiles);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(DT_THREADS) cvae_decode_image_kernel(const flo
   tc::dump_image(smem, image, DT_W_BYTES, tid, DT_THREADS);
 }
 
-__global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt, int K, const float* __restrict__ logits,
+__global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt, int K, const float* __restrict__ sqrtp,
                                                                        const float* __restrict__ dec0,
                                                                        const float* __restrict__ uniforms, int use_state_kt,
                                                                        int kt_fixed, int t_fixed, float temp, int w0_exp,
@@ -396,6 +397,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
   const float eps = 1.1920928955078125e-07f;
   int temp_exp;
   const float inv_temp = (frexpf(temp, &temp_exp) == 0.5f && temp_exp > -100 && temp_exp < 100) ? 1.f / temp : 0.f;
+  const bool sqrt_path = temp == 2.0f;
   const int n_arows = bt.live_agent != nullptr ? *bt.n_live : bt.A;  // agents of the unfinished instances, or all
   const long long n_rows = (long long)n_arows * K;
   n_tiles = (int)min((long long)n_tiles, (n_rows + 127) >> 7);
@@ -419,9 +421,68 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     }
     // a tile whose rows all belong to finished instances is skipped entirely
     if (!__syncthreads_or(live)) continue;
+    // ---- z = RelaxedOneHotCategorical(temp, probs).rsample() (cvae.py:133-136): softmax((log p + g) / temp) with
+    //      g = -log(-log u).  For temp = 2 (the trained value) exp((log p - log E) / 2) = sqrt(p / E), E = -log u, so
+    //      z_i = sqrt(p_i) rsqrt(E_i) / sum_j (...): ONE accurate logarithm per latent instead of two plus an exponential, no
+    //      max pass (sqrt(p / E) lies in [1e-4, 3e3]), and every factor carries <= 2 ulp — closer to the float64 value than
+    //      the reference's own fp32 chain, whose log / exp round at magnitude 16.  sqrt(p) comes from cvae_prior.
+    //      Any other temperature takes the literal formula below.
+    float se = 0.f;
+    if (sqrt_path) {
+      float rv[32];
+      if (live) {
+        const float* sp = sqrtp + (size_t)a * 64;
+        const float* urow = nullptr;
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
+        if (uniforms != nullptr) {
+          urow = uniforms + (size_t)orow * 64;
+        } else {
+          const int N = bt.agent_off[b + 1] - bt.agent_off[b], il = a - bt.agent_off[b];
+          const int kt = use_state_kt ? bt.k_traj[b] : kt_fixed, tt = use_state_kt ? bt.t[b] : t_fixed;
+          c0 = bt.inst_base + (uint32_t)b;
+          c1 = rng_ctr1(kt, tt);
+          c2 = (uint32_t)(k * N + il);  // the reference's row order k*N + i (learned_sampler.py:82)
+        }
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {  // 8 x 4 latents of this half
+          const int c = 32 * half + 4 * qq;
+          float4 u4;
+          if (urow != nullptr) {
+            u4 = __ldg(reinterpret_cast<const float4*>(urow + c));
+          } else {
+            const uint4 w = philox4x32(c0, c1, c2, rng_ctr3(STREAM_GUMBEL, (uint32_t)(c >> 2)), bt.seed_lo, bt.seed_hi);
+            u4 = make_float4(u32_to_f32(w.x), u32_to_f32(w.y), u32_to_f32(w.z), u32_to_f32(w.w));
+          }
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(sp + c));
+          const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float E = -logf(fminf(fmaxf(uu[j], eps), 1.f - eps));  // in [1.19e-7, 15.95]
+            rv[4 * qq + j] = pp[j] * rsqrtf(E);
+            se += rv[4 * qq + j];
+          }
+        }
+      }
+      red[half * 128 + r] = se;
+      __syncthreads();
+      se = red[r] + red[128 + r];
+      if (live) {
+        const float inv = 1.f / se;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float s8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s8[j] = fminf(rv[8 * q + j] * inv, 1.f);
+          tc::store_digits8_unit(At, DT_A_PART, r, (4 * half + q) * 8, 64, s8);
+        }
+      } else {
+        const float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int q = 4 * half; q < 4 * half + 4; ++q) tc::store_digits8_unit(At, DT_A_PART, r, q * 8, 64, v);
+      }
+    } else {
     float mx = -INFINITY;
     if (live) {
-      const float* lg = logits + (size_t)a * 64;
+      const float* sp = sqrtp + (size_t)a * 64;
       const float* urow = nullptr;
       uint32_t c0 = 0, c1 = 0, c2 = 0;
       if (uniforms != nullptr) {
@@ -446,8 +507,10 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
             u8[h2 * 4 + 2] = u32_to_f32(w.z); u8[h2 * 4 + 3] = u32_to_f32(w.w);
           }
         }
-        const float4 la = __ldg(reinterpret_cast<const float4*>(lg + q * 8)), lb = __ldg(reinterpret_cast<const float4*>(lg + q * 8 + 4));
-        const float l[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+        const float4 la = __ldg(reinterpret_cast<const float4*>(sp + q * 8)), lb = __ldg(reinterpret_cast<const float4*>(sp + q * 8 + 4));
+        // logits = log(clamp(p)) = 2 log(sqrt(clamp(p)))  (torch.distributions probs_to_logits)
+        const float l[8] = {2.f * logf(la.x), 2.f * logf(la.y), 2.f * logf(la.z), 2.f * logf(la.w),
+                            2.f * logf(lb.x), 2.f * logf(lb.y), 2.f * logf(lb.z), 2.f * logf(lb.w)};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float u = fminf(fmaxf(u8[j], eps), 1.f - eps);
@@ -466,7 +529,6 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     __syncthreads();
     // z = softmax(s): e = exp(s - max) is computed once and parked; z = e / sum(e) (torch evaluates
     // exp(s - logsumexp(s)); the two agree to an ulp and this one saves 64 expf per row)
-    float se = 0.f;
     if (live) {
       for (int q = 4 * half; q < 4 * half + 4; ++q) {
         float s[8];
@@ -494,6 +556,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     } else {
       const float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int q = 4 * half; q < 4 * half + 4; ++q) tc::store_digits8_unit(At, DT_A_PART, r, q * 8, 64, v);
+    }
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -577,17 +640,16 @@ int launch_cvae_decode_image(const float* d_blob, const ctrm_weight_offsets_t& o
   return 0;
 }
 
-int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits, const float* d_dec0, const float* d_uniforms,
+int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_sqrtp, const float* d_dec0, const float* d_uniforms,
                        int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st) {
   if (bt.A <= 0) return 0;
   const int K = bt.K;
   const long long rows = (long long)bt.A * K;
   const int n_tiles = (int)((rows + 127) / 128);
   static SmemAttrCache attr;
-  if (attr.need(DT_SMEM))
-    CTRM_CUDA_OK(cudaFuncSetAttribute(cvae_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+  CTRM_CUDA_OK(attr.ensure(cvae_decode_tc_kernel, DT_SMEM));
   const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent: two CTAs per SM
-  cvae_decode_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(bt, K, d_logits, d_dec0, d_uniforms, use_state_kt, kt_fixed, t_fixed,
+  cvae_decode_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(bt, K, d_sqrtp, d_dec0, d_uniforms, use_state_kt, kt_fixed, t_fixed,
                                                           m.desc.temp, m.dec_w0z_exp, m.decode_img, d_samples, n_tiles);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;

@@ -316,8 +316,7 @@ int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32
   if (A <= 0) return 0;
   const int n_tiles = (A + 127) / 128;
   static SmemAttrCache attr;
-  if (attr.need(FT_SMEM))
-    CTRM_CUDA_OK(cudaFuncSetAttribute(fov_encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+  CTRM_CUDA_OK(attr.ensure(fov_encode_tc_kernel, FT_SMEM));
   const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent, two CTAs per SM
   fov_encode_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(d_fov_tiles, m.fov_w0_tiles, fov_n_chunks(m.desc.fov_size), m.fov_w0_exp,
                                                          d_agent_inst, d_skip_inst, A, m.fov_img, d_e_self, d_e_vain,

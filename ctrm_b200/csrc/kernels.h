@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/ctrm_b200.h"
 
 #define CTRM_MAX_W 4          // adjacency bitmask words per vertex: slots S = 32*W >= N_traj + 1  (N_traj <= 127)
@@ -64,7 +66,7 @@ struct Batch {
   // per-step tensors
   uint8_t* fov_tiles;  // bf16 operand tiles [ceil(A/128)][n_chunks][128 x 96]
   float *e_self, *e_vain, *vain_proj, *X, *samples;
-  float *cv_logits, *cv_dec0;  // [A][64], [A][32]
+  float *cv_sqrtp, *cv_dec0;  // [A][64] sqrt of the clamped prior probabilities, [A][32] x-part of the decoder's first layer
   int32_t* ind;  // [A]
   // timed roadmaps: V[t][i] / E[t][i] as fixed slots + bitmask adjacency
   double* vpos;     // [A][L][S][2]
@@ -117,9 +119,9 @@ int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32
 int launch_compact_live(const Batch& bt, cudaStream_t st);
 int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, const double* d_prev, const float* d_e_self,
                       const float* d_vain_proj, float* d_X, cudaStream_t st);
-int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_logits, float* d_dec0, int32_t* d_ind,
+int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_sqrtp, float* d_dec0, int32_t* d_ind,
                       cudaStream_t st);
-int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_logits, const float* d_dec0, const float* d_uniforms,
+int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_sqrtp, const float* d_dec0, const float* d_uniforms,
                        int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st);
 
 int launch_step(const Batch& bt, cudaStream_t st);
@@ -131,15 +133,23 @@ int launch_csr_fill(const Batch& bt, const int64_t* d_agent_v0, const int64_t* d
                     int32_t* d_layer_ptr, double* d_pos, int64_t* d_eptr, int32_t* d_eidx, cudaStream_t st);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: remember what has been granted on each device
-// (a process may hold contexts on several GPUs), not once per process
+// (a process may hold contexts on several GPUs), not once per process.  Contexts are driven from several host threads
+// (PipelinedBuilder): check, set and record under one lock, and record only what the driver accepted, so that no thread
+// can launch (or capture) the kernel before the attribute call of another thread has taken effect.
 struct SmemAttrCache {
+  std::mutex mu;
   size_t granted[64] = {0};
-  bool need(size_t smem) {
+  template <typename Kernel>
+  cudaError_t ensure(Kernel kernel, size_t smem) {
+    std::lock_guard<std::mutex> lock(mu);
     int d = 0;
-    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
-    if (smem <= granted[d]) return false;
-    granted[d] = smem;
-    return true;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) return e;
+    const bool tracked = d >= 0 && d < 64;
+    if (tracked && smem <= granted[d]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && tracked) granted[d] = smem;
+    return e;
   }
 };
 

@@ -221,8 +221,7 @@ int launch_plan_prioritized(int B, int L, const int32_t* d_agent_off, const int3
   const size_t smem = (size_t)max_nv * (sizeof(double) + sizeof(int16_t) + 1) + 16;
   if (smem > 200 * 1024) return ctrm_fail(-1, "plan_prioritized: roadmap of one agent does not fit shared memory");
   static SmemAttrCache attr;
-  if (smem > 48 * 1024 && attr.need(smem))
-    CTRM_CUDA_OK(cudaFuncSetAttribute(plan_prioritized_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) CTRM_CUDA_OK(attr.ensure(plan_prioritized_kernel, smem));
   CTRM_CUDA_OK(cudaMemsetAsync(d_paths, 0xFF, (size_t)A * L * sizeof(int32_t), st));
   PlanArgs p;
   p.B = B; p.L = L; p.agent_off = d_agent_off; p.n_layers = d_n_layers; p.layer_ptr = d_layer_ptr; p.pos = d_pos;

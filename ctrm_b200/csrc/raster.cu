@@ -440,8 +440,7 @@ int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const i
                                                                  d_tiles, d_live_agent, d_n_live);
   } else {
     static SmemAttrCache attr;
-    if (smem > 48 * 1024 && attr.need(smem))
-      CTRM_CUDA_OK(cudaFuncSetAttribute(fov_raster_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CTRM_CUDA_OK(attr.ensure(fov_raster_tiles_kernel<0>, smem));
     fov_raster_tiles_kernel<0><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
                                                                 d_tiles, d_live_agent, d_n_live);
   }

@@ -70,16 +70,19 @@ def plan_prioritized_device(B: int, A: int, L: int, agent_off, n_layers, layer_p
                solved=torch.zeros(B, dtype=torch.int32, device=dev),
                failed_agent=torch.full((B,), -1, dtype=torch.int32, device=dev),
                counters=torch.zeros((B, 3), dtype=torch.int64, device=dev))
-    st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    _lib.check(lib.ctrm_plan_prioritized(B, A, L, agent_off.data_ptr(), n_layers.data_ptr(), layer_ptr.data_ptr(), pos.data_ptr(),
-                                         eptr.data_ptr(), eidx.data_ptr(), goals.data_ptr(), speeds.data_ptr(), rads.data_ptr(),
-                                         max_nv, out["paths"].data_ptr(), out["path_pos"].data_ptr(), out["solved"].data_ptr(),
-                                         out["failed_agent"].data_ptr(), out["counters"].data_ptr(), st), "ctrm_plan_prioritized")
-    e1.record()
-    e1.synchronize()
-    out["elapsed_ms"] = e0.elapsed_time(e1)
+    with torch.cuda.device(dev):  # events and the launch on the tensors' device, whatever the caller's current device is
+        sobj = torch.cuda.current_stream(dev) if stream is None else torch.cuda.ExternalStream(stream, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(sobj)  # on the stream the kernel is launched on
+        _lib.check(lib.ctrm_plan_prioritized(B, A, L, agent_off.data_ptr(), n_layers.data_ptr(), layer_ptr.data_ptr(),
+                                             pos.data_ptr(), eptr.data_ptr(), eidx.data_ptr(), goals.data_ptr(),
+                                             speeds.data_ptr(), rads.data_ptr(), max_nv, out["paths"].data_ptr(),
+                                             out["path_pos"].data_ptr(), out["solved"].data_ptr(),
+                                             out["failed_agent"].data_ptr(), out["counters"].data_ptr(), sobj.cuda_stream),
+                   "ctrm_plan_prioritized")
+        e1.record(sobj)
+        e1.synchronize()
+        out["elapsed_ms"] = e0.elapsed_time(e1)
     return out
 
 
@@ -126,7 +129,9 @@ def _flatten_trms(trms: Sequence) -> tuple:
 
 class PrioritizedPlanning:
     """drop-in for ctrm.planner.PrioritizedPlanning (prioritized_planning.py:25-101): same constructor, `solve()` returns
-    a Result with the same fields; `solution` holds the paths as lists of TimedNode.  `time_limit` is accepted and ignored
+    a Result with the same fields; `solution` holds the paths as lists of TimedNode.  Like the reference's solve()
+    (planner/planner.py:87-141) it runs validate() on a solved instance, whose pair tests count in cnt_continuous_collide;
+    the batch form `plan_prioritized_device` reports the counters of _solve() alone.  `time_limit` is accepted and ignored
     (the search takes milliseconds); `agent_collision=False` is not supported."""
 
     def __init__(self, ins, trms, verbose: int = 0, **kwargs):
@@ -147,6 +152,57 @@ class PrioritizedPlanning:
     def get_name(self) -> str:
         return "PrioritizedPlanning"
 
+    def validate(self) -> bool:
+        """Planner.validate (planner/planner.py:150-209): starts, goals, continuity and one swept-circle test per agent pair
+        and time step, in the reference's (t, i, j) order; every executed test counts in cnt_continuous_collide exactly as
+        the reference's collide_dynamic_agents does (:234-238).  The pair tests run as one ctrm_collide_sphere_pairs call."""
+        if not self.solved or self.path_pos is None:
+            return False
+        import torch
+
+        ins, P = self.ins, self.path_pos
+        N, T = P.shape[0], P.shape[1] - 1
+        starts = np.asarray(ins.starts, dtype=np.float64).reshape(N, 2)
+        goals = np.asarray(ins.goals, dtype=np.float64).reshape(N, 2)
+        if not np.array_equal(P[:, 0], starts):
+            return False
+        goal_rads = np.asarray(getattr(ins, "goal_rads", np.zeros(N)), dtype=np.float64)
+        if not all(np.linalg.norm(P[i, -1] - goals[i]) <= goal_rads[i] for i in range(N)):
+            return False
+        if T < 1:
+            return True
+        speeds = np.asarray(ins.max_speeds, dtype=np.float64)
+        rads = np.asarray(ins.rads, dtype=np.float64)
+        cont_bad = np.array([[np.linalg.norm(P[i, t] - P[i, t - 1]) > speeds[i] for i in range(N)] for t in range(1, T + 1)])
+        ii, jj = np.triu_indices(N, 1)  # row-major: i ascending, then j > i ascending — the reference's loop order
+        n_pairs = len(ii)
+        hit = np.zeros((T, n_pairs), dtype=bool)
+        if n_pairs:
+            dev = torch.device("cuda", self.device)
+            with torch.cuda.device(dev):
+                up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)  # noqa: E731
+                f1, t1 = up(P[ii, :-1].transpose(1, 0, 2)), up(P[ii, 1:].transpose(1, 0, 2))  # [T][pairs][2]
+                f2, t2 = up(P[jj, :-1].transpose(1, 0, 2)), up(P[jj, 1:].transpose(1, 0, 2))
+                r1, r2 = up(np.tile(rads[ii], T)), up(np.tile(rads[jj], T))
+                out = torch.zeros(T * n_pairs, dtype=torch.uint8, device=dev)
+                _lib.check(_lib.load().ctrm_collide_sphere_pairs(f1.data_ptr(), t1.data_ptr(), r1.data_ptr(), f2.data_ptr(),
+                                                                 t2.data_ptr(), r2.data_ptr(), 2, T * n_pairs, out.data_ptr(),
+                                                                 torch.cuda.current_stream(dev).cuda_stream),
+                           "ctrm_collide_sphere_pairs")
+                hit = out.cpu().numpy().reshape(T, n_pairs).astype(bool)
+        first_pair = np.searchsorted(ii, np.arange(N))  # index of agent i's first pair (i, i+1)
+        for t in range(T):
+            for i in range(N):
+                if cont_bad[t, i]:
+                    return False
+                lo, hi = int(first_pair[i]), int(first_pair[i] + (N - 1 - i))
+                h = np.nonzero(hit[t, lo:hi])[0]
+                if len(h):
+                    self.cnt_continuous_collide += int(h[0]) + 1
+                    return False
+                self.cnt_continuous_collide += hi - lo
+        return True
+
     def solve(self) -> Result:
         t0 = time.time()
         ins = self.ins
@@ -163,6 +219,10 @@ class PrioritizedPlanning:
         kw: dict[str, Any] = {}
         if self.solved:
             self.path_pos = r["path_pos"][:, :T + 1].copy()
+            if not self.validate():  # planner.py:103-105 — the reference only logs; so do we
+                import logging
+
+                logging.getLogger(__name__).error("inconsistent planner")
             self.solution = [[TimedNode(t, int(r["paths"][a, t]), self.path_pos[a, t].copy()) for t in range(T + 1)] for a in range(N)]
             goal_rads = np.asarray(getattr(ins, "goal_rads", np.zeros(N)), dtype=np.float64)
             costs = [get_cost(self.path_pos[a], np.asarray(ins.goals[a]), float(goal_rads[a])) for a in range(N)]

@@ -267,8 +267,9 @@ class PipelinedBuilder:
     Two RoadmapBuilder contexts on one GPU take the batches alternately, each from its own host thread (the C-ABI calls
     release the GIL), so the host packing, the host->device upload and the device->host export of one batch overlap the
     roll-out kernels of the other; the kernels of the two contexts share the GPU without gain or loss.  Results come back
-    in order.  A yielded CSRRoadmaps is a view of its context's pinned staging buffers: it stays valid until that context
-    finishes its next batch, i.e. while the following batch is being consumed; `.copy()` it to keep it longer."""
+    in order.  A yielded CSRRoadmaps is a view of its context's pinned staging buffers and is valid ONLY UNTIL THE NEXT
+    ITEM IS REQUESTED from the generator: asking for the next result hands the context that produced this one its next
+    batch, whose export overwrites the same buffers.  `.copy()` a result to keep it longer."""
 
     def __init__(self, pred_basename: str, device: int = 0, map_size: Optional[int] = None, depth: int = 2):
         self.builders = [RoadmapBuilder(pred_basename, device, map_size=map_size) for _ in range(max(1, int(depth)))]

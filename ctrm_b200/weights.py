@@ -104,6 +104,20 @@ def load_bundle(basename_or_npz: str) -> ModelBundle:
     fi = _unpickle(base + "_format_input.pkl")
     fo = _unpickle(base + "_format_output.Pl")
     fid, fod = fi.__dict__, fo.__dict__
+    # the kernels implement ONE architecture (the reference's defaults, trained_models/aamas22-main): anything else would
+    # load without error and sample wrongly (a sigmoid or a dropped comm vector silently ignored), so refuse it here
+    fov_v = _unpickle(base + "_fov_encoder_vain.pkl")
+    for name, hp_ in (("fov_encoder_self", fov), ("fov_encoder_vain", fov_v), ("agent_encoder", age)):
+        for key, want in (("use_sigmoid", False), ("use_batch_norm", False), ("num_mid_layers", 1), ("dim_hidden", 32)):
+            if key in hp_ and hp_[key] != want:
+                raise _lib.CtrmError(f"{name}: {key}={hp_[key]!r} is not supported (need {want!r})")
+    for key, want in (("num_mid_layers_encoder", 1), ("num_mid_layers_decoder", 1), ("dim_hidden", 32), ("dim_input", 72)):
+        if key in hyp and hyp[key] != want:
+            raise _lib.CtrmError(f"model: {key}={hyp[key]!r} is not supported (need {want!r})")
+    if fid.get("without_comm", 0):
+        raise _lib.CtrmError("format_input: without_comm=True is not supported")
+    if (int(fov["fov_size"]), int(fov["map_size"])) != (int(fov_v["fov_size"]), int(fov_v["map_size"])):
+        raise _lib.CtrmError("the two FOV encoders disagree on fov_size / map_size")
     return ModelBundle(arrays=arrays, fov_size=int(fov["fov_size"]), map_size=int(fov["map_size"]),
                        num_neighbors=int(fid.get("num_neighbors", 15)), use_k_neighbor=bool(fid.get("use_k_neighbor", True)),
                        include_self_attention=bool(fid.get("include_self_attention", False)),
@@ -152,6 +166,9 @@ def pack_blob(bundle: ModelBundle):
     def put(name, x):
         x = np.asarray(x, dtype=np.float64).reshape(-1)
         o = getattr(off, name)
+        nxt = min([v for f, _ in off._fields_ if (v := getattr(off, f)) > o] or [off.total])
+        if o + x.size > nxt:  # a checkpoint of another width must not spill into the neighbouring slot
+            raise _lib.CtrmError(f"weight block {name}: {x.size} values do not fit its slot of {nxt - o}")
         blob[o:o + x.size] = x
 
     put("fov_w0", np.concatenate([_lin_T(a["fov_self.mlp.0.weight"]), _lin_T(a["fov_vain.mlp.0.weight"])], axis=1))

@@ -188,6 +188,33 @@ def write_demo_and_trace():
     return ins, trms, rec, kw
 
 
+# Reference runs with N_traj > dim_ind = 3, where the gate `u < p_rw` / `u > 0.9`, the p_rw(t, makespan) table and the
+# dense-layer merge rules are DECIDED BY THE REFERENCE (learned_sampler.py:84-91, :148-168): with N_traj = 3 the clause
+# `k_traj < dim_ind` short-circuits all of them.  One run with the eval parameters (merge_distance_rate 0.1,
+# scripts/conf/eval/eval_large_ctrm_learned_ind.yaml) and one with the function default 0.25 (learned_sampler.py:29,
+# notebooks/CTRM_demo.ipynb).  Only what the replay needs is kept: draws, sin/cos, SAMPLES, the final roadmaps, the counter.
+EXTRA_TRACES = (("ref_trace_demo_nt8_r010.npz", 8, 0.1, 0), ("ref_trace_demo_nt6_r025.npz", 6, 0.25, 1))
+
+
+def write_extra_traces(pin=True):
+    ref_import.import_reference()
+    for name, n_traj, rate, seed in EXTRA_TRACES:
+        ins = pickle.load(open(os.path.join(REF, "notebooks", "CTRM_demo_ins.pkl"), "rb"))
+        kw = dict(N_traj=n_traj, max_T=64, merge_distance_rate=rate, max_attempt=3)
+        trms, rec = run_reference_trace(ins, seed, **kw)
+        out = dict(ins_to_arrays(ins))
+        out.update(trms_to_arrays(trms, "trm."))
+        out.update(seed=np.array(seed), N_traj=np.array(n_traj), max_T=np.array(64), merge_distance_rate=np.array(rate),
+                   max_attempt=np.array(3), draws=np.array(rec.draws), sincos=np.array(rec.sincos),
+                   SAMPLES=np.stack([s["SAMPLES"] for s in rec.steps]),
+                   cnt_continuous_collide=np.array(ins.objs.cnt_continuous_collide))
+        np.savez_compressed(os.path.join(GOLD, name), **out)
+        print(f"{name}: {len(rec.steps)} steps, {len(rec.draws)} draws, V={sum(len(v) for t in trms for v in t.V)}, "
+              f"checks={ins.objs.cnt_continuous_collide}")
+        if pin:
+            pin_oracle(ins, trms, rec, kw)
+
+
 def write_stage_goldens():
     """reference functions on seeded inputs: occupancy, cost-to-go, FOV, others_info, sweep verdicts"""
     ref_import.import_reference()
@@ -285,7 +312,11 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     assert ref_import.available(), "run `make -C oracle ref` in the build container first"
     ref_import.import_reference()
+    if "extra" in sys.argv[1:]:  # only the N_traj > dim_ind traces
+        write_extra_traces()
+        sys.exit(0)
     write_weights()
     write_stage_goldens()
     ins, trms, rec, kw = write_demo_and_trace()
     pin_oracle(ins, trms, rec, kw)
+    write_extra_traces()

@@ -26,6 +26,17 @@ def trace_gold():
     return np.load(os.path.join(GOLD, "ref_trace_demo.npz"))
 
 
+# full recorded runs of the UNMODIFIED reference on the demo instance (oracle/gen_golden.py): N_traj = 3 (= dim_ind, every
+# roll-out learned), and two with N_traj > dim_ind where the reference itself decides the gate / p_rw(t, makespan) / dense
+# merge rules — eval parameters (rate 0.1) and the function default (rate 0.25)
+TRACES = ("ref_trace_demo.npz", "ref_trace_demo_nt8_r010.npz", "ref_trace_demo_nt6_r025.npz")
+
+
+@pytest.fixture(scope="session", params=TRACES)
+def any_trace_gold(request):
+    return np.load(os.path.join(GOLD, request.param))
+
+
 @pytest.fixture(scope="session")
 def oracle_weights():
     import ctrm_oracle as O

@@ -13,10 +13,10 @@ from rng_tables import PhiloxTables
 pytestmark = pytest.mark.gpu
 
 
-def _instance(seed, n_lo, n_hi, obs_num, speeds="0.03125", rads="0.015625"):
+def _instance(seed, n_lo, n_hi, obs_num, speeds="0.03125", rads="0.015625", obs_lo=0.05, obs_hi=0.08):
     from ctrm_b200.environment import generate_ins_2d_with_obs_hetero_nonfix_agents as gen
 
-    return gen(n_lo, n_hi, speeds, rads, obs_num, 0.05, 0.08, rng=np.random.RandomState(seed))
+    return gen(n_lo, n_hi, speeds, rads, obs_num, obs_lo, obs_hi, rng=np.random.RandomState(seed))
 
 
 def _oins(ins):
@@ -38,6 +38,11 @@ CASES = [
     ("ntraj100_w4",    [(11, 3, 4, 3, "0.03125", "0.015625")],                                100, 8, 3, 0.25, 160),
     # BASELINE configs[1] at its real roll-out sizes: one benchmark instance, every one of its ~1,400 steps compared
     ("full_size",      [(46, 21, 30, 10, "0.03125", "0.015625")],                             25, 64, 3, 0.1, 160),
+    # BASELINE configs[2] ("homo-more-agents", scripts/exp_scripts/benchmark_gen_hetero.sh:31): 31-40 agents at the full
+    # N_traj = 25 x max_T = 64, every executed step compared
+    ("more_agents_full", [(47, 31, 40, 10, "0.03125", "0.015625")],                           25, 64, 3, 0.1, 160),
+    # BASELINE configs[4], the stress shape (100 agents, 64 obstacles, K = 64 candidates, map_size 250) on a short horizon
+    ("stress_short",   [(900, 100, 101, 64, "0.03125", "0.00390625", 0.02, 0.04)],            2, 8, 64, 0.1, 250),
 ]
 
 

@@ -16,8 +16,8 @@ from rng_tables import PhiloxTables
 pytestmark = pytest.mark.gpu
 
 
-def test_reference_run_replay_bit_exact(builder, trace_gold, oracle_weights):
-    z = trace_gold
+def test_reference_run_replay_bit_exact(builder, any_trace_gold, oracle_weights):
+    z = any_trace_gold
     oi = oins_from_npz(z)
     N, K = oi.num_agents, 3
     NT, MT, MA = int(z["N_traj"]), int(z["max_T"]), int(z["max_attempt"])

@@ -250,6 +250,67 @@ def test_encode_features_vs_reference(builder, trace_gold):
     assert worst <= TOL, worst
 
 
+def _near_tie_positions(rng, n_agents, k, ulps):
+    """positions around agent 0 whose k-th and (k+1)-th nearest distances differ by `ulps` float32 ulps (distinct after the
+    reference's float64 -> float32 cast, so its argsort is well defined), the nearer one carrying the LARGER index"""
+    while True:
+        c = np.array([0.5, 0.5]) + (rng.rand(2) - 0.5) * 0.2
+        radii = np.sort(rng.rand(n_agents - 1) * 0.25 + 0.05)
+        ang = rng.rand(n_agents - 1) * 2 * np.pi
+        d_k = np.float32(radii[k - 1])
+        d_k1 = d_k
+        for _ in range(ulps):
+            d_k1 = np.nextafter(d_k1, np.float32(1))
+        radii[k - 1], radii[k] = float(d_k), float(d_k1)
+        pts = c + np.stack([np.cos(ang), np.sin(ang)], 1) * radii[:, None]
+        order = rng.permutation(n_agents - 1)
+        # put the k-th nearest AFTER the (k+1)-th in index order: a tie-by-index fallback would pick the wrong one
+        ik, ik1 = int(np.where(order == k - 1)[0][0]), int(np.where(order == k)[0][0])
+        if ik < ik1:
+            order[ik], order[ik1] = order[ik1], order[ik]
+        cur = np.concatenate([c[None], pts[order]])
+        d32 = np.sqrt(((cur[1:] - cur[0]) ** 2).sum(1)).astype(np.float32)
+        srt = np.sort(d32)
+        if srt[k - 1] != srt[k] and (np.diff(srt) > 0).all() and cur.min() > 0.03 and cur.max() < 0.97:
+            return cur
+
+
+@pytest.mark.parametrize("ulps", [1, 2, 8])
+def test_kth_neighbour_near_tie(builder, oracle_weights, ulps):
+    """get_comm keeps the k = 15 nearest neighbours by argsort of float32(float64 norm) (format_input.py:239-243,
+    compiled.py:24): two candidates whose distances differ by one float32 ulp on the 15th/16th boundary must be ranked
+    like the reference does — comm (X[:, 40:72]) against the oracle for 16 such instances at once"""
+    L, lib = _lib()
+    torch = _t()
+    rng = np.random.RandomState(100 + ulps)
+    N, k = 20, 15
+    oins = []
+    for _ in range(16):
+        cur = _near_tie_positions(rng, N, k, ulps)
+        goals = np.clip(cur + (rng.rand(N, 2) - 0.5) * 0.3, 0.05, 0.95)
+        oins.append(O.OInstance.from_arrays(cur, goals, np.full(N, 1 / 32), np.full(N, 1 / 256), np.zeros((0, 2)), np.zeros(0)))
+    builder.upload([instance_from_oins(oi) for oi in oins])
+    v = builder.device_view()
+    F, M, A = v.F, v.M, v.A
+    cur_all = np.concatenate([oi.starts for oi in oins])
+    prev_all = cur_all + (rng.rand(A, 2) - 0.5) * 0.02
+    cur, prev = _dev(cur_all), _dev(prev_all)
+    fov = torch.zeros(A * 2 * F * F + 8, dtype=torch.float32, device="cuda")
+    X = torch.zeros(A * 72, dtype=torch.float32, device="cuda")
+    L.check(lib.ctrm_fov_raster(v.d_occ, v.d_ctg, v.ctg_layout, v.d_agent_inst, cur.data_ptr(), A, M, F, fov.data_ptr(), _stream()))
+    L.check(lib.ctrm_encode_features(builder.ctx, fov.data_ptr(), cur.data_ptr(), prev.data_ptr(), X.data_ptr(), _stream()))
+    got = X.cpu().numpy().reshape(A, 72)
+    worst = 0.0
+    with torch.no_grad():
+        for b, oi in enumerate(oins):
+            occ, ctgs = O.set_instance(oracle_weights, oi)
+            ref = O.feature_one_step(oracle_weights, oi, occ, ctgs, cur_all[b * N:(b + 1) * N], prev_all[b * N:(b + 1) * N]).numpy()
+            worst = max(worst, rel_err(got[b * N:(b + 1) * N, 40:72], ref[:, 40:72]))
+            # the constructed agent: a swapped 15th/16th neighbour moves comm by far more than the tolerance
+            assert rel_err(got[b * N, 40:72], ref[0, 40:72]) <= TOL
+    assert worst <= TOL, worst
+
+
 def test_cvae_sample_vs_reference(builder, trace_gold):
     """indicator + CTRMNet.sample with the reference's own X and torch.rand uniforms: SAMPLES within 1e-5 relative,
     indicators identical"""

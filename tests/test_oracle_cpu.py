@@ -111,10 +111,10 @@ def test_networks_vs_reference_trace(trace_gold, oracle_weights):
             assert np.abs(Y - z["SAMPLES"][s]).max() <= 2e-6
 
 
-def test_reference_run_replay(trace_gold, oracle_weights):
+def test_reference_run_replay(any_trace_gold, oracle_weights):
     """the whole path: the oracle fed the reference's own random streams and sampled coordinates reproduces the
     reference's timed roadmaps and collision counter bit for bit"""
-    z = trace_gold
+    z = any_trace_gold
     oi = oins_from_npz(z)
     NT, MT, MA = int(z["N_traj"]), int(z["max_T"]), int(z["max_attempt"])
     p = O.OParams(N_traj=NT, max_T=MT, merge_distance_rate=float(z["merge_distance_rate"]), max_attempt=MA)

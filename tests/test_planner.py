@@ -126,6 +126,10 @@ def test_gpu_planner_batch_vs_oracle_and_drop_in_class():
             d = np.diff(np.stack([v.pos for v in path]), axis=0)
             assert np.all(np.linalg.norm(d, axis=1) <= instances[b].max_speeds[i] * (1 + 1e-12))
         assert res.lowlevel_explored == int(counters[b][2]) and res.sum_of_costs > 0
+        # solve() = _solve() + validate() (planner/planner.py:103-105): a valid solution adds one swept test per agent pair
+        # and time step to the counter, exactly as the reference's validate does through collide_dynamic_agents
+        N_b, T_b = instances[b].num_agents, len(res.paths[0]) - 1
+        assert res.cnt_continuous_collide == int(counters[b][0]) + T_b * N_b * (N_b - 1) // 2
     finally:
         bld.close()
 
