@@ -72,6 +72,10 @@ SIGNATURES = {
     "ctrm_raster_occupancy": (C.c_int, [V, V, C.c_int, C.c_int, V, V]),
     "ctrm_cost_to_go": (C.c_int, [V, V, V, V, C.c_int, C.c_int, V, V]),
     "ctrm_others_info": (C.c_int, [V] * 5 + [C.c_int, C.c_int, V, V, V]),
+    "ctrm_collide_points": (C.c_int, [V, V, V, C.c_int64, V, V, V, V]),
+    "ctrm_pair_adjacency_words": (C.c_int64, [V, V, C.c_int]),
+    "ctrm_pair_adjacency": (C.c_int, [V, V, V, V, C.c_int, V, V, V, V, V, V, C.c_int, V, V, V]),
+    "ctrm_adjacency_csr": (C.c_int, [V, V, V, C.c_int, C.c_int, V, V, V]),
     "ctrm_plan_prioritized": (C.c_int, [C.c_int, C.c_int, C.c_int] + [V] * 9 + [C.c_int] + [V] * 6),
     "ctrm_fov_raster": (C.c_int, [V, V, C.c_int, V, V, C.c_int, C.c_int, C.c_int, V, V]),
     "ctrm_encode_features": (C.c_int, [V, V, V, V, V, V]),

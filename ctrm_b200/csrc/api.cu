@@ -963,6 +963,108 @@ extern "C" int ctrm_others_info(const double* d_cur, const double* d_goals, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// baseline samplers
+// ------------------------------------------------------------------------------------------------
+extern "C" int ctrm_collide_points(const double* d_pos, const double* d_rad, const int32_t* d_pt_inst, int64_t n,
+                                   const double* d_obs_xyr, const int32_t* d_obs_off, uint8_t* d_verdict, void* stream) {
+  CHECK(use_device_of(d_verdict));
+  if (n < 0 || (n > 0 && (!d_pos || !d_rad || !d_obs_off || !d_verdict)))
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_collide_points: NULL argument");
+  return launch_collide_points(d_pos, d_rad, d_pt_inst, n, d_obs_xyr, d_obs_off, d_verdict, (cudaStream_t)stream);
+}
+
+// layout of the bit rows / work items of n_sets (rows x columns) blocks; returns the number of 32-bit words
+static int64_t adjacency_layout(const int32_t* h_row_off, const int32_t* h_col_off, int n_sets, std::vector<int64_t>* bits_off,
+                                std::vector<int64_t>* item_off) {
+  int64_t words = 0, items = 0;
+  if (bits_off) bits_off->assign((size_t)n_sets + 1, 0);
+  if (item_off) item_off->assign((size_t)n_sets + 1, 0);
+  for (int s = 0; s < n_sets; ++s) {
+    const int64_t nr = h_row_off[s + 1] - h_row_off[s], nc = h_col_off[s + 1] - h_col_off[s];
+    if (nr < 0 || nc < 0) return -1;
+    const int64_t W = (nc + 31) / 32;
+    words += nr * W;
+    items += nr * ((W + 7) / 8);  // PA_WORDS = 8 words per warp item (sampler.cu)
+    if (bits_off) (*bits_off)[s + 1] = words;
+    if (item_off) (*item_off)[s + 1] = items;
+  }
+  return words;
+}
+
+extern "C" int64_t ctrm_pair_adjacency_words(const int32_t* h_row_off, const int32_t* h_col_off, int n_sets) {
+  if (!h_row_off || !h_col_off || n_sets < 0) return -1;
+  return adjacency_layout(h_row_off, h_col_off, n_sets, nullptr, nullptr);
+}
+
+// small per-set host arrays -> stream-ordered device scratch
+template <typename T>
+static int scratch_upload(T** d, const T* h, size_t n, cudaStream_t st) {
+  *d = nullptr;
+  CTRM_CUDA_OK(cudaMallocAsync(d, sizeof(T) * (n ? n : 1), st));
+  if (n) CTRM_CUDA_OK(cudaMemcpyAsync(*d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+extern "C" int ctrm_pair_adjacency(const double* d_rows, const int32_t* h_row_off, const double* d_cols, const int32_t* h_col_off,
+                                   int n_sets, const int32_t* h_set_inst, const double* h_speed, const double* h_speed2,
+                                   const double* h_rad, const double* d_obs_xyr, const int32_t* d_obs_off, int symmetric,
+                                   uint32_t* d_bits, int64_t* d_cnt, void* stream) {
+  CHECK(use_device_of(d_bits));
+  if (n_sets <= 0 || !d_rows || !h_row_off || !d_cols || !h_col_off || !h_speed || !h_speed2 || !h_rad || !d_obs_off || !d_bits)
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_pair_adjacency: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int64_t> bits_off, item_off;
+  if (adjacency_layout(h_row_off, h_col_off, n_sets, &bits_off, &item_off) < 0)
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_pair_adjacency: offsets must be non-decreasing");
+  if (symmetric)
+    for (int s = 0; s < n_sets; ++s)
+      if (h_row_off[s + 1] - h_row_off[s] != h_col_off[s + 1] - h_col_off[s])
+        return ctrm_fail(CTRM_ERR_ARG, "ctrm_pair_adjacency: symmetric needs rows == columns");
+  CHECK(keep_async_pool_warm());
+  int32_t *d_ro = nullptr, *d_co = nullptr, *d_si = nullptr;
+  double *d_sp = nullptr, *d_sp2 = nullptr, *d_ra = nullptr;
+  int64_t *d_bo = nullptr, *d_io = nullptr;
+  int rc = scratch_upload(&d_ro, h_row_off, (size_t)n_sets + 1, st);
+  if (!rc) rc = scratch_upload(&d_co, h_col_off, (size_t)n_sets + 1, st);
+  if (!rc && h_set_inst) rc = scratch_upload(&d_si, h_set_inst, (size_t)n_sets, st);
+  if (!rc) rc = scratch_upload(&d_sp, h_speed, (size_t)n_sets, st);
+  if (!rc) rc = scratch_upload(&d_sp2, h_speed2, (size_t)n_sets, st);
+  if (!rc) rc = scratch_upload(&d_ra, h_rad, (size_t)n_sets, st);
+  if (!rc) rc = scratch_upload(&d_bo, bits_off.data(), bits_off.size(), st);
+  if (!rc) rc = scratch_upload(&d_io, item_off.data(), item_off.size(), st);
+  if (!rc && d_cnt) {
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (size_t)n_sets, st);
+    if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "memset");
+  }
+  if (!rc)
+    rc = launch_pair_adjacency(d_rows, d_ro, d_cols, d_co, n_sets, d_si, d_sp, d_sp2, d_ra, d_obs_xyr, d_obs_off, symmetric, d_bo, d_io,
+                               item_off[n_sets], d_bits, d_cnt, st);
+  for (void* p : {(void*)d_ro, (void*)d_co, (void*)d_si, (void*)d_sp, (void*)d_sp2, (void*)d_ra, (void*)d_bo, (void*)d_io})
+    if (p) cudaFreeAsync(p, st);
+  return rc;
+}
+
+extern "C" int ctrm_adjacency_csr(const uint32_t* d_bits, const int32_t* h_row_off, const int32_t* h_col_off, int n_sets,
+                                  int self_first, int64_t* d_eptr, int32_t* d_eidx, void* stream) {
+  CHECK(use_device_of(d_eptr));
+  if (n_sets <= 0 || !d_bits || !h_row_off || !h_col_off || !d_eptr) return ctrm_fail(CTRM_ERR_ARG, "ctrm_adjacency_csr: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int64_t> bits_off;
+  if (adjacency_layout(h_row_off, h_col_off, n_sets, &bits_off, nullptr) < 0)
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_adjacency_csr: offsets must be non-decreasing");
+  CHECK(keep_async_pool_warm());
+  int32_t *d_ro = nullptr, *d_co = nullptr;
+  int64_t* d_bo = nullptr;
+  int rc = scratch_upload(&d_ro, h_row_off, (size_t)n_sets + 1, st);
+  if (!rc) rc = scratch_upload(&d_co, h_col_off, (size_t)n_sets + 1, st);
+  if (!rc) rc = scratch_upload(&d_bo, bits_off.data(), bits_off.size(), st);
+  if (!rc) rc = launch_adjacency_csr(d_bits, d_bo, d_ro, d_co, n_sets, h_row_off[n_sets] - h_row_off[0], self_first, d_eptr, d_eidx, st);
+  for (void* p : {(void*)d_ro, (void*)d_co, (void*)d_bo})
+    if (p) cudaFreeAsync(p, st);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // planner
 // ------------------------------------------------------------------------------------------------
 extern "C" int ctrm_plan_prioritized(int B, int A, int L, const int32_t* d_agent_off, const int32_t* d_n_layers,

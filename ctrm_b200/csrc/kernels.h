@@ -132,6 +132,16 @@ int launch_csr_count(const Batch& bt, int64_t* d_agent_nv, int64_t* d_agent_ne, 
 int launch_csr_fill(const Batch& bt, const int64_t* d_agent_v0, const int64_t* d_agent_e0, const int64_t* d_totals,
                     int32_t* d_layer_ptr, double* d_pos, int64_t* d_eptr, int32_t* d_eidx, cudaStream_t st);
 
+// baseline samplers (sampler.cu)
+int launch_collide_points(const double* d_pos, const double* d_rad, const int32_t* d_pt_inst, int64_t n, const double* d_obs_xyr,
+                          const int32_t* d_obs_off, uint8_t* d_verdict, cudaStream_t st);
+int launch_pair_adjacency(const double* d_rows, const int32_t* d_row_off, const double* d_cols, const int32_t* d_col_off,
+                          int n_sets, const int32_t* d_set_inst, const double* d_speed, const double* d_speed2, const double* d_rad,
+                          const double* d_obs_xyr, const int32_t* d_obs_off, int symmetric, const int64_t* d_bits_off,
+                          const int64_t* d_item_off, int64_t n_items, uint32_t* d_bits, int64_t* d_cnt, cudaStream_t st);
+int launch_adjacency_csr(const uint32_t* d_bits, const int64_t* d_bits_off, const int32_t* d_row_off, const int32_t* d_col_off,
+                         int n_sets, int n_rows, int self_first, int64_t* d_eptr, int32_t* d_eidx, cudaStream_t st);
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: remember what has been granted on each device
 // (a process may hold contexts on several GPUs), not once per process.  Contexts are driven from several host threads
 // (PipelinedBuilder): check, set and record under one lock, and record only what the driver accepted, so that no thread

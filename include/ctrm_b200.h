@@ -245,6 +245,44 @@ int ctrm_others_info(const double* d_cur /*[T][N][2]*/, const double* d_goals /*
                      float* d_info /*[T][N*N][11]*/, float* d_self_info /*[T][N][8] or NULL*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Baseline samplers on the collision / edge kernels: the device work behind
+ * get_timed_roadmaps_random / _grid / _random_common / _grid_common / _fully_random (roadmap/random_sampler.py:22-78,
+ * roadmap/grid_sampler.py:19-55, roadmap/utils.py:45-134, roadmap/timed_roadmap.py:169-210).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces StaticObjects.collide_sphere (environment/static_objects.py:44-57, :93-106) for n points at once:
+ * verdict[i] = max(pos + rad) > 1 or min(pos - rad) < 0 or the circle touches any obstacle of instance pt_inst[i].  The
+ * reference delegates the obstacle test to FCL 0.5.0 (absent here, Dockerfile:63); restated from FCL's sphereSphereIntersect:
+ * collide <=> !(||c1 - c2|| > r1 + r2), fp64. */
+int ctrm_collide_points(const double* d_pos /*[n][2]*/, const double* d_rad /*[n]*/, const int32_t* d_pt_inst /*[n] or NULL*/,
+                        int64_t n, const double* d_obs_xyr /*[O][3]*/, const int32_t* d_obs_off /*[B+1]*/,
+                        uint8_t* d_verdict /*[n]*/, void* stream);
+
+/* number of 32-bit words ctrm_pair_adjacency writes: sum over sets of rows_s * ceil(cols_s / 32); -1 on bad offsets */
+int64_t ctrm_pair_adjacency_words(const int32_t* h_row_off /*[n_sets+1]*/, const int32_t* h_col_off /*[n_sets+1]*/, int n_sets);
+
+/* replaces the all-pairs valid_move loops (roadmap/utils.py:18-42 called from timed_roadmap.py:186-193, :116-131, :259-265 and
+ * roadmap/utils.py:114-120): for every set s (one agent's samples) bit (i, j) of its row-major bit matrix is set iff
+ * valid_move(rows[i], cols[j], speed_s, rad_s, obstacles of instance set_inst[s]).  symmetric != 0: rows == columns, the pair
+ * is tested once as (min(i,j) -> max(i,j)) like the reference's `for j in range(i + 1, n)` and mirrored, the diagonal stays
+ * clear.  d_cnt[s] (optional) = number of collide_continuous_sphere calls the reference makes for the set (pairs that pass the
+ * L-inf and L2 pre-checks; symmetric: each pair once).  Offsets and per-set constants are small HOST arrays (speed2 = the
+ * caller's own max_speed ** 2); positions, obstacles and outputs are DEVICE pointers. */
+int ctrm_pair_adjacency(const double* d_rows /*[R][2]*/, const int32_t* h_row_off /*[n_sets+1]*/, const double* d_cols /*[C][2]*/,
+                        const int32_t* h_col_off /*[n_sets+1]*/, int n_sets, const int32_t* h_set_inst /*[n_sets] or NULL*/,
+                        const double* h_speed /*[n_sets]*/, const double* h_speed2 /*[n_sets]*/, const double* h_rad /*[n_sets]*/,
+                        const double* d_obs_xyr /*[O][3]*/, const int32_t* d_obs_off /*[B+1]*/, int symmetric,
+                        uint32_t* d_bits /*[ctrm_pair_adjacency_words]*/, int64_t* d_cnt /*[n_sets] or NULL*/, void* stream);
+
+/* the adjacency lists of those bit matrices as CSR by popcount + exclusive prefix scan + ranked scatter.  Two passes:
+ * d_eidx == NULL fills d_eptr[rows + 1] (d_eptr[rows] = number of entries); with d_eidx the entries are written: per row the
+ * row's own local index first when self_first != 0 (the reference's `adjs = [[i] for i ...]`), then the set columns in
+ * ascending order — exactly the order the reference's nested loops append them in. */
+int ctrm_adjacency_csr(const uint32_t* d_bits, const int32_t* h_row_off /*[n_sets+1]*/, const int32_t* h_col_off /*[n_sets+1]*/,
+                       int n_sets, int self_first, int64_t* d_eptr /*[rows+1]*/, int32_t* d_eidx /*[entries] or NULL*/,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Consumer of the roadmaps: replaces PrioritizedPlanning._solve
  * (planner/prioritized_planning.py:40-101) with its space-time A* (Planner.get_single_agent_path, planner/planner.py:311-384)
  * and its collision test against earlier agents (collide_dynamic_agents, planner.py:216-263 -> continuousCollideSpheres),

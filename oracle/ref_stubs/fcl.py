@@ -1,14 +1,19 @@
-"""Inert stand-in for python-fcl, used ONLY to import the unmodified reference in the build container.
+"""Stand-in for python-fcl, used ONLY to import the unmodified reference in the build container.
 
 The learned-sampler path constructs FCL objects (static_objects.py:31-36, obstacle.py:50-51,
 fcl_utils.py:43-55) but never queries them; every collision on the path goes through
-continuousCollideSpheres. Test infrastructure, not product code.
+continuousCollideSpheres.  The baseline samplers do query ONE thing:
+StaticObjects.collide_sphere -> DynamicAABBTreeCollisionManager.collide(sphere) against sphere obstacles
+(static_objects.py:77-106).  FCL itself (0.5.0, Dockerfile:63) is absent, so that single query is restated here from its
+published narrow phase `sphereSphereIntersect`: no collision iff ||c2 - c1|| > r1 + r2 (centres padded to 3-D, fp64).
+Everything else stays inert.  Parity at this boundary is therefore UNPINNED.  Test infrastructure, not product code.
 """
+import math
 
 
 class _Inert:
     def __init__(self, *a, **k):
-        pass
+        self.args = a
 
     def __getattr__(self, name):
         def _f(*a, **k):
@@ -40,12 +45,15 @@ class CollisionRequest(_Inert):
     pass
 
 
-class CollisionResult(_Inert):
-    pass
+class CollisionResult:
+    def __init__(self, *a, **k):
+        self.is_collision = False
 
 
-class CollisionData(_Inert):
-    pass
+class CollisionData:
+    def __init__(self, request=None, *a, **k):
+        self.request = request
+        self.result = CollisionResult()
 
 
 class ContinuousCollisionRequest(_Inert):
@@ -61,7 +69,17 @@ class DynamicAABBTreeCollisionManager:
         pass
 
     def registerObjects(self, objs):
-        pass
+        self.objs = list(objs)
+
+    def collide(self, obj, rdata, callback=None):
+        """sphere vs the registered spheres (CollisionObject(Sphere(rad), Transform(pos3)))"""
+        r1, c1 = obj.args[0].args[0], obj.args[1].args[0]
+        for o in getattr(self, "objs", []):
+            r2, c2 = o.args[0].args[0], o.args[1].args[0]
+            d = [float(c2[k]) - float(c1[k]) for k in range(3)]
+            if not (math.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) > r1 + r2):
+                rdata.result.is_collision = True
+                return
 
     def setup(self):
         pass
