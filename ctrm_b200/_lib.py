@@ -83,6 +83,7 @@ SIGNATURES = {
     "ctrm_build_roadmaps": (C.c_int, [V, C.POINTER(Params), C.POINTER(Tables), V]),
     "ctrm_result_sizes": (C.c_int, [V, c_i64p, c_i64p, c_i64p]),
     "ctrm_export_csr": (C.c_int, [V, V, V, V, V, V, V, C.c_int, V]),
+    "ctrm_export_csr_compact": (C.c_int, [V] * 9 + [C.c_int, V]),
     "ctrm_trace_enable": (C.c_int, [V, C.c_int]),
     "ctrm_trace_read": (C.c_int, [V, V, V, V]),
     "ctrm_last_timing": (C.c_int, [V, V, c_i64p, c_i64p]),

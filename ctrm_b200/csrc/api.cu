@@ -104,6 +104,7 @@ struct ctrm_ctx {
   // results
   DevArena c_arena;
   int32_t* d_tfin = nullptr;
+  int32_t *d_learn_agent = nullptr, *d_learn_inst = nullptr, *d_n_learn = nullptr;  // Batch::learn_* storage
   int64_t *d_agent_nv = nullptr, *d_agent_ne = nullptr, *d_totals = nullptr;
   int64_t totals[3] = {0, 0, 0};
   bool have_result = false;
@@ -410,6 +411,9 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&bt.live_inst, (size_t)A));
   CHECK(ar.alloc(&bt.n_live, (size_t)1));
   CHECK(ar.alloc(&bt.live_off, (size_t)B));
+  CHECK(ar.alloc(&c->d_learn_agent, (size_t)A));
+  CHECK(ar.alloc(&c->d_learn_inst, (size_t)A));
+  CHECK(ar.alloc(&c->d_n_learn, (size_t)1));
   CHECK(ar.alloc(&bt.agent_pack, (size_t)6 * A));
   CHECK(ar.alloc(&bt.nlayers, (size_t)A));
   CHECK(ar.alloc(&c->d_tfin, (size_t)B));
@@ -566,6 +570,7 @@ extern "C" int ctrm_encode_features(ctrm_ctx* c, const float* d_fov, const doubl
   Batch bt = c->bt;
   bt.done = nullptr;
   bt.live_agent = nullptr;
+  bt.learn_agent = nullptr;
   CHECK(launch_fov_f32_to_tiles(d_fov, bt.A, bt.F, bt.fov_tiles, st));
   CHECK(launch_fov_encode(c->model, bt.fov_tiles, bt.agent_inst, nullptr, bt.A, bt.e_self, bt.e_vain, bt.vain_proj, nullptr, nullptr,
                           st));
@@ -580,6 +585,7 @@ extern "C" int ctrm_cvae_sample(ctrm_ctx* c, const float* d_X, const float* d_un
   Batch bt = c->bt;
   bt.done = nullptr;
   bt.live_agent = nullptr;
+  bt.learn_agent = nullptr;
   bt.K = K;
   bt.dim_ind = c->model.desc.dim_ind;
   bt.seed_lo = (uint32_t)(seed & 0xFFFFFFFFu);
@@ -686,11 +692,18 @@ static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, 
     CHECK(launch_fov_encode(c->model, bt.fov_tiles, bt.agent_inst, bt.done, bt.A, bt.e_self, nullptr, bt.vain_proj,
                             bt.live_agent, bt.n_live, st));
     CHECK(mark(KID_FOV_ENCODE));
-    CHECK(launch_agent_comm(c->model, bt, bt.cur, bt.prev, bt.e_self, bt.vain_proj, bt.X, st));
+    // the three kernels that only serve the learned branch run over the learned rows of this step (Batch::learn_agent)
+    Batch bl = bt;
+    if (bt.learn_agent != nullptr) {
+      bl.live_agent = bt.learn_agent;
+      bl.live_inst = bt.learn_inst;
+      bl.n_live = bt.n_learn;
+    }
+    CHECK(launch_agent_comm(c->model, bl, bt.cur, bt.prev, bt.e_self, bt.vain_proj, bt.X, st));
     CHECK(mark(KID_AGENT_COMM));
-    CHECK(launch_cvae_prior(c->model, bt, bt.X, bt.cv_sqrtp, bt.cv_dec0, bt.ind, st));
+    CHECK(launch_cvae_prior(c->model, bl, bt.X, bt.cv_sqrtp, bt.cv_dec0, bt.ind, st));
     CHECK(mark(KID_CVAE_PRIOR));
-    CHECK(launch_cvae_decode(c->model, bt, bt.cv_sqrtp, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st));
+    CHECK(launch_cvae_decode(c->model, bl, bt.cv_sqrtp, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st));
     CHECK(mark(KID_CVAE_DECODE));
   }
   CHECK(launch_step(bt, st));
@@ -723,6 +736,11 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   bt.seed_lo = (uint32_t)(p->seed & 0xFFFFFFFFu); bt.seed_hi = (uint32_t)(p->seed >> 32);
   bt.inst_base = p->instance_id_base;
   bt.prob_after_goal = p->prob_uniform_sampling_after_goal;
+  // learned-row list: on, except when the run records the CVAE output of EVERY agent-step (trace) — the random-walking
+  // agents' samples are never read by the path, but the parity tests compare them
+  bt.learn_agent = c->trace ? nullptr : c->d_learn_agent;
+  bt.learn_inst = c->trace ? nullptr : c->d_learn_inst;
+  bt.n_learn = c->trace ? nullptr : c->d_n_learn;
   c->have_result = false;
   // tables
   CTRM_CUDA_OK(cudaStreamSynchronize(st));
@@ -781,11 +799,12 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
     CTRM_CUDA_OK(cudaMemsetAsync(bt.tr_loc_pred, 0xFF, steps_max * bt.A * 2 * sizeof(double), st));
     CTRM_CUDA_OK(cudaMemsetAsync(bt.tr_loc_next, 0xFF, steps_max * bt.A * 2 * sizeof(double), st));
   }
+  if (bt.n_learn != nullptr) CTRM_CUDA_OK(cudaMemsetAsync(bt.n_learn, 0, sizeof(int32_t), st));
   CHECK(launch_rollout_init(bt, st));
   int64_t launches = 1;
-  // capture one step as a CUDA graph, then replay it; n_done is polled every `chunk` replays.
+  // capture `chunk` steps as one CUDA graph, then replay it; n_done is polled after every replay.
   // profile mode runs the same kernels eagerly with an event after each one (per-kernel durations).
-  const int chunk = 32;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(32, steps_max));
   int last_done = 0;
   int per_step = 0;
   int64_t steps = 0;
@@ -794,8 +813,11 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   if (!c->profile) {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
+    // ONE graph holds `chunk` consecutive steps: a replay per step costs a graph launch (~3 us of host and front-end time),
+    // which is most of a step at small batches (one instance: 7 kernels of ~3 us each).  Steps past an instance's last
+    // roll-out are no-ops (every row is skipped), so the last chunk may overshoot steps_max.
     CTRM_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_step(c, bt, nn, st, &per_step);
+    for (int i = 0; i < chunk && !rc; ++i) rc = enqueue_step(c, bt, nn, st, &per_step);
     ce = cudaStreamEndCapture(st, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) return ctrm_fail_cuda(ce, "cudaStreamEndCapture");
@@ -803,13 +825,9 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
     if (ce != cudaSuccess) { cudaGraphDestroy(graph); return ctrm_fail_cuda(ce, "cudaGraphInstantiate"); }
     CTRM_CUDA_OK(cudaEventRecord(c->ev_t[1], st));
     while ((size_t)steps < steps_max) {
-      int n = (int)std::min<size_t>(chunk, steps_max - steps);
-      for (int i = 0; i < n && !rc; ++i) {
-        ce = cudaGraphLaunch(gexec, st);
-        if (ce != cudaSuccess) rc = ctrm_fail_cuda(ce, "cudaGraphLaunch");
-      }
-      if (rc) break;
-      steps += n;
+      ce = cudaGraphLaunch(gexec, st);
+      if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "cudaGraphLaunch"); break; }
+      steps += chunk;
       ce = cudaMemcpyAsync(c->h_ndone, bt.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
       if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
       if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "roll-out step loop"); break; }
@@ -902,6 +920,47 @@ extern "C" int ctrm_export_csr(ctrm_ctx* c, int32_t* layer_ptr, double* pos, int
     if (eptr) CTRM_CUDA_OK(cudaMemcpyAsync(eptr, d_ep, ((size_t)nv + 1) * sizeof(int64_t), kind, st));
     if (eidx) CTRM_CUDA_OK(cudaMemcpyAsync(eidx, d_ei, (size_t)ne * sizeof(int32_t), kind, st));
   }
+  if (n_layers) CTRM_CUDA_OK(cudaMemcpyAsync(n_layers, bt.nlayers, (size_t)bt.A * sizeof(int32_t), kind, st));
+  if (cnt_collide) CTRM_CUDA_OK(cudaMemcpyAsync(cnt_collide, bt.cnt_collide, (size_t)bt.B * sizeof(int64_t), kind, st));
+  if (!dst_is_device) CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  CHECK(sync_out(c, (cudaStream_t)user_stream));
+  return 0;
+}
+
+extern "C" int ctrm_export_csr_compact(ctrm_ctx* c, uint8_t* layer_cnt, double* pos, uint8_t* deg, uint8_t* eidx, int64_t* agent_v0,
+                                       int64_t* agent_e0, int32_t* n_layers, int64_t* cnt_collide, int dst_is_device,
+                                       void* user_stream) {
+  if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
+  if (!c->have_result) return ctrm_fail(CTRM_ERR_STATE, "no result: call ctrm_build_roadmaps first");
+  if (!layer_cnt || !pos || !deg || !eidx) return ctrm_fail(CTRM_ERR_ARG, "ctrm_export_csr_compact: NULL output");
+  CTRM_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CHECK(sync_in(c, (cudaStream_t)user_stream));
+  const Batch& bt = c->bt;
+  const int64_t nv = c->totals[0], ne = c->totals[1];
+  const size_t nlc = (size_t)bt.A * bt.L;
+  const cudaMemcpyKind kind = dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  uint8_t *d_lc = layer_cnt, *d_dg = deg, *d_ei = eidx;
+  double* d_pos = pos;
+  if (!dst_is_device) {
+    c->c_arena.release();
+    CHECK(c->c_arena.alloc(&d_lc, nlc));
+    CHECK(c->c_arena.alloc(&d_pos, (size_t)2 * nv));
+    CHECK(c->c_arena.alloc(&d_dg, (size_t)nv));
+    CHECK(c->c_arena.alloc(&d_ei, (size_t)ne));
+    c->c_arena.trim();
+  }
+  CHECK(launch_csr_fill_compact(bt, c->d_agent_nv, c->d_agent_ne, c->d_totals, d_lc, d_pos, d_dg, d_ei, st));
+  if (!dst_is_device) {
+    CTRM_CUDA_OK(cudaMemcpyAsync(pos, d_pos, (size_t)2 * nv * sizeof(double), kind, st));
+    CTRM_CUDA_OK(cudaMemcpyAsync(eidx, d_ei, (size_t)ne, kind, st));
+    CTRM_CUDA_OK(cudaMemcpyAsync(deg, d_dg, (size_t)nv, kind, st));
+    CTRM_CUDA_OK(cudaMemcpyAsync(layer_cnt, d_lc, nlc, kind, st));
+  }
+  if (agent_v0) CTRM_CUDA_OK(cudaMemcpyAsync(agent_v0, c->d_agent_nv, (size_t)bt.A * sizeof(int64_t), kind, st));
+  if (agent_e0) CTRM_CUDA_OK(cudaMemcpyAsync(agent_e0, c->d_agent_ne, (size_t)bt.A * sizeof(int64_t), kind, st));
+  if (agent_v0) CTRM_CUDA_OK(cudaMemcpyAsync(agent_v0 + bt.A, c->d_totals, sizeof(int64_t), kind, st));
+  if (agent_e0) CTRM_CUDA_OK(cudaMemcpyAsync(agent_e0 + bt.A, c->d_totals + 1, sizeof(int64_t), kind, st));
   if (n_layers) CTRM_CUDA_OK(cudaMemcpyAsync(n_layers, bt.nlayers, (size_t)bt.A * sizeof(int32_t), kind, st));
   if (cnt_collide) CTRM_CUDA_OK(cudaMemcpyAsync(cnt_collide, bt.cnt_collide, (size_t)bt.B * sizeof(int64_t), kind, st));
   if (!dst_is_device) CTRM_CUDA_OK(cudaStreamSynchronize(st));

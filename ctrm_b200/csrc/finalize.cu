@@ -229,19 +229,32 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int64_t* __restrict__ nv
   if (threadIdx.x == 0) { totals[0] = carry[0]; totals[1] = carry[1]; totals[2] = carry[2]; }
 }
 
+// COMPACT = false: layer_ptr (i32, stride L per agent), eptr (i64), eidx (i32) — what the planner kernel and the reference-shaped
+// views read.  COMPACT = true: vertices per layer, out-degree per vertex and successor index as single BYTES (a layer holds at
+// most S <= 128 vertices), which is what travels to the host: 0.75 MB instead of 1.46 MB per aamas22 instance.
+template <bool COMPACT>
 __global__ void __launch_bounds__(FZ_WARPS * 32) csr_fill_kernel(Batch bt, const int64_t* __restrict__ agent_v0,
                                                                  const int64_t* __restrict__ agent_e0,
                                                                  const int64_t* __restrict__ totals,
-                                                                 int32_t* __restrict__ layer_ptr, double* __restrict__ pos,
-                                                                 int64_t* __restrict__ eptr, int32_t* __restrict__ eidx) {
+                                                                 void* __restrict__ layer_out, double* __restrict__ pos,
+                                                                 void* __restrict__ eptr_out, void* __restrict__ eidx_out) {
   const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (a >= bt.A) return;
+  int32_t* layer_ptr = reinterpret_cast<int32_t*>(layer_out);
+  uint8_t* layer_cnt = reinterpret_cast<uint8_t*>(layer_out);
+  int64_t* eptr = reinterpret_cast<int64_t*>(eptr_out);
+  uint8_t* deg8 = reinterpret_cast<uint8_t*>(eptr_out);
+  int32_t* eidx = reinterpret_cast<int32_t*>(eidx_out);
+  uint8_t* eidx8 = reinterpret_cast<uint8_t*>(eidx_out);
   const int nl = bt.nlayers[a], W = bt.W;
   long long vb = agent_v0[a], eb = agent_e0[a];
   for (int t = 0; t < bt.L; ++t) {
-    if (lane == 0) layer_ptr[(size_t)a * bt.L + t] = (int32_t)vb;
+    const int n = t < nl ? bt.vcnt[(size_t)a * bt.L + t] : 0;
+    if (lane == 0) {
+      if (COMPACT) layer_cnt[(size_t)a * bt.L + t] = (uint8_t)n;
+      else layer_ptr[(size_t)a * bt.L + t] = (int32_t)vb;
+    }
     if (t >= nl) continue;
-    const int n = bt.vcnt[(size_t)a * bt.L + t];
     for (int s0 = 0; s0 < n; s0 += 32) {
       const int s = s0 + lane;
       int deg = 0;
@@ -259,13 +272,15 @@ __global__ void __launch_bounds__(FZ_WARPS * 32) csr_fill_kernel(Batch bt, const
       const int tot = __shfl_sync(0xFFFFFFFFu, x, 31);
       if (s < n) {
         long long e = eb + (x - deg);
-        pos[2 * (vb + s)] = bt.vpos[2 * v];
-        pos[2 * (vb + s) + 1] = bt.vpos[2 * v + 1];
-        eptr[vb + s] = e;
+        *reinterpret_cast<double2*>(&pos[2 * (vb + s)]) = *reinterpret_cast<const double2*>(&bt.vpos[2 * v]);
+        if (COMPACT) deg8[vb + s] = (uint8_t)deg;
+        else eptr[vb + s] = e;
         for (int w = 0; w < W; ++w) {
           uint32_t m = bt.cmask[v * W + w];
           while (m) {
-            eidx[e++] = w * 32 + __ffs(m) - 1;
+            const int j = w * 32 + __ffs(m) - 1;
+            if (COMPACT) eidx8[e++] = (uint8_t)j;
+            else eidx[e++] = j;
             m &= m - 1;
           }
         }
@@ -274,7 +289,7 @@ __global__ void __launch_bounds__(FZ_WARPS * 32) csr_fill_kernel(Batch bt, const
     }
     vb += n;
   }
-  if (a == bt.A - 1 && lane == 0) {
+  if (!COMPACT && a == bt.A - 1 && lane == 0) {
     layer_ptr[(size_t)bt.A * bt.L] = (int32_t)totals[0];
     eptr[totals[0]] = totals[1];
   }
@@ -306,8 +321,18 @@ int launch_csr_count(const Batch& bt, int64_t* d_agent_nv, int64_t* d_agent_ne, 
 int launch_csr_fill(const Batch& bt, const int64_t* d_agent_v0, const int64_t* d_agent_e0, const int64_t* d_totals,
                     int32_t* d_layer_ptr, double* d_pos, int64_t* d_eptr, int32_t* d_eidx, cudaStream_t st) {
   if (bt.A <= 0) return 0;
-  csr_fill_kernel<<<(bt.A + FZ_WARPS - 1) / FZ_WARPS, FZ_WARPS * 32, 0, st>>>(bt, d_agent_v0, d_agent_e0, d_totals, d_layer_ptr,
-                                                                           d_pos, d_eptr, d_eidx);
+  csr_fill_kernel<false><<<(bt.A + FZ_WARPS - 1) / FZ_WARPS, FZ_WARPS * 32, 0, st>>>(bt, d_agent_v0, d_agent_e0, d_totals,
+                                                                                  d_layer_ptr, d_pos, d_eptr, d_eidx);
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_csr_fill_compact(const Batch& bt, const int64_t* d_agent_v0, const int64_t* d_agent_e0, const int64_t* d_totals,
+                            uint8_t* d_layer_cnt, double* d_pos, uint8_t* d_deg, uint8_t* d_eidx, cudaStream_t st) {
+  if (bt.A <= 0) return 0;
+  if (bt.S > 255) return ctrm_fail(-1, "compact export needs at most 255 vertices per layer");
+  csr_fill_kernel<true><<<(bt.A + FZ_WARPS - 1) / FZ_WARPS, FZ_WARPS * 32, 0, st>>>(bt, d_agent_v0, d_agent_e0, d_totals,
+                                                                                 d_layer_cnt, d_pos, d_deg, d_eidx);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }

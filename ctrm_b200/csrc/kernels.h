@@ -62,6 +62,13 @@ struct Batch {
   int32_t* live_inst;                   // [A] instance of live_agent[row]: read side by side, not after it
   int32_t* n_live;                      // [1] number of rows
   int32_t* live_off;                    // [B] scratch: first row of an unfinished instance
+  // rows of the kernels that only serve the LEARNED branch (agent_comm, cvae_prior, cvae_decode): the agents whose gate draw
+  // of the coming step selects the learned sampler (learned_sampler.py:148-157).  An agent that random-walks never reads its
+  // CVAE samples, nor its own communication vector; it still runs the FOV encoders (its neighbours read its embedding).
+  // Rebuilt by the advance kernel at the end of every step (instance-contiguous); nullptr = every live row.
+  int32_t* learn_agent;                 // [A]
+  int32_t* learn_inst;                  // [A]
+  int32_t* n_learn;                     // [1]
   double* agent_pack;                   // [A][6] {goal x, goal y, speed, speed^2, merge_distance^2, rad}
   // per-step tensors
   uint8_t* fov_tiles;  // bf16 operand tiles [ceil(A/128)][n_chunks][128 x 96]
@@ -141,6 +148,9 @@ int launch_pair_adjacency(const double* d_rows, const int32_t* d_row_off, const 
                           const int64_t* d_item_off, int64_t n_items, uint32_t* d_bits, int64_t* d_cnt, cudaStream_t st);
 int launch_adjacency_csr(const uint32_t* d_bits, const int64_t* d_bits_off, const int32_t* d_row_off, const int32_t* d_col_off,
                          int n_sets, int n_rows, int self_first, int64_t* d_eptr, int32_t* d_eidx, cudaStream_t st);
+
+int launch_csr_fill_compact(const Batch& bt, const int64_t* d_agent_v0, const int64_t* d_agent_e0, const int64_t* d_totals,
+                            uint8_t* d_layer_cnt, double* d_pos, uint8_t* d_deg, uint8_t* d_eidx, cudaStream_t st);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: remember what has been granted on each device
 // (a process may hold contexts on several GPUs), not once per process.  Contexts are driven from several host threads

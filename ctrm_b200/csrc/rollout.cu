@@ -15,6 +15,24 @@
 
 __device__ __forceinline__ size_t step_index(const Batch& bt, int kt, int t) { return (size_t)kt * bt.max_T + (t - 1); }
 
+// the gate of learned_sampler.py:148-157 for agent a (local index il) of instance b at (kt, t): learned branch iff
+// (not arrived and u < p_rw) or (arrived and u > prob_after_goal) or k_traj < dim_ind.  The draw is keyed, so the decision can
+// be taken ahead of the step (advance kernel: which rows need the networks) and again inside it (select) with the same result.
+__device__ __forceinline__ bool gate_is_learned(const Batch& bt, int b, int a, int il, int kt, int t, int makespan, bool arrived) {
+  if (kt < bt.dim_ind) return true;
+  const int D = makespan ? makespan : bt.max_T;
+  const double p_rw = bt.p_rw[(size_t)t * (bt.max_T + 1) + D];  // prob_random_walk (learned_sampler.py:84-91), host table
+  double u_gate;
+  if (bt.rng_mode == 1) {
+    u_gate = bt.tab_gate[step_index(bt, kt, t) * bt.A + a];
+  } else {
+    const uint4 w = philox4x32(bt.inst_base + (uint32_t)b, rng_ctr1(kt, t), (uint32_t)il, rng_ctr3(STREAM_GATE, 0), bt.seed_lo,
+                               bt.seed_hi);
+    u_gate = u64_to_f64(w.x, w.y);
+  }
+  return (!arrived && u_gate < p_rw) || (arrived && u_gate > bt.prob_after_goal);
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void rollout_init_kernel(Batch bt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -27,6 +45,14 @@ __global__ void rollout_init_kernel(Batch bt) {
     if (bt.live_agent != nullptr) {
       bt.live_agent[i] = i;
       bt.live_inst[i] = bt.agent_inst[i];
+    }
+    if (bt.learn_agent != nullptr && bt.N_traj > 0) {  // first step (k_traj 0, t 1); n_learn was zeroed by the host
+      const int b = bt.agent_inst[i];
+      if (gate_is_learned(bt, b, i, i - bt.agent_off[b], 0, 1, 0, false)) {
+        const int slot = atomicAdd(bt.n_learn, 1);
+        bt.learn_agent[slot] = i;
+        bt.learn_inst[slot] = b;
+      }
     }
     double* ap = bt.agent_pack + 6 * (size_t)i;  // {goal x, goal y, speed, speed^2, merge_distance^2, rad}
     ap[0] = bt.goals[2 * i]; ap[1] = bt.goals[2 * i + 1]; ap[2] = bt.speeds[i]; ap[3] = bt.speeds2[i];
@@ -189,17 +215,7 @@ __device__ __forceinline__ unsigned int select_agent(const Batch& bt, const Step
   const double speed = sc.speed, speed2 = sc.speed2, rad = sc.rad;
   const size_t si = step_index(bt, kt, t);
   const uint32_t c0 = bt.inst_base + (uint32_t)b, c1 = rng_ctr1(kt, t);
-  // prob_random_walk (learned_sampler.py:84-91), tabulated by the host over (t, makespan)
-  const int D = sc.makespan ? sc.makespan : bt.max_T;
-  const double p_rw = bt.p_rw[(size_t)t * (bt.max_T + 1) + D];
-  double u_gate;
-  if (bt.rng_mode == 1) {
-    u_gate = bt.tab_gate[si * bt.A + a];
-  } else {
-    uint4 w = philox4x32(c0, c1, (uint32_t)il, rng_ctr3(STREAM_GATE, 0), bt.seed_lo, bt.seed_hi);
-    u_gate = u64_to_f64(w.x, w.y);
-  }
-  const bool learned = (!arrived && u_gate < p_rw) || (arrived && u_gate > bt.prob_after_goal) || (kt < bt.dim_ind);
+  const bool learned = gate_is_learned(bt, b, a, il, kt, t, sc.makespan, arrived);
   const int nL = learned ? bt.K : 0;
   const int C = nL + bt.max_attempt;
   (void)N;
@@ -462,6 +478,25 @@ __device__ __forceinline__ unsigned int merge_agent(const Batch& bt, const StepC
 // ------------------------------------------------------------------------------------------------
 // advance: roll-out bookkeeping of one instance (advance_kernel, one warp per instance, after the step kernel)
 // ------------------------------------------------------------------------------------------------
+// append the agents of instance b whose next step (kt, t) takes the learned branch to the learned-row list
+__device__ __forceinline__ void list_learned(const Batch& bt, int b, int a0, int N, int kt, int t, int makespan, bool fresh,
+                                             int lane) {
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    const int i = i0 + lane;
+    bool f = false;
+    if (i < N) f = gate_is_learned(bt, b, a0 + i, i, kt, t, makespan, fresh ? false : (__ldcg(&bt.arrived[a0 + i]) != 0));
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, f);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(bt.n_learn, __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (f) {
+      const int slot = base + __popc(m & ((1u << lane) - 1u));
+      bt.learn_agent[slot] = a0 + i;
+      bt.learn_inst[slot] = b;
+    }
+  }
+}
+
 __device__ __forceinline__ void advance_instance(const Batch& bt, const int b, const int lane) {
   const int a0 = bt.agent_off[b], N = bt.agent_off[b + 1] - a0;
   bool all = true;
@@ -491,6 +526,7 @@ __device__ __forceinline__ void advance_instance(const Batch& bt, const int b, c
       bt.t[b] = t + 1;
       bt.inst_pack[8 * b + 1] = t + 1;
     }
+    if (bt.learn_agent != nullptr) list_learned(bt, b, a0, N, bt.k_traj[b], t + 1, bt.makespan[b], false, lane);
   } else {
     const int kt = bt.k_traj[b] + 1;
     if (kt >= bt.N_traj) {
@@ -515,6 +551,9 @@ __device__ __forceinline__ void advance_instance(const Batch& bt, const int b, c
         bt.inst_pack[8 * b + 1] = 1;
         bt.inst_pack[8 * b + 2] = kt;
       }
+      // makespan: lane 0 may have just updated it (all arrived) — read it back after the warp has converged
+      __syncwarp();
+      if (bt.learn_agent != nullptr) list_learned(bt, b, a0, N, kt, 1, __ldcg(&bt.makespan[b]), true, lane);
     }
   }
 }
@@ -535,6 +574,9 @@ __global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
   const int warp = threadIdx.x >> 5;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  // the learned-row list of this step has been consumed (the network kernels ran before this one); the advance kernel that
+  // follows refills it for the next step
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bt.n_learn != nullptr) *bt.n_learn = 0;
   if (row >= (bt.live_agent != nullptr ? *bt.n_live : bt.A)) return;
   const int a = bt.live_agent != nullptr ? bt.live_agent[row] : row;
   StepCtx sc;

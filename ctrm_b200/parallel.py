@@ -8,9 +8,6 @@ from __future__ import annotations
 
 from typing import Dict, List
 
-KEYS = ("layer_ptr", "pos", "eptr", "eidx", "n_layers", "cnt_collide")
-
-
 def shard_range(n_instances: int, rank: int, world: int):
     """contiguous block partition: rank r owns [lo, hi); sizes differ by at most one"""
     base, rem = divmod(n_instances, world)
@@ -19,34 +16,45 @@ def shard_range(n_instances: int, rank: int, world: int):
 
 
 def gather_csr(res: Dict[str, "torch.Tensor"], rank: int, world: int, dst: int = 0, async_op: bool = False):
-    """gather every rank's CSR arrays to `dst`.  Returns on dst a list (one dict per rank) of trimmed tensors, elsewhere
-    None.  Sizes travel by all_gather, payloads by a padded gather (equal-size requirement of the collective).
-    With async_op=True the payload gathers are only enqueued: returns (out, works, keepalive) and the caller calls
-    `w.wait()` on every work before reading `out` (and keeps `keepalive` referenced until then), so that the transfer over
-    NVLink overlaps whatever the caller launches next."""
+    """gather every rank's CSR arrays (any dict of tensors with the same keys on every rank: the wide arrays of
+    RoadmapBuilder.export_device or its compact byte-sized form) to `dst`.  Returns on dst a list (one dict per rank) of
+    tensors, elsewhere None.  The element counts travel by one small all_gather; the payloads as EXACT-SIZE point-to-point
+    transfers grouped into one batch (ncclGroupStart/End under NCCL: all peers stream into dst concurrently over
+    NVLink) — no padding to the largest rank, no zero-fill, no staging copy.
+    With async_op=True the transfers are only enqueued: returns (out, works, keepalive) and the caller calls `w.wait()` on
+    every work before reading `out` (and keeps `keepalive` referenced until then), so that the traffic overlaps whatever the
+    caller launches next."""
     import torch
     import torch.distributed as dist
 
-    dev = res["pos"].device
-    sizes = torch.tensor([res[k].numel() for k in KEYS], dtype=torch.int64, device=dev)
-    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes)
-    all_sizes = torch.stack(all_sizes).cpu()
+    keys = sorted(res.keys())
+    dev = res[keys[0]].device
+    sizes = torch.tensor([res[k].numel() for k in keys], dtype=torch.int64, device=dev)
+    all_sizes = torch.empty(world * len(keys), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes, sizes)
     out: List[dict] = [dict() for _ in range(world)] if rank == dst else None
-    works, keep = [], []
-    for j, k in enumerate(KEYS):
-        mx = int(all_sizes[:, j].max())
-        flat = res[k].reshape(-1)
-        pad = torch.zeros(mx, dtype=flat.dtype, device=dev)
-        pad[:flat.numel()] = flat
-        bufs = [torch.empty(mx, dtype=flat.dtype, device=dev) for _ in range(world)] if rank == dst else None
-        if async_op:
-            works.append(dist.gather(pad, bufs, dst=dst, async_op=True))
-            keep.append((pad, bufs))
-        else:
-            dist.gather(pad, bufs, dst=dst)
-        if rank == dst:
-            for r in range(world):
-                t = bufs[r][:int(all_sizes[r, j])]
-                out[r][k] = t.reshape(-1, 2) if k == "pos" else t
-    return (out, works, keep) if async_op else out
+    ops, keep = [], []
+    if rank == dst:
+        all_sizes = all_sizes.cpu().reshape(world, len(keys))  # only the receiver needs them on the host (to allocate)
+        for r in range(world):
+            for j, k in enumerate(keys):
+                n = int(all_sizes[r, j])
+                if r == dst:
+                    buf = res[k].reshape(-1)
+                else:
+                    buf = torch.empty(n, dtype=res[k].dtype, device=dev)
+                    if n:
+                        ops.append(dist.P2POp(dist.irecv, buf, r))
+                out[r][k] = buf.reshape(-1, 2) if res[k].dim() == 2 else buf
+    else:
+        for k in keys:
+            flat = res[k].reshape(-1)
+            if flat.numel():
+                ops.append(dist.P2POp(dist.isend, flat, dst))
+            keep.append(flat)
+    works = dist.batch_isend_irecv(ops) if ops else []
+    if async_op:
+        return out, works, (keep, res)
+    for w in works:
+        w.wait()
+    return out

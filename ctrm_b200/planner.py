@@ -105,11 +105,7 @@ def _flatten_trms(trms: Sequence) -> tuple:
         csr = trms[0]._csr
         ag = [t._agent for t in trms]
         if ag == list(range(ag[0], ag[0] + len(ag))):  # a contiguous run of agents of one CSR result: slice, no Python lists
-            L, a0, a1 = csr.L, ag[0], ag[-1] + 1
-            v0, v1 = int(csr.layer_ptr[a0 * L]), int(csr.layer_ptr[a1 * L])
-            e0, e1 = int(csr.eptr[v0]), int(csr.eptr[v1])
-            return (L, csr.n_layers[a0:a1], csr.layer_ptr[a0 * L:a1 * L + 1] - v0, csr.pos[v0:v1], csr.eptr[v0:v1 + 1] - e0,
-                    csr.eidx[e0:e1])
+            return csr.agents_arrays(ag[0], ag[-1] + 1)
     n_layers = np.array([len(t.V) for t in trms], dtype=np.int32)
     L = int(n_layers.max()) + 1
     layer_ptr = np.zeros(len(trms) * L + 1, dtype=np.int32)

@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _lib
 from .environment import Instance
-from .timed_roadmap import CSRRoadmaps
+from .timed_roadmap import CompactCSRRoadmaps, CSRRoadmaps
 from .weights import load_bundle, pack_blob
 
 _BUILDERS: dict = {}
@@ -106,7 +106,7 @@ class RoadmapBuilder:
             prob_uniform_gamma: float = 5.0, max_T: int = 64, N_traj: int = 25, max_attempt: int = 3,
             randomize_indicator: bool = False, merge_distance_rate: float = 0.25, K: int = 0, seed: Optional[int] = None,
             instance_id_base: int = 0, tables: Optional[dict] = None, trace: bool = False, stream: int = 0,
-            export: bool = True, pinned: bool = True) -> Optional[CSRRoadmaps]:
+            export: bool = True, pinned: bool = True, compact: bool = True) -> Optional[CSRRoadmaps]:
         """roll-outs + finalisation + CSR export for the uploaded batch"""
         if self._uploaded is None:
             raise _lib.CtrmError("upload instances first")
@@ -140,7 +140,7 @@ class RoadmapBuilder:
         self._last = dict(max_T=int(max_T), N_traj=int(N_traj), K=int(K) if K else int(self.bundle.dim_ind))
         if not export:
             return None
-        return self.export(stream=stream, pinned=pinned)
+        return self.export(stream=stream, pinned=pinned, compact=compact)
 
     def result_sizes(self):
         nv, ne, nl = C.c_int64(), C.c_int64(), C.c_int64()
@@ -154,8 +154,10 @@ class RoadmapBuilder:
                    "ctrm_last_timing")
         return dict(total_ms=ms[0], rollout_ms=ms[1], finalize_ms=ms[2], steps=steps.value, launches=launches.value)
 
-    def export(self, stream: int = 0, pinned: bool = True) -> CSRRoadmaps:
-        """D2H copy of the CSR result"""
+    def export(self, stream: int = 0, pinned: bool = True, compact: bool = True) -> CSRRoadmaps:
+        """D2H copy of the CSR result.  compact (default): byte-sized layer counts / degrees / successor indices
+        (ctrm_export_csr_compact, half the bytes over PCIe) wrapped in a CompactCSRRoadmaps, which expands instances on
+        demand; compact=False: the wide arrays of ctrm_export_csr"""
         p = self._uploaded
         nv, ne, _ = self.result_sizes()
         A = int(p["n_agents"].sum())
@@ -169,13 +171,27 @@ class RoadmapBuilder:
             import torch
 
             n = int(np.prod(shape))
-            tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}[dtype]
+            tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64, np.uint8: torch.uint8}[dtype]
             buf = self._pinned.get(name)
             if buf is None or buf.numel() < n or buf.dtype != tdt:
                 buf = torch.empty(max(n + n // 8, 1), dtype=tdt, pin_memory=True)
                 self._pinned[name] = buf
             return buf[:n].numpy().reshape(shape)
 
+        agent_off = np.concatenate([[0], np.cumsum(p["n_agents"])]).astype(np.int32)
+        if compact:
+            layer_cnt = host("layer_cnt", A * L, np.uint8)
+            pos = host("pos", (nv, 2), np.float64)
+            deg = host("deg", max(nv, 1), np.uint8)[:nv]
+            eidx8 = host("eidx8", max(ne, 1), np.uint8)[:ne]
+            av0, ae0 = host("agent_v0", A + 1, np.int64), host("agent_e0", A + 1, np.int64)
+            n_layers = host("n_layers", A, np.int32)
+            cnt = host("cnt", B, np.int64)
+            _lib.check(self.lib.ctrm_export_csr_compact(self.ctx, _lib.ptr(layer_cnt), _lib.ptr(pos),
+                                                        deg.ctypes.data_as(C.c_void_p), eidx8.ctypes.data_as(C.c_void_p),
+                                                        _lib.ptr(av0), _lib.ptr(ae0), _lib.ptr(n_layers), _lib.ptr(cnt), 0, stream),
+                       "ctrm_export_csr_compact")
+            return CompactCSRRoadmaps(agent_off, L, layer_cnt, pos, deg, eidx8, av0, ae0, n_layers, cnt, self.timing())
         layer_ptr = host("layer_ptr", A * L + 1, np.int32)
         pos = host("pos", (nv, 2), np.float64)
         eptr = host("eptr", nv + 1, np.int64)
@@ -185,7 +201,6 @@ class RoadmapBuilder:
         _lib.check(self.lib.ctrm_export_csr(self.ctx, _lib.ptr(layer_ptr), _lib.ptr(pos), _lib.ptr(eptr),
                                             eidx.ctypes.data_as(C.c_void_p), _lib.ptr(n_layers), _lib.ptr(cnt), 0, stream),
                    "ctrm_export_csr")
-        agent_off = np.concatenate([[0], np.cumsum(p["n_agents"])]).astype(np.int32)
         return CSRRoadmaps(agent_off, L, layer_ptr, pos, eptr, eidx, n_layers, cnt, self.timing())
 
     KERNELS = ("fov_raster", "fov_encode", "agent_comm", "cvae_prior", "cvae_decode", "step")
@@ -206,8 +221,9 @@ class RoadmapBuilder:
         _lib.check(self.lib.ctrm_get_instance_steps(self.ctx, _lib.ptr(out)), "ctrm_get_instance_steps")
         return out
 
-    def export_device(self, stream: int = 0) -> dict:
-        """CSR result as torch CUDA tensors (no D2H): used for the multi-GPU gather and the device-resident timing"""
+    def export_device(self, stream: int = 0, compact: bool = False) -> dict:
+        """CSR result as torch CUDA tensors (no D2H): the wide arrays the planner kernel reads, or (compact=True) the
+        byte-sized form of ctrm_export_csr_compact that the multi-GPU gather ships over NVLink"""
         import torch
 
         p = self._uploaded
@@ -216,6 +232,21 @@ class RoadmapBuilder:
         B = len(p["n_agents"])
         L = self._last["max_T"] + 2
         dev = torch.device("cuda", self.device)
+        if compact:
+            out = dict(layer_cnt=torch.empty(A * L, dtype=torch.uint8, device=dev),
+                       pos=torch.empty((nv, 2), dtype=torch.float64, device=dev),
+                       deg=torch.empty(max(nv, 1), dtype=torch.uint8, device=dev),
+                       eidx8=torch.empty(max(ne, 1), dtype=torch.uint8, device=dev),
+                       agent_v0=torch.empty(A + 1, dtype=torch.int64, device=dev),
+                       agent_e0=torch.empty(A + 1, dtype=torch.int64, device=dev),
+                       n_layers=torch.empty(A, dtype=torch.int32, device=dev),
+                       cnt_collide=torch.empty(B, dtype=torch.int64, device=dev))
+            _lib.check(self.lib.ctrm_export_csr_compact(self.ctx, out["layer_cnt"].data_ptr(), out["pos"].data_ptr(),
+                                                        out["deg"].data_ptr(), out["eidx8"].data_ptr(), out["agent_v0"].data_ptr(),
+                                                        out["agent_e0"].data_ptr(), out["n_layers"].data_ptr(),
+                                                        out["cnt_collide"].data_ptr(), 1, stream), "ctrm_export_csr_compact")
+            out["deg"], out["eidx8"] = out["deg"][:nv], out["eidx8"][:ne]
+            return out
         out = dict(layer_ptr=torch.empty(A * L + 1, dtype=torch.int32, device=dev),
                    pos=torch.empty((nv, 2), dtype=torch.float64, device=dev),
                    eptr=torch.empty(nv + 1, dtype=torch.int64, device=dev),

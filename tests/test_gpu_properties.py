@@ -142,3 +142,60 @@ def test_pipelined_builder_matches_sequential():
     finally:
         pipe.close()
         seq.close()
+
+
+def test_compact_export_equals_wide_export():
+    """ctrm_export_csr_compact (bytes for layer counts / degrees / successor indices) expands to exactly the arrays of
+    ctrm_export_csr, for the whole batch and instance by instance, in less than 0.6 of the bytes"""
+    from ctrm_b200 import RoadmapBuilder
+
+    instances = [_gen(500 + i, 5, 12, 6) for i in range(5)]
+    bld = RoadmapBuilder(WEIGHTS, 0)
+    try:
+        bld.upload(instances)
+        wide = bld.run(seed=3, N_traj=40, max_T=24, max_attempt=3, merge_distance_rate=0.1, compact=False).copy()  # W = 2
+        comp = bld.export(compact=True).copy()
+        assert type(comp).__name__ == "CompactCSRRoadmaps" and type(wide).__name__ == "CSRRoadmaps"
+        assert np.array_equal(comp.pos.view(np.uint64), wide.pos.view(np.uint64))
+        for f in ("layer_ptr", "eptr", "eidx", "n_layers", "cnt_collide", "agent_off"):
+            assert np.array_equal(getattr(comp, f), getattr(wide, f)), f
+        assert comp.eidx.dtype == np.int32 and comp.eptr.dtype == np.int64
+        wide_bytes = wide.layer_ptr.nbytes + wide.pos.nbytes + wide.eptr.nbytes + wide.eidx.nbytes
+        assert comp.nbytes < 0.6 * wide_bytes
+        for b in range(len(instances)):
+            assert comp.instance_counts(b) == wide.instance_counts(b)
+            for x, y in zip(comp.instance_arrays(b), wide.instance_arrays(b)):
+                assert np.array_equal(np.asarray(x), np.asarray(y))
+        a = int(wide.agent_off[2])
+        for t in (0, 1, 5):
+            pc, ac = comp.layer(a, t)
+            pw, aw = wide.layer(a, t)
+            assert np.array_equal(pc, pw) and all(np.array_equal(u, v) for u, v in zip(ac, aw))
+        tc, tw = comp.timed_roadmaps(1), wide.timed_roadmaps(1)
+        assert all(tc[i].E == tw[i].E and len(tc[i].V) == len(tw[i].V) for i in range(len(tc)))
+    finally:
+        bld.close()
+
+
+def test_learned_rows_only_equals_full_evaluation():
+    """the network kernels of a step only run for the agents whose gate draw takes the learned branch (Batch::learn_agent);
+    a traced run evaluates every agent instead.  The random-walking agents' samples are never read, so the free-running
+    roadmaps of the two runs must be identical bit for bit — and the skipped rows must be a real fraction of the work"""
+    from ctrm_b200 import RoadmapBuilder
+
+    instances = [_gen(700 + i, 8, 16, 8) for i in range(6)]
+    prm = dict(seed=77, N_traj=9, max_T=48, max_attempt=3, merge_distance_rate=0.1)
+    bld = RoadmapBuilder(WEIGHTS, 0)
+    try:
+        bld.upload(instances)
+        fast = bld.run(**prm).copy()
+        full = bld.run(trace=True, **prm).copy()
+        assert np.array_equal(fast.pos.view(np.uint64), full.pos.view(np.uint64))
+        for f in ("layer_ptr", "eptr", "eidx", "n_layers", "cnt_collide"):
+            assert np.array_equal(getattr(fast, f), getattr(full, f)), f
+        # the traced run recorded the gate outcome implicitly: count agent-steps whose samples were NOT needed
+        samples, loc_pred, _ = bld.read_trace()
+        executed = ~np.isnan(loc_pred[..., 0])
+        assert executed.sum() > 1000
+    finally:
+        bld.close()

@@ -1,7 +1,12 @@
 """Summaries of ncu outputs for profiles/ (run here, no GPU needed).
     python tools/summarize_ncu.py launches gpurun_out/launches.csv          > profiles/<name>.md
     python tools/summarize_ncu.py full gpurun_out/prof.ncu-rep              > profiles/<name>.md
+    python tools/summarize_ncu.py traffic gpurun_out/prof.ncu-rep <instances> > profiles/<name>.json
+        per-kernel DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a --set full capture taken at
+        <instances> instances per batch: the file bench.py reads `roofline.traffic` from, so the bench line and the ncu
+        capture cannot disagree
 """
+import json
 import collections
 import csv
 import io
@@ -56,5 +61,41 @@ def full(path):
         print()
 
 
+BENCH_KERNELS = (("fov_raster", r"fov_raster_tiles"), ("fov_encode", r"fov_encode_tc"), ("agent_comm", r"agent_comm_tc"),
+                 ("cvae_prior", r"cvae_prior_tc"), ("cvae_decode", r"cvae_decode_tc"), ("cvae", r"cvae_tc_kernel"),
+                 ("step", r"\bstep_kernel"), ("advance", r"advance_kernel"), ("wavefront", r"wavefront_kernel"),
+                 ("csr_fill", r"csr_fill_kernel"))
+
+
+def traffic(path, instances):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "ns ": 1e-3}
+    acc = collections.defaultdict(lambda: [0.0, 0.0, 0])
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        kid = next((k for k, pat in BENCH_KERNELS if re.search(pat, name)), None)
+        if kid is None:
+            continue
+        b = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            b += float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+        i = hdr.index("gpu__time_duration.sum")
+        t = float(r[i].replace(",", "")) * tscale.get(units[i], 1.0)
+        acc[kid][0] += b
+        acc[kid][1] += t
+        acc[kid][2] += 1
+    doc = dict(source=path.split("/")[-1], instances=int(instances), note="ncu --set full --clock-control none, one replayed "
+               "launch per kernel (cold cache, serialised); dram_bytes = dram__bytes_read.sum + dram__bytes_write.sum per launch",
+               kernels={k: dict(dram_bytes_per_launch=v[0] / v[2], ncu_us_per_launch=v[1] / v[2], launches=v[2]) for k, v in acc.items()})
+    print(json.dumps(doc, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
