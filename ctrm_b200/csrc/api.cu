@@ -113,6 +113,7 @@ struct ctrm_ctx {
   float ms[3] = {0, 0, 0};
   int64_t steps = 0, launches = 0;
   bool profile = false;
+  int step_mode = 0;
   double kernel_ms[16] = {0};
   int64_t kernel_n[16] = {0};
 };
@@ -736,6 +737,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   bt.seed_lo = (uint32_t)(p->seed & 0xFFFFFFFFu); bt.seed_hi = (uint32_t)(p->seed >> 32);
   bt.inst_base = p->instance_id_base;
   bt.prob_after_goal = p->prob_uniform_sampling_after_goal;
+  bt.step_mode = c->step_mode;
   // learned-row list: on, except when the run records the CVAE output of EVERY agent-step (trace) — the random-walking
   // agents' samples are never read by the path, but the parity tests compare them
   bt.learn_agent = c->trace ? nullptr : c->d_learn_agent;
@@ -985,6 +987,13 @@ extern "C" int ctrm_get_instance_steps(ctrm_ctx* c, int32_t* h_steps) {
   if (!c->have_result) return ctrm_fail(CTRM_ERR_STATE, "no result");
   CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
   CTRM_CUDA_OK(cudaMemcpy(h_steps, c->bt.steps_done, (size_t)c->bt.B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ctrm_set_step_kernel(ctrm_ctx* c, int mode) {
+  if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
+  if (mode < 0 || mode > 2) return ctrm_fail(CTRM_ERR_ARG, "ctrm_set_step_kernel: mode must be 0 (auto), 1 (warp per agent) or 2 (thread per agent)");
+  c->step_mode = mode;
   return 0;
 }
 

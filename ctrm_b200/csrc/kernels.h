@@ -41,6 +41,7 @@ struct Batch {
   int B, A, O, M, F, L, S, W, K;
   int n_max;  // largest num_agents of the batch
   int max_T, N_traj, max_attempt, dim_ind, randomize_indicator;
+  int step_mode;  // select + merge kernel: 0 = by batch size, 1 = one warp per agent, 2 = one thread per agent
   // static problem data (flat over agents / obstacles)
   const int32_t *agent_off, *obs_off, *agent_inst;
   const double *starts, *goals, *speeds, *speeds2, *merge2, *rads, *obs_xyr;

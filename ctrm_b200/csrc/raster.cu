@@ -79,6 +79,39 @@ __global__ void __launch_bounds__(256) raster_occupancy_kernel(const int4* __res
   }
 }
 
+// The same raster for M % 16 == 0 (the trained M = 160): a 16-byte chunk never straddles a row, the map index comes from
+// blockIdx.y (no 64-bit division per chunk — that division, not the memory system, was what bounded the general kernel at
+// 15% of the HBM rate), and the map's integer disks are staged once per block in shared memory.
+#define RO_MAX_SOBS 64
+__global__ void __launch_bounds__(256) raster_occupancy_rows_kernel(const int4* __restrict__ cells,
+                                                                    const int32_t* __restrict__ obs_off, int B, int M,
+                                                                    uint8_t* __restrict__ occ) {
+  __shared__ int4 s_cells[RO_MAX_SOBS];
+  const int chunks = (M * M) >> 4;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int base = c << 4;
+  const int x = base / M, y = base - x * M;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const int o0 = obs_off[b], nO = obs_off[b + 1] - o0, nS = min(nO, RO_MAX_SOBS);
+    __syncthreads();  // the previous map's disks have been consumed
+    if (threadIdx.x < nS) s_cells[threadIdx.x] = __ldg(&cells[o0 + threadIdx.x]);
+    __syncthreads();
+    if (c >= chunks) continue;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    for (int o = 0; o < nO; ++o) {
+      const int4 d = o < nS ? s_cells[o] : __ldg(&cells[o0 + o]);
+      const int dx = x - d.x, rem2 = d.z - dx * dx;  // dy^2 < rem2 <=> inside
+      if (rem2 <= 0 || y + 15 <= d.y - d.w || y >= d.y + d.w) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int dy = y + j - d.y;
+        w[j >> 2] |= (uint32_t)(dy * dy < rem2) << (8 * (j & 3));
+      }
+    }
+    __stcs(reinterpret_cast<uint4*>(occ + (size_t)b * M * M + base), make_uint4(w[0], w[1], w[2], w[3]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // passability masks: bit (x, y) of mask p set iff the agent footprint centred on (x,y) is collision-free
 // (cost_to_go.cpp:68-97): occ[x][y]==0 and no stencil cell with agent==1 is outside the map or occupied.
@@ -242,6 +275,33 @@ __global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __r
       bool centre_in = cx < M && cy < M;
       int cc = centre_in ? (int)c[ctg_index(cx, cy, M, layout)] : CTRM_UNREACH;
       bool c_reach = cc != CTRM_UNREACH;
+      if ((M & 3) == 0 && centre_in) {
+        // the crop as (row xf, aligned group of four y cells): one 4-byte occupancy load and one 8-byte load of the cost
+        // field per work item instead of eight scattered 1-2 byte loads (the kernel was bound by its load-request rate)
+        for (int i = lane; i < ROW; i += 32) t[i] = 0.f;
+        __syncwarp();
+        const int ylo = cy - buf;
+        const int g0 = ylo >> 2;                    // floor(ylo / 4), also for negative ylo
+        const int NG = ((cy + buf) >> 2) - g0 + 1;  // groups per crop row
+        for (int it = lane; it < F * NG; it += 32) {
+          const int xf = it / NG, gy = it - xf * NG;
+          const int x = cx - buf + xf, yb = (g0 + gy) << 2;
+          if (x < 0 || x >= M || yb < 0 || yb >= M) continue;  // yb is a multiple of 4 and so is M: all four cells inside or none
+          const uint32_t ow = __ldg(reinterpret_cast<const uint32_t*>(&o[x * M + yb]));
+          uint32_t cv[4];
+          // both layouts keep 4 aligned y cells of a row contiguous and 8-byte aligned (row-major: M % 4 == 0)
+          const uint2 cw = __ldg(reinterpret_cast<const uint2*>(&c[ctg_index(x, yb, M, layout)]));
+          cv[0] = cw.x & 0xFFFFu; cv[1] = cw.x >> 16; cv[2] = cw.y & 0xFFFFu; cv[3] = cw.y >> 16;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int yf = yb - ylo + j;
+            if (yf < 0 || yf >= F) continue;
+            const int _c = (int)cv[j];
+            t[xf * F + yf] = ((ow >> (8 * j)) & 0xFFu) ? 0.f : 1.f;
+            t[FF + xf * F + yf] = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 1.f : 0.f;
+          }
+        }
+      } else
       for (int i = lane; i < FF; i += 32) {
         int xf = i / F, yf = i - xf * F;
         int x = cx - buf + xf, y = cy - buf + yf;
@@ -377,6 +437,12 @@ int launch_obs_to_cells(const double* d_obs_xyr, int O, int M, int4* d_cells, cu
 }
 
 int launch_raster_occupancy(const int4* d_cells, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, cudaStream_t st) {
+  if ((M & 15) == 0 && (reinterpret_cast<uintptr_t>(d_occ) & 15) == 0) {
+    dim3 grid((unsigned)(((M * M) >> 4) + 255) / 256, (unsigned)(B < 32768 ? B : 32768));
+    raster_occupancy_rows_kernel<<<grid, 256, 0, st>>>(d_cells, d_obs_off, B, M, d_occ);
+    CTRM_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   long long chunks = ((long long)B * M * M + 15) / 16;
   int blocks = (int)((chunks + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;

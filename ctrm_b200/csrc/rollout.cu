@@ -9,6 +9,8 @@
 // All geometry is fp64 without FMA in the reference's operation order: verdicts and topology are bit-exact.
 #include "common.cuh"
 #include "geometry.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 
 #define RO_WARPS 4
@@ -612,6 +614,210 @@ __global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
   if (lane == 0 && count) atomicAdd(&bt.cnt_collide[sc.b], (unsigned long long)count);
 }
 
+// ------------------------------------------------------------------------------------------------
+// step, ONE THREAD PER AGENT (large batches).  The warp-per-agent kernel above spends most of its ~1,150 warp instructions
+// per agent-step on work that is uniform across the warp (context, addressing, rule evaluation, loop control) with 6-26 useful
+// lanes in the parallel parts; with tens of thousands of agents per step there is enough parallelism ACROSS agents, so here
+// a thread walks its agent's candidates, layers and obstacles serially, in the reference's own loop order
+// (learned_sampler.py:123-183, roadmap_learned/utils.py:21-137).  Same device functions for every fp64 operation and the same
+// counting rules, hence the same bits; the warp kernel stays the choice for small batches, where the serial walk of one
+// thread would be the latency of the whole step.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool hits_any_serial(const Batch& bt, int o0, int nO, double rad, double fx, double fy, double tx,
+                                                double ty) {
+  bool hit = false;
+  const double lox = fmin(fx, tx), hix = fmax(fx, tx), loy = fmin(fy, ty), hiy = fmax(fy, ty);
+  for (int o = 0; o < nO; ++o) {
+    const double* g = bt.obs_xyr + 3 * (size_t)(o0 + o);
+    const double ox = __ldg(g), oy = __ldg(g + 1), rs = f64add(rad, __ldg(g + 2));
+    const double R = rs + 1e-9;  // sweep_far with the segment's box hoisted (geometry.cuh)
+    if (ox < lox - R || ox > hix + R || oy < loy - R || oy > hiy + R) continue;
+    hit = hit || sweep_static(fx, fy, tx, ty, ox, oy, rs);
+  }
+  return hit;
+}
+
+template <int W>
+__global__ void __launch_bounds__(128) step_thread_kernel(Batch bt) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row == 0 && bt.n_learn != nullptr) *bt.n_learn = 0;  // see step_kernel
+  if (row >= (bt.live_agent != nullptr ? *bt.n_live : bt.A)) return;
+  const int a = bt.live_agent != nullptr ? bt.live_agent[row] : row;
+  const int b = bt.live_agent != nullptr ? bt.live_inst[row] : bt.agent_inst[a];
+  const int4 p0 = *reinterpret_cast<const int4*>(bt.inst_pack + 8 * b);
+  if (p0.x) return;  // instance finished
+  const int4 p1 = *reinterpret_cast<const int4*>(bt.inst_pack + 8 * b + 4);
+  const int t = p0.y, kt = p0.z, makespan = p0.w, a0 = p1.x, o0 = p1.z, nO = p1.w;
+  const int il = a - a0;
+  const double2 q0 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a);
+  const double2 q1 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a + 2);
+  const double2 q2 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a + 4);
+  const double2 cur = *reinterpret_cast<const double2*>(bt.cur + 2 * (size_t)a);
+  const bool arrived = bt.arrived[a] != 0;
+  const double gx = q0.x, gy = q0.y, speed = q1.x, speed2 = q1.y, merge2 = q2.x, rad = q2.y;
+  const double cx = cur.x, cy = cur.y;
+  const size_t si = step_index(bt, kt, t);
+  unsigned int count = 0;
+  // layer sizes first: their latency overlaps the candidate scan
+  const int nl = bt.nlayers[a];
+  const int32_t* vc = bt.vcnt + (size_t)a * bt.L;
+  const int n_prev = vc[t - 1];
+  const int n_t = (nl > t) ? vc[t] : 0;
+  const int n_next = (nl > t + 1) ? vc[t + 1] : 0;
+  const bool has_next = nl > t + 1;
+
+  // ---- select (learned_sampler.py:148-168): candidates in order, the first valid one wins
+  double lx = cx, ly = cy;  // fallback of sample_uniform_i: stay (learned_sampler.py:145)
+  {
+    const bool learned = gate_is_learned(bt, b, a, il, kt, t, makespan, arrived);
+    const int nL = learned ? bt.K : 0, C = nL + bt.max_attempt;
+    const uint32_t c0 = bt.inst_base + (uint32_t)b, c1 = rng_ctr1(kt, t);
+    for (int c = 0; c < C; ++c) {
+      double x, y;
+      if (c < nL) {
+        const float* s3 = (bt.tab_teacher != nullptr) ? bt.tab_teacher + ((si * bt.A + a) * (size_t)bt.K + c) * 3
+                                                      : bt.samples + ((size_t)a * bt.K + c) * 3;
+        x = f64add(cx, (double)__fmul_rn(s3[0], s3[2]));  // Y = cur + SAMPLES[:, :2] * SAMPLES[:, 2]   :114-121
+        y = f64add(cy, (double)__fmul_rn(s3[1], s3[2]));
+      } else {
+        const int att = c - nL;
+        double u_mag, sn, cs;
+        if (bt.rng_mode == 1) {
+          const double* r = bt.tab_rw + ((si * bt.A + a) * (size_t)bt.max_attempt + att) * 3;
+          u_mag = r[0]; sn = r[1]; cs = r[2];
+        } else {
+          const uint4 w = philox4x32(c0, c1, (uint32_t)il, rng_ctr3(STREAM_RW, (uint32_t)att), bt.seed_lo, bt.seed_hi);
+          u_mag = u64_to_f64(w.x, w.y);
+          det_sincos_2pi(u64_to_f64(w.z, w.w), &sn, &cs);
+        }
+        const double mag = f64mul(speed, u_mag);  // learned_sampler.py:137-142
+        x = f64add(f64mul(sn, mag), cx);
+        y = f64add(f64mul(cs, mag), cy);
+      }
+      if (!(bounds_ok(x, y, rad) && speed_ok(cx, cy, x, y, speed, speed2))) continue;
+      ++count;
+      if (!hits_any_serial(bt, o0, nO, rad, cx, cy, x, y)) {
+        lx = x;
+        ly = y;
+        break;
+      }
+    }
+    if (bt.tr_loc_pred != nullptr) {
+      bt.tr_loc_pred[2 * (si * bt.A + a)] = lx;
+      bt.tr_loc_pred[2 * (si * bt.A + a) + 1] = ly;
+    }
+    if (bt.tr_samples != nullptr && bt.samples != nullptr)
+      for (int i = 0; i < bt.K * 3; ++i) bt.tr_samples[(si * bt.A + a) * (size_t)bt.K * 3 + i] = bt.samples[(size_t)a * bt.K * 3 + i];
+  }
+
+  // ---- merge_samples (roadmap_learned/utils.py:21-137)
+  uint32_t P[W], Cm[W], Mg[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) { P[w] = 0u; Cm[w] = 0u; Mg[w] = 0u; }
+  for (int sl = 0; sl < n_prev; ++sl) {  // parents, tested as (parent -> loc)   utils.py:58-69
+    const double2 p = *reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t - 1, sl)]);
+    if (dist2(p.x, p.y, lx, ly) <= speed2) {
+      ++count;
+      if (!hits_any_serial(bt, o0, nO, rad, p.x, p.y, lx, ly)) P[sl >> 5] |= 1u << (sl & 31);
+    }
+  }
+  for (int sl = 0; sl < n_next; ++sl) {  // children, tested as (child -> loc)   utils.py:72-84
+    const double2 p = *reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t + 1, sl)]);
+    if (dist2(p.x, p.y, lx, ly) <= speed2) {
+      ++count;
+      if (!hits_any_serial(bt, o0, nO, rad, p.x, p.y, lx, ly)) Cm[sl >> 5] |= 1u << (sl & 31);
+    }
+  }
+  for (int sl = 0; sl < n_t; ++sl) {  // merge candidates   utils.py:86-89
+    const double2 p = *reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t, sl)]);
+    if (dist2(p.x, p.y, lx, ly) <= merge2) Mg[sl >> 5] |= 1u << (sl & 31);
+  }
+  double rx = lx, ry = ly;
+  int target = -1;
+  bool add_edges = false, resolved = false;
+  const double h_loc = dist2(lx, ly, gx, gy);
+#pragma unroll
+  for (int w = 0; w < W; ++w) {  // rules (utils.py:94-133), candidates in index order
+    uint32_t m = Mg[w];
+    while (m && !resolved) {
+      const int u = w * 32 + __ffs(m) - 1;
+      m &= m - 1;
+      const size_t v = vslot(bt, a, t, u);
+      bool eq = true, sup = true, sub = true;
+#pragma unroll
+      for (int q = 0; q < W; ++q) {
+        const uint32_t pu = bt.pmask[v * W + q], cu = bt.cmask[v * W + q];
+        eq = eq && pu == P[q] && cu == Cm[q];
+        sup = sup && (P[q] & ~pu) == 0u && (Cm[q] & ~cu) == 0u;
+        sub = sub && (pu & ~P[q]) == 0u && (cu & ~Cm[q]) == 0u;
+      }
+      const double ux = bt.vpos[2 * v], uy = bt.vpos[2 * v + 1];
+      if (eq) {
+        if (h_loc < dist2(ux, uy, gx, gy)) target = u;
+        else { rx = ux; ry = uy; }
+        resolved = true;
+      } else if (sup) {
+        rx = ux; ry = uy;
+        resolved = true;
+      } else if (sub) {
+        target = u;
+        add_edges = true;
+        resolved = true;
+      }
+    }
+  }
+  if (!resolved) {  // trm.append_sample(loc, t, parents, children)   utils.py:136
+    target = n_t;
+    add_edges = true;
+    if (target >= bt.S) target = -1;
+  }
+  if (target >= 0) {
+    const size_t v = vslot(bt, a, t, target);
+    bt.vpos[2 * v] = lx;
+    bt.vpos[2 * v + 1] = ly;
+    if (!resolved) {
+      bt.vcnt[(size_t)a * bt.L + t] = n_t + 1;
+      if (nl < t + 1) bt.nlayers[a] = t + 1;
+    }
+    if (add_edges) {
+      const uint32_t tbit = 1u << (target & 31);
+      const int tw = target >> 5;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint32_t pu = resolved ? bt.pmask[v * W + w] : 0u;
+        const uint32_t cu = resolved ? bt.cmask[v * W + w] : 0u;
+        uint32_t m = P[w] & ~pu;  // E[t-1][p].append(u): this thread is the only writer of its agent's roadmap
+        while (m) {
+          const int sl = w * 32 + __ffs(m) - 1;
+          m &= m - 1;
+          bt.cmask[vslot(bt, a, t - 1, sl) * W + tw] |= tbit;
+        }
+        m = Cm[w] & ~cu;          // mirror of E[t][u] += children
+        while (m) {
+          const int sl = w * 32 + __ffs(m) - 1;
+          m &= m - 1;
+          bt.pmask[vslot(bt, a, t + 1, sl) * W + tw] |= tbit;
+        }
+        bt.pmask[v * W + w] = pu | P[w];
+        bt.cmask[v * W + w] = cu | Cm[w];
+      }
+    }
+  }
+  // goal test: valid_edge(loc_next, goal)   learned_sampler.py:182-183
+  if (bounds_ok(gx, gy, rad) && speed_ok(rx, ry, gx, gy, speed, speed2)) {
+    ++count;
+    if (!hits_any_serial(bt, o0, nO, rad, rx, ry, gx, gy)) bt.arrived[a] = 1;
+  }
+  bt.nxt[2 * a] = rx;
+  bt.nxt[2 * a + 1] = ry;
+  if (bt.tr_loc_next != nullptr) {
+    bt.tr_loc_next[2 * (si * bt.A + a)] = rx;
+    bt.tr_loc_next[2 * (si * bt.A + a) + 1] = ry;
+  }
+  if (count) atomicAdd(&bt.cnt_collide[b], (unsigned long long)count);
+  (void)has_next;
+}
+
 // roll-out bookkeeping, one warp per instance, after every agent of the step has been processed (a kernel boundary is
 // cheaper than electing the instance's last warp with __threadfence + atomics, which was 12% of the step kernel's stalls)
 __global__ void __launch_bounds__(RO_WARPS * 32) advance_kernel(Batch bt) {
@@ -621,8 +827,34 @@ __global__ void __launch_bounds__(RO_WARPS * 32) advance_kernel(Batch bt) {
   advance_instance(bt, b, lane);
 }
 
+// batches from this many agents on take the thread-per-agent kernel unless ctrm_set_step_kernel pins one of the two
+// (CTRM_STEP_THREAD_MIN_AGENTS moves the threshold)
+static int step_thread_min_agents() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTRM_STEP_THREAD_MIN_AGENTS");
+    v = e ? atoi(e) : 8192;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+
 int launch_step(const Batch& bt, cudaStream_t st) {
   if (bt.A <= 0) return 0;
+  if (bt.step_mode == 2 || (bt.step_mode == 0 && bt.A >= step_thread_min_agents())) {
+    const int tb = (bt.A + 127) / 128;
+    switch (bt.W) {
+      case 1: step_thread_kernel<1><<<tb, 128, 0, st>>>(bt); break;
+      case 2: step_thread_kernel<2><<<tb, 128, 0, st>>>(bt); break;
+      case 3: step_thread_kernel<3><<<tb, 128, 0, st>>>(bt); break;
+      case 4: step_thread_kernel<4><<<tb, 128, 0, st>>>(bt); break;
+      default: return ctrm_fail(-1, "unsupported adjacency mask width");
+    }
+    CTRM_CUDA_OK(cudaGetLastError());
+    advance_kernel<<<(bt.B + RO_WARPS - 1) / RO_WARPS, RO_WARPS * 32, 0, st>>>(bt);
+    CTRM_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const int blocks = (bt.A + RO_WARPS - 1) / RO_WARPS;
   switch (bt.W) {
     case 1: step_kernel<1><<<blocks, RO_WARPS * 32, 0, st>>>(bt); break;

@@ -205,6 +205,10 @@ class RoadmapBuilder:
 
     KERNELS = ("fov_raster", "fov_encode", "agent_comm", "cvae_prior", "cvae_decode", "step")
 
+    def set_step_kernel(self, mode: int):
+        """0 = by batch size, 1 = one warp per agent, 2 = one thread per agent (ctrm_set_step_kernel); same results"""
+        _lib.check(self.lib.ctrm_set_step_kernel(self.ctx, int(mode)), "ctrm_set_step_kernel")
+
     def set_profile(self, enable: bool):
         """eager launches with a CUDA event after every kernel (per-kernel device times, see kernel_times)"""
         _lib.check(self.lib.ctrm_set_profile(self.ctx, int(enable)), "ctrm_set_profile")

@@ -230,6 +230,11 @@ int ctrm_last_timing(ctrm_ctx* ctx, float ms[3], int64_t* steps, int64_t* launch
 /* executed roll-out steps per instance of the last build (sum over its N_traj roll-outs) */
 int ctrm_get_instance_steps(ctrm_ctx* ctx, int32_t* h_steps /*[B]*/);
 int ctrm_set_profile(ctrm_ctx* ctx, int enable);
+
+/* which kernel runs the per-agent select + merge of a roll-out step (learned_sampler.py:123-183, utils.py:21-137):
+ * 0 = chosen by batch size (default), 1 = one warp per agent (low latency, small batches), 2 = one thread per agent
+ * (throughput, large batches).  Both produce identical roadmaps and counters. */
+int ctrm_set_step_kernel(ctrm_ctx* ctx, int mode);
 int ctrm_last_kernel_times(ctrm_ctx* ctx, double ms[8], int64_t launches[8]);
 
 /* raw views of the context's device state for stage-level tests (valid until the next upload) */

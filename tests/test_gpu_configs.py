@@ -65,20 +65,22 @@ def test_teacher_forced_parity(name, specs, NT, MT, K, rate, M):
     builder = RoadmapBuilder(WEIGHTS, 0, map_size=M)
     try:
         builder.upload(instances)
-        csr = builder.run(N_traj=NT, max_T=MT, max_attempt=3, merge_distance_rate=rate, K=K, seed=seed, instance_id_base=3,
-                          tables=dict(teacher=teacher), trace=True)
-        samples, _, loc_next = builder.read_trace()
-        a0, worst = 0, 0.0
-        for b, oi in enumerate(oins):
-            assert_same_roadmaps(csr_to_arrays(csr, b), otrms_to_arrays(trms_all[b]))
-            assert int(csr.cnt_collide[b]) == oi.cnt_continuous_collide
-            N = oi.num_agents
-            for r in recs_all[b]:
-                k, t = r["k_traj"], r["t"] - 1
-                assert np.array_equal(loc_next[k, t, a0:a0 + N], np.array(r["loc_next"]))
-                worst = max(worst, rel_err(samples[k, t, a0:a0 + N], r["SAMPLES_nn"].reshape(K, N, 3).transpose(1, 0, 2)))
-            a0 += N
-        assert worst <= 1e-5, worst
+        for mode in (1, 2):  # one warp per agent / one thread per agent: the same bits
+            builder.set_step_kernel(mode)
+            csr = builder.run(N_traj=NT, max_T=MT, max_attempt=3, merge_distance_rate=rate, K=K, seed=seed, instance_id_base=3,
+                              tables=dict(teacher=teacher), trace=True)
+            samples, _, loc_next = builder.read_trace()
+            a0, worst = 0, 0.0
+            for b, oi in enumerate(oins):
+                assert_same_roadmaps(csr_to_arrays(csr, b), otrms_to_arrays(trms_all[b]))
+                assert int(csr.cnt_collide[b]) == oi.cnt_continuous_collide
+                N = oi.num_agents
+                for r in recs_all[b]:
+                    k, t = r["k_traj"], r["t"] - 1
+                    assert np.array_equal(loc_next[k, t, a0:a0 + N], np.array(r["loc_next"]))
+                    worst = max(worst, rel_err(samples[k, t, a0:a0 + N], r["SAMPLES_nn"].reshape(K, N, 3).transpose(1, 0, 2)))
+                a0 += N
+            assert worst <= 1e-5, worst
     finally:
         builder.close()
 

@@ -40,10 +40,12 @@ def test_reference_run_replay_bit_exact(builder, any_trace_gold, oracle_weights)
     gate = np.nan_to_num(rng.t_gate, nan=0.5)
     rw = np.nan_to_num(rng.t_rw, nan=0.0)
     builder.upload([instance_from_oins(oi)])
-    csr = builder.run(N_traj=NT, max_T=MT, max_attempt=MA, merge_distance_rate=rate,
-                      tables=dict(gate=gate, rw=rw, teacher=teacher))
-    assert_same_roadmaps(csr_to_arrays(csr, 0), want)
-    assert int(csr.cnt_collide[0]) == int(z["cnt_continuous_collide"])
+    for mode in (2, 1, 0):  # thread-per-agent kernel, warp-per-agent kernel, then back to the default choice
+        builder.set_step_kernel(mode)
+        csr = builder.run(N_traj=NT, max_T=MT, max_attempt=MA, merge_distance_rate=rate,
+                          tables=dict(gate=gate, rw=rw, teacher=teacher))
+        assert_same_roadmaps(csr_to_arrays(csr, 0), want)
+        assert int(csr.cnt_collide[0]) == int(z["cnt_continuous_collide"])
     nv, ne = csr.instance_counts(0)
     assert (nv, ne) == (len(want[2]), len(want[4]))
     # planner contract (prioritized_planning.py:41, :57-59): equal lengths, V[0] = [start], V[t][-1] = goal

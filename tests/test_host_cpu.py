@@ -165,3 +165,24 @@ def test_prob_random_walk_table_matches_reference_expression():
     tab = prob_random_walk_table(64, 5.0, 0.0)
     for t, D in ((1, 64), (64, 64), (17, 33), (5, 1)):
         assert tab[t, D] == (1 - np.exp(-5.0 * t / D)) * (1 - 0.0) + 0.0
+
+
+def test_ctrm_alias_package_resolves_and_unpickles():
+    """ctrm_b200/shims on sys.path makes `ctrm.*` of the replaced paths importable (hydra _target_ strings, reference pickles)"""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, pickle, os; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import ctrm.roadmap_learned as rl, ctrm.environment as env, ctrm.roadmap as rm, ctrm.planner as pl\n"
+        "import ctrm_b200\n"
+        "assert rl.get_timed_roadmaps_multiple_paths_with_learned_indicator is ctrm_b200.get_timed_roadmaps_multiple_paths_with_learned_indicator\n"
+        "assert env.Instance is ctrm_b200.Instance and pl.PrioritizedPlanning is ctrm_b200.PrioritizedPlanning\n"
+        "assert callable(rm.get_timed_roadmaps_random) and rm.TimedRoadmap is ctrm_b200.TimedRoadmap\n"
+        "p = '/root/reference/notebooks/CTRM_demo_ins.pkl'\n"
+        "if os.path.exists(p):\n"
+        "    ins = pickle.load(open(p, 'rb'))\n"
+        "    assert type(ins) is ctrm_b200.Instance and ins.num_agents == 28 and len(ins.objs.obs) == 10\n"
+        "print('ok')\n") % (os.path.join(ROOT, "ctrm_b200", "shims"), ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
