@@ -55,10 +55,27 @@ struct DevArena {  // tracked device allocations with reuse: cudaMalloc / cudaFr
         *out = reinterpret_cast<T*>(b.p);
         return 0;
       }
+    // no exact fit: the smallest free block that is large enough and not wastefully larger.  Batches of a stream differ a
+    // little in size (agents, vertices, edges); without this every upload / export of a new size pays cudaMalloc + cudaFree,
+    // and cudaFree synchronises the whole device — it stalls the OTHER context of a PipelinedBuilder in mid roll-out
+    Blk* best = nullptr;
+    for (Blk& b : blks)
+      if (!b.used && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 + 4096 && (!best || b.bytes < best->bytes)) best = &b;
+    if (best) {
+      best->used = true;
+      *out = reinterpret_cast<T*>(best->p);
+      return 0;
+    }
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, bytes);
+    const size_t grown = bytes >= (1u << 20) ? bytes + bytes / 16 : bytes;  // head room for the next, slightly larger batch
+    cudaError_t e = cudaMalloc(&p, grown);
+    if (e != cudaSuccess && grown != bytes) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      if (e == cudaSuccess) { blks.push_back({p, bytes, true}); *out = reinterpret_cast<T*>(p); return 0; }
+    }
     if (e != cudaSuccess) return ctrm_fail_cuda(e, "cudaMalloc");
-    blks.push_back({p, bytes, true});
+    blks.push_back({p, grown, true});
     *out = reinterpret_cast<T*>(p);
     return 0;
   }
@@ -375,10 +392,14 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(upload(ar, &d_speeds2, speeds2, (size_t)A, st));
   CHECK(upload(ar, &d_rads, rads, (size_t)A, st));
   CHECK(upload(ar, &d_obs, obs_xyr, (size_t)3 * O, st));
+  std::vector<float4> obs_f4((size_t)(O > 0 ? O : 1), make_float4(0.f, 0.f, 0.f, 0.f));
+  for (int o = 0; o < O; ++o) obs_f4[o] = make_float4((float)obs_xyr[3 * o], (float)obs_xyr[3 * o + 1], (float)obs_xyr[3 * o + 2], 0.f);
+  float4* d_obs_f4 = nullptr;
+  CHECK(upload(ar, &d_obs_f4, obs_f4.data(), obs_f4.size(), st));
   CHECK(ar.alloc(&d_merge2, (size_t)A));
   bt.agent_off = d_aoff; bt.obs_off = d_ooff; bt.agent_inst = d_ainst;
   bt.starts = d_starts; bt.goals = d_goals; bt.speeds = d_speeds; bt.speeds2 = d_speeds2; bt.rads = d_rads;
-  bt.obs_xyr = d_obs; bt.merge2 = d_merge2;
+  bt.obs_xyr = d_obs; bt.merge2 = d_merge2; bt.obs_f4 = d_obs_f4;
   uint8_t* d_occ;
   uint16_t* d_ctg;
   CHECK(ar.alloc(&d_occ, (size_t)B * M * M + 16));
@@ -422,9 +443,8 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&c->d_agent_ne, (size_t)A));
   CHECK(ar.alloc(&c->d_totals, (size_t)4));
   ar.trim();
-  if (A != prev_A) {  // the roadmap store is sized by the agent count: keep it across same-shaped batches
-    c->r_arena.destroy();
-    c->r_L = c->r_S = 0;
+  if (A != prev_A) {  // the roadmap store is sized by the agent count: re-carve it from the arena (whose blocks are reused
+    c->r_L = c->r_S = 0;  // when the new batch is about the same size) at the next build
   } else {
     bt.L = old_bt.L; bt.S = old_bt.S; bt.W = old_bt.W; bt.K = old_bt.K;
     bt.vpos = old_bt.vpos; bt.vcnt = old_bt.vcnt; bt.cmask = old_bt.cmask; bt.pmask = old_bt.pmask;

@@ -45,6 +45,7 @@ struct Batch {
   // static problem data (flat over agents / obstacles)
   const int32_t *agent_off, *obs_off, *agent_inst;
   const double *starts, *goals, *speeds, *speeds2, *merge2, *rads, *obs_xyr;
+  const float4* obs_f4;  // [O] (x, y, rad, 0) rounded to float: conservative far-obstacle rejects off the fp64 pipe
   const uint8_t* occ;   // [B][M][M]
   const uint16_t* ctg;  // [A][field]: cost-to-go in the 8 x 4 micro-tiled layout (common.cuh ctg_index, layout 1)
   // roll-out state

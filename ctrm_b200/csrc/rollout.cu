@@ -623,15 +623,22 @@ __global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
 // counting rules, hence the same bits; the warp kernel stays the choice for small batches, where the serial walk of one
 // thread would be the latency of the whole step.
 // ------------------------------------------------------------------------------------------------
+// StaticObjects.collide_continuous_sphere for one segment, one thread walking the instance's obstacles.  Far obstacles are
+// rejected in fp32 from a float copy of the obstacle (Batch::obs_f4, one 16-byte load): the centre lies outside the segment's
+// bounding box grown by rad_sum + 1e-5.  That is conservative — coordinates live in the unit square, where the float copies and
+// the float box are each within 1.2e-7 of the doubles, so a rejected obstacle is at least 9e-6 further away than rad_sum and the
+// exact test (closest approach on the segment) could only say "no hit" — and it keeps the common case off the fp64 pipe.
 __device__ __forceinline__ bool hits_any_serial(const Batch& bt, int o0, int nO, double rad, double fx, double fy, double tx,
                                                 double ty) {
   bool hit = false;
-  const double lox = fmin(fx, tx), hix = fmax(fx, tx), loy = fmin(fy, ty), hiy = fmax(fy, ty);
+  const float lox = (float)fmin(fx, tx), hix = (float)fmax(fx, tx), loy = (float)fmin(fy, ty), hiy = (float)fmax(fy, ty);
+  const float radf = (float)rad + 1e-5f;
   for (int o = 0; o < nO; ++o) {
+    const float4 q = __ldg(&bt.obs_f4[o0 + o]);
+    const float R = radf + q.z;
+    if (q.x < lox - R || q.x > hix + R || q.y < loy - R || q.y > hiy + R) continue;
     const double* g = bt.obs_xyr + 3 * (size_t)(o0 + o);
     const double ox = __ldg(g), oy = __ldg(g + 1), rs = f64add(rad, __ldg(g + 2));
-    const double R = rs + 1e-9;  // sweep_far with the segment's box hoisted (geometry.cuh)
-    if (ox < lox - R || ox > hix + R || oy < loy - R || oy > hiy + R) continue;
     hit = hit || sweep_static(fx, fy, tx, ty, ox, oy, rs);
   }
   return hit;
@@ -714,23 +721,49 @@ __global__ void __launch_bounds__(128) step_thread_kernel(Batch bt) {
   uint32_t P[W], Cm[W], Mg[W];
 #pragma unroll
   for (int w = 0; w < W; ++w) { P[w] = 0u; Cm[w] = 0u; Mg[w] = 0u; }
-  for (int sl = 0; sl < n_prev; ++sl) {  // parents, tested as (parent -> loc)   utils.py:58-69
-    const double2 p = *reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t - 1, sl)]);
-    if (dist2(p.x, p.y, lx, ly) <= speed2) {
-      ++count;
-      if (!hits_any_serial(bt, o0, nO, rad, p.x, p.y, lx, ly)) P[sl >> 5] |= 1u << (sl & 31);
-    }
+  // pass 1: distances to V[t-1], V[t+1], V[t] (get_dist_arr, utils.py:50-56) — nothing but independent loads and compares, so
+  // the loads of a layer are in flight together; a serial walk that tested each vertex as it arrived paid one memory round
+  // trip per vertex and made a thread's latency, not the SM's throughput, the time of the kernel
+  uint32_t Pc[W], Cc[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) { Pc[w] = 0u; Cc[w] = 0u; }
+  const double2* vp_prev = reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t - 1, 0)]);
+  const double2* vp_t = reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t, 0)]);
+  const double2* vp_next = reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t + 1, 0)]);
+#pragma unroll 4
+  for (int sl = 0; sl < n_prev; ++sl) {
+    const double2 p = vp_prev[sl];
+    if (dist2(p.x, p.y, lx, ly) <= speed2) Pc[sl >> 5] |= 1u << (sl & 31);
   }
-  for (int sl = 0; sl < n_next; ++sl) {  // children, tested as (child -> loc)   utils.py:72-84
-    const double2 p = *reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t + 1, sl)]);
-    if (dist2(p.x, p.y, lx, ly) <= speed2) {
-      ++count;
-      if (!hits_any_serial(bt, o0, nO, rad, p.x, p.y, lx, ly)) Cm[sl >> 5] |= 1u << (sl & 31);
-    }
+#pragma unroll 4
+  for (int sl = 0; sl < n_next; ++sl) {
+    const double2 p = vp_next[sl];
+    if (dist2(p.x, p.y, lx, ly) <= speed2) Cc[sl >> 5] |= 1u << (sl & 31);
   }
+#pragma unroll 4
   for (int sl = 0; sl < n_t; ++sl) {  // merge candidates   utils.py:86-89
-    const double2 p = *reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t, sl)]);
+    const double2 p = vp_t[sl];
     if (dist2(p.x, p.y, lx, ly) <= merge2) Mg[sl >> 5] |= 1u << (sl & 31);
+  }
+  // pass 2: swept tests of the vertices within reach; parents as (parent -> loc) utils.py:58-69, children as (child -> loc) :72-84
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    uint32_t m = Pc[w];
+    count += __popc(m);
+    while (m) {
+      const int sl = w * 32 + __ffs(m) - 1;
+      m &= m - 1;
+      const double2 p = vp_prev[sl];
+      if (!hits_any_serial(bt, o0, nO, rad, p.x, p.y, lx, ly)) P[w] |= 1u << (sl & 31);
+    }
+    m = Cc[w];
+    count += __popc(m);
+    while (m) {
+      const int sl = w * 32 + __ffs(m) - 1;
+      m &= m - 1;
+      const double2 p = vp_next[sl];
+      if (!hits_any_serial(bt, o0, nO, rad, p.x, p.y, lx, ly)) Cm[w] |= 1u << (sl & 31);
+    }
   }
   double rx = lx, ry = ly;
   int target = -1;
@@ -833,7 +866,7 @@ static int step_thread_min_agents() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CTRM_STEP_THREAD_MIN_AGENTS");
-    v = e ? atoi(e) : 8192;
+    v = e ? atoi(e) : 20000;  // measured crossover: profiles/r2_step_kernel_ab.md (warp 52 us vs thread 44 us at 25 k agents, 34 vs 41 at 13 k)
     if (v < 0) v = 0;
   }
   return v;

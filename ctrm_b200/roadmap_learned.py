@@ -292,8 +292,20 @@ class RoadmapBuilder:
         return s, lp, ln
 
     def build(self, instances: Sequence[Instance], **kw) -> CSRRoadmaps:
-        self.upload(instances)
-        return self.run(**kw)
+        import time
+
+        t0 = time.perf_counter()
+        packed = self.pack_instances(instances)
+        t1 = time.perf_counter()
+        self.upload(None, packed=packed)
+        t2 = time.perf_counter()
+        export = kw.pop("export", True)
+        self.run(export=False, **{k: v for k, v in kw.items() if k not in ("pinned", "compact")})
+        t3 = time.perf_counter()
+        out = self.export(stream=kw.get("stream", 0), pinned=kw.get("pinned", True), compact=kw.get("compact", True)) if export else None
+        # host wall time of the four phases of the last build (ms): pack, upload (H2D + occupancy + wavefront), roll-outs, export
+        self.last_phases_ms = tuple(1e3 * (b - a) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, time.perf_counter())))
+        return out
 
 
 class PipelinedBuilder:
