@@ -89,6 +89,7 @@ SIGNATURES = {
     "ctrm_last_timing": (C.c_int, [V, V, c_i64p, c_i64p]),
     "ctrm_get_instance_steps": (C.c_int, [V, V]),
     "ctrm_set_step_kernel": (C.c_int, [V, C.c_int]),
+    "ctrm_set_stream_priority": (C.c_int, [V, C.c_int]),
     "ctrm_set_profile": (C.c_int, [V, C.c_int]),
     "ctrm_last_kernel_times": (C.c_int, [V, V, V]),
     "ctrm_get_device_view": (C.c_int, [V, C.POINTER(DeviceView)]),

@@ -169,6 +169,22 @@ extern "C" int ctrm_ctx_create(int device, ctrm_ctx** out) {
   return 0;
 }
 
+// Contexts that share a GPU (PipelinedBuilder) finish their batches in lock step when their kernels time-share the device
+// evenly: both then export / pack / upload at the same moment and the GPU idles.  A higher stream priority for one of them
+// staggers the two: its kernels go first, the other context fills the gaps its host phases leave.
+extern "C" int ctrm_set_stream_priority(ctrm_ctx* c, int high) {
+  if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
+  CTRM_CUDA_OK(cudaSetDevice(c->device));
+  CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  int least = 0, greatest = 0;
+  CTRM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  cudaStream_t ns = nullptr;
+  CTRM_CUDA_OK(cudaStreamCreateWithPriority(&ns, cudaStreamNonBlocking, high ? greatest : least));
+  cudaStreamDestroy(c->stream);
+  c->stream = ns;
+  return 0;
+}
+
 extern "C" void ctrm_ctx_destroy(ctrm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);

@@ -118,6 +118,8 @@ class Instance:
     def __getstate__(self):
         state = self.__dict__.copy()
         del state["objs"]
+        state.pop("_arrays", None)
+        state.pop("_speeds2", None)
         return state
 
     def __setstate__(self, state):
@@ -126,13 +128,38 @@ class Instance:
 
     # ---- plain-array views used by the batch path ----
     def arrays(self):
-        """(starts (N,2), goals (N,2), speeds (N,), rads (N,), obs_xyr (O,3)) float64"""
-        s = np.array([np.asarray(p, dtype=np.float64)[:2] for p in self.starts], dtype=np.float64).reshape(-1, 2)
-        g = np.array([np.asarray(p, dtype=np.float64)[:2] for p in self.goals], dtype=np.float64).reshape(-1, 2)
-        sp = np.array([float(v) for v in self.max_speeds], dtype=np.float64)
-        r = np.array([float(v) for v in self.rads], dtype=np.float64)
-        o = np.array([[float(ob.pos[0]), float(ob.pos[1]), float(ob.rad)] for ob in self.obs], dtype=np.float64).reshape(-1, 3)
-        return s, g, sp, r, o
+        """(starts (N,2), goals (N,2), speeds (N,), rads (N,), obs_xyr (O,3)) float64; computed once per instance (frozen)"""
+        c = self.__dict__.get("_arrays")
+        if c is not None:
+            return c
+        try:  # fast path: homogeneous lists of (dim,) arrays / floats
+            s = np.array(self.starts, dtype=np.float64).reshape(self.num_agents, -1)[:, :2]
+            g = np.array(self.goals, dtype=np.float64).reshape(self.num_agents, -1)[:, :2]
+            sp = np.array(self.max_speeds, dtype=np.float64).reshape(-1)
+            r = np.array(self.rads, dtype=np.float64).reshape(-1)
+            o = np.empty((len(self.obs), 3), dtype=np.float64)
+            for k, ob in enumerate(self.obs):
+                o[k, 0] = ob.pos[0]
+                o[k, 1] = ob.pos[1]
+                o[k, 2] = ob.rad
+            s, g = np.ascontiguousarray(s), np.ascontiguousarray(g)
+        except Exception:
+            s = np.array([np.asarray(p, dtype=np.float64)[:2] for p in self.starts], dtype=np.float64).reshape(-1, 2)
+            g = np.array([np.asarray(p, dtype=np.float64)[:2] for p in self.goals], dtype=np.float64).reshape(-1, 2)
+            sp = np.array([float(v) for v in self.max_speeds], dtype=np.float64)
+            r = np.array([float(v) for v in self.rads], dtype=np.float64)
+            o = np.array([[float(ob.pos[0]), float(ob.pos[1]), float(ob.rad)] for ob in self.obs], dtype=np.float64).reshape(-1, 3)
+        c = (s, g, sp, r, o)
+        object.__setattr__(self, "_arrays", c)
+        return c
+
+    def speeds2(self) -> np.ndarray:
+        """max_speed ** 2 per agent with CPython's float pow, exactly as roadmap/utils.py:40 evaluates it (cached)"""
+        c = self.__dict__.get("_speeds2")
+        if c is None:
+            c = np.array([float(v) ** 2 for v in self.max_speeds], dtype=np.float64)
+            object.__setattr__(self, "_speeds2", c)
+        return c
 
     @staticmethod
     def from_arrays(starts, goals, max_speeds, rads, obs_pos, obs_rad, goal_rads=None) -> "Instance":

@@ -79,8 +79,10 @@ class RoadmapBuilder:
         speeds = np.ascontiguousarray(np.concatenate([p[2] for p in parts]))
         rads = np.ascontiguousarray(np.concatenate([p[3] for p in parts]))
         obs = np.ascontiguousarray(np.concatenate([p[4] for p in parts]).reshape(-1, 3))
-        # max_speed ** 2 in Python-float arithmetic, as roadmap/utils.py:40 and roadmap_learned/utils.py:60 do
-        speeds2 = np.array([float(s) ** 2 for s in speeds], dtype=np.float64)
+        # max_speed ** 2 in Python-float arithmetic, as roadmap/utils.py:40 and roadmap_learned/utils.py:60 do: CPython's
+        # float ** 2 goes through libm pow, which is NOT always the correctly rounded square numpy's s * s gives
+        speeds2 = np.concatenate([ins.speeds2() for ins in instances]) if all(hasattr(i, "speeds2") for i in instances) else \
+            np.array([float(s) ** 2 for s in speeds], dtype=np.float64)
         return dict(n_agents=n_agents, n_obs=n_obs, starts=starts, goals=goals, speeds=speeds, speeds2=speeds2, rads=rads,
                     obs=obs)
 
@@ -320,6 +322,10 @@ class PipelinedBuilder:
 
     def __init__(self, pred_basename: str, device: int = 0, map_size: Optional[int] = None, depth: int = 2):
         self.builders = [RoadmapBuilder(pred_basename, device, map_size=map_size) for _ in range(max(1, int(depth)))]
+        # stagger the contexts: with equal priorities their kernels time-share the GPU evenly, both batches finish together
+        # and the GPU idles while both export / pack / upload; the first context's kernels go first instead
+        for i, b in enumerate(self.builders):
+            _lib.check(b.lib.ctrm_set_stream_priority(b.ctx, 1 if i == 0 else 0), "ctrm_set_stream_priority")
 
     def close(self):
         for b in self.builders:

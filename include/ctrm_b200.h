@@ -97,6 +97,12 @@ int ctrm_abi_version(void);
 /* one context per (process, device, caller thread).  */
 int ctrm_ctx_create(int device, ctrm_ctx** out);
 void ctrm_ctx_destroy(ctrm_ctx* ctx);
+
+/* scheduling priority of the context's internal stream (high != 0: the device's greatest priority, else the least).  For two
+ * contexts that share one GPU and alternate batches: the kernels of the high-priority context go first, the other context's
+ * fill the gaps its host phases (packing, copies) leave, so the two do not finish — and idle the GPU — in lock step.  Call
+ * while the context is idle. */
+int ctrm_set_stream_priority(ctrm_ctx* ctx, int high);
 const char* ctrm_last_error(const ctrm_ctx* ctx); /* ctx may be NULL: process-wide last error */
 
 /* replaces learning/utils.py:32-53 `reconstruct` + model/__init__.py:19-59 (the device half): upload the
