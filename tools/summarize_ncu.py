@@ -63,7 +63,7 @@ def full(path):
 
 BENCH_KERNELS = (("fov_raster", r"fov_raster_tiles"), ("fov_encode", r"fov_encode_tc"), ("agent_comm", r"agent_comm_tc"),
                  ("cvae_prior", r"cvae_prior_tc"), ("cvae_decode", r"cvae_decode_tc"), ("cvae", r"cvae_tc_kernel"),
-                 ("step", r"\bstep_kernel"), ("advance", r"advance_kernel"), ("wavefront", r"wavefront_kernel"),
+                 ("step", r"step(_thread)?_kernel"), ("advance", r"advance_kernel"), ("wavefront", r"wavefront_kernel"),
                  ("csr_fill", r"csr_fill_kernel"))
 
 
