@@ -475,8 +475,8 @@ def gpu_arm(args):
     from ctrm_b200 import PipelinedBuilder
 
     e2e_steps = max(2, args.steps)
-    pipe = PipelinedBuilder(WEIGHTS, local)
-    for _ in pipe.map([instances] * 2, seed=seed, instance_id_base=rank * B, **PARAMS):
+    pipe = PipelinedBuilder(WEIGHTS, local, depth=3)
+    for _ in pipe.map([instances] * 3, seed=seed, instance_id_base=rank * B, **PARAMS):
         pass
     barrier()
     t0 = time.perf_counter()
@@ -599,7 +599,8 @@ def gpu_arm(args):
                 device_ms=dict(total=tim["total_ms"], rollout=tim["rollout_ms"], finalize=tim["finalize_ms"], graph_replays=tim["steps"]),
                 clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                         ms_per_step=e2e_t[0].item(), steps=e2e_steps,
-                                        api="PipelinedBuilder.map (2 contexts, copies of one batch overlap the other's kernels)"),
+                                        api="PipelinedBuilder.map (3 contexts on the GPU, the first with a high-priority stream: packing, copies and "
+                                            "export of one batch overlap the roll-out kernels of another)"),
                 gpu_launches=int(launches_all), roofline=roofline, kernels=kernels, cpu_baseline=cpu, planner=planner,
                 strong_scaling=strong, other_configs=other,
                 latency_ms_single_instance=(other or {}).get("demo_instance", {}).get("latency_ms"))
@@ -617,7 +618,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("CTRM_BENCH_BATCH", "2960")), help="instances per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("CTRM_BENCH_BATCH", "5920")), help="instances per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra single-GPU configs (demo instance, 31-40 agents, stress)")
     ap.add_argument("--cpu-worker", action="store_true")

@@ -428,8 +428,9 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&bt.e_vain, (size_t)A * 32));
   CHECK(ar.alloc(&bt.vain_proj, (size_t)A * 32));
   CHECK(ar.alloc(&bt.X, (size_t)A * CTRM_DIM_X));
-  CHECK(ar.alloc(&bt.cv_sqrtp, (size_t)A * 64));
-  CHECK(ar.alloc(&bt.cv_dec0, (size_t)A * 32));
+  // one [A]-sized slot per indicator value: slot 0 alone in the usual run, all of them with randomize_indicator
+  CHECK(ar.alloc(&bt.cv_sqrtp, (size_t)A * 64 * c->model.desc.dim_ind));
+  CHECK(ar.alloc(&bt.cv_dec0, (size_t)A * 32 * c->model.desc.dim_ind));
   CHECK(ar.alloc(&bt.ind, (size_t)A));
   CHECK(ar.alloc(&bt.cur, (size_t)2 * A));
   CHECK(ar.alloc(&bt.prev, (size_t)2 * A));
@@ -739,8 +740,15 @@ static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, 
     CHECK(launch_agent_comm(c->model, bl, bt.cur, bt.prev, bt.e_self, bt.vain_proj, bt.X, st));
     CHECK(mark(KID_AGENT_COMM));
     CHECK(launch_cvae_prior(c->model, bl, bt.X, bt.cv_sqrtp, bt.cv_dec0, bt.ind, st));
+    if (bt.randomize_indicator) {  // learned_sampler.py:93-97: the encoder / decoder-x paths for every indicator value; the
+      for (int v = 0; v < bt.dim_ind; ++v) {  // decoder rows pick theirs (random per row, or the argmax written above)
+        CHECK(launch_cvae_prior(c->model, bl, bt.X, bt.cv_sqrtp + (size_t)v * bt.A * 64, bt.cv_dec0 + (size_t)v * bt.A * 32, nullptr,
+                                st, v));
+        ++k;
+      }
+    }
     CHECK(mark(KID_CVAE_PRIOR));
-    CHECK(launch_cvae_decode(c->model, bl, bt.cv_sqrtp, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st));
+    CHECK(launch_cvae_decode(c->model, bl, bt.cv_sqrtp, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st, bt.randomize_indicator));
     CHECK(mark(KID_CVAE_DECODE));
   }
   CHECK(launch_step(bt, st));
@@ -756,8 +764,9 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   if (p->N_traj < 0 || p->N_traj > 32 * CTRM_MAX_W - 1) return ctrm_fail(CTRM_ERR_ARG, "N_traj must be in 0..127");
   if (p->max_T < 1 || p->max_T > 4096) return ctrm_fail(CTRM_ERR_ARG, "max_T must be in 1..4096");
   if (p->max_attempt < 0 || p->max_attempt > 255) return ctrm_fail(CTRM_ERR_ARG, "max_attempt must be in 0..255");
-  if (p->randomize_indicator)
-    return ctrm_fail(CTRM_ERR_ARG, "randomize_indicator=True is not supported (per-row random indicators, learned_sampler.py:93-97)");
+  if (p->randomize_indicator && p->rng_mode == 1)
+    return ctrm_fail(CTRM_ERR_ARG, "randomize_indicator=True needs counter-based randomness (rng_mode 0): the recorded-stream "
+                                   "tables hold no torch.randint draws");
   const int K = p->K > 0 ? p->K : c->model.desc.dim_ind;
   if (K > 4096) return ctrm_fail(CTRM_ERR_ARG, "K too large");
   if (p->rng_mode == 1 && (!tb || !tb->h_gate || (p->max_attempt > 0 && !tb->h_rw)))
@@ -768,7 +777,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   CHECK(ensure_rollout_store(c, p, K));
   Batch& bt = c->bt;
   bt.max_T = p->max_T; bt.N_traj = p->N_traj; bt.max_attempt = p->max_attempt;
-  bt.dim_ind = c->model.desc.dim_ind; bt.randomize_indicator = 0;
+  bt.dim_ind = c->model.desc.dim_ind; bt.randomize_indicator = p->randomize_indicator ? 1 : 0;
   bt.rng_mode = p->rng_mode;
   bt.seed_lo = (uint32_t)(p->seed & 0xFFFFFFFFu); bt.seed_hi = (uint32_t)(p->seed >> 32);
   bt.inst_base = p->instance_id_base;

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(PR_THREADS) cvae_prior_image_kernel(const floa
 __global__ void __launch_bounds__(PR_THREADS, 2) cvae_prior_tc_kernel(Batch bt, const float* __restrict__ X,
                                                                    const uint8_t* __restrict__ w_image,
                                                                    float* __restrict__ sqrtp_out, float* __restrict__ dec0_out,
-                                                                   int32_t* __restrict__ ind_out, int n_tiles) {
+                                                                   int32_t* __restrict__ ind_out, int n_tiles, int force_ind) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Xt = smem;                        // X parts 1..3 [128 x 80]; after layer 0: hidden tiles [128 x 32] x 3 | head weights
   uint8_t* W0t = Xt + 3 * PR_X_PART;         // [96 x 80] x 3 : ind_w0 | enc_w0 | dec_w0 rows 64..135
@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(PR_THREADS, 2) cvae_prior_tc_kernel(Batch bt, 
       float best = o0;
       if (o1 > best) { best = o1; ind = 1; }
       if (o2 > best) { best = o2; ind = 2; }
-      if (live && half == 0 && ind_out != nullptr) ind_out[a] = ind;
+      if (force_ind >= 0) ind = force_ind;  // one launch per indicator value (randomize_indicator, learned_sampler.py:93-97)
+      else if (live && half == 0 && ind_out != nullptr) ind_out[a] = ind;
     }
     // ---- decoder first layer, [X, onehot] part (TMEM columns 64..95 of the shared chain)
     tc::tmem_ld16_sum2(tbase, warp, 64 + 16 * half, 96, h);
@@ -289,13 +290,13 @@ int launch_cvae_prior_image(const float* d_blob, const ctrm_weight_offsets_t& of
 }
 
 int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_sqrtp, float* d_dec0, int32_t* d_ind,
-                      cudaStream_t st) {
+                      cudaStream_t st, int force_ind) {
   if (bt.A <= 0) return 0;
   const int n_tiles = (bt.A + 127) / 128;
   static SmemAttrCache attr;
   CTRM_CUDA_OK(attr.ensure(cvae_prior_tc_kernel, PR_SMEM));
   const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent, two CTAs per SM (114 KB of shared memory each)
-  cvae_prior_tc_kernel<<<grid, PR_THREADS, PR_SMEM, st>>>(bt, d_X, m.prior_img, d_sqrtp, d_dec0, d_ind, n_tiles);
+  cvae_prior_tc_kernel<<<grid, PR_THREADS, PR_SMEM, st>>>(bt, d_X, m.prior_img, d_sqrtp, d_dec0, d_ind, n_tiles, force_ind);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
                                                                        const float* __restrict__ uniforms, int use_state_kt,
                                                                        int kt_fixed, int t_fixed, float temp, int w0_exp,
                                                                        const uint8_t* __restrict__ w_image,
-                                                                       float* __restrict__ samples, int n_tiles) {
+                                                                       float* __restrict__ samples, int n_tiles, int variants) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* At = smem;                       // z digits 1..4, [128 x 64] bf16 each
   uint8_t* W0t = At + 4 * DT_A_PART;        // W0z digits 1..4, [32 x 64]
@@ -419,6 +420,24 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
       b = bt.agent_inst[a];
       live = !(bt.done != nullptr && bt.done[b]);
     }
+    // indicator variant of this row (randomize_indicator, learned_sampler.py:93-97): one draw per (instance, step) decides
+    // whether the step's indicators are random; then every row k*N + i draws its own, else all copies take the argmax
+    size_t voff = 0;
+    if (variants && live) {
+      const int kt = use_state_kt ? bt.k_traj[b] : kt_fixed, tt = use_state_kt ? bt.t[b] : t_fixed;
+      const uint32_t c0v = bt.inst_base + (uint32_t)b, c1v = rng_ctr1(kt, tt);
+      const uint4 ws = philox4x32(c0v, c1v, 0u, rng_ctr3(STREAM_STEP, 0), bt.seed_lo, bt.seed_hi);
+      const int mk = bt.makespan[b], D = mk ? mk : bt.max_T;
+      int v;
+      if (u64_to_f64(ws.x, ws.y) > bt.p_rw[(size_t)tt * (bt.max_T + 1) + D]) {
+        const int N = bt.agent_off[b + 1] - bt.agent_off[b], il = a - bt.agent_off[b];
+        v = (int)(philox4x32(c0v, c1v, (uint32_t)(k * N + il), rng_ctr3(STREAM_RANDIND, 0), bt.seed_lo, bt.seed_hi).x %
+                  (uint32_t)bt.dim_ind);
+      } else {
+        v = bt.ind[a];
+      }
+      voff = (size_t)v * bt.A;
+    }
     // a tile whose rows all belong to finished instances is skipped entirely
     if (!__syncthreads_or(live)) continue;
     // ---- z = RelaxedOneHotCategorical(temp, probs).rsample() (cvae.py:133-136): softmax((log p + g) / temp) with
@@ -431,7 +450,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     if (sqrt_path) {
       float rv[32];
       if (live) {
-        const float* sp = sqrtp + (size_t)a * 64;
+        const float* sp = sqrtp + (voff + (size_t)a) * 64;
         const float* urow = nullptr;
         uint32_t c0 = 0, c1 = 0, c2 = 0;
         if (uniforms != nullptr) {
@@ -482,7 +501,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     } else {
     float mx = -INFINITY;
     if (live) {
-      const float* sp = sqrtp + (size_t)a * 64;
+      const float* sp = sqrtp + (voff + (size_t)a) * 64;
       const float* urow = nullptr;
       uint32_t c0 = 0, c1 = 0, c2 = 0;
       if (uniforms != nullptr) {
@@ -572,7 +591,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     float h[16];
     {
       double pre[16];
-      const float4* d0 = reinterpret_cast<const float4*>(dec0 + (size_t)a * 32 + 16 * half);
+      const float4* d0 = reinterpret_cast<const float4*>(dec0 + (voff + (size_t)a) * 32 + 16 * half);
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         const float4 v = live ? __ldg(&d0[j4]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -641,7 +660,7 @@ int launch_cvae_decode_image(const float* d_blob, const ctrm_weight_offsets_t& o
 }
 
 int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_sqrtp, const float* d_dec0, const float* d_uniforms,
-                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st) {
+                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st, int variants) {
   if (bt.A <= 0) return 0;
   const int K = bt.K;
   const long long rows = (long long)bt.A * K;
@@ -650,7 +669,7 @@ int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_sqrtp,
   CTRM_CUDA_OK(attr.ensure(cvae_decode_tc_kernel, DT_SMEM));
   const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent: two CTAs per SM
   cvae_decode_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(bt, K, d_sqrtp, d_dec0, d_uniforms, use_state_kt, kt_fixed, t_fixed,
-                                                          m.desc.temp, m.dec_w0z_exp, m.decode_img, d_samples, n_tiles);
+                                                          m.desc.temp, m.dec_w0z_exp, m.decode_img, d_samples, n_tiles, variants);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -128,10 +128,14 @@ int launch_fov_encode(const DevModel& m, const uint8_t* d_fov_tiles, const int32
 int launch_compact_live(const Batch& bt, cudaStream_t st);
 int launch_agent_comm(const DevModel& m, const Batch& bt, const double* d_cur, const double* d_prev, const float* d_e_self,
                       const float* d_vain_proj, float* d_X, cudaStream_t st);
+// force_ind >= 0: evaluate the encoder / decoder-x paths with that indicator instead of the argmax (one launch per indicator
+// value feeds the per-row random indicators of randomize_indicator=True); d_ind is then not written
 int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, float* d_sqrtp, float* d_dec0, int32_t* d_ind,
-                      cudaStream_t st);
+                      cudaStream_t st, int force_ind = -1);
+// variants != 0: d_sqrtp / d_dec0 hold one [A]-sized slot per indicator value and every row picks its own
+// (learned_sampler.py:93-97: torch.randint indicators when the step's draw exceeds p_rw, else the argmax)
 int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_sqrtp, const float* d_dec0, const float* d_uniforms,
-                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st);
+                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st, int variants = 0);
 
 int launch_step(const Batch& bt, cudaStream_t st);
 int launch_rollout_init(const Batch& bt, cudaStream_t st);

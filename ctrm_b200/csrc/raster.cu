@@ -88,27 +88,30 @@ __global__ void __launch_bounds__(256) raster_occupancy_rows_kernel(const int4* 
                                                                     uint8_t* __restrict__ occ) {
   __shared__ int4 s_cells[RO_MAX_SOBS];
   const int chunks = (M * M) >> 4;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int base = c << 4;
-  const int x = base / M, y = base - x * M;
-  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+  // one block rasterises whole maps (blockIdx.x, strided): 57 k tiny blocks of one chunk per thread spent their time in block
+  // scheduling and barriers, not in stores
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int o0 = obs_off[b], nO = obs_off[b + 1] - o0, nS = min(nO, RO_MAX_SOBS);
     __syncthreads();  // the previous map's disks have been consumed
     if (threadIdx.x < nS) s_cells[threadIdx.x] = __ldg(&cells[o0 + threadIdx.x]);
     __syncthreads();
-    if (c >= chunks) continue;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    for (int o = 0; o < nO; ++o) {
-      const int4 d = o < nS ? s_cells[o] : __ldg(&cells[o0 + o]);
-      const int dx = x - d.x, rem2 = d.z - dx * dx;  // dy^2 < rem2 <=> inside
-      if (rem2 <= 0 || y + 15 <= d.y - d.w || y >= d.y + d.w) continue;
+    uint8_t* out = occ + (size_t)b * M * M;
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+      const int base = c << 4;
+      const int x = base / M, y = base - x * M;
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      for (int o = 0; o < nO; ++o) {
+        const int4 d = o < nS ? s_cells[o] : __ldg(&cells[o0 + o]);
+        const int dx = x - d.x, rem2 = d.z - dx * dx;  // dy^2 < rem2 <=> inside
+        if (rem2 <= 0 || y + 15 <= d.y - d.w || y >= d.y + d.w) continue;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int dy = y + j - d.y;
-        w[j >> 2] |= (uint32_t)(dy * dy < rem2) << (8 * (j & 3));
+        for (int j = 0; j < 16; ++j) {
+          const int dy = y + j - d.y;
+          w[j >> 2] |= (uint32_t)(dy * dy < rem2) << (8 * (j & 3));
+        }
       }
+      __stcs(reinterpret_cast<uint4*>(out + base), make_uint4(w[0], w[1], w[2], w[3]));
     }
-    __stcs(reinterpret_cast<uint4*>(occ + (size_t)b * M * M + base), make_uint4(w[0], w[1], w[2], w[3]));
   }
 }
 
@@ -438,7 +441,7 @@ int launch_obs_to_cells(const double* d_obs_xyr, int O, int M, int4* d_cells, cu
 
 int launch_raster_occupancy(const int4* d_cells, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, cudaStream_t st) {
   if ((M & 15) == 0 && (reinterpret_cast<uintptr_t>(d_occ) & 15) == 0) {
-    dim3 grid((unsigned)(((M * M) >> 4) + 255) / 256, (unsigned)(B < 32768 ? B : 32768));
+    const int grid = B < 148 * 8 ? B : 148 * 8;  // persistent: eight 256-thread blocks per SM
     raster_occupancy_rows_kernel<<<grid, 256, 0, st>>>(d_cells, d_obs_off, B, M, d_occ);
     CTRM_CUDA_OK(cudaGetLastError());
     return 0;

@@ -633,13 +633,19 @@ __device__ __forceinline__ bool hits_any_serial(const Batch& bt, int o0, int nO,
   bool hit = false;
   const float lox = (float)fmin(fx, tx), hix = (float)fmax(fx, tx), loy = (float)fmin(fy, ty), hiy = (float)fmax(fy, ty);
   const float radf = (float)rad + 1e-5f;
-  for (int o = 0; o < nO; ++o) {
-    const float4 q = __ldg(&bt.obs_f4[o0 + o]);
-    const float R = radf + q.z;
-    if (q.x < lox - R || q.x > hix + R || q.y < loy - R || q.y > hiy + R) continue;
-    const double* g = bt.obs_xyr + 3 * (size_t)(o0 + o);
-    const double ox = __ldg(g), oy = __ldg(g + 1), rs = f64add(rad, __ldg(g + 2));
-    hit = hit || sweep_static(fx, fy, tx, ty, ox, oy, rs);
+  for (int o = 0; o < nO; o += 4) {  // four obstacle loads in flight: the walk is bound by their latency, not by the tests
+    float4 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = __ldg(&bt.obs_f4[o0 + min(o + j, nO - 1)]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (o + j >= nO) break;
+      const float R = radf + q[j].z;
+      if (q[j].x < lox - R || q[j].x > hix + R || q[j].y < loy - R || q[j].y > hiy + R) continue;
+      const double* g = bt.obs_xyr + 3 * (size_t)(o0 + o + j);
+      const double ox = __ldg(g), oy = __ldg(g + 1), rs = f64add(rad, __ldg(g + 2));
+      hit = hit || sweep_static(fx, fy, tx, ty, ox, oy, rs);
+    }
   }
   return hit;
 }

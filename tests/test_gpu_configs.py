@@ -85,6 +85,48 @@ def test_teacher_forced_parity(name, specs, NT, MT, K, rate, M):
         builder.close()
 
 
+def test_randomize_indicator_parity():
+    """randomize_indicator=True (learned_sampler.py:93-97): when the step's draw exceeds p_rw every row k*N + i takes a
+    torch.randint indicator instead of the argmax.  Oracle with the same keyed draws: CVAE samples within 1e-5 at every
+    executed step (they depend on the per-row indicators), roadmaps bit-identical under teacher forcing"""
+    from ctrm_b200 import RoadmapBuilder
+
+    w = O.OWeights.load(WEIGHTS)
+    instances = [_instance(21, 9, 10, 6), _instance(22, 5, 6, 3)]
+    oins = [_oins(i) for i in instances]
+    NT, MT, K, rate, seed = 5, 24, 3, 0.1, 4242
+    p = O.OParams(N_traj=NT, max_T=MT, merge_distance_rate=rate, max_attempt=3, K=K, randomize_indicator=True)
+    recs_all, trms_all = [], []
+    for b, oi in enumerate(oins):
+        recs = []
+        trms_all.append(O.build_timed_roadmaps(oi, w, p, PhiloxTables(seed, 11 + b), recorder=recs))
+        recs_all.append(recs)
+    n_random = sum(1 for recs in recs_all for r in recs if r["ind_logits"] is None)
+    assert 0 < n_random < sum(len(r) for r in recs_all)  # both branches of learned_sampler.py:93 are exercised
+    teacher = np.concatenate([teacher_table(r, oi.num_agents, K, NT, MT, key="SAMPLES_nn") for r, oi in zip(recs_all, oins)], axis=2)
+    builder = RoadmapBuilder(WEIGHTS, 0)
+    try:
+        builder.upload(instances)
+        csr = builder.run(N_traj=NT, max_T=MT, max_attempt=3, merge_distance_rate=rate, K=K, seed=seed, instance_id_base=11,
+                          randomize_indicator=True, tables=dict(teacher=teacher), trace=True)
+        samples, _, _ = builder.read_trace()
+        a0, worst = 0, 0.0
+        for b, oi in enumerate(oins):
+            assert_same_roadmaps(csr_to_arrays(csr, b), otrms_to_arrays(trms_all[b]))
+            N = oi.num_agents
+            for r in recs_all[b]:
+                k, t = r["k_traj"], r["t"] - 1
+                worst = max(worst, rel_err(samples[k, t, a0:a0 + N], r["SAMPLES_nn"].reshape(K, N, 3).transpose(1, 0, 2)))
+            a0 += N
+        assert worst <= 1e-5, worst
+        # free-running (no teacher, learned rows only) with the option on: runs and is repeatable
+        c1 = builder.run(N_traj=NT, max_T=MT, merge_distance_rate=rate, seed=seed, randomize_indicator=True).copy()
+        c2 = builder.run(N_traj=NT, max_T=MT, merge_distance_rate=rate, seed=seed, randomize_indicator=True).copy()
+        assert np.array_equal(c1.pos.view(np.uint64), c2.pos.view(np.uint64)) and np.array_equal(c1.eidx, c2.eidx)
+    finally:
+        builder.close()
+
+
 def test_api_error_paths():
     """bad arguments come back as negative status codes with a message, never as exceptions from native code"""
     import ctypes as C
@@ -102,8 +144,9 @@ def test_api_error_paths():
         b.upload([_instance(11, 4, 5, 2)])
         with pytest.raises(_lib.CtrmError, match="N_traj"):
             b.run(N_traj=500)
-        with pytest.raises(_lib.CtrmError, match="randomize_indicator"):
-            b.run(N_traj=1, randomize_indicator=True)
+        with pytest.raises(_lib.CtrmError, match="randomize_indicator"):  # recorded-stream tables hold no torch.randint draws
+            b.run(N_traj=1, max_T=4, randomize_indicator=True,
+                  tables=dict(gate=np.full((1, 4, 4), 0.5), rw=np.zeros((1, 4, 4, 3, 3))))
         nv = C.c_int64()
         assert lib.ctrm_result_sizes(b.ctx, C.byref(nv), None, None) == -3  # CTRM_ERR_STATE: no result yet
         csr = b.run(N_traj=0, max_T=8)  # zero roll-outs: only the start layer, extended once, plus goals
