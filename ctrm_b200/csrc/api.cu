@@ -324,7 +324,11 @@ static int cost_to_go_device(const uint8_t* d_occ, int M, const std::vector<uint
     if ((rc = upload(tmp, &d_pms, pm_st.data(), pm_st.size(), st))) break;
     if ((rc = upload(tmp, &d_apm, agent_pm.data(), agent_pm.size(), st))) break;
     if ((rc = tmp.alloc(&d_pmask, (size_t)P * M * MW))) break;
-    if ((rc = launch_passable_masks(d_occ, M, d_st, d_str, st_ld, d_pmi, d_pms, P, d_pmask, st))) break;
+    int nB = 0;  // maps referenced by the masks
+    for (int32_t b : pm_inst) nB = b + 1 > nB ? b + 1 : nB;
+    uint32_t* d_blocked = nullptr;
+    if ((rc = tmp.alloc(&d_blocked, (size_t)nB * M * MW))) break;
+    if ((rc = launch_passable_masks(d_occ, nB, M, d_st, d_str, st_ld, d_pmi, d_pms, P, d_blocked, d_pmask, st))) break;
     if ((rc = launch_wavefront(d_pmask, d_apm, d_goals, A, M, layout, d_ctg, st))) break;
     cudaError_t e = cudaStreamSynchronize(st);  // the host vectors and temporaries die here
     if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "cost_to_go sync");
@@ -474,7 +478,7 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
     int4* d_cells = nullptr;
     int rc = c->s_arena.alloc(&d_cells, (size_t)O);
     if (!rc) rc = launch_obs_to_cells(d_obs, O, M, d_cells, st);
-    if (!rc) rc = launch_raster_occupancy(d_cells, d_ooff, B, M, d_occ, st);
+    if (!rc) rc = launch_raster_occupancy(d_cells, d_ooff, B, O, M, d_occ, st);
     if (!rc) {
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) rc = ctrm_fail_cuda(e, "raster sync");
@@ -557,7 +561,7 @@ extern "C" int ctrm_raster_occupancy(const double* d_obs_xyr, const int32_t* d_o
   CHECK(keep_async_pool_warm());
   CTRM_CUDA_OK(cudaMallocAsync(&d_cells, sizeof(int4) * (size_t)(O > 0 ? O : 1), st));
   int rc = launch_obs_to_cells(d_obs_xyr, O, M, d_cells, st);
-  if (!rc) rc = launch_raster_occupancy(d_cells, d_obs_off, B, M, d_occ, st);
+  if (!rc) rc = launch_raster_occupancy(d_cells, d_obs_off, B, O, M, d_occ, st);
   cudaFreeAsync(d_cells, st);
   return rc;
 }

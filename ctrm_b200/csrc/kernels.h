@@ -99,9 +99,10 @@ __host__ __device__ inline size_t vslot(const Batch& bt, int a, int t, int s) { 
 
 // ---- launchers (each returns 0 or a negative ctrm_status) ----
 int launch_obs_to_cells(const double* d_obs_xyr, int O, int M, int4* d_cells, cudaStream_t st);
-int launch_raster_occupancy(const int4* d_cells, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, cudaStream_t st);
-int launch_passable_masks(const uint8_t* d_occ, int M, const uint8_t* d_stencils, const int32_t* d_stencil_r, int st_ld,
-                          const int32_t* d_pm_inst, const int32_t* d_pm_stencil, int P, uint32_t* d_pmask, cudaStream_t st);
+int launch_raster_occupancy(const int4* d_cells, const int32_t* d_obs_off, int B, int O, int M, uint8_t* d_occ, cudaStream_t st);
+int launch_passable_masks(const uint8_t* d_occ, int B, int M, const uint8_t* d_stencils, const int32_t* d_stencil_r, int st_ld,
+                          const int32_t* d_pm_inst, const int32_t* d_pm_stencil, int P, uint32_t* d_blocked /*[B][M][ceil(M/32)]*/,
+                          uint32_t* d_pmask, cudaStream_t st);
 int launch_wavefront(const uint32_t* d_pmask, const int32_t* d_agent_pm, const double* d_goals, int A, int M, int layout,
                      uint16_t* d_ctg, cudaStream_t st);
 int launch_fov_raster(const uint8_t* d_occ, const uint16_t* d_ctg, const int32_t* d_agent_inst, const double* d_pos,

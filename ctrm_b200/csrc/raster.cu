@@ -22,95 +22,29 @@ __global__ void obs_to_cells_kernel(const double* __restrict__ obs_xyr, int O, i
 
 // occ[b][x][y] = any_o ( (x-X)^2 + (y-Y)^2 < R^2 ) — the integer form of skimage.draw.disk's float test
 // ((r-r0)/R)^2 + ((c-c0)/R)^2 < 1 (exhaustively identical for R <= 40, SURVEY §8a note (i); R = 0 is empty).
-// One thread produces 16 consecutive bytes of the flat [B][M][M] array and stores them as one uint4.
-__global__ void __launch_bounds__(256) raster_occupancy_kernel(const int4* __restrict__ cells,
-                                                               const int32_t* __restrict__ obs_off, int B, int M,
-                                                               uint8_t* __restrict__ occ) {
-  const long long total = (long long)B * M * M;
-  const int MM = M * M;
-  for (long long chunk = (long long)blockIdx.x * blockDim.x + threadIdx.x; chunk * 16 < total;
-       chunk += (long long)gridDim.x * blockDim.x) {
-    long long base = chunk * 16;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    int b = (int)(base / MM);
-    int rem = (int)(base - (long long)b * MM);
-    int x = rem / M, y = rem - x * M;
-    int o0 = obs_off[b], o1 = obs_off[b + 1];
-    if (y + 16 <= M) {
-      // the 16 cells lie in one row: an obstacle whose disk misses the row segment is rejected with three compares, the
-      // others contribute through their integer test (a disk covers ~1% of the map: most chunks see no obstacle at all)
-      for (int o = o0; o < o1; ++o) {
-        const int4 c = __ldg(&cells[o]);
-        const int dx = x - c.x, rem2 = c.z - dx * dx;  // dy^2 < rem2 <=> inside
-        if (rem2 <= 0 || y + 15 <= c.y - c.w || y >= c.y + c.w) continue;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int dy = y + j - c.y;
-          w[j >> 2] |= (uint32_t)(dy * dy < rem2) << (8 * (j & 3));
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (base + j < total) {
-          uint32_t v = 0u;
-          for (int o = o0; o < o1; ++o) {
-            int4 c = __ldg(&cells[o]);
-            int dx = x - c.x, dy = y - c.y;
-            v |= (uint32_t)(dx * dx + dy * dy < c.z);
-          }
-          w[j >> 2] |= v << (8 * (j & 3));
-          if (++y == M) {
-            y = 0;
-            if (++x == M) {
-              x = 0;
-              ++b;
-              if (b < B) { o0 = obs_off[b]; o1 = obs_off[b + 1]; }
-            }
-          }
-        }
-      }
-    }
-    if (base + 16 <= total) {
-      *reinterpret_cast<uint4*>(occ + base) = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-      for (int j = 0; base + j < total; ++j) occ[base + j] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
-    }
+// The same raster as O(output) + O(disk areas): the maps are cleared with one memset at the HBM write rate and every
+// obstacle then writes the cells of ITS disk (a few hundred bytes), instead of every 16-byte chunk of every map testing every
+// obstacle of its instance (ncu: that kernel was ALU-bound, 330 instructions per chunk, 12 % of the DRAM rate).  occ = max
+// over obstacles, and every writer writes 1, so the order does not matter.  One warp per obstacle; lanes = the y cells of a row.
+__global__ void __launch_bounds__(256) raster_disks_kernel(const int4* __restrict__ cells, const int32_t* __restrict__ obs_off,
+                                                           int B, int O, int M, uint8_t* __restrict__ occ) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (o >= O) return;
+  int lo = 0, hi = B - 1;  // instance of obstacle o: last b with obs_off[b] <= o
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (obs_off[mid] <= o) lo = mid; else hi = mid - 1;
   }
-}
-
-// The same raster for M % 16 == 0 (the trained M = 160): a 16-byte chunk never straddles a row, the map index comes from
-// blockIdx.y (no 64-bit division per chunk — that division, not the memory system, was what bounded the general kernel at
-// 15% of the HBM rate), and the map's integer disks are staged once per block in shared memory.
-#define RO_MAX_SOBS 64
-__global__ void __launch_bounds__(256) raster_occupancy_rows_kernel(const int4* __restrict__ cells,
-                                                                    const int32_t* __restrict__ obs_off, int B, int M,
-                                                                    uint8_t* __restrict__ occ) {
-  __shared__ int4 s_cells[RO_MAX_SOBS];
-  const int chunks = (M * M) >> 4;
-  // one block rasterises whole maps (blockIdx.x, strided): 57 k tiny blocks of one chunk per thread spent their time in block
-  // scheduling and barriers, not in stores
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
-    const int o0 = obs_off[b], nO = obs_off[b + 1] - o0, nS = min(nO, RO_MAX_SOBS);
-    __syncthreads();  // the previous map's disks have been consumed
-    if (threadIdx.x < nS) s_cells[threadIdx.x] = __ldg(&cells[o0 + threadIdx.x]);
-    __syncthreads();
-    uint8_t* out = occ + (size_t)b * M * M;
-    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
-      const int base = c << 4;
-      const int x = base / M, y = base - x * M;
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
-      for (int o = 0; o < nO; ++o) {
-        const int4 d = o < nS ? s_cells[o] : __ldg(&cells[o0 + o]);
-        const int dx = x - d.x, rem2 = d.z - dx * dx;  // dy^2 < rem2 <=> inside
-        if (rem2 <= 0 || y + 15 <= d.y - d.w || y >= d.y + d.w) continue;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int dy = y + j - d.y;
-          w[j >> 2] |= (uint32_t)(dy * dy < rem2) << (8 * (j & 3));
-        }
-      }
-      __stcs(reinterpret_cast<uint4*>(out + base), make_uint4(w[0], w[1], w[2], w[3]));
+  const int4 d = __ldg(&cells[o]);  // (X, Y, R^2, R)
+  if (d.w <= 0) return;             // R = 0: empty disk
+  uint8_t* out = occ + (size_t)lo * M * M;
+  const int x0 = max(0, d.x - d.w + 1), x1 = min(M - 1, d.x + d.w - 1);
+  const int y0 = max(0, d.y - d.w + 1), y1 = min(M - 1, d.y + d.w - 1);
+  for (int x = x0; x <= x1; ++x) {
+    const int dx = x - d.x, rem2 = d.z - dx * dx;  // dy^2 < rem2 <=> inside
+    for (int y = y0 + lane; y <= y1; y += 32) {
+      const int dy = y - d.y;
+      if (dy * dy < rem2) out[x * M + y] = 1;
     }
   }
 }
@@ -118,43 +52,58 @@ __global__ void __launch_bounds__(256) raster_occupancy_rows_kernel(const int4* 
 // ------------------------------------------------------------------------------------------------
 // passability masks: bit (x, y) of mask p set iff the agent footprint centred on (x,y) is collision-free
 // (cost_to_go.cpp:68-97): occ[x][y]==0 and no stencil cell with agent==1 is outside the map or occupied.
-// One warp per (mask p, row x, word w); lane = y & 31; ballot packs the word.  MW = ceil(M/32).
-// stencils: [n_st][st_ld*st_ld] uint8, the (2r+1)^2 footprint stored top-left aligned with leading dim st_ld.
+// Bit-parallel: the instance's "blocked" grid (occupied, or outside the map) is packed one bit per cell; the footprint test
+// is then a dilation — for every set stencil cell (k, l) OR the blocked row x + k shifted by l — 32 cells per word operation
+// instead of one byte load and compare per (cell, stencil cell) (ncu: the per-cell kernel was ALU-bound at 1 ms per 1,024
+// masks).  MW = ceil(M/32).  stencils: [n_st][st_ld*st_ld] uint8, the (2r+1)^2 footprint with leading dimension st_ld.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) passable_mask_kernel(const uint8_t* __restrict__ occ, int M, int MW,
+// blocked[b][x][w]: bit y of word w = occ[b][x][32 w + y] != 0; bits at y >= M are set (outside the map counts as blocked)
+__global__ void __launch_bounds__(256) pack_blocked_kernel(const uint8_t* __restrict__ occ, int B, int M, int MW,
+                                                           uint32_t* __restrict__ blocked) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)B * M * MW) return;
+  const int w = (int)(warp % MW);
+  const long long t = warp / MW;
+  const int x = (int)(t % M), b = (int)(t / M);
+  const int y = w * 32 + lane;
+  const bool blk = (y >= M) || (occ[((size_t)b * M + x) * M + y] != 0);
+  const uint32_t bits = __ballot_sync(0xFFFFFFFFu, blk);
+  if (lane == 0) blocked[((size_t)b * M + x) * MW + w] = bits;
+}
+
+// one thread per (mask p, row x, word w)
+__global__ void __launch_bounds__(256) passable_mask_kernel(const uint32_t* __restrict__ blocked, int M, int MW,
                                                             const uint8_t* __restrict__ stencils,
                                                             const int32_t* __restrict__ stencil_r, int st_ld,
                                                             const int32_t* __restrict__ pm_inst,
                                                             const int32_t* __restrict__ pm_stencil, int P,
                                                             uint32_t* __restrict__ pmask) {
-  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  long long nwarps = (long long)P * M * MW;
-  if (warp >= nwarps) return;
-  int w = (int)(warp % MW);
-  long long t = warp / MW;
-  int x = (int)(t % M);
-  int p = (int)(t / M);
-  int y = w * 32 + lane;
-  const uint8_t* o = occ + (size_t)pm_inst[p] * M * M;
-  int st = pm_stencil[p];
-  int r = stencil_r[st];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * M * MW) return;
+  const int w = (int)(i % MW);
+  const long long t = i / MW;
+  const int x = (int)(t % M), p = (int)(t / M);
+  const uint32_t* Bk = blocked + (size_t)pm_inst[p] * M * MW;
+  const int st = pm_stencil[p], r = stencil_r[st];
   const uint8_t* s = stencils + (size_t)st * st_ld * st_ld;
-  bool ok = false;
-  if (y < M) {
-    ok = (o[x * M + y] == 0);
-    for (int k = -r; ok && k <= r; ++k) {
-      int xk = x + k;
-      for (int l = -r; l <= r; ++l) {
-        if (s[(k + r) * st_ld + (l + r)] == 0) continue;
-        int yl = y + l;
-        if (xk < 0 || xk >= M || yl < 0 || yl >= M) { ok = false; break; }
-        if (o[xk * M + yl] != 0) { ok = false; break; }
-      }
+  uint32_t bad = Bk[(size_t)x * MW + w];  // the cell itself must be free (cost_to_go.cpp:68)
+  for (int k = -r; k <= r; ++k) {
+    const int xk = x + k;
+    const bool row_in = xk >= 0 && xk < M;
+    const uint32_t* row = Bk + (size_t)(row_in ? xk : 0) * MW;
+    for (int l = -r; l <= r; ++l) {
+      if (s[(k + r) * st_ld + (l + r)] == 0) continue;
+      // bit y of the result reads blocked(xk, 32 w + y + l): a 32-bit window of the row starting at bit 32 w + l; words
+      // outside the row (and the whole row when xk is outside the map) read as all ones
+      const int pos = 32 * w + l;
+      const int q = pos >> 5, sft = pos & 31;  // arithmetic shift = floor for negative positions
+      const uint32_t w0 = (row_in && q >= 0 && q < MW) ? row[q] : 0xFFFFFFFFu;
+      const uint32_t w1 = (row_in && q + 1 >= 0 && q + 1 < MW) ? row[q + 1] : 0xFFFFFFFFu;
+      bad |= sft ? (w0 >> sft) | (w1 << (32 - sft)) : w0;
     }
   }
-  uint32_t bits = __ballot_sync(0xFFFFFFFFu, ok);
-  if (lane == 0) pmask[((size_t)p * M + x) * MW + w] = bits;
+  pmask[((size_t)p * M + x) * MW + w] = ~bad;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -439,28 +388,26 @@ int launch_obs_to_cells(const double* d_obs_xyr, int O, int M, int4* d_cells, cu
   return 0;
 }
 
-int launch_raster_occupancy(const int4* d_cells, const int32_t* d_obs_off, int B, int M, uint8_t* d_occ, cudaStream_t st) {
-  if ((M & 15) == 0 && (reinterpret_cast<uintptr_t>(d_occ) & 15) == 0) {
-    const int grid = B < 148 * 8 ? B : 148 * 8;  // persistent: eight 256-thread blocks per SM
-    raster_occupancy_rows_kernel<<<grid, 256, 0, st>>>(d_cells, d_obs_off, B, M, d_occ);
+int launch_raster_occupancy(const int4* d_cells, const int32_t* d_obs_off, int B, int O, int M, uint8_t* d_occ, cudaStream_t st) {
+  if (B <= 0) return 0;
+  CTRM_CUDA_OK(cudaMemsetAsync(d_occ, 0, (size_t)B * M * M, st));
+  if (O > 0) {
+    raster_disks_kernel<<<(unsigned)((O + 7) / 8), 256, 0, st>>>(d_cells, d_obs_off, B, O, M, d_occ);
     CTRM_CUDA_OK(cudaGetLastError());
-    return 0;
   }
-  long long chunks = ((long long)B * M * M + 15) / 16;
-  int blocks = (int)((chunks + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks < 1) blocks = 1;
-  raster_occupancy_kernel<<<blocks, 256, 0, st>>>(d_cells, d_obs_off, B, M, d_occ);
-  CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int launch_passable_masks(const uint8_t* d_occ, int M, const uint8_t* d_stencils, const int32_t* d_stencil_r, int st_ld,
-                          const int32_t* d_pm_inst, const int32_t* d_pm_stencil, int P, uint32_t* d_pmask, cudaStream_t st) {
-  int MW = (M + 31) / 32;
-  long long threads = (long long)P * M * MW * 32;
-  if (threads <= 0) return 0;
-  passable_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_occ, M, MW, d_stencils, d_stencil_r, st_ld,
+int launch_passable_masks(const uint8_t* d_occ, int B, int M, const uint8_t* d_stencils, const int32_t* d_stencil_r, int st_ld,
+                          const int32_t* d_pm_inst, const int32_t* d_pm_stencil, int P, uint32_t* d_blocked, uint32_t* d_pmask,
+                          cudaStream_t st) {
+  const int MW = (M + 31) / 32;
+  if (P <= 0 || B <= 0) return 0;
+  const long long pw = (long long)B * M * MW * 32;
+  pack_blocked_kernel<<<(unsigned)((pw + 255) / 256), 256, 0, st>>>(d_occ, B, M, MW, d_blocked);
+  CTRM_CUDA_OK(cudaGetLastError());
+  const long long threads = (long long)P * M * MW;
+  passable_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_blocked, M, MW, d_stencils, d_stencil_r, st_ld,
                                                                        d_pm_inst, d_pm_stencil, P, d_pmask);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;

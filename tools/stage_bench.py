@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--md", default=None)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--quick", action="store_true", help="one un-warmed launch per kernel on smaller inputs (the target of an ncu capture)")
     args = ap.parse_args()
     import torch
 
@@ -34,7 +35,9 @@ def main():
     rows = []
 
     def timed(fn, iters=args.iters):
-        for _ in range(2):
+        if args.quick:
+            iters = 1
+        for _ in range(0 if args.quick else 2):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -104,7 +107,7 @@ def main():
     # ---------------- swept-circle collision with survivor compaction, O = 10 and O = 64 obstacles per instance
     rng = np.random.RandomState(0)
     for O_per in (10, 64):
-        n = 1 << 25
+        n = 1 << (22 if args.quick else 25)
         Bc = 4096
         ob = np.concatenate([rng.rand(Bc * O_per, 2), rng.uniform(0.025, 0.04, (Bc * O_per, 1))], axis=1)
         ooff = dev((np.arange(Bc + 1) * O_per).astype(np.int32))
