@@ -15,7 +15,7 @@ __device__ __forceinline__ bool valid_move_dev(const Batch& bt, double ax, doubl
                                                double speed2, double rad, int o0, int o1, unsigned int* count) {
   if (!speed_ok(ax, ay, bx, by, speed, speed2)) return false;
   *count += 1;
-  return !any_obstacle_hit(ax, ay, bx, by, rad, bt.obs_xyr, o0, o1);
+  return !any_obstacle_hit_f4(ax, ay, bx, by, rad, bt.obs_xyr, bt.obs_f4, o0, o1);
 }
 
 // T = max_i len(trm_i.V) - 1 per instance   (utils.py:147)

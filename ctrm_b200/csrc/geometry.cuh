@@ -28,3 +28,30 @@ __device__ __forceinline__ bool any_obstacle_hit(double fx, double fy, double tx
   }
   return hit;
 }
+
+// The same `any over obstacles`, with the far obstacles rejected in fp32 from a float copy (x, y, rad, 0) of each obstacle:
+// one 16-byte load and eight fp32 operations per far obstacle instead of three 8-byte loads and ten fp64 operations.
+// Conservative: the box is grown by rad_sum + 1e-5 while the float copies and the float box are each within 1.2e-7 of the
+// doubles for coordinates in the unit square (|coordinate| <= 16 keeps the total rounding below 1e-5), so a rejected obstacle
+// is farther than rad_sum from every point of the segment and the exact test could only answer "no hit".
+__device__ __forceinline__ bool any_obstacle_hit_f4(double fx, double fy, double tx, double ty, double rad,
+                                                    const double* __restrict__ obs_xyr, const float4* __restrict__ obs_f4,
+                                                    int o0, int o1) {
+  bool hit = false;
+  const float lox = (float)fmin(fx, tx), hix = (float)fmax(fx, tx), loy = (float)fmin(fy, ty), hiy = (float)fmax(fy, ty);
+  const float radf = (float)rad + 1e-5f;
+  for (int o = o0; o < o1; o += 4) {
+    float4 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = __ldg(&obs_f4[min(o + j, o1 - 1)]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (o + j >= o1) break;
+      const float R = radf + q[j].z;
+      if (q[j].x < lox - R || q[j].x > hix + R || q[j].y < loy - R || q[j].y > hiy + R) continue;
+      const double* g = obs_xyr + 3 * (size_t)(o + j);
+      hit = hit || sweep_static(fx, fy, tx, ty, __ldg(g), __ldg(g + 1), f64add(rad, __ldg(g + 2)));
+    }
+  }
+  return hit;
+}
