@@ -475,8 +475,9 @@ def gpu_arm(args):
     from ctrm_b200 import PipelinedBuilder
 
     e2e_steps = max(2, args.steps)
-    pipe = PipelinedBuilder(WEIGHTS, local, depth=3)
-    for _ in pipe.map([instances] * 3, seed=seed, instance_id_base=rank * B, **PARAMS):
+    depth = 3 if world == 1 else 2  # per rank; every context owns pinned staging for one batch's result (4.4 GB)
+    pipe = PipelinedBuilder(WEIGHTS, local, depth=depth)
+    for _ in pipe.map([instances] * depth, seed=seed, instance_id_base=rank * B, **PARAMS):
         pass
     barrier()
     t0 = time.perf_counter()
@@ -599,8 +600,8 @@ def gpu_arm(args):
                 device_ms=dict(total=tim["total_ms"], rollout=tim["rollout_ms"], finalize=tim["finalize_ms"], graph_replays=tim["steps"]),
                 clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                         ms_per_step=e2e_t[0].item(), steps=e2e_steps,
-                                        api="PipelinedBuilder.map (3 contexts on the GPU, the first with a high-priority stream: packing, copies and "
-                                            "export of one batch overlap the roll-out kernels of another)"),
+                                        api=f"PipelinedBuilder.map ({depth} contexts on the GPU, the first with a high-priority stream: packing, "
+                                            "copies and export of one batch overlap the roll-out kernels of another)"),
                 gpu_launches=int(launches_all), roofline=roofline, kernels=kernels, cpu_baseline=cpu, planner=planner,
                 strong_scaling=strong, other_configs=other,
                 latency_ms_single_instance=(other or {}).get("demo_instance", {}).get("latency_ms"))

@@ -100,6 +100,7 @@ struct ctrm_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;  // internal non-blocking stream of the driver (graph capture is illegal on stream 0)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: the host thread sleeps instead of spinning while a long chunk runs
   // weights
   DevArena w_arena;
   DevModel model{};
@@ -135,6 +136,16 @@ struct ctrm_ctx {
   int64_t kernel_n[16] = {0};
 };
 
+// wait for the context's stream.  Large batches (a chunk of steps runs for tens of milliseconds, an export for a hundred): the
+// thread sleeps on a blocking event — several contexts per GPU and several ranks per box otherwise keep one host core each
+// spinning in cudaStreamSynchronize and starve the threads that pack, copy and launch.  Small batches: spin (lowest latency).
+static cudaError_t wait_stream(ctrm_ctx* c, bool blocking) {
+  if (!blocking) return cudaStreamSynchronize(c->stream);
+  cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(c->ev_block);
+}
+
 static int sync_in(ctrm_ctx* c, cudaStream_t user) {
   CTRM_CUDA_OK(cudaEventRecord(c->ev_in, user));
   CTRM_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
@@ -164,6 +175,7 @@ extern "C" int ctrm_ctx_create(int device, ctrm_ctx** out) {
   CTRM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
   CTRM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
   for (int i = 0; i < 4; ++i) CTRM_CUDA_OK(cudaEventCreate(&c->ev_t[i]));
+  CTRM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
   CTRM_CUDA_OK(cudaMallocHost(&c->h_ndone, sizeof(int32_t)));
   *out = c;
   return 0;
@@ -198,6 +210,7 @@ extern "C" void ctrm_ctx_destroy(ctrm_ctx* c) {
   if (c->h_ndone) cudaFreeHost(c->h_ndone);
   for (int i = 0; i < 4; ++i)
     if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
+  if (c->ev_block) cudaEventDestroy(c->ev_block);
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -880,7 +893,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
       if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "cudaGraphLaunch"); break; }
       steps += chunk;
       ce = cudaMemcpyAsync(c->h_ndone, bt.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-      if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+      if (ce == cudaSuccess) ce = wait_stream(c, bt.A >= 20000);
       if (ce != cudaSuccess) { rc = ctrm_fail_cuda(ce, "roll-out step loop"); break; }
       if (*c->h_ndone >= bt.B) break;
       if (*c->h_ndone > last_done) {  // instances finished during this chunk: drop their rows
@@ -924,7 +937,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   launches += 6;
   CTRM_CUDA_OK(cudaEventRecord(c->ev_t[3], st));
   CTRM_CUDA_OK(cudaMemcpyAsync(c->totals, c->d_totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  CTRM_CUDA_OK(wait_stream(c, bt.A >= 20000));
   CTRM_CUDA_OK(cudaEventElapsedTime(&c->ms[0], c->ev_t[0], c->ev_t[3]));
   CTRM_CUDA_OK(cudaEventElapsedTime(&c->ms[1], c->ev_t[1], c->ev_t[2]));
   CTRM_CUDA_OK(cudaEventElapsedTime(&c->ms[2], c->ev_t[2], c->ev_t[3]));
@@ -973,7 +986,7 @@ extern "C" int ctrm_export_csr(ctrm_ctx* c, int32_t* layer_ptr, double* pos, int
   }
   if (n_layers) CTRM_CUDA_OK(cudaMemcpyAsync(n_layers, bt.nlayers, (size_t)bt.A * sizeof(int32_t), kind, st));
   if (cnt_collide) CTRM_CUDA_OK(cudaMemcpyAsync(cnt_collide, bt.cnt_collide, (size_t)bt.B * sizeof(int64_t), kind, st));
-  if (!dst_is_device) CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  if (!dst_is_device) CTRM_CUDA_OK(wait_stream(c, bt.A >= 20000));
   CHECK(sync_out(c, (cudaStream_t)user_stream));
   return 0;
 }
@@ -1014,7 +1027,7 @@ extern "C" int ctrm_export_csr_compact(ctrm_ctx* c, uint8_t* layer_cnt, double* 
   if (agent_e0) CTRM_CUDA_OK(cudaMemcpyAsync(agent_e0 + bt.A, c->d_totals + 1, sizeof(int64_t), kind, st));
   if (n_layers) CTRM_CUDA_OK(cudaMemcpyAsync(n_layers, bt.nlayers, (size_t)bt.A * sizeof(int32_t), kind, st));
   if (cnt_collide) CTRM_CUDA_OK(cudaMemcpyAsync(cnt_collide, bt.cnt_collide, (size_t)bt.B * sizeof(int64_t), kind, st));
-  if (!dst_is_device) CTRM_CUDA_OK(cudaStreamSynchronize(st));
+  if (!dst_is_device) CTRM_CUDA_OK(wait_stream(c, bt.A >= 20000));
   CHECK(sync_out(c, (cudaStream_t)user_stream));
   return 0;
 }

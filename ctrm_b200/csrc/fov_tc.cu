@@ -2,8 +2,10 @@
 // learning/formats/format_input.py:311-312) + the fov_vain rows of the AgentEncoder's first layer
 // (learning/model/agent_encoder.py:57-60; format_input.py:328-331).
 //
-// The FOV tensor is binary, so it travels as UNSIGNED 8-BIT operand tiles: [tile of 128 agents][chunk of 96 inputs]
-// [128 x 96 canonical UMMA tile] (12,288 B each, written in that form by the raster kernel, raster.cu).
+// The FOV tensor is binary, so it crosses HBM as BITS: [tile of 128 agents][chunk of 96 inputs][row][12 bytes] (1,536 B per
+// chunk, written by the raster kernel, raster.cu).  The TMA producer drops a chunk's bits into the tail of the stage's A area
+// and four otherwise idle warps expand them in place to the UNSIGNED 8-BIT canonical UMMA tile [128 x 96] (12,288 B) while the
+// previous chunk's MMAs run.
 // First layers of both encoders side by side: D[128 x 64] = FOV[128 x 2F^2] . W0[2F^2 x 64] on the INTEGER tensor cores
 // (tcgen05.mma kind::i8): the weights are cut into four signed base-128 fixed-point digits (tc.cuh), every digit product
 // is an integer and the int32 accumulators are exact; the four digit accumulators are combined in fp64.  One byte per
@@ -18,6 +20,7 @@
 #define FT_THREADS 256
 #define FT_CHUNK 96
 #define FT_A_CHUNK 12288u   // tile_bytes8(128, 96)
+#define FT_A_BITS 1536u     // the same chunk as bits: 128 rows x 12 bytes
 #define FT_W_DIGIT 6144u    // tile_bytes8(64, 96)
 #define FT_W_CHUNK 24576u   // four digits
 #define FT_STAGES 3
@@ -58,24 +61,22 @@ __global__ void fov_w0_prep_kernel(const float* __restrict__ w0 /*[KD][64]*/, in
   }
 }
 
-// ---- f32 FOV tensor [A][KD] -> bf16 operand tiles (stage entry point ctrm_encode_features only) ----
+// ---- f32 FOV tensor [A][KD] -> bit tiles (stage entry point ctrm_encode_features only) ----
 __global__ void fov_f32_to_tiles_kernel(const float* __restrict__ fov, int A, int KD, int n_chunks, uint8_t* __restrict__ tiles) {
-  const long long total = (long long)((A + 127) / 128) * 128 * n_chunks * (FT_CHUNK / 16);
+  const int nw = n_chunks * 3;  // 32-bit words per row
+  const long long total = (long long)((A + 127) / 128) * 128 * nw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int per_row = n_chunks * (FT_CHUNK / 16);
-    const int a = (int)(i / per_row), k16 = (int)(i - (long long)a * per_row);
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    const int a = (int)(i / nw), w = (int)(i - (long long)a * nw);
+    uint32_t bits = 0u;
     if (a < A) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int k = k16 * 16 + j;
-        const float v = (k < KD) ? fov[(size_t)a * KD + k] : 0.f;
-        w[j >> 2] |= (v != 0.f ? 1u : 0u) << (8 * (j & 3));  // the FOV tensor is {0, 1}
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const int k = 32 * w + j;
+        if (k < KD && fov[(size_t)a * KD + k] != 0.f) bits |= 1u << j;  // the FOV tensor is {0, 1}
       }
     }
-    const int c = k16 / (FT_CHUNK / 16), kk = (k16 - c * (FT_CHUNK / 16)) * 16;
-    uint8_t* dst = tiles + ((size_t)(a >> 7) * n_chunks + c) * FT_A_CHUNK + tc::elem_offset8(a & 127, kk, FT_CHUNK);
-    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    const int c = w / 3, jw = w - 3 * c;
+    *reinterpret_cast<uint32_t*>(tiles + ((size_t)((a >> 7) * n_chunks + c) * 128 + (a & 127)) * 12 + 4 * jw) = bits;
   }
 }
 
@@ -128,8 +129,9 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fov_encode_tc_kernel(const uint
   float* b1 = cf + 64;     // 64
   float* b2 = cf + 128;    // 64
   float* bp = cf + 192;    // 32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cf + FT_NF);  // full[FT_STAGES], empty[FT_STAGES], done, tail weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FT_STAGES + 2);
+  // full[FT_STAGES], empty[FT_STAGES], done, tail weights landed, ready[FT_STAGES] (A chunk expanded: 128 arrivals)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cf + FT_NF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * FT_STAGES + 2);
   uint8_t* Ht = stage0;    // hidden tiles reuse the operand stages once layer 0 has completed
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;  // two threads per row; TMEM lane group = warp % 4 for both halves
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fov_encode_tc_kernel(const uint
   if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
   if (tid == 0) {
     for (int i = 0; i < 2 * FT_STAGES + 2; ++i) tc::mbar_init(tc::smem_u32(&bars[i]), 1);
+    for (int i = 0; i < FT_STAGES; ++i) tc::mbar_init(tc::smem_u32(&bars[2 * FT_STAGES + 2 + i]), 128);
     // biases: the constant tail of the prebuilt image (fov_encode_image_kernel), through the TMA engine
     tc::tma_load_image(cf, w_image + FT_TAILW_BYTES, 224 * 4, tc::smem_u32(&bars[2 * FT_STAGES]));
   }
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fov_encode_tc_kernel(const uint
   const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[FT_STAGES]),
                  done = tc::smem_u32(&bars[2 * FT_STAGES]);
   const uint32_t hb = tc::smem_u32(&bars[2 * FT_STAGES + 1]);
+  const uint32_t ready0 = tc::smem_u32(&bars[2 * FT_STAGES + 2]);
   uint32_t hphase = 0;
   tc::mbar_wait(done, 0);  // biases have landed; the tail MMA rounds continue on the same barrier with phase 1
   const uint32_t sStage = tc::smem_u32(stage0), sH = tc::smem_u32(Ht), sW1 = tc::smem_u32(W1c), sW2 = tc::smem_u32(W2c),
@@ -183,18 +187,42 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fov_encode_tc_kernel(const uint
     if (!__syncthreads_or(live)) continue;
     // ---- layer 0: streamed exact digit products
     if (tid == 0) {  // producer
-      const uint8_t* gA = fov_tiles + (size_t)tile * n_chunks * FT_A_CHUNK;
+      const uint8_t* gA = fov_tiles + (size_t)tile * n_chunks * FT_A_BITS;
       for (int c = 0; c < n_chunks; ++c) {
         const uint32_t u = it + c, s = u % FT_STAGES;
         if (u >= FT_STAGES) tc::mbar_wait(empty0 + 8 * s, ((u / FT_STAGES) - 1) & 1u);
-        tc::mbar_expect_tx(full0 + 8 * s, FT_STAGE);
-        tc::tma_bulk_g2s_evict_first(sStage + s * FT_STAGE, gA + (size_t)c * FT_A_CHUNK, FT_A_CHUNK, full0 + 8 * s);
+        tc::mbar_expect_tx(full0 + 8 * s, FT_A_BITS + FT_W_CHUNK);
+        // the chunk's bits land in the LAST 1,536 bytes of the stage's A area and are expanded in place below
+        tc::tma_bulk_g2s_evict_first(sStage + s * FT_STAGE + (FT_A_CHUNK - FT_A_BITS), gA + (size_t)c * FT_A_BITS, FT_A_BITS,
+                                     full0 + 8 * s);
         tc::tma_bulk_g2s(sStage + s * FT_STAGE + FT_A_CHUNK, w0_tiles + (size_t)c * FT_W_CHUNK, FT_W_CHUNK, full0 + 8 * s);
+      }
+    } else if (tid >= 128) {  // expanders: thread = row; 96 bits -> 96 bytes {0, 1} in the canonical 8-bit UMMA layout
+      const int er = tid - 128;
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t u = it + c, s = u % FT_STAGES;
+        uint8_t* sa = stage0 + (size_t)s * FT_STAGE;
+        tc::mbar_wait(full0 + 8 * s, (u / FT_STAGES) & 1u);
+        const uint32_t* bp = reinterpret_cast<const uint32_t*>(sa + (FT_A_CHUNK - FT_A_BITS) + er * 12);
+        const uint32_t bw[3] = {bp[0], bp[1], bp[2]};
+        // rows 112..127 expand INTO the region the bits arrived in: everybody reads before anybody writes
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* dst = sa + (size_t)(er >> 3) * tc::sbo_bytes8(FT_CHUNK) + (er & 7) * 16;
+#pragma unroll
+        for (int g = 0; g < 6; ++g) {
+          const uint32_t b16 = (bw[g >> 1] >> (16 * (g & 1))) & 0xFFFFu;
+          // a nibble times 0x00204081 puts bit i at bit 8 i: four bytes of 0 / 1
+          *reinterpret_cast<uint4*>(dst + g * 128) =
+              make_uint4(((b16 & 0xFu) * 0x00204081u) & 0x01010101u, (((b16 >> 4) & 0xFu) * 0x00204081u) & 0x01010101u,
+                         (((b16 >> 8) & 0xFu) * 0x00204081u) & 0x01010101u, ((b16 >> 12) * 0x00204081u) & 0x01010101u);
+        }
+        tc::fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        tc::mbar_arrive(ready0 + 8 * s);
       }
     } else if (tid == 32) {  // MMA issuer
       for (int c = 0; c < n_chunks; ++c) {
         const uint32_t u = it + c, s = u % FT_STAGES;
-        tc::mbar_wait(full0 + 8 * s, (u / FT_STAGES) & 1u);
+        tc::mbar_wait(ready0 + 8 * s, (u / FT_STAGES) & 1u);  // the weights landed (full) and the A chunk is expanded
         tc::fence_after_sync();
         const uint32_t sa = sStage + s * FT_STAGE, sw = sa + FT_A_CHUNK;
 #pragma unroll
@@ -285,7 +313,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fov_encode_tc_kernel(const uint
 
 // ---- host side ----
 int fov_n_chunks(int F) { return (2 * F * F + FT_CHUNK - 1) / FT_CHUNK; }
-size_t fov_tiles_bytes(int A, int F) { return (size_t)((A + 127) / 128) * fov_n_chunks(F) * FT_A_CHUNK; }
+size_t fov_tiles_bytes(int A, int F) { return (size_t)((A + 127) / 128) * fov_n_chunks(F) * FT_A_BITS; }
 size_t fov_w0_tiles_bytes(int F) { return (size_t)fov_n_chunks(F) * FT_W_CHUNK; }
 
 int launch_fov_w0_prep(const float* d_w0, int F, int w0_exp, uint8_t* d_out, cudaStream_t st) {

@@ -283,9 +283,10 @@ __global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// FOV raster, operand-tile output for the tensor-core encoders (fov_tc.cu): the same crop, written as unsigned bytes {0, 1}
-// into [tile of 128 rows][chunk of 96 inputs][128 x 96 canonical 8-bit UMMA tile].  A block rasterises 8 consecutive rows
-// into shared memory; 8 rows x 16 bytes are one 128-byte line of a core matrix, so every global store is a full line.
+// FOV raster for the tensor-core encoders (fov_tc.cu): the same crop, one BIT per input, stored as
+// [tile of 128 rows][chunk of 96 inputs][row][12 bytes].  A warp rasterises its agent's crop into a byte row in shared
+// memory (cells outside the map stay 0), packs it and stores 24 words; fov_encode expands a chunk to the canonical 8-bit UMMA
+// tile inside ITS shared memory, so the FOV tensor crosses HBM as 96 bytes per agent-step in each direction instead of 768.
 // ------------------------------------------------------------------------------------------------
 #define RT_APB 8
 #define RT_CHUNK 96
@@ -302,7 +303,6 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
   const int F = FT > 0 ? FT : F_rt;
   const int FF = F * F, KD = 2 * FF, Kpad = n_chunks * RT_CHUNK;
   const int row_bytes = Kpad + 16;  // one byte per input; +16: rows land in different banks for the 16-byte read-out
-  __shared__ int live_row[RT_APB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // rows: agents of the unfinished instances (live_agent, rebuilt between graph chunks) or all agents
   const int n_rows = live_agent != nullptr ? *n_live : A;
@@ -361,20 +361,21 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
       }
     }
   }
-  if (lane == 0) live_row[warp] = live ? 1 : 0;
-  if (!__syncthreads_or(live)) return;
-  const int n16 = RT_APB * (Kpad / 16);
-  for (int idx = threadIdx.x; idx < n16; idx += blockDim.x) {
-    const int rr = idx & (RT_APB - 1), k16 = idx >> 3;
-    if (!live_row[rr]) continue;  // finished instance (or beyond A: zero-filled at upload): nothing to write
-    const int ar = a0 + rr;
-    const int c = k16 / (RT_CHUNK / 16), kk = (k16 - c * (RT_CHUNK / 16)) * 16;
-    const int r = ar & 127;
-    const size_t off = ((size_t)(ar >> 7) * n_chunks + c) * (size_t)(128 * RT_CHUNK) +
-                       (size_t)(r >> 3) * (RT_CHUNK / 16) * 128 + (size_t)(kk >> 4) * 128 + (size_t)(r & 7) * 16;
-    // streaming store: the tiles are read exactly once (by fov_encode); keeping them out of the way lets the cost-to-go
-    // crops, which overlap ~85% between consecutive steps, survive in L2
-    __stcs(reinterpret_cast<uint4*>(tiles + off), *reinterpret_cast<const uint4*>(rt_smem + (size_t)rr * row_bytes + (size_t)k16 * 16));
+  // ---- pack the row to BITS and store it: [tile of 128 rows][chunk of 96 inputs][row][12 bytes].  fov_encode expands a
+  //      chunk back to the 8-bit UMMA operand layout inside shared memory (fov_tc.cu), so the crop leaves the SM as 96 bytes
+  //      per agent-step instead of 768 and is read back as 96.  Word w of the row = inputs 32 w .. 32 w + 31, bit = input.
+  if (live) {
+    __syncwarp();
+    const int nw = Kpad >> 5;  // 24 words for the trained F = 19 (n_chunks x 96 inputs)
+    for (int w = lane; w < nw; w += 32) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(t + 32 * w);
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bits |= (((src[q] * 0x01020408u) >> 24) & 0xFu) << (4 * q);  // four 0/1 bytes -> a nibble
+      const int c = w / 3, j = w - 3 * c;
+      const int r = row & 127;
+      __stcs(reinterpret_cast<uint32_t*>(tiles + ((size_t)((row >> 7) * n_chunks + c) * 128 + r) * 12 + 4 * j), bits);
+    }
   }
 }
 

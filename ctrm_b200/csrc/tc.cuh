@@ -244,6 +244,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
