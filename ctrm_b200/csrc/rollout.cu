@@ -651,7 +651,7 @@ __device__ __forceinline__ bool hits_any_serial(const Batch& bt, int o0, int nO,
 }
 
 template <int W>
-__global__ void __launch_bounds__(128) step_thread_kernel(Batch bt) {
+__global__ void __launch_bounds__(128, 5) step_thread_kernel(Batch bt) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row == 0 && bt.n_learn != nullptr) *bt.n_learn = 0;  // see step_kernel
   if (row >= (bt.live_agent != nullptr ? *bt.n_live : bt.A)) return;
@@ -736,20 +736,28 @@ __global__ void __launch_bounds__(128) step_thread_kernel(Batch bt) {
   const double2* vp_prev = reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t - 1, 0)]);
   const double2* vp_t = reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t, 0)]);
   const double2* vp_next = reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, t + 1, 0)]);
-#pragma unroll 4
-  for (int sl = 0; sl < n_prev; ++sl) {
-    const double2 p = vp_prev[sl];
-    if (dist2(p.x, p.y, lx, ly) <= speed2) Pc[sl >> 5] |= 1u << (sl & 31);
-  }
-#pragma unroll 4
-  for (int sl = 0; sl < n_next; ++sl) {
-    const double2 p = vp_next[sl];
-    if (dist2(p.x, p.y, lx, ly) <= speed2) Cc[sl >> 5] |= 1u << (sl & 31);
-  }
-#pragma unroll 4
-  for (int sl = 0; sl < n_t; ++sl) {  // merge candidates   utils.py:86-89
-    const double2 p = vp_t[sl];
-    if (dist2(p.x, p.y, lx, ly) <= merge2) Mg[sl >> 5] |= 1u << (sl & 31);
+  {
+    // the three layers side by side, three slots of each per round: nine independent 16-byte loads in flight, so the pass costs
+    // ceil(max layer size / 3) memory round trips instead of one per four vertices of every layer in turn
+    const int n_max3 = max(n_prev, max(n_next, n_t));
+    for (int s0 = 0; s0 < n_max3; s0 += 3) {
+      double2 pp[3], pn[3], pt[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int sl = s0 + j;
+        pp[j] = sl < n_prev ? vp_prev[sl] : make_double2(0.0, 0.0);
+        pn[j] = sl < n_next ? vp_next[sl] : make_double2(0.0, 0.0);
+        pt[j] = sl < n_t ? vp_t[sl] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int sl = s0 + j;
+        const uint32_t bit = 1u << (sl & 31);
+        if (sl < n_prev && dist2(pp[j].x, pp[j].y, lx, ly) <= speed2) Pc[sl >> 5] |= bit;
+        if (sl < n_next && dist2(pn[j].x, pn[j].y, lx, ly) <= speed2) Cc[sl >> 5] |= bit;
+        if (sl < n_t && dist2(pt[j].x, pt[j].y, lx, ly) <= merge2) Mg[sl >> 5] |= bit;  // merge candidates   utils.py:86-89
+      }
+    }
   }
   // pass 2: swept tests of the vertices within reach; parents as (parent -> loc) utils.py:58-69, children as (child -> loc) :72-84
 #pragma unroll
