@@ -290,20 +290,6 @@ __global__ void __launch_bounds__(APB * 32) fov_raster_kernel(const uint8_t* __r
 // ------------------------------------------------------------------------------------------------
 #define RT_APB 8
 #define RT_CHUNK 96
-// OR a nibble of cell bits into a bit row at bit position p (p may be negative by up to 3 for a group that starts left of the
-// crop: those low bits are already masked out)
-__device__ __forceinline__ void rt_place(uint32_t* tw, int p, uint32_t m) {
-  if (!m) return;
-  if (p < 0) {
-    m >>= -p;
-    p = 0;
-    if (!m) return;
-  }
-  const int w = p >> 5, sft = p & 31;
-  atomicOr(&tw[w], m << sft);
-  if (sft > 28 && (m >> (32 - sft))) atomicOr(&tw[w + 1], m >> (32 - sft));
-}
-
 template <int FT>  // FT > 0: compile-time fov_size (constant divisions, unrolled loads); 0: run-time F
 __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uint8_t* __restrict__ occ,
                                                                       const uint16_t* __restrict__ ctg,
@@ -315,8 +301,8 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
                                                                       const int32_t* __restrict__ n_live) {
   extern __shared__ __align__(16) uint8_t rt_smem[];
   const int F = FT > 0 ? FT : F_rt;
-  const int FF = F * F, Kpad = n_chunks * RT_CHUNK;
-  const int nw = Kpad >> 5;  // 32-bit words of a bit row (24 for the trained F = 19)
+  const int FF = F * F, KD = 2 * FF, Kpad = n_chunks * RT_CHUNK;
+  const int row_bytes = Kpad + 16;  // one byte per input; +16: rows land in different banks for the 16-byte read-out
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // rows: agents of the unfinished instances (live_agent, rebuilt between graph chunks) or all agents
   const int n_rows = live_agent != nullptr ? *n_live : A;
@@ -324,65 +310,72 @@ __global__ void __launch_bounds__(RT_APB * 32) fov_raster_tiles_kernel(const uin
   if (a0 >= n_rows) return;
   const int row = a0 + warp;
   const int a = row < n_rows ? (live_agent != nullptr ? live_agent[row] : row) : A;
-  uint32_t* tw = reinterpret_cast<uint32_t*>(rt_smem) + (size_t)warp * (nw + 1);  // the warp's bit row (+1: spill-over word)
-  if (a >= A) return;
-  const int b = agent_inst[a];
-  if (skip_inst != nullptr && skip_inst[b] != 0) return;  // finished instance
-  const uint8_t* o = occ + (size_t)b * M * M;
-  const uint16_t* c = ctg + (size_t)a * ctg_field_elems(M, 1);
-  const int cx = grid_cell(pos[2 * a + 0], M), cy = grid_cell(pos[2 * a + 1], M);
-  const int buf = (F - 1) / 2;
-  const bool centre_in = cx < M && cy < M;
-  const int cc = centre_in ? (int)c[ctg_index(cx, cy, M, 1)] : CTRM_UNREACH;
-  const bool c_reach = cc != CTRM_UNREACH;
-  // The crop is built as BITS from the start (cells outside the map stay 0 in both channels): a lane visits (row xf, aligned
-  // group of four y cells) work items — one 8-byte load of the micro-tiled cost field and one 4-byte load of the occupancy row
-  // each — forms the two 4-bit nibbles of the group (free space; strictly closer to the goal than the centre cell) and ORs them
-  // into the warp's 24-word row in shared memory.  Half the instructions of writing bytes and packing them afterwards.
-  for (int i = lane; i <= nw; i += 32) tw[i] = 0u;
-  __syncwarp();
-  if (centre_in) {
-    const int ylo = cy - buf;
-    const int g0 = ylo >> 2;                          // floor(ylo / 4), also for negative ylo
-    const int NG = ((cy + buf) >> 2) - g0 + 1;        // groups per crop row
-    const unsigned inv = 65536u / (unsigned)NG + 1u;  // it / NG == (it * inv) >> 16 for it < F * NG <= 1071
-    const bool occ_vec = (M & 3) == 0;
-    for (int it = lane; it < F * NG; it += 32) {
-      const int xf = (int)(((unsigned)it * inv) >> 16), gy = it - xf * NG;
-      const int x = cx - buf + xf, yb = (g0 + gy) << 2;
-      if (x < 0 || x >= M || yb < 0 || yb >= M) continue;  // yb is a multiple of 4: negative groups are entirely outside
-      const uint2 cw = __ldg(reinterpret_cast<const uint2*>(&c[ctg_index(x, yb, M, 1)]));
-      uint32_t ow;
-      if (occ_vec) {
-        ow = __ldg(reinterpret_cast<const uint32_t*>(&o[x * M + yb]));
-      } else {
-        ow = 0u;
+  uint8_t* t = rt_smem + (size_t)warp * row_bytes;
+  bool live = false;
+  if (a < A) {
+    const int b = agent_inst[a];
+    live = (skip_inst == nullptr) || (skip_inst[b] == 0);
+    if (live) {
+      const uint8_t* o = occ + (size_t)b * M * M;
+      const uint16_t* c = ctg + (size_t)a * ctg_field_elems(M, 1);
+      const int cx = grid_cell(pos[2 * a + 0], M), cy = grid_cell(pos[2 * a + 1], M);
+      const int buf = (F - 1) / 2;
+      const bool centre_in = cx < M && cy < M;
+      const int cc = centre_in ? (int)c[ctg_index(cx, cy, M, 1)] : CTRM_UNREACH;
+      const bool c_reach = cc != CTRM_UNREACH;
+      // zero the row (cells outside the map stay 0 in both channels), then visit the crop as (row xf, aligned group of four
+      // y cells): one 8-byte load of the micro-tiled cost field and one 4-byte load of the occupancy row per work item
+      for (int i = lane; i < Kpad / 16; i += 32) reinterpret_cast<uint4*>(t)[i] = make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();
+      if (centre_in) {
+        const int ylo = cy - buf;
+        const int g0 = ylo >> 2;                          // floor(ylo / 4), also for negative ylo
+        const int NG = ((cy + buf) >> 2) - g0 + 1;        // groups per crop row
+        const unsigned inv = 65536u / (unsigned)NG + 1u;  // it / NG == (it * inv) >> 16 for it < F * NG <= 1071
+        const bool occ_vec = (M & 3) == 0;
+        for (int it = lane; it < F * NG; it += 32) {
+          const int xf = (int)(((unsigned)it * inv) >> 16), gy = it - xf * NG;
+          const int x = cx - buf + xf, yb = (g0 + gy) << 2;
+          if (x < 0 || x >= M || yb < 0 || yb >= M) continue;  // yb is a multiple of 4: negative groups are entirely outside
+          const uint2 cw = __ldg(reinterpret_cast<const uint2*>(&c[ctg_index(x, yb, M, 1)]));
+          uint32_t ow;
+          if (occ_vec) {
+            ow = __ldg(reinterpret_cast<const uint32_t*>(&o[x * M + yb]));
+          } else {
+            ow = 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (yb + j < M) ow |= (uint32_t)__ldg(&o[x * M + yb + j]) << (8 * j);
-      }
-      const uint32_t cv[4] = {cw.x & 0xFFFFu, cw.x >> 16, cw.y & 0xFFFFu, cw.y >> 16};
-      uint32_t m0 = 0u, m1 = 0u;
+            for (int j = 0; j < 4; ++j)
+              if (yb + j < M) ow |= (uint32_t)__ldg(&o[x * M + yb + j]) << (8 * j);
+          }
+          const uint32_t cv[4] = {cw.x & 0xFFFFu, cw.x >> 16, cw.y & 0xFFFFu, cw.y >> 16};
+          uint8_t* t0 = t + xf * F + (yb - ylo);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int yf = yb - ylo + j;
-        if (yf < 0 || yf >= F || yb + j >= M) continue;
-        const int _c = (int)cv[j];
-        m0 |= (((ow >> (8 * j)) & 0xFFu) ? 0u : 1u) << j;
-        m1 |= ((_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 1u : 0u) << j;
+          for (int j = 0; j < 4; ++j) {
+            const int yf = yb - ylo + j;
+            if (yf < 0 || yf >= F || yb + j >= M) continue;
+            const int _c = (int)cv[j];
+            t0[j] = ((ow >> (8 * j)) & 0xFFu) ? 0 : 1;
+            t0[FF + j] = (_c != CTRM_UNREACH && (!c_reach || _c < cc)) ? 1 : 0;
+          }
+        }
       }
-      const int p0 = xf * F + (yb - ylo);  // input index of cell j = 0 (channel 0); channel 1 sits F^2 further
-      rt_place(tw, p0, m0);
-      rt_place(tw, p0 + FF, m1);
     }
   }
-  __syncwarp();
-  // ---- store the bit row: [tile of 128 rows][chunk of 96 inputs][row][12 bytes].  fov_encode expands a chunk back to the
-  //      8-bit UMMA operand layout inside shared memory (fov_tc.cu), so the crop leaves the SM as 96 bytes per agent-step
-  //      instead of 768 and is read back as 96.  Word w of the row = inputs 32 w .. 32 w + 31, bit = input.
-  for (int w = lane; w < nw; w += 32) {
-    const int cch = w / 3, j = w - 3 * cch;
-    __stcs(reinterpret_cast<uint32_t*>(tiles + ((size_t)((row >> 7) * n_chunks + cch) * 128 + (row & 127)) * 12 + 4 * j), tw[w]);
+  // ---- pack the row to BITS and store it: [tile of 128 rows][chunk of 96 inputs][row][12 bytes].  fov_encode expands a
+  //      chunk back to the 8-bit UMMA operand layout inside shared memory (fov_tc.cu), so the crop leaves the SM as 96 bytes
+  //      per agent-step instead of 768 and is read back as 96.  Word w of the row = inputs 32 w .. 32 w + 31, bit = input.
+  if (live) {
+    __syncwarp();
+    const int nw = Kpad >> 5;  // 24 words for the trained F = 19 (n_chunks x 96 inputs)
+    for (int w = lane; w < nw; w += 32) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(t + 32 * w);
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bits |= (((src[q] * 0x01020408u) >> 24) & 0xFu) << (4 * q);  // four 0/1 bytes -> a nibble
+      const int c = w / 3, j = w - 3 * c;
+      const int r = row & 127;
+      __stcs(reinterpret_cast<uint32_t*>(tiles + ((size_t)((row >> 7) * n_chunks + c) * 128 + r) * 12 + 4 * j), bits);
+    }
   }
 }
 
@@ -457,7 +450,7 @@ int launch_fov_raster_tiles(const uint8_t* d_occ, const uint16_t* d_ctg, const i
                             const int32_t* d_live_agent, const int32_t* d_n_live, cudaStream_t st) {
   if (layout != 1) return ctrm_fail(-1, "fov_raster_tiles reads the micro-tiled cost-to-go layout only");
   if (A <= 0) return 0;
-  const size_t smem = (size_t)RT_APB * ((size_t)n_chunks * 3 + 1) * sizeof(uint32_t);  // one bit row per warp
+  const size_t smem = (size_t)RT_APB * ((size_t)n_chunks * RT_CHUNK + 16);
   const int blocks = (A + RT_APB - 1) / RT_APB;
   if (F == 19) {  // the trained configuration
     fov_raster_tiles_kernel<19><<<blocks, RT_APB * 32, smem, st>>>(d_occ, d_ctg, d_agent_inst, d_pos, d_skip_inst, A, M, F, n_chunks,
