@@ -234,8 +234,8 @@ class ClockSampler:
 def algorithmic_work(kernel, agent_steps, pair_steps, K, F=19, avg_layer=20.0):
     """ALGORITHMIC bytes / flops of one kernel over the counted units (DESIGN.md 'Kernels')"""
     FF = F * F
-    if kernel == "fov_raster":      # write 2F^2 one-byte {0,1} operand-tile entries, read F^2 (1 B occ + 2 B cost) + position
-        return dict(bound="hbm", work=agent_steps * (2 * FF * 1 + FF * 3 + 16), unit="GB/s")
+    if kernel == "fov_raster":      # write 2F^2 BITS (96 B per row), read F^2 (1 B occ + 2 B cost) + position
+        return dict(bound="hbm", work=agent_steps * (96 * ((2 * FF + 767) // 768) + FF * 3 + 16), unit="GB/s")
     if kernel == "fov_encode":      # 2 x (722->32->32->32) + the 32x32 vain projection
         return dict(bound="tensor", work=agent_steps * 2.0 * (2 * FF * 64 + 4 * 1024 + 1024), unit="TFLOP/s")
     if kernel == "agent_comm":      # per ordered pair: 11x32 + 32x32 + 32x42 MAC
@@ -474,7 +474,7 @@ def gpu_arm(args):
     #      other's kernels (two contexts on this GPU, alternating)
     from ctrm_b200 import PipelinedBuilder
 
-    e2e_steps = max(2, args.steps)
+    e2e_steps = max(6, args.steps)  # a stream of batches: the fill and drain of the pipeline are 1 / e2e_steps of it
     depth = 3 if world == 1 else 2  # per rank; every context owns pinned staging for one batch's result (4.4 GB)
     pipe = PipelinedBuilder(WEIGHTS, local, depth=depth)
     for _ in pipe.map([instances] * depth, seed=seed, instance_id_base=rank * B, **PARAMS):
