@@ -123,6 +123,7 @@ struct ctrm_ctx {
   DevArena c_arena;
   int32_t* d_tfin = nullptr;
   int32_t *d_learn_agent = nullptr, *d_learn_inst = nullptr, *d_n_learn = nullptr;  // Batch::learn_* storage
+  int32_t *d_retry_agent = nullptr, *d_retry_inst = nullptr, *d_n_retry = nullptr;  // Batch::retry_* storage
   int64_t *d_agent_nv = nullptr, *d_agent_ne = nullptr, *d_totals = nullptr;
   int64_t totals[3] = {0, 0, 0};
   bool have_result = false;
@@ -470,6 +471,9 @@ extern "C" int ctrm_upload_instances(ctrm_ctx* c, int B, const int32_t* n_agents
   CHECK(ar.alloc(&c->d_learn_agent, (size_t)A));
   CHECK(ar.alloc(&c->d_learn_inst, (size_t)A));
   CHECK(ar.alloc(&c->d_n_learn, (size_t)1));
+  CHECK(ar.alloc(&c->d_retry_agent, (size_t)A));
+  CHECK(ar.alloc(&c->d_retry_inst, (size_t)A));
+  CHECK(ar.alloc(&c->d_n_retry, (size_t)1));
   CHECK(ar.alloc(&bt.agent_pack, (size_t)6 * A));
   CHECK(ar.alloc(&bt.nlayers, (size_t)A));
   CHECK(ar.alloc(&c->d_tfin, (size_t)B));
@@ -765,7 +769,18 @@ static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, 
       }
     }
     CHECK(mark(KID_CVAE_PRIOR));
-    CHECK(launch_cvae_decode(c->model, bl, bt.cv_sqrtp, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st, bt.randomize_indicator));
+    if (bt.n_retry != nullptr) {
+      CHECK(launch_cvae_decode(c->model, bl, bt.cv_sqrtp, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st, bt.randomize_indicator, 0, 1, 1));
+      Batch br = bt;  // the agents whose first candidate failed
+      br.live_agent = bt.retry_agent;
+      br.live_inst = bt.retry_inst;
+      br.n_live = bt.n_retry;
+      CHECK(launch_cvae_decode(c->model, br, bt.cv_sqrtp, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st, bt.randomize_indicator, 1,
+                               bt.K - 1, 0));
+      ++k;
+    } else {
+      CHECK(launch_cvae_decode(c->model, bl, bt.cv_sqrtp, bt.cv_dec0, nullptr, 1, 0, 0, bt.samples, st, bt.randomize_indicator));
+    }
     CHECK(mark(KID_CVAE_DECODE));
   }
   CHECK(launch_step(bt, st));
@@ -805,6 +820,13 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   bt.learn_agent = c->trace ? nullptr : c->d_learn_agent;
   bt.learn_inst = c->trace ? nullptr : c->d_learn_inst;
   bt.n_learn = c->trace ? nullptr : c->d_n_learn;
+  // lazy candidates: the first CVAE copy for every learned agent, the others only where it fails valid_edge.  Off when the run
+  // records every sample (trace) and when the step takes its samples from a teacher table (validity must be tested on the
+  // samples the step will use)
+  const bool lazy = !c->trace && !(tb && tb->h_teacher) && K > 1;
+  bt.retry_agent = lazy ? c->d_retry_agent : nullptr;
+  bt.retry_inst = lazy ? c->d_retry_inst : nullptr;
+  bt.n_retry = lazy ? c->d_n_retry : nullptr;
   c->have_result = false;
   // tables
   CTRM_CUDA_OK(cudaStreamSynchronize(st));
@@ -864,6 +886,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
     CTRM_CUDA_OK(cudaMemsetAsync(bt.tr_loc_next, 0xFF, steps_max * bt.A * 2 * sizeof(double), st));
   }
   if (bt.n_learn != nullptr) CTRM_CUDA_OK(cudaMemsetAsync(bt.n_learn, 0, sizeof(int32_t), st));
+  if (bt.n_retry != nullptr) CTRM_CUDA_OK(cudaMemsetAsync(bt.n_retry, 0, sizeof(int32_t), st));
   CHECK(launch_rollout_init(bt, st));
   int64_t launches = 1;
   // capture `chunk` steps as one CUDA graph, then replay it; n_done is polled after every replay.

@@ -11,6 +11,7 @@
 //   5. thread r: ld, + b1, ReLU, the 32x3 output layer on CUDA cores, store (dx, dy, mag)
 // Weights are split and staged once per (persistent) CTA.  fp32-accurate: see tc.cuh.
 #include "common.cuh"
+#include "geometry.cuh"
 #include "kernels.h"
 #include "tc.cuh"
 
@@ -367,7 +368,13 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
                                                                        const float* __restrict__ uniforms, int use_state_kt,
                                                                        int kt_fixed, int t_fixed, float temp, int w0_exp,
                                                                        const uint8_t* __restrict__ w_image,
-                                                                       float* __restrict__ samples, int n_tiles, int variants) {
+                                                                       float* __restrict__ samples, int n_tiles, int variants,
+                                                                       int k_first, int k_count, int emit_retry) {
+  // This launch computes copies k_first .. k_first + k_count - 1 of every agent row (K = the agent-major stride of `samples`).
+  // emit_retry: the copy is the FIRST candidate of the scan of learned_sampler.py:159-166; its validity (the valid_edge closure
+  // :127-132) is tested here with the step kernels' own predicates and the agents whose first candidate fails are appended to
+  // Batch::retry_agent — only those need the remaining copies (a second, small launch): 94 % of the learned agent-steps of
+  // the benchmark take their first candidate.
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* At = smem;                       // z digits 1..4, [128 x 64] bf16 each
   uint8_t* W0t = At + 4 * DT_A_PART;        // W0z digits 1..4, [32 x 64]
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
   const float inv_temp = (frexpf(temp, &temp_exp) == 0.5f && temp_exp > -100 && temp_exp < 100) ? 1.f / temp : 0.f;
   const bool sqrt_path = temp == 2.0f;
   const int n_arows = bt.live_agent != nullptr ? *bt.n_live : bt.A;  // agents of the unfinished instances, or all
-  const long long n_rows = (long long)n_arows * K;
+  const long long n_rows = (long long)n_arows * k_count;
   n_tiles = (int)min((long long)n_tiles, (n_rows + 127) >> 7);
   // accumulator g (digit index sum, 0-based) carries weight 256^-(g+1) * 2^(w0_exp - 7)
   double acc_scale[4];
@@ -413,8 +420,8 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
     int a = 0, k = 0, b = 0;
     long long orow = 0;  // row of this (agent, copy) in the agent-major output / uniform tables
     if (live) {
-      const int arow = (int)(row / K);
-      k = (int)(row - (long long)arow * K);
+      const int arow = (int)(row / k_count);
+      k = k_first + (int)(row - (long long)arow * k_count);
       a = bt.live_agent != nullptr ? bt.live_agent[arow] : arow;
       orow = (long long)a * K + k;
       b = bt.agent_inst[a];
@@ -642,9 +649,27 @@ __global__ void __launch_bounds__(DT_THREADS, 2) cvae_decode_tc_kernel(Batch bt,
       tc::fence_after_sync();
       if (half == 0 && live) {
         float* out = samples + (size_t)orow * 3;
-        out[0] = (B2[0] + o0) + red3[r * 4 + 0];
-        out[1] = (B2[1] + o1) + red3[r * 4 + 1];
-        out[2] = (B2[2] + o2) + red3[r * 4 + 2];
+        const float s0 = (B2[0] + o0) + red3[r * 4 + 0], s1 = (B2[1] + o1) + red3[r * 4 + 1], s2 = (B2[2] + o2) + red3[r * 4 + 2];
+        out[0] = s0;
+        out[1] = s1;
+        out[2] = s2;
+        if (emit_retry) {
+          // valid_edge(cur, Y) exactly as select evaluates it (rollout.cu): Y = cur + f32(dx * mag), bounds, speed, obstacles
+          const double2 cp = *reinterpret_cast<const double2*>(bt.cur + 2 * (size_t)a);
+          const double2 q1 = *reinterpret_cast<const double2*>(bt.agent_pack + 6 * (size_t)a + 2);  // speed, speed^2
+          const double rad = bt.agent_pack[6 * (size_t)a + 5];
+          const double x = f64add(cp.x, (double)__fmul_rn(s0, s2)), y = f64add(cp.y, (double)__fmul_rn(s1, s2));
+          bool ok = bounds_ok(x, y, rad) && speed_ok(cp.x, cp.y, x, y, q1.x, q1.y);
+          if (ok) {
+            const int o0b = bt.obs_off[b], o1b = bt.obs_off[b + 1];
+            ok = !any_obstacle_hit_f4(cp.x, cp.y, x, y, rad, bt.obs_xyr, bt.obs_f4, o0b, o1b);
+          }
+          if (!ok) {
+            const int slot = atomicAdd(bt.n_retry, 1);
+            bt.retry_agent[slot] = a;
+            bt.retry_inst[slot] = b;
+          }
+        }
       }
     }
   }
@@ -660,16 +685,20 @@ int launch_cvae_decode_image(const float* d_blob, const ctrm_weight_offsets_t& o
 }
 
 int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_sqrtp, const float* d_dec0, const float* d_uniforms,
-                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st, int variants) {
+                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st, int variants, int k_first,
+                       int k_count, int emit_retry) {
   if (bt.A <= 0) return 0;
   const int K = bt.K;
-  const long long rows = (long long)bt.A * K;
+  if (k_count < 0) k_count = K - k_first;  // default: all remaining copies
+  if (k_count <= 0) return 0;
+  const long long rows = (long long)bt.A * k_count;
   const int n_tiles = (int)((rows + 127) / 128);
   static SmemAttrCache attr;
   CTRM_CUDA_OK(attr.ensure(cvae_decode_tc_kernel, DT_SMEM));
   const int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;  // persistent: two CTAs per SM
   cvae_decode_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(bt, K, d_sqrtp, d_dec0, d_uniforms, use_state_kt, kt_fixed, t_fixed,
-                                                          m.desc.temp, m.dec_w0z_exp, m.decode_img, d_samples, n_tiles, variants);
+                                                          m.desc.temp, m.dec_w0z_exp, m.decode_img, d_samples, n_tiles, variants, k_first, k_count,
+                                                          emit_retry);
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -71,6 +71,10 @@ struct Batch {
   int32_t* learn_agent;                 // [A]
   int32_t* learn_inst;                  // [A]
   int32_t* n_learn;                     // [1]
+  // agents whose FIRST CVAE candidate failed valid_edge in this step: only they need copies 1 .. K-1 (cvae_decode, second launch)
+  int32_t* retry_agent;                 // [A]
+  int32_t* retry_inst;                  // [A]
+  int32_t* n_retry;                     // [1]
   double* agent_pack;                   // [A][6] {goal x, goal y, speed, speed^2, merge_distance^2, rad}
   // per-step tensors
   uint8_t* fov_tiles;  // bf16 operand tiles [ceil(A/128)][n_chunks][128 x 96]
@@ -136,7 +140,8 @@ int launch_cvae_prior(const DevModel& m, const Batch& bt, const float* d_X, floa
 // variants != 0: d_sqrtp / d_dec0 hold one [A]-sized slot per indicator value and every row picks its own
 // (learned_sampler.py:93-97: torch.randint indicators when the step's draw exceeds p_rw, else the argmax)
 int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_sqrtp, const float* d_dec0, const float* d_uniforms,
-                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st, int variants = 0);
+                       int use_state_kt, int kt_fixed, int t_fixed, float* d_samples, cudaStream_t st, int variants = 0,
+                       int k_first = 0, int k_count = -1, int emit_retry = 0);
 
 int launch_step(const Batch& bt, cudaStream_t st);
 int launch_rollout_init(const Batch& bt, cudaStream_t st);

@@ -579,6 +579,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32, 8) step_kernel(Batch bt) {
   // the learned-row list of this step has been consumed (the network kernels ran before this one); the advance kernel that
   // follows refills it for the next step
   if (blockIdx.x == 0 && threadIdx.x == 0 && bt.n_learn != nullptr) *bt.n_learn = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 1 && bt.n_retry != nullptr) *bt.n_retry = 0;
   if (row >= (bt.live_agent != nullptr ? *bt.n_live : bt.A)) return;
   const int a = bt.live_agent != nullptr ? bt.live_agent[row] : row;
   StepCtx sc;
@@ -654,6 +655,7 @@ template <int W>
 __global__ void __launch_bounds__(128, 5) step_thread_kernel(Batch bt) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row == 0 && bt.n_learn != nullptr) *bt.n_learn = 0;  // see step_kernel
+  if (row == 1 && bt.n_retry != nullptr) *bt.n_retry = 0;
   if (row >= (bt.live_agent != nullptr ? *bt.n_live : bt.A)) return;
   const int a = bt.live_agent != nullptr ? bt.live_agent[row] : row;
   const int b = bt.live_agent != nullptr ? bt.live_inst[row] : bt.agent_inst[a];
