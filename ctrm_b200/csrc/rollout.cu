@@ -652,7 +652,7 @@ __device__ __forceinline__ bool hits_any_serial(const Batch& bt, int o0, int nO,
 }
 
 template <int W>
-__global__ void __launch_bounds__(128, 5) step_thread_kernel(Batch bt) {
+__global__ void __launch_bounds__(128, 4) step_thread_kernel(Batch bt) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row == 0 && bt.n_learn != nullptr) *bt.n_learn = 0;  // see step_kernel
   if (row == 1 && bt.n_retry != nullptr) *bt.n_retry = 0;
