@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libctrm_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "raster.cu", "collide.cu", "agent_tc.cu", "fov_tc.cu", "cvae_tc.cu", "rollout.cu", "finalize.cu", "plan.cu", "features.cu", "sampler.cu"]
+SOURCES = ["api.cu", "raster.cu", "collide.cu", "agent_tc.cu", "fov_tc.cu", "cvae_tc.cu", "rollout.cu", "instance.cu", "finalize.cu", "plan.cu", "features.cu", "sampler.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]

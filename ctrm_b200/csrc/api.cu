@@ -2,6 +2,7 @@
 // roll-out driver and the host-buffer wrappers with the pybind11 helpers' call shapes.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -730,6 +731,29 @@ struct StepProfiler {
   }
 };
 
+// batches up to this many instances take the per-instance kernel (CTRM_INSTANCE_MAX_BATCH moves the threshold, 0 = never)
+static int instance_kernel_max_batch() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTRM_INSTANCE_MAX_BATCH");
+    v = e ? atoi(e) : 148;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+// CTAs per instance: as many as keep every cluster resident at once on the 148 SMs (CTRM_INSTANCE_CLUSTER pins 1, 2, 4 or 8)
+static int instance_cluster_size(int B) {
+  const char* e = getenv("CTRM_INSTANCE_CLUSTER");
+  if (e) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+  }
+  if (B <= 16) return 8;
+  if (B <= 33) return 4;
+  if (B <= 70) return 2;
+  return 1;
+}
+
 // one roll-out step for every unfinished instance; `nn` = run the networks (skipped for teacher-forced runs
 // that do not trace the CVAE output)
 static int enqueue_step(ctrm_ctx* c, const Batch& bt, bool nn, cudaStream_t st, int* n_kernels, StepProfiler* prof = nullptr,
@@ -872,6 +896,9 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   }
   if (bt.tab_uniforms != nullptr)
     return ctrm_fail(CTRM_ERR_ARG, "per-step uniform tables are only supported through ctrm_cvae_sample (stage entry point)");
+  float* d_part = nullptr;  // scratch of the per-instance kernel, taken before the arena lets go of what this build did not ask for
+  const bool inst_candidate = c->step_mode == 3 || (c->step_mode == 0 && !c->profile && bt.B <= instance_kernel_max_batch());
+  if (inst_candidate) CHECK(c->t_arena.alloc(&d_part, instance_part_floats(bt)));
   c->t_arena.trim();
   const bool nn = (bt.tab_teacher == nullptr) || c->trace;
   // reset the roadmap store and the roll-out state
@@ -887,6 +914,21 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   }
   if (bt.n_learn != nullptr) CTRM_CUDA_OK(cudaMemsetAsync(bt.n_learn, 0, sizeof(int32_t), st));
   if (bt.n_retry != nullptr) CTRM_CUDA_OK(cudaMemsetAsync(bt.n_retry, 0, sizeof(int32_t), st));
+  // per-instance kernel (instance.cu): the whole roll-out loop in one launch, one cluster per instance.  Chosen for small
+  // batches, where the batch path is one mostly empty tile per kernel and a step costs seven kernel latencies.
+  bool use_inst = false;
+  int inst_C = 1;
+  if (inst_candidate) {
+    use_inst = instance_kernel_supports(c->model, bt) != 0;
+    if (!use_inst && c->step_mode == 3)
+      return ctrm_fail(CTRM_ERR_ARG, "per-instance kernel: batch outside its limits (<= 64 agents per instance, K <= 8, temp 2, "
+                                     "<= 15 neighbours, no randomize_indicator)");
+    if (use_inst) {
+      inst_C = instance_cluster_size(bt.B);
+      bt.learn_agent = nullptr; bt.learn_inst = nullptr; bt.n_learn = nullptr;
+      bt.retry_agent = nullptr; bt.retry_inst = nullptr; bt.n_retry = nullptr;
+    }
+  }
   CHECK(launch_rollout_init(bt, st));
   int64_t launches = 1;
   // capture `chunk` steps as one CUDA graph, then replay it; n_done is polled after every replay.
@@ -897,7 +939,13 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   int64_t steps = 0;
   int rc = 0;
   cudaError_t ce = cudaSuccess;
-  if (!c->profile) {
+  if (use_inst) {
+    CTRM_CUDA_OK(cudaEventRecord(c->ev_t[1], st));
+    CHECK(launch_instance_rollout(c->model, bt, nn ? 1 : 0, inst_C, d_part, st));
+    steps = (int64_t)steps_max;
+    per_step = 0;
+    launches += 1;
+  } else if (!c->profile) {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     // ONE graph holds `chunk` consecutive steps: a replay per step costs a graph launch (~3 us of host and front-end time),
@@ -1077,7 +1125,8 @@ extern "C" int ctrm_get_instance_steps(ctrm_ctx* c, int32_t* h_steps) {
 
 extern "C" int ctrm_set_step_kernel(ctrm_ctx* c, int mode) {
   if (!c) return ctrm_fail(CTRM_ERR_ARG, "NULL ctx");
-  if (mode < 0 || mode > 2) return ctrm_fail(CTRM_ERR_ARG, "ctrm_set_step_kernel: mode must be 0 (auto), 1 (warp per agent) or 2 (thread per agent)");
+  if (mode < 0 || mode > 3)
+    return ctrm_fail(CTRM_ERR_ARG, "ctrm_set_step_kernel: mode must be 0 (auto), 1 (warp per agent), 2 (thread per agent) or 3 (per-instance kernel)");
   c->step_mode = mode;
   return 0;
 }

@@ -41,7 +41,7 @@ struct Batch {
   int B, A, O, M, F, L, S, W, K;
   int n_max;  // largest num_agents of the batch
   int max_T, N_traj, max_attempt, dim_ind, randomize_indicator;
-  int step_mode;  // select + merge kernel: 0 = by batch size, 1 = one warp per agent, 2 = one thread per agent
+  int step_mode;  // select + merge kernel: 0 = by batch size, 1 = one warp per agent, 2 = one thread per agent (3: instance kernel, api.cu)
   // static problem data (flat over agents / obstacles)
   const int32_t *agent_off, *obs_off, *agent_inst;
   const double *starts, *goals, *speeds, *speeds2, *merge2, *rads, *obs_xyr;
@@ -144,6 +144,10 @@ int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_sqrtp,
                        int k_first = 0, int k_count = -1, int emit_retry = 0);
 
 int launch_step(const Batch& bt, cudaStream_t st);
+// the whole roll-out loop of an instance inside one kernel, one cluster of C CTAs per instance (instance.cu): small batches
+int instance_kernel_supports(const DevModel& m, const Batch& bt);
+size_t instance_part_floats(const Batch& bt);
+int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, float* d_part, cudaStream_t st);
 int launch_rollout_init(const Batch& bt, cudaStream_t st);
 
 int launch_finalize(const Batch& bt, int32_t* d_tfin, cudaStream_t st);

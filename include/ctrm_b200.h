@@ -237,9 +237,16 @@ int ctrm_last_timing(ctrm_ctx* ctx, float ms[3], int64_t* steps, int64_t* launch
 int ctrm_get_instance_steps(ctrm_ctx* ctx, int32_t* h_steps /*[B]*/);
 int ctrm_set_profile(ctrm_ctx* ctx, int enable);
 
-/* which kernel runs the per-agent select + merge of a roll-out step (learned_sampler.py:123-183, utils.py:21-137):
- * 0 = chosen by batch size (default), 1 = one warp per agent (low latency, small batches), 2 = one thread per agent
- * (throughput, large batches).  Both produce identical roadmaps and counters. */
+/* which kernels run the roll-out loop (learned_sampler.py:65-196):
+ *   0 = chosen by batch size (default): a few hundred instances or fewer take the per-instance kernel (3) when the batch
+ *       fits its limits (<= 64 agents per instance, K <= 8, temperature 2, <= 15 neighbours), larger batches the batch path
+ *       with select + merge as (2) from ~20k agents and as (1) below;
+ *   1 = batch path (one kernel sequence per step over all instances), select + merge one warp per agent;
+ *   2 = batch path, select + merge one thread per agent (throughput, large batches);
+ *   3 = per-instance kernel: one thread-block cluster per instance runs all N_traj x max_T steps inside ONE launch (single-
+ *       instance latency); CTRM_ERR_ARG at build time if the batch does not fit its limits.
+ * 1 and 2 produce identical roadmaps and counters.  3 evaluates the networks on the CUDA cores in plain fp32: samples agree
+ * with 1/2 to ~1e-6, geometry and roadmap updates are the same code, results are bit-identical under teacher forcing. */
 int ctrm_set_step_kernel(ctrm_ctx* ctx, int mode);
 int ctrm_last_kernel_times(ctrm_ctx* ctx, double ms[8], int64_t launches[8]);
 

@@ -40,7 +40,7 @@ def test_reference_run_replay_bit_exact(builder, any_trace_gold, oracle_weights)
     gate = np.nan_to_num(rng.t_gate, nan=0.5)
     rw = np.nan_to_num(rng.t_rw, nan=0.0)
     builder.upload([instance_from_oins(oi)])
-    for mode in (2, 1, 0):  # thread-per-agent kernel, warp-per-agent kernel, then back to the default choice
+    for mode in (2, 1, 3, 0):  # thread-per-agent kernel, warp-per-agent kernel, per-instance kernel, then the default choice
         builder.set_step_kernel(mode)
         csr = builder.run(N_traj=NT, max_T=MT, max_attempt=MA, merge_distance_rate=rate,
                           tables=dict(gate=gate, rw=rw, teacher=teacher))
