@@ -736,22 +736,20 @@ static int instance_kernel_max_batch() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CTRM_INSTANCE_MAX_BATCH");
-    v = e ? atoi(e) : 148;
+    v = e ? atoi(e) : 64;  // measured (profiles/r2_instance_kernel.md): 2 CTAs per instance still win at 64 instances, 1 CTA does not at 148
     if (v < 0) v = 0;
   }
   return v;
 }
-// CTAs per instance: as many as keep every cluster resident at once on the 148 SMs (CTRM_INSTANCE_CLUSTER pins 1, 2, 4 or 8)
-static int instance_cluster_size(int B) {
+// CTAs per instance: 0 = chosen by the launcher (the largest of 8, 4, 2, 1 that keeps every cluster resident at once);
+// CTRM_INSTANCE_CLUSTER pins 1, 2, 4 or 8
+static int instance_cluster_size() {
   const char* e = getenv("CTRM_INSTANCE_CLUSTER");
   if (e) {
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) return v;
   }
-  if (B <= 16) return 8;
-  if (B <= 33) return 4;
-  if (B <= 70) return 2;
-  return 1;
+  return 0;
 }
 
 // one roll-out step for every unfinished instance; `nn` = run the networks (skipped for teacher-forced runs
@@ -917,14 +915,14 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   // per-instance kernel (instance.cu): the whole roll-out loop in one launch, one cluster per instance.  Chosen for small
   // batches, where the batch path is one mostly empty tile per kernel and a step costs seven kernel latencies.
   bool use_inst = false;
-  int inst_C = 1;
+  int inst_C = 0;
   if (inst_candidate) {
     use_inst = instance_kernel_supports(c->model, bt) != 0;
     if (!use_inst && c->step_mode == 3)
       return ctrm_fail(CTRM_ERR_ARG, "per-instance kernel: batch outside its limits (<= 64 agents per instance, K <= 8, temp 2, "
                                      "<= 15 neighbours, no randomize_indicator)");
     if (use_inst) {
-      inst_C = instance_cluster_size(bt.B);
+      inst_C = instance_cluster_size();
       bt.learn_agent = nullptr; bt.learn_inst = nullptr; bt.n_learn = nullptr;
       bt.retry_agent = nullptr; bt.retry_inst = nullptr; bt.n_retry = nullptr;
     }

@@ -94,13 +94,66 @@ def test_full_size_batch_properties_and_batch_independence():
         assert np.array_equal(csr.pos.view(np.uint64), again.pos.view(np.uint64))
         # an instance built alone (same instance id) equals its result inside the batch
         b = 37
+        bld.set_step_kernel(1)  # the batch path (a single instance would take the per-instance kernel, tested below)
         alone = bld.build([instances[b]], seed=7, instance_id_base=b, **prm).copy()
+        bld.set_step_kernel(0)
         a0, a1 = int(csr.agent_off[b]), int(csr.agent_off[b + 1])
         v0, v1 = int(csr.layer_ptr[a0 * csr.L]), int(csr.layer_ptr[a1 * csr.L])
         assert np.array_equal(alone.pos.view(np.uint64), csr.pos[v0:v1].view(np.uint64))
         assert np.array_equal(alone.eidx, csr.eidx[int(csr.eptr[v0]):int(csr.eptr[v1])])
         assert np.array_equal(alone.n_layers, csr.n_layers[a0:a1])
     finally:
+        bld.close()
+
+
+def test_instance_kernel_properties_and_cluster_sizes():
+    """The per-instance cluster kernel (ctrm_set_step_kernel 3; the default for small batches) free-running at the headline
+    roll-out sizes: every edge valid, deterministic, an instance's result independent of the batch it is built in, and — for
+    the cluster sizes that evaluate the FOV first layer on the CUDA cores (1, 2, 4 CTAs per instance; 8 uses mma.sync) —
+    independent of the cluster size"""
+    import os
+
+    from ctrm_b200 import RoadmapBuilder
+
+    prm = dict(N_traj=25, max_T=64, max_attempt=3, merge_distance_rate=0.1)
+    instances = [_gen(146 + i, 21, 30, 10) for i in range(5)] + [_gen(200, 33, 40, 10)]
+    bld = RoadmapBuilder(WEIGHTS, 0)
+    saved = os.environ.pop("CTRM_INSTANCE_CLUSTER", None)
+
+    def same(x, y):
+        return (np.array_equal(x.pos.view(np.uint64), y.pos.view(np.uint64))
+                and all(np.array_equal(getattr(x, f), getattr(y, f)) for f in ("layer_ptr", "eptr", "eidx", "n_layers", "cnt_collide")))
+
+    try:
+        bld.set_step_kernel(3)
+        csr = bld.build(instances, seed=3, **prm).copy()
+        for b in range(len(instances)):
+            nv, ne = _check_instance(csr, b, instances[b])
+            assert nv > 20_000 and ne > nv
+        assert same(csr, bld.build(instances, seed=3, **prm).copy())
+        b = 2
+        alone = bld.build([instances[b]], seed=3, instance_id_base=b, **prm).copy()
+        a0, a1 = int(csr.agent_off[b]), int(csr.agent_off[b + 1])
+        v0, v1 = int(csr.layer_ptr[a0 * csr.L]), int(csr.layer_ptr[a1 * csr.L])
+        assert np.array_equal(alone.pos.view(np.uint64), csr.pos[v0:v1].view(np.uint64))
+        assert np.array_equal(alone.eidx, csr.eidx[int(csr.eptr[v0]):int(csr.eptr[v1])])
+        by_c = {}
+        for c in (1, 2, 4, 8):
+            os.environ["CTRM_INSTANCE_CLUSTER"] = str(c)
+            by_c[c] = bld.build(instances, seed=3, **prm).copy()
+        assert same(by_c[8], csr)
+        assert same(by_c[1], by_c[2]) and same(by_c[1], by_c[4])
+        for b in (0, 5):
+            _check_instance(by_c[1], b, instances[b])
+        # the default choice for a handful of instances is this kernel
+        os.environ.pop("CTRM_INSTANCE_CLUSTER", None)
+        bld.set_step_kernel(0)
+        assert same(bld.build(instances, seed=3, **prm).copy(), csr)
+    finally:
+        if saved is not None:
+            os.environ["CTRM_INSTANCE_CLUSTER"] = saved
+        else:
+            os.environ.pop("CTRM_INSTANCE_CLUSTER", None)
         bld.close()
 
 
