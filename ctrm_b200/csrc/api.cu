@@ -289,7 +289,7 @@ extern "C" int ctrm_load_weights(ctrm_ctx* c, const ctrm_model_desc* d, const fl
     c->model.fov_w0_tiles = tiles;
   }
   {  // shared-memory weight images of the other tensor-core kernels
-    uint8_t *pi = nullptr, *di = nullptr, *ai = nullptr, *fi = nullptr;
+    uint8_t *pi = nullptr, *di = nullptr, *ai = nullptr, *fi = nullptr, *wi = nullptr;
     CHECK(c->w_arena.alloc(&pi, cvae_prior_image_bytes()));
     CHECK(c->w_arena.alloc(&di, cvae_decode_image_bytes()));
     CHECK(c->w_arena.alloc(&ai, agent_comm_image_bytes()));
@@ -298,8 +298,11 @@ extern "C" int ctrm_load_weights(ctrm_ctx* c, const ctrm_model_desc* d, const fl
     CHECK(launch_cvae_prior_image(blob, off, pi, c->stream));
     CHECK(launch_cvae_decode_image(blob, off, c->model.dec_w0z_exp, di, c->stream));
     CHECK(launch_agent_comm_image(blob, off, ai, c->stream));
+    CHECK(c->w_arena.alloc(&wi, instance_w0_image_bytes()));
+    CHECK(launch_instance_w0_image(blob, off, d->fov_size, wi, c->stream));
     CTRM_CUDA_OK(cudaStreamSynchronize(c->stream));
     c->model.prior_img = pi; c->model.decode_img = di; c->model.agent_img = ai; c->model.fov_img = fi;
+    c->model.inst_w0_img = wi;
   }
   c->have_weights = true;
   return 0;
@@ -894,9 +897,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   }
   if (bt.tab_uniforms != nullptr)
     return ctrm_fail(CTRM_ERR_ARG, "per-step uniform tables are only supported through ctrm_cvae_sample (stage entry point)");
-  float* d_part = nullptr;  // scratch of the per-instance kernel, taken before the arena lets go of what this build did not ask for
   const bool inst_candidate = c->step_mode == 3 || (c->step_mode == 0 && !c->profile && bt.B <= instance_kernel_max_batch());
-  if (inst_candidate) CHECK(c->t_arena.alloc(&d_part, instance_part_floats(bt)));
   c->t_arena.trim();
   const bool nn = (bt.tab_teacher == nullptr) || c->trace;
   // reset the roadmap store and the roll-out state
@@ -939,7 +940,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   cudaError_t ce = cudaSuccess;
   if (use_inst) {
     CTRM_CUDA_OK(cudaEventRecord(c->ev_t[1], st));
-    CHECK(launch_instance_rollout(c->model, bt, nn ? 1 : 0, inst_C, d_part, st));
+    CHECK(launch_instance_rollout(c->model, bt, nn ? 1 : 0, inst_C, st));
     steps = (int64_t)steps_max;
     per_step = 0;
     launches += 1;

@@ -5,28 +5,36 @@
 // instances each of those kernels is one 128-row tensor-core tile that is 80 % padding and costs a launch plus three to seven
 // dependent MMA round trips (12-18 us per kernel, 63 us per step, 96 ms for one 28-agent instance).  Here the N_traj x max_T
 // steps of an instance never leave the chip: a cluster of C = 1, 2, 4 or 8 CTAs owns the instance, every CTA keeps all network
-// weights but the FOV encoders' first layer resident in shared memory (92 KB fp32), the agents are split over the CTAs, and the
-// per-step phases are separated by __syncthreads / barrier.cluster instead of kernel boundaries:
+// weights but the FOV encoders' first layer resident in shared memory (92 KB fp32), the agents are split evenly over the CTAs,
+// and everything the CTAs exchange travels through DISTRIBUTED SHARED MEMORY (stores into the consumer's shared memory, then one
+// barrier.cluster) — a step has four cluster barriers and no global-memory round trip between its phases:
 //
-//   raster   FOV crops as bits (cost_to_go.cpp:109-186), every CTA for all agents but only its K-slices of the 2 F^2 inputs
-//   fov L0   the 2F^2 -> 64 first layers of both FOV encoders (fov_encoder.py:34-59): K is cut into 8 slices of 96 inputs, CTA r
-//            accumulates the slices it owns for ALL agents (its part of W0 stays in its L1), partial sums go through L2
-//   -- cluster barrier --
-//   fov tail own agents: sum of the 8 partials in slice order (the result does not depend on C), 32->32->32 tails, vain_proj
-//   -- cluster barrier --
-//   comm     own agents on the learned branch: k nearest neighbours, pair features (compiled.py:30-97), AgentEncoder
-//            43->32->32->42 on the k+1 pairs, attention softmax and message sum (format_input.py:212-277)
-//   cvae     indicator + argmax, prior, K relaxed one-hot samples, decoder (cvae.py:57-79, :128-138; learned_sampler.py:99-121)
-//   step     select + merge_samples, one warp per own agent: the device functions of the batch kernels (rollout.cuh), hence
-//            the same bits for every fp64 operation, verdict and counter
-//   -- cluster barrier --
-//   advance  every CTA reads all agents' arrival flags / next positions and advances its own copy of (k_traj, t, makespan)
-//   -- cluster barrier --
+//   gate     which agents take the learned branch (learned_sampler.py:148-157), every CTA for all agents
+//   raster   FOV crops of the own agents as bits (cost_to_go.cpp:109-186): a warp builds eight 32-bit words with eight
+//            coalesced loads per lane and a ballot each, and stores every word into the CTA that owns its K-slice
+//   -- cluster barrier 1 --
+//   fov L0   the 2F^2 -> 64 first layers of both FOV encoders (fov_encoder.py:34-59) on the tensor cores (mma.sync, bf16 x 3 =
+//            fp32-exact weights, 0/1 activations): K is cut into 8 slices of 96 inputs, CTA r multiplies the slices it owns for
+//            ALL agents (C = 8: its slice's B fragments are resident; smaller clusters stream the prebuilt fragment image through
+//            L2) and stores the partial sums into the shared memory of the CTA that owns the agent
+//   -- cluster barrier 2 --
+//   fov tail own agents: the partials summed as a fixed binary tree over the slices (the result does not depend on C),
+//            32->32->32 tails, vain_proj stored into EVERY CTA's shared memory
+//   -- cluster barrier 3 --
+//   agent    the 16 warps form four GROUPS of four warps; a group takes one own agent at a time through
+//            comm (k nearest neighbours, pair features compiled.py:30-97, AgentEncoder 43->32->32->42 on the k+1 pairs, attention
+//            softmax and message sum, format_input.py:212-277), cvae (indicator + argmax, the prior for all three indicator
+//            values side by side, K relaxed one-hot samples, decoder; cvae.py:57-79, :128-138; learned_sampler.py:99-121) and
+//            the step (select, then merge_samples with the parents / children / merge candidates / goal test on one warp each),
+//            synchronised by named barriers of 128 threads; the agent's next position and arrival flag are stored into every CTA
+//   -- cluster barrier 4 --
+//   advance  every CTA advances its own copy of (k_traj, t, makespan) and of all positions
 //
-// The networks run on the CUDA cores in plain fp32 (FMA, fixed summation orders): at 28 rows per step a 128-row MMA tile with a
+// The MLPs run on the CUDA cores in plain fp32 (FMA, fixed summation orders): at 28 rows per step a 128-row MMA tile with a
 // TMEM round trip per layer is slower than 512 threads walking 32-wide layers out of shared memory.  They agree with the
 // tensor-core kernels of the batch path (fp32-exact BF16x3 / integer digits) and with the reference to ~1e-6 relative; all
-// geometry, draws and roadmap updates are the same code as the batch path.  Under teacher forcing the two paths are bit-identical.
+// geometry, draws and roadmap updates use the device functions of the batch path (rollout.cuh) — the same bits for every fp64
+// operation, verdict and counter.  Under teacher forcing the two paths are bit-identical.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
@@ -47,29 +55,54 @@ namespace cg = cooperative_groups;
 
 #define IK_THREADS 512
 #define IK_WARPS 16
+#define IK_GROUPS 4    // groups of four warps: one own agent at a time through comm, cvae and the step
 #define IK_NMAX 64     // agents per instance
 #define IK_SLICES 8    // K-slices of the FOV first layer (96 inputs each)
 #define IK_WORDS 24    // 32-bit words of one agent's crop bits
-#define IK_CHUNK 8     // learned agents per pass of the comm / cvae phases
 #define IK_PMAX 16     // pairs per agent: itself + at most 15 neighbours
-#define IK_OBS_MAX 32  // obstacles staged per warp in shared memory (more: read through L1)
+#define IK_OBS_MAX 64  // obstacles staged per group in shared memory (more: read through L1)
 #define IK_KMAX 8      // CVAE candidates per agent
 #define IK_NPROF 16
+#define IK_FRAG_SLICE (8 * 6 * 3 * 32)  // uint2 entries of one K-slice of the fragment image: [n-tile][k-step][bf16 part][lane]
+
+// byte offsets of the shared-memory regions (computed by the host, ik_layout)
+struct IkLayout {
+  int cur, prev, goal, nxt, bits, vp, eself, part, radf, speedf, flags, w0f, pack, samples, nl, vcnt, obs, prof, U, total;
+};
 
 struct InstArgs {
   const float* blob;
+  const uint2* w0img;  // [IK_SLICES][IK_FRAG_SLICE] mma.sync B fragments of the FOV first layer, bf16 x 3 (instance_w0_image_kernel)
   ctrm_weight_offsets_t off;
   int F, num_neighbors, use_k_neighbor, include_self;
   int nn;        // run the networks (0: teacher-forced run that does not record the CVAE output)
   int C;         // CTAs per instance
   int n_w;       // floats of the blob from fov_b0 on (resident in shared memory)
-  int w0_frag;   // the CTA's K-slice of the FOV first layer is resident as bf16 x 3 mma.sync fragments (C = 8: one slice per CTA)
-  int chunk;     // learned agents per pass of the comm / cvae phases (4 or 8)
-  int u_bytes;   // size of the phase scratch
+  int w0_frag;   // the CTA's K-slice of the fragment image is resident in shared memory (C = 8: one slice per CTA)
   int vc_smem;   // the own agents' layer counts live in shared memory during the roll-outs
   int own_max;   // ceil(n_max / C)
-  float* part;   // [B][IK_SLICES][n_max][64] partial sums of the FOV first layers
+  IkLayout lay;
   long long* prof;  // optional [B * C][IK_NPROF] clock cycles per phase (CTRM_INSTANCE_PROF=1)
+};
+
+// scratch of one group (one agent at a time)
+struct __align__(16) GroupScratch {
+  float info[IK_PMAX * 12];  // pair features, K padded to 12
+  float hA[IK_PMAX * 36];
+  float hB[IK_PMAX * 36];
+  float y[IK_PMAX * 48];     // [message 32 | attention 10 | pad]
+  float X[CTRM_DIM_X];       // [self_info 8 | e_self 32 | comm 32]
+  float p0[96];              // first layers of indicator | encoder_input | decoder (x rows), without bias
+  float sp[3 * 64];          // sqrt of the clamped prior probabilities, one row per indicator value
+  float d0[3 * 32];          // x part of the decoder's first layer, one row per indicator value
+  unsigned long long keys[IK_NMAX];
+  double lx, ly;             // loc_pred of the step
+  uint32_t P[CTRM_MAX_W], Cm[CTRM_MAX_W];
+  int order[IK_PMAX];
+  int pj[IK_PMAX];
+  int ind;
+  int spec_tested, spec_arr;  // goal test of (lx, ly), evaluated beside the parent / child scans
+  int pad;
 };
 
 // get_normed_vec_mag (compiled.py:11-27), as in agent_tc.cu: difference in fp64, rounded once, normalised in fp32
@@ -96,7 +129,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // out[lane] = bias[lane] + sum_k in_k * W[k][lane] for a 32-wide input held one value per lane (W: [32][ld] in shared memory)
 __device__ __forceinline__ float warp_layer32(float in, const float* __restrict__ W, int ld, int col, float bias) {
   float acc = bias;
-#pragma unroll
+#pragma unroll 8
   for (int k = 0; k < 32; ++k) acc = fmaf(__shfl_sync(0xFFFFFFFFu, in, k), W[k * ld + col], acc);
   return acc;
 }
@@ -114,7 +147,7 @@ __device__ __forceinline__ void warp_rows4(const float* __restrict__ in, int ldi
     acc[r] = brow[r] != nullptr ? brow[r][lane] : 0.f;
     acc2[r] = (NC2 > 0 && lane < NC2 && brow[r] != nullptr) ? brow[r][32 + lane] : 0.f;
   }
-#pragma unroll
+#pragma unroll 2
   for (int k = 0; k < K; k += 4) {
     float w[4], w2[4];
 #pragma unroll
@@ -138,9 +171,11 @@ __device__ __forceinline__ void warp_rows4(const float* __restrict__ in, int ldi
   }
 }
 
-// four output columns 4q .. 4q + 3 of a 32-input layer row; the inputs are cut into four strands (kq = lane & 3, adjacent lanes)
-// that meet by shuffle: chains of 8 instead of 32 — these small layers run with a handful of warps and are bound by the
-// length of one thread's dependent chain.  Whole warps must call this together.
+// four output columns 4q .. 4q + 3 of a 32-input layer row; the inputs are cut into four strands kq that meet by shuffle: chains
+// of 8 instead of 32.  Lane layout inside a warp: q = lane & 7, kq = (lane >> 3) & 3 — the eight lanes of a quarter-warp read
+// eight different 16-byte columns of ONE weight row (a conflict-free 128-byte wavefront) and the same input (a broadcast);
+// strands on adjacent lanes put four rows on the same banks (4-way conflicts, measured as the bound of these phases).
+// Whole warps must call this together.
 __device__ __forceinline__ float4 splitk_32(const float* __restrict__ x, const float* __restrict__ Wm, int q, int kq) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -151,7 +186,7 @@ __device__ __forceinline__ float4 splitk_32(const float* __restrict__ x, const f
     acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y); acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
   }
 #pragma unroll
-  for (int d = 1; d <= 2; d <<= 1) {
+  for (int d = 8; d <= 16; d <<= 1) {
     acc.x += __shfl_xor_sync(0xFFFFFFFFu, acc.x, d); acc.y += __shfl_xor_sync(0xFFFFFFFFu, acc.y, d);
     acc.z += __shfl_xor_sync(0xFFFFFFFFu, acc.z, d); acc.w += __shfl_xor_sync(0xFFFFFFFFu, acc.w, d);
   }
@@ -176,63 +211,99 @@ __device__ __forceinline__ uint32_t bf16_part(float w, int sp) {
   return (uint32_t)__bfloat16_as_ushort(sp == 0 ? hi : (sp == 1 ? mid : lo));
 }
 
-template <int W>
+// the prebuilt B fragments of the FOV first layer: [slice][n-tile of 8 columns][k-step of 16][bf16 part][lane] (mma.m16n8k16 col)
+__global__ void instance_w0_image_kernel(const float* __restrict__ W0, int KD, uint2* __restrict__ img) {
+  const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= IK_SLICES * IK_FRAG_SLICE) return;
+  const int s = gidx / IK_FRAG_SLICE, idx = gidx - s * IK_FRAG_SLICE;
+  const int ln = idx & 31, sp = (idx >> 5) % 3, ks = (idx / 96) % 6, nt = idx / 576;
+  const int col = 8 * nt + (ln >> 2), k0 = 96 * s + 16 * ks + 2 * (ln & 3);
+  auto wv = [&](int j) { return j < KD ? W0[(size_t)j * 64 + col] : 0.f; };
+  img[gidx] = make_uint2(bf16_part(wv(k0), sp) | (bf16_part(wv(k0 + 1), sp) << 16),
+                         bf16_part(wv(k0 + 8), sp) | (bf16_part(wv(k0 + 9), sp) << 16));
+}
+
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+
+// one K-slice of the FOV first layer for a 16-agent m-tile and an 8-column n-tile: fragments f[ks][part]
+__device__ __forceinline__ void l0_slice_mma(const uint32_t* __restrict__ s_bits, int r0, int r1, int slice, int tig,
+                                             const uint2 (&f)[18], float (&p)[4]) {
+  float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ks = 0; ks < 6; ++ks) {
+    const int widx = 3 * slice + (ks >> 1), sh = 16 * (ks & 1) + 2 * tig;
+    const uint32_t x0 = s_bits[r0 * IK_WORDS + widx] >> sh, x1 = s_bits[r1 * IK_WORDS + widx] >> sh;
+    const uint32_t a[4] = {bits2_bf16(x0), bits2_bf16(x1), bits2_bf16(x0 >> 8), bits2_bf16(x1 >> 8)};
+    mma_bf16_16816(accH, a, f[3 * ks].x, f[3 * ks].y);
+    mma_bf16_16816(accL, a, f[3 * ks + 1].x, f[3 * ks + 1].y);
+    mma_bf16_16816(accL, a, f[3 * ks + 2].x, f[3 * ks + 2].y);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = accH[i] + accL[i];
+}
+
+// valid_edge(loc, goal) of learned_sampler.py:182-183 for one warp: bit 0 = the swept test ran (counted by the reference's
+// collision counter), bit 1 = the agent arrives
+__device__ __noinline__ int goal_test(const Batch& bt, const StepCtx& sc, double x, double y, int lane) {
+  if (!(bounds_ok(sc.gx, sc.gy, sc.rad) && speed_ok(x, y, sc.gx, sc.gy, sc.speed, sc.speed2))) return 0;
+  bool hit = false;
+  for (int o = lane; o < sc.nO; o += 32) {
+    double ox, oy, rs;
+    obstacle_at(bt, sc, o, &ox, &oy, &rs);
+    hit = hit || (!sweep_far(x, y, sc.gx, sc.gy, ox, oy, rs) && sweep_static(x, y, sc.gx, sc.gy, ox, oy, rs));
+  }
+  return __any_sync(0xFFFFFFFFu, hit) ? 1 : 3;
+}
+
+// WIDE: select + merge_samples as one warp per agent (many agents per CTA: one or two CTAs per instance) instead of one group
+// of four warps per agent.  Both are the same fp64 operations: the roadmaps do not depend on it.
+template <int W, bool WIDE>
 __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch bt, InstArgs ia) {
   extern __shared__ __align__(16) uint8_t ik_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int C = ia.C;
   const int b = blockIdx.x / C, r = blockIdx.x - b * C;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = warp >> 2, gt = tid & 127;
+  // role of the warp inside its group, rotated by the group number: warp w runs on scheduler w & 3, and the same role of all
+  // four groups (the select warp, the resolving warp ...) would otherwise share one scheduler while three idle
+  const int gw = ((warp & 3) + g) & 3;
   const int a0 = bt.agent_off[b], n = bt.agent_off[b + 1] - a0;
   const int o0 = bt.obs_off[b], nO = bt.obs_off[b + 1] - o0;
   const int M = bt.M, F = ia.F, FF = F * F, KD = 2 * FF, buf = (F - 1) / 2;
-  const int q_own = (n + C - 1) / C;
-  const int own_lo = min(n, r * q_own), own_hi = min(n, own_lo + q_own), n_own = own_hi - own_lo;
-  const int spc = IK_SLICES / C, s_lo = r * spc, s_hi = s_lo + spc;  // K-slices of this CTA
+  const int own_lo = (r * n) / C, own_hi = ((r + 1) * n) / C, n_own = own_hi - own_lo;  // even split, sizes differ by at most one
+  const int own_max = ia.own_max;
+  const int spc = IK_SLICES / C, s_lo = r * spc;  // K-slices of this CTA
   const ctrm_weight_offsets_t& off = ia.off;
+  const IkLayout& ly_ = ia.lay;
 
   // ---- shared memory
   float* Wsm = reinterpret_cast<float*>(ik_smem);  // blob[fov_b0 .. total)
-  uint8_t* p = ik_smem + (((size_t)ia.n_w * 4 + 15) & ~(size_t)15);
-  auto carve = [&](size_t bytes) { uint8_t* q = p; p += (bytes + 15) & ~(size_t)15; return q; };
-  double* s_cur = reinterpret_cast<double*>(carve(IK_NMAX * 2 * 8));
-  double* s_prev = reinterpret_cast<double*>(carve(IK_NMAX * 2 * 8));
-  double* s_obs = reinterpret_cast<double*>(carve(IK_WARPS * 3 * IK_OBS_MAX * 8));
-  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(carve(IK_CHUNK * IK_NMAX * 8));
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(carve(IK_NMAX * IK_WORDS * 4));
-  float* s_vp = reinterpret_cast<float*>(carve(IK_NMAX * 32 * 4));
-  float* s_eself = reinterpret_cast<float*>(carve(IK_NMAX * 32 * 4));
-  float* s_X = reinterpret_cast<float*>(carve(IK_CHUNK * CTRM_DIM_X * 4));
-  int* s_order = reinterpret_cast<int*>(carve(IK_CHUNK * IK_PMAX * 4));
-  int* s_pj = reinterpret_cast<int*>(carve(IK_CHUNK * IK_PMAX * 4));
-  int* s_cx = reinterpret_cast<int*>(carve(IK_NMAX * 4));
-  int* s_cy = reinterpret_cast<int*>(carve(IK_NMAX * 4));
-  int* s_cc = reinterpret_cast<int*>(carve(IK_NMAX * 4));
-  int* s_lrn = reinterpret_cast<int*>(carve(IK_NMAX * 4));
-  int* s_ind = reinterpret_cast<int*>(carve(IK_CHUNK * 4));
-  uint8_t* s_arrived = carve(IK_NMAX);
-  uint8_t* s_learned = carve(IK_NMAX);
-  int* s_misc = reinterpret_cast<int*>(carve(16 * 4));  // [0] n_lrn  [1] any learned
-  uint8_t* U = carve((size_t)ia.u_bytes);
-  double* s_goal = reinterpret_cast<double*>(carve(IK_NMAX * 2 * 8));
-  float* s_radf = reinterpret_cast<float*>(carve(IK_NMAX * 4));
-  float* s_speedf = reinterpret_cast<float*>(carve(IK_NMAX * 4));
-  uint2* s_w0f = ia.w0_frag ? reinterpret_cast<uint2*>(carve(8 * 6 * 3 * 32 * 8)) : nullptr;  // [n-tile][k-step][part][lane]
-  const int CH = ia.chunk;
-  double* s_pack = reinterpret_cast<double*>(carve((size_t)ia.own_max * 6 * 8));         // own agents' constants (Batch::agent_pack)
-  float* s_samples = reinterpret_cast<float*>(carve((size_t)ia.own_max * bt.K * 3 * 4));  // own agents' CVAE samples of the step
-  int32_t* s_nl = reinterpret_cast<int32_t*>(carve((size_t)ia.own_max * 4));
-  int32_t* s_vcnt = ia.vc_smem ? reinterpret_cast<int32_t*>(carve((size_t)ia.own_max * bt.L * 4)) : nullptr;
-  // union scratch U
-  float* u_h0 = reinterpret_cast<float*>(U);            // fov: [own agents][64]
-  float* u_h1 = u_h0 + q_own * 64;                      //      [own agents][64]
-  float* u_info = reinterpret_cast<float*>(U);          // comm: [CH * 16][12]
-  float* u_hA = u_info + CH * IK_PMAX * 12;             //       [CH * 16][36]
-  float* u_hB = u_hA + CH * IK_PMAX * 36;               //       [CH * 16][36]
-  float* u_y = u_hB + CH * IK_PMAX * 36;                //       [CH * 16][48]
-  float* u_p0 = reinterpret_cast<float*>(U);            // cvae: [IK_CHUNK][96]
-  float* u_sp = u_p0 + IK_CHUNK * 96;                   //       [IK_CHUNK][64]
-  float* u_d0 = u_sp + IK_CHUNK * 64;                   //       [IK_CHUNK][32]
+  double* s_cur = reinterpret_cast<double*>(ik_smem + ly_.cur);
+  double* s_prev = reinterpret_cast<double*>(ik_smem + ly_.prev);
+  double* s_goal = reinterpret_cast<double*>(ik_smem + ly_.goal);
+  double* s_nxt = reinterpret_cast<double*>(ik_smem + ly_.nxt);      // [2][IK_NMAX][2]: stored by the owners, by step parity
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(ik_smem + ly_.bits);  // [IK_NMAX][IK_WORDS], the words of this CTA's slices
+  float* s_vp = reinterpret_cast<float*>(ik_smem + ly_.vp);           // [IK_NMAX][32] vain_proj of all agents
+  float* s_eself = reinterpret_cast<float*>(ik_smem + ly_.eself);     // [own][32]
+  float* s_part = reinterpret_cast<float*>(ik_smem + ly_.part);       // [C][own_max][64] partial sums, stored by the slice owners
+  float* s_radf = reinterpret_cast<float*>(ik_smem + ly_.radf);
+  float* s_speedf = reinterpret_cast<float*>(ik_smem + ly_.speedf);
+  uint8_t* s_arrived = ik_smem + ly_.flags;             // [IK_NMAX]
+  uint8_t* s_learned = s_arrived + IK_NMAX;             // [IK_NMAX]
+  uint8_t* s_arrn = s_learned + IK_NMAX;                // [2][IK_NMAX] arrival flags after the step, stored by the owners
+  uint8_t* s_owner = s_arrn + 2 * IK_NMAX;              // [IK_NMAX] CTA that owns the agent
+  uint8_t* s_oidx = s_owner + IK_NMAX;                  // [IK_NMAX] its index among that CTA's agents
+  uint2* s_w0f = ia.w0_frag ? reinterpret_cast<uint2*>(ik_smem + ly_.w0f) : nullptr;
+  double* s_pack = reinterpret_cast<double*>(ik_smem + ly_.pack);      // own agents' constants (Batch::agent_pack)
+  float* s_samples = reinterpret_cast<float*>(ik_smem + ly_.samples);  // own agents' CVAE samples of the step
+  int32_t* s_nl = reinterpret_cast<int32_t*>(ik_smem + ly_.nl);
+  int32_t* s_vcnt = ia.vc_smem ? reinterpret_cast<int32_t*>(ik_smem + ly_.vcnt) : nullptr;
+  double* s_obs = reinterpret_cast<double*>(ik_smem + ly_.obs);        // [IK_GROUPS][3 * IK_OBS_MAX]
+  uint8_t* U = ik_smem + ly_.U;
+  GroupScratch& gs = reinterpret_cast<GroupScratch*>(U)[g];  // agent phases
+  float* u_h0 = reinterpret_cast<float*>(U);                 // fov tail: [own agents][64]
+  float* u_h1 = u_h0 + own_max * 64;                         //           [own agents][64]
   auto Wp = [&](int o) -> const float* { return Wsm + (o - off.fov_b0); };
 
   for (int i = tid; i < ia.n_w; i += IK_THREADS) Wsm[i] = __ldg(&ia.blob[off.fov_b0 + i]);
@@ -244,6 +315,9 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
     s_goal[2 * i] = bt.goals[2 * (a0 + i)]; s_goal[2 * i + 1] = bt.goals[2 * (a0 + i) + 1];
     s_radf[i] = (float)bt.rads[a0 + i];
     s_speedf[i] = (float)bt.speeds[a0 + i];
+    const int ow = (i * C + C - 1) / n;  // the r with r * n / C <= i < (r + 1) * n / C
+    s_owner[i] = (uint8_t)ow;
+    s_oidx[i] = (uint8_t)(i - (ow * n) / C);
   }
   for (int i = tid; i < n_own * 6; i += IK_THREADS) s_pack[i] = bt.agent_pack[6 * (size_t)(a0 + own_lo) + i];
   // the own agents' layer counts and sizes in shared memory (TimedRoadmap(start): one layer with the start vertex), written
@@ -252,36 +326,35 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
     for (int i = tid; i < n_own * bt.L; i += IK_THREADS) s_vcnt[i] = (i % bt.L) == 0 ? 1 : 0;
     for (int i = tid; i < n_own; i += IK_THREADS) s_nl[i] = 1;
   }
-  if (s_w0f != nullptr) {  // this CTA's slice of W0 as mma.sync B fragments: [n-tile of 8 columns][k-step of 16][bf16 part][lane]
-    const float* W0 = ia.blob + off.fov_w0;
-    for (int idx = tid; idx < 8 * 6 * 3 * 32; idx += IK_THREADS) {
-      const int ln = idx & 31, sp = (idx >> 5) % 3, ks = (idx / 96) % 6, nt = idx / 576;
-      const int col = 8 * nt + (ln >> 2), k0 = 96 * s_lo + 16 * ks + 2 * (ln & 3);
-      auto wv = [&](int j) { return j < KD ? __ldg(&W0[(size_t)j * 64 + col]) : 0.f; };
-      s_w0f[idx] = make_uint2(bf16_part(wv(k0), sp) | (bf16_part(wv(k0 + 1), sp) << 16),
-                              bf16_part(wv(k0 + 8), sp) | (bf16_part(wv(k0 + 9), sp) << 16));
-    }
-  }
+  if (s_w0f != nullptr)
+    for (int idx = tid; idx < IK_FRAG_SLICE; idx += IK_THREADS) s_w0f[idx] = __ldg(&ia.w0img[(size_t)s_lo * IK_FRAG_SLICE + idx]);
   __syncthreads();
 
   int t = 1, kt = 0, makespan = 0, steps = 0;
   const bool all_rows = bt.tr_samples != nullptr;  // trace: the CVAE output of every agent-step is recorded
   const int k_nb = ia.use_k_neighbor ? min(ia.num_neighbors, n - 1) : n - 1;
   const float eps = 1.1920928955078125e-07f;
-  float* part = ia.part + (size_t)b * IK_SLICES * bt.n_max * 64;
   const bool run = bt.N_traj > 0 && n > 0;
-  long long pacc[IK_NPROF];
+  unsigned int cnt_acc = 0;  // collide_continuous_sphere calls of this warp (warp-uniform)
+  long long* s_prof = reinterpret_cast<long long*>(ik_smem + ly_.prof);  // cycles per phase, thread 0's view
   long long pt0 = 0;
-#pragma unroll
-  for (int i = 0; i < IK_NPROF; ++i) pacc[i] = 0;
   const bool prof = ia.prof != nullptr && tid == 0;
-  if (prof) pt0 = clock64();
+  if (prof) {
+    if (tid == 0)
+      for (int i = 0; i < IK_NPROF; ++i) s_prof[i] = 0;
+    pt0 = clock64();
+  }
 #define IK_MARK(k)                      \
   if (prof) {                           \
     const long long now = clock64();    \
-    pacc[k] += now - pt0;               \
+    s_prof[k] += now - pt0;             \
     pt0 = now;                          \
   }
+#define IK_CLUSTER_SYNC()            \
+  do {                               \
+    if (C > 1) cluster.sync();       \
+    else __syncthreads();            \
+  } while (0)
 
   // the batch kernels' device functions index per-agent state by the global agent number: hand them a view of the batch whose
   // hot per-agent arrays are the shared-memory copies of the own agents
@@ -291,168 +364,172 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
     bv.vcnt = s_vcnt - (size_t)(a0 + own_lo) * bt.L;
     bv.nlayers = s_nl - (size_t)(a0 + own_lo);
   }
-  const bool obs_static = n_own <= IK_WARPS && nO <= IK_OBS_MAX;  // warp w serves own agent w in every step: stage its obstacles once
-  if (obs_static && warp < n_own) {
-    double* so = s_obs + warp * 3 * IK_OBS_MAX;
-    const double rad = s_pack[6 * warp + 5];
-    for (int o = lane; o < nO; o += 32) {
-      const double* g = bt.obs_xyr + 3 * (size_t)(o0 + o);
-      so[3 * o] = __ldg(g);
-      so[3 * o + 1] = __ldg(g + 1);
-      so[3 * o + 2] = f64add(rad, __ldg(g + 2));  // rad1 + rad2, rounded once (collision_check.cpp:56)
+  // obstacles of the group's agent as (x, y, rad_agent + rad_obstacle); a group that serves one agent stages them once
+  const bool obs_smem = nO <= IK_OBS_MAX;
+  constexpr bool wide_step = WIDE;
+  const bool obs_static = !wide_step && n_own <= IK_GROUPS && obs_smem;
+  double* g_obs = s_obs + g * 3 * IK_OBS_MAX;
+  auto stage_obstacles = [&](double rad) {
+    for (int o = gt; o < nO; o += 128) {
+      const double* gp = bt.obs_xyr + 3 * (size_t)(o0 + o);
+      g_obs[3 * o] = __ldg(gp);
+      g_obs[3 * o + 1] = __ldg(gp + 1);
+      g_obs[3 * o + 2] = f64add(rad, __ldg(gp + 2));  // rad1 + rad2, rounded once (collision_check.cpp:56)
     }
-  }
+  };
+  if (obs_static && g < n_own) stage_obstacles(s_pack[6 * g + 5]);
   cluster.sync();  // every CTA of the cluster is running before anyone stores into a neighbour's shared memory
 
   while (run) {
     // ---- which agents take the learned branch in this step (learned_sampler.py:148-157): every CTA for all agents
-    for (int i = tid; i < n; i += IK_THREADS)
-      s_learned[i] = (all_rows || gate_is_learned(bt, b, a0 + i, i, kt, t, makespan, s_arrived[i] != 0)) ? 1 : 0;
-    __syncthreads();
-    if (warp == 0) {  // own learned agents in index order; whether any agent of the instance is learned
-      int cnt = 0;
-      bool any = false;
-      for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        const bool f = i < n && s_learned[i];
-        any = any || f;
-        const bool mine = f && i >= own_lo && i < own_hi;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
-        if (mine) s_lrn[cnt + __popc(m & ((1u << lane) - 1u))] = i;
-        cnt += __popc(m);
-      }
-      any = __any_sync(0xFFFFFFFFu, any);
-      if (lane == 0) { s_misc[0] = cnt; s_misc[1] = any ? 1 : 0; }
+    bool lrn = false;
+    if (tid < n) {
+      const bool gate = gate_is_learned(bt, b, a0 + tid, tid, kt, t, makespan, s_arrived[tid] != 0);
+      lrn = all_rows || gate;
+      s_learned[tid] = (lrn ? 1 : 0) | (gate ? 2 : 0);  // bit 0: run the networks for this agent, bit 1: the gate itself
     }
-    __syncthreads();
-    const int n_lrn = s_misc[0];
-    const bool any_learned = s_misc[1] != 0;
+    const bool any_learned = __syncthreads_or(lrn ? 1 : 0) != 0;  // also publishes the positions of the previous advance
     IK_MARK(0)
 
     if (ia.nn && any_learned) {
-      // ================= raster: crop bits of the OWN agents (their cost fields and crops stay in this SM's L1 from step to
-      // step), every word stored straight into the shared memory of the CTA that owns its K-slice (distributed shared memory)
-      for (int io = tid; io < n_own; io += IK_THREADS) {
-        const int i = own_lo + io;
-        const int cx = grid_cell(s_cur[2 * i], M), cy = grid_cell(s_cur[2 * i + 1], M);
-        const bool centre_in = cx < M && cy < M;
-        s_cx[io] = cx; s_cy[io] = cy;
-        s_cc[io] = centre_in ? (int)__ldg(&bt.ctg[(size_t)(a0 + i) * ctg_field_elems(M, 1) + ctg_index(cx, cy, M, 1)]) : -1;
-      }
-      __syncthreads();
+      // ================= raster: crop bits of the OWN agents; task = (own agent, eight consecutive words): lane l reads input
+      // 32 w + l of word w, so a load instruction covers 32 consecutive crop cells (two or three map rows), and a ballot is
+      // the word.  The centre's cost is loaded beside the crop (whether it is inside the map is known without it).
       {
-        // item = (own agent, word, quarter of the word): eight independent loads per thread, all in flight at once; the four
-        // quarters meet by shuffle
         const uint8_t* occ = bt.occ + (size_t)b * M * M;
         const unsigned invF = 65536u / (unsigned)F + 1u;  // jj / F == (jj * invF) >> 16 for jj < F * F, F <= 41
-        const int n_items = n_own * IK_WORDS * 4;
-        for (int it0 = 0; it0 < n_items; it0 += IK_THREADS) {
-          const int it = it0 + tid;
-          const bool act = it < n_items;
-          const int qd = it & 3, iw = it >> 2;
-          const int io = act ? iw / IK_WORDS : 0, w = iw - io * IK_WORDS;
-          const int cc = act ? s_cc[io] : -1;
-          const int cx = s_cx[io] - buf, cy = s_cy[io] - buf;
-          const uint16_t* cf = bt.ctg + (size_t)(a0 + own_lo + io) * ctg_field_elems(M, 1);
-          // loads first, branch-free (a cell outside the crop / the map reads as "unreachable" / "occupied": bit 0), tests after
+        for (int task = warp; task < n_own * 3; task += IK_WARPS) {
+          const int io = task / 3, oct = task - 3 * io, i = own_lo + io;
+          const int cx0 = grid_cell(s_cur[2 * i], M), cy0 = grid_cell(s_cur[2 * i + 1], M);
+          const bool centre_in = cx0 < M && cy0 < M;
+          const uint16_t* cf = bt.ctg + (size_t)(a0 + i) * ctg_field_elems(M, 1);
+          const int cc = centre_in ? (int)__ldg(&cf[ctg_index(cx0, cy0, M, 1)]) : -1;
+          const int cx = cx0 - buf, cy = cy0 - buf;
           int vc[8], vo[8];
           bool isc[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int j = 32 * w + 8 * qd + e;
+            const int j = 32 * (8 * oct + e) + lane;
             const int ch = j >= FF ? 1 : 0, jj = j - ch * FF;
             const int xf = (int)(((unsigned)jj * invF) >> 16), yf = jj - xf * F;
             const int x = cx + xf, y = cy + yf;
-            const bool ok = j < KD && cc >= 0 && x >= 0 && x < M && y >= 0 && y < M;
+            const bool ok = j < KD && centre_in && x >= 0 && x < M && y >= 0 && y < M;
             isc[e] = ch != 0;
-            vc[e] = (ok && ch) ? (int)__ldg(&cf[ctg_index(x, y, M, 1)]) : CTRM_UNREACH;
-            vo[e] = (ok && !ch) ? (int)__ldg(&occ[x * M + y]) : 1;
+            vc[e] = CTRM_UNREACH;
+            vo[e] = 1;
+            // a word lies in one channel except the one that straddles F^2: warp-uniform tests skip the other channel's index math
+            if (32 * (8 * oct + e) + 31 >= FF) vc[e] = (ok && ch) ? (int)__ldg(&cf[ctg_index(x, y, M, 1)]) : CTRM_UNREACH;
+            if (32 * (8 * oct + e) < FF) vo[e] = (ok && !ch) ? (int)__ldg(&occ[x * M + y]) : 1;
           }
-          uint32_t byte = 0u;
+          uint32_t mine = 0u;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const bool bit = isc[e] ? (vc[e] != CTRM_UNREACH && (cc == CTRM_UNREACH || vc[e] < cc)) : (vo[e] == 0);
-            byte |= (bit ? 1u : 0u) << e;
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+            if (lane == e) mine = word;
           }
-          uint32_t word = byte << (8 * qd);
-          word |= __shfl_xor_sync(0xFFFFFFFFu, word, 1);
-          word |= __shfl_xor_sync(0xFFFFFFFFu, word, 2);
-          if (act && qd == 0) {
+          if (lane < 8) {
+            const int w = 8 * oct + lane;
             uint32_t* dst = cluster.map_shared_rank(s_bits, (unsigned)((w / 3) / spc));
-            dst[(own_lo + io) * IK_WORDS + w] = word;
+            dst[i * IK_WORDS + w] = mine;
           }
         }
       }
-      cluster.sync();  // every agent's bits of this CTA's slices have arrived
       IK_MARK(1)
-      // ================= fov L0: partial sums of this CTA's slices =================
-      if (s_w0f != nullptr) {
-        // one slice per CTA, on the tensor cores: A = crop bits as bf16 0/1 (exact), B = the resident three-way bf16 split of W0
-        // (exact to 24 bits), fp32 accumulators, the large (hi) and the small (mid, lo) products in separate accumulators.
-        // warp = (n-tile of 8 columns, m-tile of 16 agents)
-        const int nt = warp & 7, gid = lane >> 2, tig = lane & 3;
-        for (int mt = warp >> 3; 16 * mt < n; mt += 2) {
-          float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
+      IK_CLUSTER_SYNC();  // every agent's bits of this CTA's slices have arrived
+      IK_MARK(2)
+      // ================= fov L0 on the tensor cores: A = crop bits as bf16 0/1 (exact), B = the three-way bf16 split of W0
+      // (exact to 24 bits), fp32 accumulators, the large (hi) and the small (mid, lo) products in separate accumulators.
+      // task = (n-tile of 8 columns, m-tile of 16 agents); the CTA's slices are summed as a binary tree in slice order.
+      {
+        const int gid = lane >> 2, tig = lane & 3;
+        const int n_mt = (n + 15) >> 4;
+        for (int task = warp; task < 8 * n_mt; task += IK_WARPS) {
+          const int nt = task & 7, mt = task >> 3;
           const int r0 = 16 * mt + gid, r1 = r0 + 8;
+          float tot[4] = {0.f, 0.f, 0.f, 0.f};
+          if (s_w0f != nullptr) {  // one resident slice
+            uint2 f[18];
 #pragma unroll
-          for (int ks = 0; ks < 6; ++ks) {
-            const int widx = 3 * s_lo + (ks >> 1), sh = 16 * (ks & 1) + 2 * tig;
-            const uint32_t x0 = s_bits[r0 * IK_WORDS + widx] >> sh, x1 = s_bits[r1 * IK_WORDS + widx] >> sh;
-            const uint32_t a[4] = {bits2_bf16(x0), bits2_bf16(x1), bits2_bf16(x0 >> 8), bits2_bf16(x1 >> 8)};
-            const uint2* f = s_w0f + ((nt * 6 + ks) * 3) * 32 + lane;
-            const uint2 fh = f[0], fm = f[32], fl = f[64];
-            mma_bf16_16816(accH, a, fh.x, fh.y);
-            mma_bf16_16816(accL, a, fm.x, fm.y);
-            mma_bf16_16816(accL, a, fl.x, fl.y);
+            for (int q = 0; q < 18; ++q) f[q] = s_w0f[(nt * 18 + q) * 32 + lane];
+            l0_slice_mma(s_bits, r0, r1, s_lo, tig, f, tot);
+          } else {
+            float l0v[4], l1v[4], l2v[4];
+            uint2 f[18], fn[18];
+            const uint2* img = ia.w0img + (size_t)nt * 18 * 32 + lane;
+#pragma unroll
+            for (int q = 0; q < 18; ++q) f[q] = __ldg(img + (size_t)s_lo * IK_FRAG_SLICE + q * 32);
+#pragma unroll 1
+            for (int si = 0; si < spc; ++si) {
+              {
+                if (si + 1 < spc) {
+#pragma unroll
+                  for (int q = 0; q < 18; ++q) fn[q] = __ldg(img + (size_t)(s_lo + si + 1) * IK_FRAG_SLICE + q * 32);
+                }
+                float p[4];
+                l0_slice_mma(s_bits, r0, r1, s_lo + si, tig, f, p);
+                // binary-tree carry: slices (0 1) (2 3) ... then pairs of pairs
+                if (si & 1) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) p[i] = l0v[i] + p[i];
+                  if (si & 2) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) p[i] = l1v[i] + p[i];
+                    if (si & 4) {
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) p[i] = l2v[i] + p[i];
+                    } else {
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) l2v[i] = p[i];
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) l1v[i] = p[i];
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) l0v[i] = p[i];
+                }
+                if (si + 1 == spc) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) tot[i] = p[i];
+                }
+#pragma unroll
+                for (int q = 0; q < 18; ++q) f[q] = fn[q];
+              }
+            }
           }
           const int col = 8 * nt + 2 * tig;
-          if (r0 < n) __stcg(reinterpret_cast<float2*>(part + ((size_t)s_lo * bt.n_max + r0) * 64 + col),
-                             make_float2(accH[0] + accL[0], accH[1] + accL[1]));
-          if (r1 < n) __stcg(reinterpret_cast<float2*>(part + ((size_t)s_lo * bt.n_max + r1) * 64 + col),
-                             make_float2(accH[2] + accL[2], accH[3] + accL[3]));
-        }
-      } else {
-        // CUDA cores, W0 streamed through L1 / L2: thread = (agent, four of the 64 columns)
-        const float* W0 = ia.blob + off.fov_w0;
-        const int quad = tid & 15;
-        for (int i = tid >> 4; i < n; i += IK_THREADS / 16) {
-          for (int s = s_lo; s < s_hi; ++s) {
-            float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int w = 0; w < 3; ++w) {
-              const uint32_t bits = s_bits[i * IK_WORDS + 3 * s + w];
-              const int jb = 96 * s + 32 * w;
-              const int nb = min(32, KD - jb);
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-              for (int bp = 0; bp < nb; ++bp) {
-                const float4 wv = __ldg(reinterpret_cast<const float4*>(W0 + (size_t)(jb + bp) * 64 + 4 * quad));
-                const float m = (bits >> bp) & 1u ? 1.f : 0.f;
-                acc.x = fmaf(wv.x, m, acc.x); acc.y = fmaf(wv.y, m, acc.y); acc.z = fmaf(wv.z, m, acc.z); acc.w = fmaf(wv.w, m, acc.w);
-              }
-              tot.x += acc.x; tot.y += acc.y; tot.z += acc.z; tot.w += acc.w;
-            }
-            __stcg(reinterpret_cast<float4*>(part + ((size_t)s * bt.n_max + i) * 64 + 4 * quad), tot);
+          if (r0 < n) {
+            float* dst = cluster.map_shared_rank(s_part, (unsigned)s_owner[r0]);
+            *reinterpret_cast<float2*>(dst + ((size_t)r * own_max + s_oidx[r0]) * 64 + col) = make_float2(tot[0], tot[1]);
+          }
+          if (r1 < n) {
+            float* dst = cluster.map_shared_rank(s_part, (unsigned)s_owner[r1]);
+            *reinterpret_cast<float2*>(dst + ((size_t)r * own_max + s_oidx[r1]) * 64 + col) = make_float2(tot[2], tot[3]);
           }
         }
       }
-      IK_MARK(2)
-      cluster.sync();
+      IK_CLUSTER_SYNC();
       IK_MARK(3)
       // ================= fov tails of the own agents =================
       {
         const float* b0 = Wp(off.fov_b0);
         for (int it = tid; it < n_own * 64; it += IK_THREADS) {
           const int io = it >> 6, o = it & 63;
-          float acc = b0[o];
-#pragma unroll
-          for (int s = 0; s < IK_SLICES; ++s) acc += __ldcg(part + ((size_t)s * bt.n_max + own_lo + io) * 64 + o);
-          u_h0[io * 64 + o] = fmaxf(acc, 0.f);
+          const float* q = s_part + (size_t)io * 64 + o;
+          const size_t st = (size_t)own_max * 64;
+          float sum;
+          if (C == 8) sum = ((q[0] + q[st]) + (q[2 * st] + q[3 * st])) + ((q[4 * st] + q[5 * st]) + (q[6 * st] + q[7 * st]));
+          else if (C == 4) sum = (q[0] + q[st]) + (q[2 * st] + q[3 * st]);
+          else if (C == 2) sum = q[0] + q[st];
+          else sum = q[0];
+          u_h0[io * 64 + o] = fmaxf(b0[o] + sum, 0.f);
         }
         __syncthreads();
         // item = (own agent, encoder e, four columns, k strand): hidden 1 -> hidden 2
         for (int it = tid; it < n_own * 64; it += IK_THREADS) {
-          const int kq = it & 3, q = (it >> 2) & 7, e = (it >> 5) & 1, io = it >> 6;
+          const int q = it & 7, kq = (it >> 3) & 3, e = (it >> 5) & 1, io = it >> 6;
           float4 acc = splitk_32(u_h0 + io * 64 + 32 * e, Wp(e ? off.fovv_w1 : off.fovs_w1), q, kq);
           if (kq == 0) {
             const float4 bb = *reinterpret_cast<const float4*>(Wp(e ? off.fovv_b1 : off.fovs_b1) + 4 * q);
@@ -463,7 +540,7 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
         __syncthreads();
         // hidden 2 -> e_self (shared memory) | e_vain (back into u_h0)
         for (int it = tid; it < n_own * 64; it += IK_THREADS) {
-          const int kq = it & 3, q = (it >> 2) & 7, e = (it >> 5) & 1, io = it >> 6;
+          const int q = it & 7, kq = (it >> 3) & 3, e = (it >> 5) & 1, io = it >> 6;
           float4 acc = splitk_32(u_h1 + io * 64 + 32 * e, Wp(e ? off.fovv_w2 : off.fovs_w2), q, kq);
           if (kq == 0) {
             const float4 bb = *reinterpret_cast<const float4*>(Wp(e ? off.fovv_b2 : off.fovs_b2) + 4 * q);
@@ -472,98 +549,117 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
           }
         }
         __syncthreads();
-        // vain_proj = b0 + W0[11:43]^T e_vain (agent_encoder.py:57-60), for every CTA of the cluster through L2
+        // vain_proj = b0 + W0[11:43]^T e_vain (agent_encoder.py:57-60), stored into every CTA of the cluster (strand kq -> CTAs
+        // kq and kq + 4: the four strands hold the same sum after the shuffles)
         for (int it = tid; it < n_own * 32; it += IK_THREADS) {
-          const int kq = it & 3, q = (it >> 2) & 7, io = it >> 5;
+          const int q = it & 7, kq = (it >> 3) & 3, io = it >> 5;
           float4 acc = splitk_32(u_h0 + io * 64, Wp(off.ag_w0v), q, kq);
-          if (kq == 0) {
-            const float4 bb = *reinterpret_cast<const float4*>(Wp(off.ag_b0) + 4 * q);
-            __stcg(reinterpret_cast<float4*>(bt.vain_proj + (size_t)(a0 + own_lo + io) * 32 + 4 * q),
-                   make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w));
-          }
+          const float4 bb = *reinterpret_cast<const float4*>(Wp(off.ag_b0) + 4 * q);
+          const float4 v = make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w);
+          for (int c = kq; c < C; c += 4)
+            *reinterpret_cast<float4*>(cluster.map_shared_rank(s_vp, (unsigned)c) + (size_t)(own_lo + io) * 32 + 4 * q) = v;
         }
       }
       IK_MARK(4)
-      cluster.sync();
+      IK_CLUSTER_SYNC();
       IK_MARK(5)
-      // ================= comm + cvae for the own learned agents, IK_CHUNK at a time =================
-      if (n_lrn > 0) {
-        for (int i = tid; i < n * 8; i += IK_THREADS)
-          reinterpret_cast<float4*>(s_vp)[i] = __ldcg(reinterpret_cast<const float4*>(bt.vain_proj + (size_t)a0 * 32) + i);
+    }
+
+    // ================= the own agents, one per group at a time: comm -> cvae -> select -> merge =================
+    const int pb = steps & 1;
+    for (int io = g; io < n_own; io += IK_GROUPS) {
+      const int i = own_lo + io, a = a0 + i;
+      const bool learned = (s_learned[i] & 1) != 0;
+      const double* ap = s_pack + 6 * io;
+      if (!wide_step && !obs_static && obs_smem) {
+        stage_obstacles(ap[5]);
+        group_bar(g);
       }
-      for (int c0 = 0; c0 < n_lrn; c0 += CH) {
-        const int nc = min(CH, n_lrn - c0);
-        __syncthreads();  // s_vp loaded / the previous chunk has left the scratch
+      if (ia.nn && learned) {
         // ---- k nearest neighbours (format_input.py:239-243): float32(sqrt_f64(dx^2 + dy^2)) keys, ties by index, self first
-        if (warp < nc) {
-          const int il = s_lrn[c0 + warp];
-          const double cix = s_cur[2 * il], ciy = s_cur[2 * il + 1];
-          unsigned long long* key = s_keys + warp * IK_NMAX;
-          for (int j = lane; j < n; j += 32) {
-            const double dx = f64sub(s_cur[2 * j], cix), dy = f64sub(s_cur[2 * j + 1], ciy);
-            const float d = __double2float_rn(__dsqrt_rn(f64add(f64mul(dx, dx), f64mul(dy, dy))));
-            key[j] = (j == il) ? 0ull : (((unsigned long long)(__float_as_uint(d) + 1u) << 32) | (unsigned)j);
+        const double cix = s_cur[2 * i], ciy = s_cur[2 * i + 1];
+        if (gt < n) {
+          const int j = gt;
+          const double dx = f64sub(s_cur[2 * j], cix), dy = f64sub(s_cur[2 * j + 1], ciy);
+          const float d = __double2float_rn(__dsqrt_rn(f64add(f64mul(dx, dx), f64mul(dy, dy))));
+          gs.keys[j] = (j == i) ? 0ull : (((unsigned long long)(__float_as_uint(d) + 1u) << 32) | (unsigned)j);
+        }
+        group_bar(g);
+        {  // thread = (agent j, a part of the comparison range); the parts meet by shuffle
+          const int sh = n <= 32 ? 2 : 1, parts = 1 << sh;
+          const int j = gt >> sh, part = gt & (parts - 1);
+          const int len = (n + parts - 1) >> sh;
+          const int lo = part * len, hi = min(n, lo + len);
+          const bool act = j < n;
+          const unsigned long long kj = act ? gs.keys[j] : 0ull;
+          int rank = 0;
+          for (int j2 = lo; j2 < hi; ++j2) rank += gs.keys[j2] < kj ? 1 : 0;
+          rank += __shfl_xor_sync(0xFFFFFFFFu, rank, 1);
+          if (sh == 2) rank += __shfl_xor_sync(0xFFFFFFFFu, rank, 2);
+          if (act && part == 0 && rank <= k_nb) gs.order[rank] = j;
+        }
+        group_bar(g);
+        IK_MARK(6)
+        // ---- a warp takes four (agent, slot) pair rows through the pair features (compiled.py:30-97; slot 0 = the agent
+        //      itself, slot s = its s-th nearest) and the three layers of AgentEncoder (agent_encoder.py:34-65), lane = column
+        {
+          const int p0 = 4 * gw;
+          if (lane < 4) {
+            const int s = p0 + lane;
+            float* info = gs.info + s * 12;
+            if (s <= k_nb) {
+              const int j = gs.order[s];
+              ik_nvm(f64sub(s_cur[2 * j], cix), f64sub(s_cur[2 * j + 1], ciy), info + 0);
+              ik_nvm(f64sub(s_goal[2 * j], cix), f64sub(s_goal[2 * j + 1], ciy), info + 3);
+              ik_nvm(f64sub(s_prev[2 * j], cix), f64sub(s_prev[2 * j + 1], ciy), info + 6);
+              info[9] = s_radf[j];
+              info[10] = s_speedf[j];
+              info[11] = 0.f;  // K padded to 12 (the weight row it meets is finite)
+              gs.pj[s] = j;
+              if (s == 0) {  // get_self_info (compiled.py:100-125): row (i, i), columns 3..10
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gs.X[k] = info[3 + k];
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 12; ++k) info[k] = 0.f;
+              gs.pj[s] = -1;
+            }
           }
           __syncwarp();
-          for (int j = lane; j < n; j += 32) {
-            const unsigned long long kj = key[j];
-            int rank = 0;
-            for (int j2 = 0; j2 < n; ++j2) rank += key[j2] < kj ? 1 : 0;
-            if (rank <= k_nb) s_order[warp * IK_PMAX + rank] = j;
-          }
-        }
-        __syncthreads();
-        IK_MARK(6)
-        // ---- pair features (compiled.py:30-97) of (agent, slot): slot 0 = the agent itself, slot s = its s-th nearest
-        if (tid < nc * IK_PMAX) {
-          const int c = tid / IK_PMAX, s = tid - c * IK_PMAX;
-          if (s <= k_nb) {
-            const int il = s_lrn[c0 + c], j = s_order[c * IK_PMAX + s];
-            const double cix = s_cur[2 * il], ciy = s_cur[2 * il + 1];
-            float* info = u_info + tid * 12;
-            ik_nvm(f64sub(s_cur[2 * j], cix), f64sub(s_cur[2 * j + 1], ciy), info + 0);
-            ik_nvm(f64sub(s_goal[2 * j], cix), f64sub(s_goal[2 * j + 1], ciy), info + 3);
-            ik_nvm(f64sub(s_prev[2 * j], cix), f64sub(s_prev[2 * j + 1], ciy), info + 6);
-            info[9] = s_radf[j];
-            info[10] = s_speedf[j];
-            info[11] = 0.f;  // K padded to 12 (the weight row it meets is finite)
-            s_pj[tid] = j;
-            if (s == 0) {  // get_self_info (compiled.py:100-125): row (i, i), columns 3..10
-              float* xr = s_X + c * CTRM_DIM_X;
-#pragma unroll
-              for (int k = 0; k < 8; ++k) xr[k] = info[3 + k];
-            }
-          } else {
-            s_pj[tid] = -1;
-          }
-        }
-        __syncthreads();
-        IK_MARK(7)
-        // ---- AgentEncoder on the pairs (agent_encoder.py:34-65): a warp takes four pair rows, lane = output column
-        for (int p0 = 4 * warp; p0 < nc * IK_PMAX; p0 += 4 * IK_WARPS) {
           const float* brow[4];
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) brow[rr] = s_pj[p0 + rr] >= 0 ? s_vp + s_pj[p0 + rr] * 32 : nullptr;
-          warp_rows4<12, 0, true>(u_info, 12, Wp(off.ag_w0i), 32, brow, u_hA, 36, p0, lane);
-        }
-        __syncthreads();
-        for (int p0 = 4 * warp; p0 < nc * IK_PMAX; p0 += 4 * IK_WARPS) {
+          for (int rr = 0; rr < 4; ++rr) brow[rr] = gs.pj[p0 + rr] >= 0 ? s_vp + gs.pj[p0 + rr] * 32 : nullptr;
+          warp_rows4<12, 0, true>(gs.info, 12, Wp(off.ag_w0i), 32, brow, gs.hA, 36, p0, lane);
+          __syncwarp();
           const float* b1 = Wp(off.ag_b1);
-          const float* brow[4] = {b1, b1, b1, b1};
-          warp_rows4<32, 0, true>(u_hA, 36, Wp(off.ag_w1), 32, brow, u_hB, 36, p0, lane);
-        }
-        __syncthreads();
-        for (int p0 = 4 * warp; p0 < nc * IK_PMAX; p0 += 4 * IK_WARPS) {
+          const float* brow1[4] = {b1, b1, b1, b1};
+          warp_rows4<32, 0, true>(gs.hA, 36, Wp(off.ag_w1), 32, brow1, gs.hB, 36, p0, lane);
+          __syncwarp();
           const float* b2 = Wp(off.ag_b2);
-          const float* brow[4] = {b2, b2, b2, b2};
-          warp_rows4<32, 12, false>(u_hB, 36, Wp(off.ag_w2), 44, brow, u_y, 48, p0, lane);
+          const float* brow2[4] = {b2, b2, b2, b2};
+          warp_rows4<32, 12, false>(gs.hB, 36, Wp(off.ag_w2), 44, brow2, gs.y, 48, p0, lane);
         }
-        __syncthreads();
-        IK_MARK(8)
+        group_bar(g);
+        IK_MARK(7)
         // ---- attention softmax over the neighbours and message sum (format_input.py:250-275); X = [self_info | e_self | comm]
-        if (warp < nc) {
-          const int il = s_lrn[c0 + warp];
-          const float* y0 = u_y + (warp * IK_PMAX) * 48;
+        //      on role 0; the other roles meanwhile draw the Gumbel noise of their decoder copy (it depends on the step's
+        //      counters only): rsqrt(E) with E = -log u for latents 2 lane and 2 lane + 1
+        const int dk0 = (gw + 3) & 3;  // the decoder copies of this role: dk0, dk0 + 4, ...
+        float rsa = 0.f, rsb = 0.f;
+        auto gumbel_rsqrt = [&](int k, float* pa, float* pb) {
+          const uint4 w4 = philox4x32(bt.inst_base + (uint32_t)b, rng_ctr1(kt, t), (uint32_t)(k * n + i),
+                                      rng_ctr3(STREAM_GUMBEL, (uint32_t)(lane >> 1)), bt.seed_lo, bt.seed_hi);
+          const float ua = u32_to_f32((lane & 1) ? w4.z : w4.x), ub = u32_to_f32((lane & 1) ? w4.w : w4.y);
+          *pa = rsqrtf(-logf(fminf(fmaxf(ua, eps), 1.f - eps)));
+          *pb = rsqrtf(-logf(fminf(fmaxf(ub, eps), 1.f - eps)));
+        };
+        if (gw != 0 && dk0 < bt.K) {
+          gumbel_rsqrt(dk0, &rsa, &rsb);
+          asm volatile("" : "+f"(rsa), "+f"(rsb));  // materialise here, beside the softmax: the compiler would sink it to its use
+        }
+        if (gw == 0) {
+          const float* y0 = gs.y;
           const int s = lane;
           const bool has_pair = s <= k_nb && s < IK_PMAX;
           float sim = 0.f;
@@ -584,34 +680,39 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
           const float wgt = in_softmax ? ev / sum : 0.f;
           float comm = 0.f;
           for (int rr = 1; rr <= k_nb; ++rr) comm += y0[rr * 48 + lane] * __shfl_sync(0xFFFFFFFFu, wgt, rr);
-          float* xr = s_X + warp * CTRM_DIM_X;
-          xr[40 + lane] = comm;
-          xr[8 + lane] = s_eself[(il - own_lo) * 32 + lane];
+          gs.X[40 + lane] = comm;
+          gs.X[8 + lane] = s_eself[io * 32 + lane];
         }
-        __syncthreads();
-        IK_MARK(9)
-        // ---- first layers of indicator | encoder_input | decoder (x rows) side by side: item = (agent, net, four columns)
-        for (int it = tid; it < nc * 24; it += IK_THREADS) {
-          const int c = it / 24, rem = it - c * 24, net = rem >> 3, q = rem & 7;
+        group_bar(g);
+        IK_MARK(8)
+        // ---- first layers of indicator | encoder_input | decoder (x rows) side by side: warp = net, lane = (k strand of 18, four
+        //      columns) in the conflict-free layout of splitk_32
+        if (gt < 96) {
+          const int net = gt >> 5, kq = (gt >> 3) & 3, q = gt & 7;
           const float* Wm = net == 0 ? Wp(off.ind_w0) : (net == 1 ? Wp(off.enc_w0) : Wp(off.dec_w0) + 64 * 32);
-          const float* x = s_X + c * CTRM_DIM_X;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-          for (int k = 0; k < CTRM_DIM_X; ++k) {
+#pragma unroll 6
+          for (int kk = 0; kk < CTRM_DIM_X / 4; ++kk) {
+            const int k = (CTRM_DIM_X / 4) * kq + kk;
             const float4 w = *reinterpret_cast<const float4*>(Wm + k * 32 + 4 * q);
-            const float v = x[k];
+            const float v = gs.X[k];
             acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y); acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
           }
-          float* o = u_p0 + c * 96 + 32 * net + 4 * q;
-          o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+#pragma unroll
+          for (int d = 8; d <= 16; d <<= 1) {
+            acc.x += __shfl_xor_sync(0xFFFFFFFFu, acc.x, d); acc.y += __shfl_xor_sync(0xFFFFFFFFu, acc.y, d);
+            acc.z += __shfl_xor_sync(0xFFFFFFFFu, acc.z, d); acc.w += __shfl_xor_sync(0xFFFFFFFFu, acc.w, d);
+          }
+          if (kq == 0) *reinterpret_cast<float4*>(gs.p0 + 32 * net + 4 * q) = acc;
         }
-        __syncthreads();
-        IK_MARK(10)
-        // ---- indicator -> argmax (learned_sampler.py:99-104); prior -> sqrt of the clamped probabilities (cvae.py:57-68,
-        //      :132-136; cvae_tc.cu); decoder first layer without its z rows.  One warp per agent, a hidden vector = a register
-        if (warp < nc) {
-          const float* p0 = u_p0 + warp * 96;
-          float h = fmaxf(p0[lane] + Wp(off.ind_b0)[lane], 0.f);
+        group_bar(g);
+        IK_MARK(9)
+        // ---- role 0: indicator -> argmax (learned_sampler.py:99-104).  roles 1..3: the prior for indicator value v = role - 1
+        //      (cvae.py:57-68, :132-136; sqrt of the clamped probabilities, cvae_tc.cu) and the decoder's first layer without its
+        //      z rows — the three values side by side instead of waiting for the argmax (a phase costs what its longest warp
+        //      costs: three short warps beat one warp that shares the weight loads)
+        if (gw == 0) {
+          float h = fmaxf(gs.p0[lane] + Wp(off.ind_b0)[lane], 0.f);
           h = fmaxf(warp_layer32(h, Wp(off.ind_w1), 32, lane, Wp(off.ind_b1)[lane]), 0.f);
           const float lg = warp_layer32(h, Wp(off.ind_w2), 4, lane & 3, Wp(off.ind_b2)[lane & 3]);
           const float l0 = __shfl_sync(0xFFFFFFFFu, lg, 0), l1 = __shfl_sync(0xFFFFFFFFu, lg, 1), l2 = __shfl_sync(0xFFFFFFFFu, lg, 2);
@@ -619,11 +720,11 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
           float best = l0;
           if (l1 > best) { best = l1; ind = 1; }
           if (l2 > best) { best = l2; ind = 2; }
-          if (lane == 0) {
-            s_ind[warp] = ind;
-          }
-          u_d0[warp * 32 + lane] = (p0[64 + lane] + Wp(off.dec_b0)[lane]) + Wp(off.dec_w0)[(64 + CTRM_DIM_X + ind) * 32 + lane];
-          float he = fmaxf((p0[32 + lane] + Wp(off.enc_b0)[lane]) + Wp(off.enc_w0)[(CTRM_DIM_X + ind) * 32 + lane], 0.f);
+          if (lane == 0) gs.ind = ind;
+        } else {
+          const int v = gw - 1;
+          gs.d0[v * 32 + lane] = (gs.p0[64 + lane] + Wp(off.dec_b0)[lane]) + Wp(off.dec_w0)[(64 + CTRM_DIM_X + v) * 32 + lane];
+          float he = fmaxf((gs.p0[32 + lane] + Wp(off.enc_b0)[lane]) + Wp(off.enc_w0)[(CTRM_DIM_X + v) * 32 + lane], 0.f);
           he = fmaxf(warp_layer32(he, Wp(off.enc_w1), 32, lane, Wp(off.enc_b1)[lane]), 0.f);
           const float g0 = warp_layer32(he, Wp(off.enc_w2), 64, lane, Wp(off.enc_b2)[lane]);
           const float g1 = warp_layer32(he, Wp(off.enc_w2), 64, 32 + lane, Wp(off.enc_b2)[32 + lane]);
@@ -631,86 +732,268 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
           const float lse = logf(warp_sum(expf(g0 - mx) + expf(g1 - mx)));
           const float q0 = expf((g0 - mx) - lse), q1 = expf((g1 - mx) - lse);  // probs = exp(log_softmax)
           const float ps = warp_sum(q0 + q1);                                  // Categorical normalises probs / sum
-          u_sp[warp * 64 + lane] = sqrtf(fminf(fmaxf(q0 / ps, eps), 1.f - eps));
-          u_sp[warp * 64 + 32 + lane] = sqrtf(fminf(fmaxf(q1 / ps, eps), 1.f - eps));
+          gs.sp[v * 64 + lane] = sqrtf(fminf(fmaxf(q0 / ps, eps), 1.f - eps));
+          gs.sp[v * 64 + 32 + lane] = sqrtf(fminf(fmaxf(q1 / ps, eps), 1.f - eps));
         }
-        __syncthreads();
-        IK_MARK(11)
-        // ---- K relaxed one-hot samples and the decoder, one warp per (agent, copy): z_i = sqrt(p_i / E_i) / sum (temperature 2,
+        group_bar(g);
+        IK_MARK(10)
+        // ---- K relaxed one-hot samples and the decoder, one warp per copy: z_i = sqrt(p_i / E_i) / sum (temperature 2,
         //      cvae_tc.cu), lane holds latents 2 lane and 2 lane + 1
-        for (int task = warp; task < nc * bt.K; task += IK_WARPS) {
-          const int c = task / bt.K, k = task - c * bt.K;
-          const int il = s_lrn[c0 + c];
-          const uint4 w4 = philox4x32(bt.inst_base + (uint32_t)b, rng_ctr1(kt, t), (uint32_t)(k * n + il),
-                                      rng_ctr3(STREAM_GUMBEL, (uint32_t)(lane >> 1)), bt.seed_lo, bt.seed_hi);
-          const float ua = u32_to_f32((lane & 1) ? w4.z : w4.x), ub = u32_to_f32((lane & 1) ? w4.w : w4.y);
-          const float Ea = -logf(fminf(fmaxf(ua, eps), 1.f - eps)), Eb = -logf(fminf(fmaxf(ub, eps), 1.f - eps));
-          const float ra = u_sp[c * 64 + 2 * lane] * rsqrtf(Ea), rb = u_sp[c * 64 + 2 * lane + 1] * rsqrtf(Eb);
+        for (int k = dk0; k < bt.K; k += 4) {
+          const int ind = gs.ind;
+          const float* sp = gs.sp + ind * 64;
+          if (gw == 0 || k != dk0) gumbel_rsqrt(k, &rsa, &rsb);
+          const float ra = sp[2 * lane] * rsa, rb = sp[2 * lane + 1] * rsb;
           const float inv = 1.f / warp_sum(ra + rb);
           const float za = fminf(ra * inv, 1.f), zb = fminf(rb * inv, 1.f);
           const float* Wz = Wp(off.dec_w0);
-          float h = u_d0[c * 32 + lane];
-#pragma unroll
+          float h = gs.d0[ind * 32 + lane], h1 = 0.f;  // two chains: even and odd latents
+#pragma unroll 4
           for (int m = 0; m < 32; ++m) {
             h = fmaf(__shfl_sync(0xFFFFFFFFu, za, m), Wz[(2 * m) * 32 + lane], h);
-            h = fmaf(__shfl_sync(0xFFFFFFFFu, zb, m), Wz[(2 * m + 1) * 32 + lane], h);
+            h1 = fmaf(__shfl_sync(0xFFFFFFFFu, zb, m), Wz[(2 * m + 1) * 32 + lane], h1);
           }
-          h = fmaxf(h, 0.f);
+          h = fmaxf(h + h1, 0.f);
           h = fmaxf(warp_layer32(h, Wp(off.dec_w1), 32, lane, Wp(off.dec_b1)[lane]), 0.f);
           const float o = warp_layer32(h, Wp(off.dec_w2), 4, lane & 3, Wp(off.dec_b2)[lane & 3]);
-          if (lane < 3) s_samples[((size_t)(il - own_lo) * bt.K + k) * 3 + lane] = o;
+          if (lane < 3) s_samples[((size_t)io * bt.K + k) * 3 + lane] = o;
         }
+        group_bar(g);
+        IK_MARK(11)
       }
-      __syncthreads();  // the samples are in place
-      IK_MARK(12)
-    }
 
-    // ================= step: select + merge_samples, one warp per own agent (rollout.cuh) =================
-    for (int i = own_lo + warp; i < own_hi; i += IK_WARPS) {
-      const int a = a0 + i;
-      StepCtx sc;
-      sc.b = b; sc.t = t; sc.kt = kt; sc.makespan = makespan;
-      sc.a0 = a0; sc.N = n; sc.o0 = o0; sc.nO = nO;
-      sc.inv_nO = (nO >= 1 && nO <= 128) ? c_pair_inv.v[nO] : 0u;
-      const double* ap = s_pack + 6 * (i - own_lo);
-      sc.gx = ap[0]; sc.gy = ap[1]; sc.speed = ap[2]; sc.speed2 = ap[3]; sc.merge2 = ap[4]; sc.rad = ap[5];
-      sc.sobs = nullptr;
-      if (obs_static) {
-        sc.sobs = s_obs + warp * 3 * IK_OBS_MAX;
-      } else if (nO <= IK_OBS_MAX) {
-        double* so = s_obs + warp * 3 * IK_OBS_MAX;
-        __syncwarp();
-        for (int o = lane; o < nO; o += 32) {
-          const double* g = bt.obs_xyr + 3 * (size_t)(o0 + o);
-          so[3 * o] = __ldg(g);
-          so[3 * o + 1] = __ldg(g + 1);
-          so[3 * o + 2] = f64add(sc.rad, __ldg(g + 2));  // rad1 + rad2, rounded once (collision_check.cpp:56)
+      // ---- step (rollout.cuh): warp 0 selects loc_pred while warps 0..2 already hold V[t-1] / V[t+1] / V[t]; then the
+      //      parents, the children, the merge candidates and the goal test of merge_samples run side by side
+      if (!wide_step) {
+        StepCtx sc;
+        sc.b = b; sc.t = t; sc.kt = kt; sc.makespan = makespan;
+        sc.a0 = a0; sc.N = n; sc.o0 = o0; sc.nO = nO;
+        sc.inv_nO = (nO >= 1 && nO <= 128) ? c_pair_inv.v[nO] : 0u;
+        sc.gx = ap[0]; sc.gy = ap[1]; sc.speed = ap[2]; sc.speed2 = ap[3]; sc.merge2 = ap[4]; sc.rad = ap[5];
+        sc.sobs = obs_smem ? g_obs : nullptr;
+        const double cx = s_cur[2 * i], cy = s_cur[2 * i + 1];
+        const bool arrived = s_arrived[i] != 0;
+        const int nl = bv.nlayers[a];
+        const int32_t* vcn = bv.vcnt + (size_t)a * bt.L;
+        const int n_prev = vcn[t - 1], n_t = (nl > t) ? vcn[t] : 0, n_next = (nl > t + 1) ? vcn[t + 1] : 0;
+        const bool has_next = nl > t + 1;
+        // this warp's layer: 0 parents V[t-1], 1 children V[t+1], 2 merge candidates V[t]
+        const int lay_t = gw == 0 ? t - 1 : (gw == 1 ? t + 1 : t);
+        const int lay_n = gw == 0 ? n_prev : (gw == 1 ? n_next : (gw == 2 ? n_t : 0));
+        double px[W], py[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          px[w] = 0.0; py[w] = 0.0;
+          const int sl = w * 32 + lane;
+          if (sl < lay_n) {
+            const double2 p = *reinterpret_cast<const double2*>(&bt.vpos[2 * vslot(bt, a, lay_t, sl)]);
+            px[w] = p.x; py[w] = p.y;
+          }
         }
-        __syncwarp();
-        sc.sobs = so;
+        unsigned int count = 0;
+        if (gw == 0) {
+          double sx, sy;
+          count = select_agent(bv, sc, a, lane, cx, cy, arrived, &sx, &sy, (s_learned[i] >> 1) & 1);
+          if (lane == 0) { gs.lx = sx; gs.ly = sy; }
+        }
+        group_bar(g);
+        IK_MARK(12)
+        const double lx = gs.lx, ly = gs.ly;
+        uint32_t Mg[W], mpu[W][W], mcu[W][W];
+        if (gw < 2) {
+          // warp 0, parents: V[t-1] within speed and collision free, tested as (parent -> loc)   utils.py:58-69
+          // warp 1, children: V[t+1], tested as (child -> loc)   utils.py:72-84
+          const bool on = gw == 0 || has_next;
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            uint32_t Ew = 0u;
+            if (on && w * 32 < lay_n) {
+              const bool cand = (w * 32 + lane < lay_n) && dist2(px[w], py[w], lx, ly) <= sc.speed2;
+              const uint32_t cm = __ballot_sync(0xFFFFFFFFu, cand);
+              count += __popc(cm);
+              Ew = cm & ~hits_any_flat(bt, sc, cm, px[w], py[w], lx, ly, lane);
+            }
+            if (lane == 0) (gw == 0 ? gs.P : gs.Cm)[w] = Ew;
+          }
+        } else if (gw == 2) {  // merge candidates: V[t] within merge_distance (utils.py:86-89), their edge masks loaded ahead
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            Mg[w] = 0u;
+            bool cand = false;
+            if (w * 32 < n_t) {
+              cand = (w * 32 + lane < n_t) && dist2(px[w], py[w], lx, ly) <= sc.merge2;
+              Mg[w] = __ballot_sync(0xFFFFFFFFu, cand);
+            }
+            const size_t v = vslot(bt, a, t, w * 32 + lane);
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+              mpu[w][q] = cand ? bt.pmask[v * W + q] : 0u;
+              mcu[w][q] = cand ? bt.cmask[v * W + q] : 0u;
+            }
+          }
+        } else {  // the goal test valid_edge(loc, goal) (learned_sampler.py:182-183) for loc_next = loc_pred, the common outcome
+          const int res = goal_test(bt, sc, lx, ly, lane);
+          if (lane == 0) { gs.spec_tested = res & 1; gs.spec_arr = res >> 1; }
+        }
+        group_bar(g);
+        if (gw == 2) {
+          // rules (utils.py:94-133) over the candidates in index order, every candidate's test on its own lane
+          uint32_t P[W], Cm[W];
+#pragma unroll
+          for (int w = 0; w < W; ++w) { P[w] = gs.P[w]; Cm[w] = gs.Cm[w]; }
+          const double gx = sc.gx, gy = sc.gy;
+          double rx = lx, ry = ly;
+          int target = -1;  // vertex of layer t that receives loc (replace) or -1
+          bool add_edges = false, resolved = false;
+          const double h_loc = dist2(lx, ly, gx, gy);
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            if (!resolved && Mg[w]) {
+              bool eq = true, sup = true, sub = true;
+#pragma unroll
+              for (int q = 0; q < W; ++q) {
+                const uint32_t pu = mpu[w][q], cu = mcu[w][q];
+                eq = eq && pu == P[q] && cu == Cm[q];
+                sup = sup && (P[q] & ~pu) == 0u && (Cm[q] & ~cu) == 0u;
+                sub = sub && (pu & ~P[q]) == 0u && (cu & ~Cm[q]) == 0u;
+              }
+              const bool cand = (Mg[w] >> lane) & 1u;
+              const uint32_t hitm = __ballot_sync(0xFFFFFFFFu, cand && (eq || sup || sub));
+              if (hitm) {
+                const int src = __ffs(hitm) - 1, u = w * 32 + src;
+                const int code = __shfl_sync(0xFFFFFFFFu, eq ? 1 : (sup ? 2 : 3), src);
+                const double ux = __shfl_sync(0xFFFFFFFFu, px[w], src), uy = __shfl_sync(0xFFFFFFFFu, py[w], src);
+                if (code == 1) {
+                  if (h_loc < dist2(ux, uy, gx, gy)) target = u;  // replace u by loc
+                  else { rx = ux; ry = uy; }                       // abandon loc
+                } else if (code == 2) {
+                  rx = ux; ry = uy;
+                } else {
+                  target = u;
+                  add_edges = true;
+                }
+                resolved = true;
+              }
+            }
+          }
+          if (!resolved) {  // trm.append_sample(loc, t, parents, children)   utils.py:136, timed_roadmap.py:67-104
+            target = n_t;
+            add_edges = true;
+            if (target >= bt.S) target = -1;  // cannot happen: one insert per (k_traj, t, agent) and S >= N_traj + 1
+          }
+          if (target >= 0) {
+            const size_t v = vslot(bt, a, t, target);
+            if (lane == 0) {
+              bt.vpos[2 * v] = lx;
+              bt.vpos[2 * v + 1] = ly;
+              if (!resolved) {
+                bv.vcnt[(size_t)a * bt.L + t] = n_t + 1;
+                if (nl < t + 1) bv.nlayers[a] = t + 1;
+              }
+            }
+            if (add_edges) {
+              const uint32_t tbit = 1u << (target & 31);
+              const int tw = target >> 5;
+#pragma unroll
+              for (int w = 0; w < W; ++w) {
+                const uint32_t pu = resolved ? bt.pmask[v * W + w] : 0u;
+                const uint32_t cu = resolved ? bt.cmask[v * W + w] : 0u;
+                const int s = w * 32 + lane;
+                // reductions without a return value: the group is the only writer of its agent's roadmap
+                if ((P[w] & ~pu) >> lane & 1u) atomicOr(&bt.cmask[vslot(bt, a, t - 1, s) * W + tw], tbit);   // E[t-1][p].append(u)
+                if ((Cm[w] & ~cu) >> lane & 1u) atomicOr(&bt.pmask[vslot(bt, a, t + 1, s) * W + tw], tbit);  // mirror of E[t][u] += ...
+                __syncwarp();
+                if (lane == 0) {
+                  bt.pmask[v * W + w] = pu | P[w];
+                  bt.cmask[v * W + w] = cu | Cm[w];
+                }
+              }
+            }
+          }
+          // goal test: valid_edge(loc_next, goal)   learned_sampler.py:182-183
+          bool arr = false;
+          if (rx == lx && ry == ly) {
+            count += (unsigned)gs.spec_tested;
+            arr = gs.spec_arr != 0;
+          } else {
+            const int res = goal_test(bt, sc, rx, ry, lane);
+            count += (unsigned)(res & 1);
+            arr = (res >> 1) != 0;
+          }
+          // next position and arrival flag into every CTA of the cluster
+          const bool arr_new = arr || arrived;
+          if (lane < C) {
+            double* dn = cluster.map_shared_rank(s_nxt, (unsigned)lane) + (size_t)pb * 2 * IK_NMAX;
+            *reinterpret_cast<double2*>(dn + 2 * i) = make_double2(rx, ry);
+            cluster.map_shared_rank(s_arrn, (unsigned)lane)[pb * IK_NMAX + i] = arr_new ? 1 : 0;
+          }
+          if (lane == 0 && bt.tr_loc_next != nullptr) {
+            const size_t si = step_index(bt, kt, t);
+            bt.tr_loc_next[2 * (si * bt.A + a)] = rx;
+            bt.tr_loc_next[2 * (si * bt.A + a) + 1] = ry;
+          }
+        }
+        cnt_acc += count;
+        IK_MARK(13)
       }
-      const double cx = s_cur[2 * i], cy = s_cur[2 * i + 1];
-      MergePrefetch<W> pf;
-      merge_prefetch<W>(bv, a, t, lane, pf);
-      double lx, ly;
-      unsigned int count = select_agent(bv, sc, a, lane, cx, cy, s_arrived[i] != 0, &lx, &ly);
-      count += merge_agent<W>(bv, sc, a, lane, lx, ly, pf);
-      if (lane == 0 && count) atomicAdd(&bt.cnt_collide[b], (unsigned long long)count);
+      if (io + IK_GROUPS < n_own) group_bar(g);  // the group's scratch and obstacles are free for its next agent
     }
-    IK_MARK(13)
-    cluster.sync();
+    if (wide_step) {
+      // many agents per CTA (one or two CTAs per instance): sixteen agents at a time, select + merge_samples of an agent on one
+      // warp (the batch path's merge_agent) — four groups would take them four at a time
+      __syncthreads();  // every agent's samples are in place
+      Batch bw = bv;    // next positions / arrival flags land in this CTA's copy of the step's exchange buffers
+      bw.nxt = s_nxt + (size_t)pb * 2 * IK_NMAX - 2 * (size_t)a0;
+      bw.arrived = s_arrn + pb * IK_NMAX - a0;
+      const bool obs_w = nO <= (IK_GROUPS * IK_OBS_MAX) / IK_WARPS;
+      double* w_obs = s_obs + warp * 3 * ((IK_GROUPS * IK_OBS_MAX) / IK_WARPS);
+      for (int i = own_lo + warp; i < own_hi; i += IK_WARPS) {
+        const int a = a0 + i;
+        const double* ap = s_pack + 6 * (i - own_lo);
+        StepCtx sc;
+        sc.b = b; sc.t = t; sc.kt = kt; sc.makespan = makespan;
+        sc.a0 = a0; sc.N = n; sc.o0 = o0; sc.nO = nO;
+        sc.inv_nO = (nO >= 1 && nO <= 128) ? c_pair_inv.v[nO] : 0u;
+        sc.gx = ap[0]; sc.gy = ap[1]; sc.speed = ap[2]; sc.speed2 = ap[3]; sc.merge2 = ap[4]; sc.rad = ap[5];
+        sc.sobs = nullptr;
+        __syncwarp();
+        if (obs_w) {
+          for (int o = lane; o < nO; o += 32) {
+            const double* gp = bt.obs_xyr + 3 * (size_t)(o0 + o);
+            w_obs[3 * o] = __ldg(gp);
+            w_obs[3 * o + 1] = __ldg(gp + 1);
+            w_obs[3 * o + 2] = f64add(sc.rad, __ldg(gp + 2));  // rad1 + rad2, rounded once (collision_check.cpp:56)
+          }
+          sc.sobs = w_obs;
+        }
+        const bool arrived = s_arrived[i] != 0;
+        if (lane == 0) s_arrn[pb * IK_NMAX + i] = arrived ? 1 : 0;  // merge_agent only ever sets the flag
+        __syncwarp();
+        MergePrefetch<W> pf;
+        merge_prefetch<W>(bw, a, t, lane, pf);
+        double lx, ly;
+        unsigned int count = select_agent(bw, sc, a, lane, s_cur[2 * i], s_cur[2 * i + 1], arrived, &lx, &ly, (s_learned[i] >> 1) & 1);
+        count += merge_agent<W>(bw, sc, a, lane, lx, ly, pf);
+        cnt_acc += count;
+        __syncwarp();
+        if (lane < C && lane != r) {  // the other CTAs' copies
+          double* dn = cluster.map_shared_rank(s_nxt, (unsigned)lane) + (size_t)pb * 2 * IK_NMAX;
+          *reinterpret_cast<double2*>(dn + 2 * i) = *reinterpret_cast<const double2*>(s_nxt + (size_t)pb * 2 * IK_NMAX + 2 * i);
+          cluster.map_shared_rank(s_arrn, (unsigned)lane)[pb * IK_NMAX + i] = s_arrn[pb * IK_NMAX + i];
+        }
+      }
+    }
+    IK_CLUSTER_SYNC();
     IK_MARK(14)
     // ================= advance (learned_sampler.py:186-196, :65-73): every CTA keeps its own copy of the instance state ====
     bool arr_ok = true;
     double2 nx = make_double2(0.0, 0.0);
     if (tid < n) {
-      arr_ok = __ldcg(&bt.arrived[a0 + tid]) != 0;
-      nx = __ldcg(reinterpret_cast<const double2*>(bt.nxt + 2 * (size_t)(a0 + tid)));
+      arr_ok = s_arrn[pb * IK_NMAX + tid] != 0;
+      nx = *reinterpret_cast<const double2*>(s_nxt + (size_t)pb * 2 * IK_NMAX + 2 * tid);
       s_arrived[tid] = arr_ok ? 1 : 0;
     }
     const bool all = __syncthreads_and(arr_ok) != 0;
-    cluster.sync();  // every CTA has read this step's flags and positions before the next step overwrites them
-    IK_MARK(15)
     ++steps;
     bool end_roll = false;
     if (all) {
@@ -733,19 +1016,19 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
         s_cur[2 * tid] = sx; s_cur[2 * tid + 1] = sy;
         s_prev[2 * tid] = sx; s_prev[2 * tid + 1] = sy;
         s_arrived[tid] = 0;
-        if (tid >= own_lo && tid < own_hi) bt.arrived[a0 + tid] = 0;
       }
       t = 1;
     }
-    __syncthreads();
+    IK_MARK(15)
   }
+  __syncthreads();
   if (s_vcnt != nullptr) {
-    __syncthreads();
     for (int i = tid; i < n_own * bt.L; i += IK_THREADS) bt.vcnt[(size_t)(a0 + own_lo) * bt.L + i] = s_vcnt[i];
     for (int i = tid; i < n_own; i += IK_THREADS) bt.nlayers[a0 + own_lo + i] = s_nl[i];
   }
-  if (prof)
-    for (int i = 0; i < IK_NPROF; ++i) ia.prof[(size_t)blockIdx.x * IK_NPROF + i] = pacc[i];
+  if (lane == 0 && cnt_acc) atomicAdd(&bt.cnt_collide[b], (unsigned long long)cnt_acc);
+  if (prof && tid == 0)
+    for (int i = 0; i < IK_NPROF; ++i) ia.prof[(size_t)blockIdx.x * IK_NPROF + i] = s_prof[i];
   if (r == 0 && tid == 0) {
     bt.k_traj[b] = kt; bt.t[b] = t; bt.makespan[b] = makespan; bt.done[b] = 1;
     bt.steps_done[b] = steps;
@@ -753,29 +1036,51 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
     ip[0] = 1; ip[1] = t; ip[2] = kt; ip[3] = makespan;
     atomicAdd(bt.n_done, 1);
   }
+  cluster.sync();  // no CTA leaves while a neighbour may still store into its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+size_t instance_w0_image_bytes() { return (size_t)IK_SLICES * IK_FRAG_SLICE * sizeof(uint2); }
+
+int launch_instance_w0_image(const float* d_blob, const ctrm_weight_offsets_t& off, int F, uint8_t* d_image, cudaStream_t st) {
+  const int total = IK_SLICES * IK_FRAG_SLICE;
+  instance_w0_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_blob + off.fov_w0, 2 * F * F, reinterpret_cast<uint2*>(d_image));
+  CTRM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // shared memory of one CTA at cluster size C; fills the layout-dependent fields of `ia`
 static size_t instance_smem_bytes(InstArgs& ia, int n_max, int K, int L, int C) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
-  ia.w0_frag = C == 8 ? 1 : 0;        // one K-slice per CTA: its mma.sync fragments stay resident
-  ia.chunk = C == 8 ? 4 : IK_CHUNK;   // own agents <= 8 at C = 8: smaller passes leave room for the fragments
+  ia.w0_frag = C == 8 ? 1 : 0;  // one K-slice per CTA: its mma.sync fragments stay resident
   const int own = (n_max + C - 1) / C;
   ia.own_max = own;
   ia.vc_smem = (size_t)own * L * 4 <= 12288 ? 1 : 0;
-  const size_t u_comm = (size_t)ia.chunk * IK_PMAX * (12 + 36 + 36 + 48) * 4, u_fov = (size_t)own * 64 * 2 * 4;
-  ia.u_bytes = (int)al(u_comm > u_fov ? u_comm : u_fov);
   size_t s = al((size_t)ia.n_w * 4);
-  s += 2 * al(IK_NMAX * 2 * 8) + al((size_t)IK_WARPS * 3 * IK_OBS_MAX * 8) + al((size_t)IK_CHUNK * IK_NMAX * 8);
-  s += al(IK_NMAX * IK_WORDS * 4) + 2 * al(IK_NMAX * 32 * 4) + al(IK_CHUNK * CTRM_DIM_X * 4) + 2 * al(IK_CHUNK * IK_PMAX * 4);
-  s += 4 * al(IK_NMAX * 4) + al(IK_CHUNK * 4) + 2 * al(IK_NMAX) + al(16 * 4) + (size_t)ia.u_bytes;
-  s += al(IK_NMAX * 2 * 8) + 2 * al(IK_NMAX * 4);
-  if (ia.w0_frag) s += 8 * 6 * 3 * 32 * 8;
-  s += al((size_t)own * 6 * 8) + al((size_t)own * K * 3 * 4) + al((size_t)own * 4);
-  if (ia.vc_smem) s += al((size_t)own * L * 4);
+  auto take = [&](size_t bytes) { const size_t at = s; s += al(bytes); return (int)at; };
+  IkLayout& y = ia.lay;
+  y.cur = take(IK_NMAX * 2 * 8);
+  y.prev = take(IK_NMAX * 2 * 8);
+  y.goal = take(IK_NMAX * 2 * 8);
+  y.nxt = take(2 * IK_NMAX * 2 * 8);
+  y.bits = take(IK_NMAX * IK_WORDS * 4);
+  y.vp = take(IK_NMAX * 32 * 4);
+  y.eself = take((size_t)own * 32 * 4);
+  y.part = take((size_t)C * own * 64 * 4);
+  y.radf = take(IK_NMAX * 4);
+  y.speedf = take(IK_NMAX * 4);
+  y.flags = take(6 * IK_NMAX);
+  y.w0f = ia.w0_frag ? take((size_t)IK_FRAG_SLICE * 8) : 0;
+  y.pack = take((size_t)own * 6 * 8);
+  y.samples = take((size_t)own * K * 3 * 4);
+  y.nl = take((size_t)own * 4);
+  y.vcnt = ia.vc_smem ? take((size_t)own * L * 4) : 0;
+  y.obs = take((size_t)IK_GROUPS * 3 * IK_OBS_MAX * 8);
+  y.prof = take(IK_NPROF * 8);
+  y.U = take(std::max((size_t)IK_GROUPS * sizeof(GroupScratch), (size_t)own * 128 * 4));
+  y.total = (int)s;
   return s;
 }
 
@@ -783,7 +1088,7 @@ static size_t instance_smem_bytes(InstArgs& ia, int n_max, int K, int L, int C) 
 int instance_kernel_supports(const DevModel& m, const Batch& bt) {
   const ctrm_model_desc& d = m.desc;
   if (bt.n_max > IK_NMAX || bt.K > IK_KMAX || bt.randomize_indicator) return 0;
-  if (d.temp != 2.0f) return 0;
+  if (d.temp != 2.0f || d.dim_ind != 3) return 0;
   if (2 * d.fov_size * d.fov_size > 32 * IK_WORDS) return 0;
   const int k_nb = d.use_k_neighbor ? (d.num_neighbors < bt.n_max - 1 ? d.num_neighbors : bt.n_max - 1) : bt.n_max - 1;
   if (k_nb + 1 > IK_PMAX) return 0;
@@ -791,10 +1096,10 @@ int instance_kernel_supports(const DevModel& m, const Batch& bt) {
   return 1;
 }
 
-size_t instance_part_floats(const Batch& bt) { return (size_t)bt.B * IK_SLICES * (bt.n_max > 0 ? bt.n_max : 1) * 64; }
-
+// `narrow`: a group of four warps per agent in the step (at most two agents per group), `wide`: one warp per agent
 template <typename Kernel>
-static int launch_instance_with(Kernel kernel, SmemAttrCache& attr, const Batch& bt, InstArgs& ia, int C_req, cudaStream_t st) {
+static int launch_instance_with(Kernel narrow, Kernel wide, SmemAttrCache& attr_n, SmemAttrCache& attr_w, const Batch& bt,
+                                InstArgs& ia, int C_req, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -810,7 +1115,8 @@ static int launch_instance_with(Kernel kernel, SmemAttrCache& attr, const Batch&
     size_t most = 0;
     for (int c = 1; c <= 8; c <<= 1) most = std::max(most, instance_smem_bytes(ia, bt.n_max, bt.K, bt.L, c));
     if (most > 227 * 1024) return ctrm_fail(-1, "instance kernel: weights do not fit in shared memory");
-    CTRM_CUDA_OK(attr.ensure(kernel, most));
+    CTRM_CUDA_OK(attr_n.ensure(narrow, most));
+    CTRM_CUDA_OK(attr_w.ensure(wide, most));
   }
   int C = 1;
   for (int c = C_req > 0 ? C_req : 8; c >= 1; c >>= 1) {
@@ -818,7 +1124,7 @@ static int launch_instance_with(Kernel kernel, SmemAttrCache& attr, const Batch&
     cfg.dynamicSmemBytes = instance_smem_bytes(ia, bt.n_max, bt.K, bt.L, c);
     at[0].val.clusterDim.x = (unsigned)c;
     int n_clusters = 0;
-    CTRM_CUDA_OK(cudaOccupancyMaxActiveClusters(&n_clusters, kernel, &cfg));
+    CTRM_CUDA_OK(cudaOccupancyMaxActiveClusters(&n_clusters, narrow, &cfg));
     C = c;
     if (n_clusters >= bt.B || C_req > 0) break;
   }
@@ -826,16 +1132,19 @@ static int launch_instance_with(Kernel kernel, SmemAttrCache& attr, const Batch&
   cfg.gridDim = dim3((unsigned)(bt.B * C), 1, 1);
   cfg.dynamicSmemBytes = instance_smem_bytes(ia, bt.n_max, bt.K, bt.L, C);
   at[0].val.clusterDim.x = (unsigned)C;
-  CTRM_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, bt, ia));
+  const bool use_wide = ia.own_max > 2 * IK_GROUPS;
+  CTRM_CUDA_OK(cudaLaunchKernelEx(&cfg, use_wide ? wide : narrow, bt, ia));
   return 0;
 }
 
 // C = 0: as many CTAs per instance (8, 4, 2, 1) as keep every cluster of the batch resident at once
-int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, float* d_part, cudaStream_t st) {
+int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, cudaStream_t st) {
   if (bt.B <= 0) return 0;
   if (C != 0 && C != 1 && C != 2 && C != 4 && C != 8) return ctrm_fail(-1, "instance kernel: cluster size must be 0 (auto), 1, 2, 4 or 8");
+  if (m.inst_w0_img == nullptr) return ctrm_fail(-1, "instance kernel: fragment image of the FOV first layer missing");
   InstArgs ia;
   ia.blob = m.blob;
+  ia.w0img = reinterpret_cast<const uint2*>(m.inst_w0_img);
   ia.off = m.off;
   ia.F = m.desc.fov_size;
   ia.num_neighbors = m.desc.num_neighbors;
@@ -845,30 +1154,28 @@ int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, f
   ia.C = 1;
   ia.n_w = m.off.total - m.off.fov_b0;
   ia.w0_frag = 0;
-  ia.chunk = IK_CHUNK;
-  ia.u_bytes = 0;
   ia.vc_smem = 0;
   ia.own_max = bt.n_max;
-  ia.part = d_part;
+  ia.lay = IkLayout{};
   ia.prof = nullptr;
   const bool want_prof = getenv("CTRM_INSTANCE_PROF") != nullptr;
   if (want_prof) CTRM_CUDA_OK(cudaMalloc(&ia.prof, (size_t)bt.B * 8 * IK_NPROF * sizeof(long long)));
-  static SmemAttrCache attr[4];
+  static SmemAttrCache attr[8];
   switch (bt.W) {
-    case 1: CHECK_RC(launch_instance_with(instance_rollout_kernel<1>, attr[0], bt, ia, C, st)); break;
-    case 2: CHECK_RC(launch_instance_with(instance_rollout_kernel<2>, attr[1], bt, ia, C, st)); break;
-    case 3: CHECK_RC(launch_instance_with(instance_rollout_kernel<3>, attr[2], bt, ia, C, st)); break;
-    case 4: CHECK_RC(launch_instance_with(instance_rollout_kernel<4>, attr[3], bt, ia, C, st)); break;
+    case 1: CHECK_RC(launch_instance_with(instance_rollout_kernel<1, false>, instance_rollout_kernel<1, true>, attr[0], attr[4], bt, ia, C, st)); break;
+    case 2: CHECK_RC(launch_instance_with(instance_rollout_kernel<2, false>, instance_rollout_kernel<2, true>, attr[1], attr[5], bt, ia, C, st)); break;
+    case 3: CHECK_RC(launch_instance_with(instance_rollout_kernel<3, false>, instance_rollout_kernel<3, true>, attr[2], attr[6], bt, ia, C, st)); break;
+    case 4: CHECK_RC(launch_instance_with(instance_rollout_kernel<4, false>, instance_rollout_kernel<4, true>, attr[3], attr[7], bt, ia, C, st)); break;
     default: return ctrm_fail(-1, "unsupported adjacency mask width");
   }
-  if (want_prof) {  // debugging aid: cycles per phase of the first and the last CTA, thread 0's view
+  if (want_prof) {  // debugging aid: cycles per phase of the first and the last CTA, thread 0's view (group 0, warp 0)
     const int Cu = ia.C;
     std::vector<long long> h((size_t)bt.B * Cu * IK_NPROF);
     CTRM_CUDA_OK(cudaStreamSynchronize(st));
     CTRM_CUDA_OK(cudaMemcpy(h.data(), ia.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(ia.prof);
-    static const char* names[IK_NPROF] = {"gate", "raster", "fov_l0", "bar1", "fov_tail", "bar2", "vp+rank", "info", "agent_mlp",
-                                          "softmax", "cvae_l0", "prior", "decode", "step", "bar3", "advance+bar4"};
+    static const char* names[IK_NPROF] = {"gate", "raster", "bar1", "fov_l0+bar2", "fov_tail", "bar3", "rank", "pair_mlp", "softmax",
+                                          "cvae_l0", "prior", "decode", "select", "merge", "bar4", "advance"};
     for (size_t cta : {(size_t)0, (size_t)bt.B * Cu - 1}) {
       fprintf(stderr, "[instance kernel] C=%d CTA %zu Mcycles:", Cu, cta);
       for (int i = 0; i < IK_NPROF; ++i) fprintf(stderr, " %s %.2f", names[i], 1e-6 * (double)h[cta * IK_NPROF + i]);

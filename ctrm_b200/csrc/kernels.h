@@ -26,6 +26,7 @@ struct DevModel {
   const uint8_t* decode_img;
   const uint8_t* agent_img;
   const uint8_t* fov_img;
+  const uint8_t* inst_w0_img;  // mma.sync B fragments of the FOV first layer for the per-instance kernel (instance.cu)
 };
 size_t fov_encode_image_bytes();
 int launch_fov_encode_image(const float* d_blob, const ctrm_weight_offsets_t& off, uint8_t* d_image, cudaStream_t st);
@@ -146,8 +147,9 @@ int launch_cvae_decode(const DevModel& m, const Batch& bt, const float* d_sqrtp,
 int launch_step(const Batch& bt, cudaStream_t st);
 // the whole roll-out loop of an instance inside one kernel, one cluster of C CTAs per instance (instance.cu): small batches
 int instance_kernel_supports(const DevModel& m, const Batch& bt);
-size_t instance_part_floats(const Batch& bt);
-int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, float* d_part, cudaStream_t st);
+size_t instance_w0_image_bytes();
+int launch_instance_w0_image(const float* d_blob, const ctrm_weight_offsets_t& off, int F, uint8_t* d_image, cudaStream_t st);
+int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, cudaStream_t st);
 int launch_rollout_init(const Batch& bt, cudaStream_t st);
 
 int launch_finalize(const Batch& bt, int32_t* d_tfin, cudaStream_t st);

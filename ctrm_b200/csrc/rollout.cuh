@@ -95,13 +95,14 @@ __device__ __forceinline__ uint32_t hits_any_flat(const Batch& bt, const StepCtx
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int select_agent(const Batch& bt, const StepCtx& sc, const int a, const int lane,
                                                      const double cx, const double cy, const bool arrived, double* out_x,
-                                                     double* out_y) {
+                                                     double* out_y, const int gate_hint = -1) {
   const int b = sc.b, t = sc.t, kt = sc.kt;
   const int a0 = sc.a0, il = a - a0, N = sc.N, nO = sc.nO;
   const double speed = sc.speed, speed2 = sc.speed2, rad = sc.rad;
   const size_t si = step_index(bt, kt, t);
   const uint32_t c0 = bt.inst_base + (uint32_t)b, c1 = rng_ctr1(kt, t);
-  const bool learned = gate_is_learned(bt, b, a, il, kt, t, sc.makespan, arrived);
+  // gate_hint: the caller has already evaluated the gate of this agent-step (0 / 1)
+  const bool learned = gate_hint >= 0 ? gate_hint != 0 : gate_is_learned(bt, b, a, il, kt, t, sc.makespan, arrived);
   const int nL = learned ? bt.K : 0;
   const int C = nL + bt.max_attempt;
   (void)N;
