@@ -10,7 +10,7 @@
 // barrier.cluster) — a step has four cluster barriers and no global-memory round trip between its phases:
 //
 //   gate     which agents take the learned branch (learned_sampler.py:148-157), every CTA for all agents
-//   raster   FOV crops of the own agents as bits (cost_to_go.cpp:109-186): a warp builds eight 32-bit words with eight
+//   raster   FOV crops of the own agents as bits (cost_to_go.cpp:109-186): a warp builds six 32-bit words with six
 //            coalesced loads per lane and a ballot each, and stores every word into the CTA that owns its K-slice
 //   -- cluster barrier 1 --
 //   fov L0   the 2F^2 -> 64 first layers of both FOV encoders (fov_encoder.py:34-59) on the tensor cores (mma.sync, bf16 x 3 =
@@ -392,24 +392,24 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
     IK_MARK(0)
 
     if (ia.nn && any_learned) {
-      // ================= raster: crop bits of the OWN agents; task = (own agent, eight consecutive words): lane l reads input
+      // ================= raster: crop bits of the OWN agents; task = (own agent, six consecutive words = two K-slices): lane l reads input
       // 32 w + l of word w, so a load instruction covers 32 consecutive crop cells (two or three map rows), and a ballot is
       // the word.  The centre's cost is loaded beside the crop (whether it is inside the map is known without it).
       {
         const uint8_t* occ = bt.occ + (size_t)b * M * M;
         const unsigned invF = 65536u / (unsigned)F + 1u;  // jj / F == (jj * invF) >> 16 for jj < F * F, F <= 41
-        for (int task = warp; task < n_own * 3; task += IK_WARPS) {
-          const int io = task / 3, oct = task - 3 * io, i = own_lo + io;
+        for (int task = warp; task < n_own * 4; task += IK_WARPS) {
+          const int io = task >> 2, oct = task & 3, i = own_lo + io;
           const int cx0 = grid_cell(s_cur[2 * i], M), cy0 = grid_cell(s_cur[2 * i + 1], M);
           const bool centre_in = cx0 < M && cy0 < M;
           const uint16_t* cf = bt.ctg + (size_t)(a0 + i) * ctg_field_elems(M, 1);
           const int cc = centre_in ? (int)__ldg(&cf[ctg_index(cx0, cy0, M, 1)]) : -1;
           const int cx = cx0 - buf, cy = cy0 - buf;
-          int vc[8], vo[8];
-          bool isc[8];
+          int vc[6], vo[6];
+          bool isc[6];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int j = 32 * (8 * oct + e) + lane;
+          for (int e = 0; e < 6; ++e) {
+            const int j = 32 * (6 * oct + e) + lane;
             const int ch = j >= FF ? 1 : 0, jj = j - ch * FF;
             const int xf = (int)(((unsigned)jj * invF) >> 16), yf = jj - xf * F;
             const int x = cx + xf, y = cy + yf;
@@ -418,18 +418,18 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
             vc[e] = CTRM_UNREACH;
             vo[e] = 1;
             // a word lies in one channel except the one that straddles F^2: warp-uniform tests skip the other channel's index math
-            if (32 * (8 * oct + e) + 31 >= FF) vc[e] = (ok && ch) ? (int)__ldg(&cf[ctg_index(x, y, M, 1)]) : CTRM_UNREACH;
-            if (32 * (8 * oct + e) < FF) vo[e] = (ok && !ch) ? (int)__ldg(&occ[x * M + y]) : 1;
+            if (32 * (6 * oct + e) + 31 >= FF) vc[e] = (ok && ch) ? (int)__ldg(&cf[ctg_index(x, y, M, 1)]) : CTRM_UNREACH;
+            if (32 * (6 * oct + e) < FF) vo[e] = (ok && !ch) ? (int)__ldg(&occ[x * M + y]) : 1;
           }
           uint32_t mine = 0u;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < 6; ++e) {
             const bool bit = isc[e] ? (vc[e] != CTRM_UNREACH && (cc == CTRM_UNREACH || vc[e] < cc)) : (vo[e] == 0);
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
             if (lane == e) mine = word;
           }
-          if (lane < 8) {
-            const int w = 8 * oct + lane;
+          if (lane < 6) {
+            const int w = 6 * oct + lane;
             uint32_t* dst = cluster.map_shared_rank(s_bits, (unsigned)((w / 3) / spc));
             dst[i * IK_WORDS + w] = mine;
           }
@@ -512,52 +512,54 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
       }
       IK_CLUSTER_SYNC();
       IK_MARK(3)
-      // ================= fov tails of the own agents =================
+      // ================= fov tails of the own agents: warp = (own agent, encoder), the whole chain partial sums -> hidden 1 ->
+      // hidden 2 -> embedding (-> vain_proj) inside the warp with __syncwarp between the layers — no block-wide barrier
       {
         const float* b0 = Wp(off.fov_b0);
-        for (int it = tid; it < n_own * 64; it += IK_THREADS) {
-          const int io = it >> 6, o = it & 63;
-          const float* q = s_part + (size_t)io * 64 + o;
-          const size_t st = (size_t)own_max * 64;
-          float sum;
-          if (C == 8) sum = ((q[0] + q[st]) + (q[2 * st] + q[3 * st])) + ((q[4 * st] + q[5 * st]) + (q[6 * st] + q[7 * st]));
-          else if (C == 4) sum = (q[0] + q[st]) + (q[2 * st] + q[3 * st]);
-          else if (C == 2) sum = q[0] + q[st];
-          else sum = q[0];
-          u_h0[io * 64 + o] = fmaxf(b0[o] + sum, 0.f);
-        }
-        __syncthreads();
-        // item = (own agent, encoder e, four columns, k strand): hidden 1 -> hidden 2
-        for (int it = tid; it < n_own * 64; it += IK_THREADS) {
-          const int q = it & 7, kq = (it >> 3) & 3, e = (it >> 5) & 1, io = it >> 6;
-          float4 acc = splitk_32(u_h0 + io * 64 + 32 * e, Wp(e ? off.fovv_w1 : off.fovs_w1), q, kq);
-          if (kq == 0) {
-            const float4 bb = *reinterpret_cast<const float4*>(Wp(e ? off.fovv_b1 : off.fovs_b1) + 4 * q);
-            float* o = u_h1 + io * 64 + 32 * e + 4 * q;
-            o[0] = fmaxf(acc.x + bb.x, 0.f); o[1] = fmaxf(acc.y + bb.y, 0.f); o[2] = fmaxf(acc.z + bb.z, 0.f); o[3] = fmaxf(acc.w + bb.w, 0.f);
+        const int q = lane & 7, kq = lane >> 3;
+        for (int task = warp; task < 2 * n_own; task += IK_WARPS) {
+          const int io = task >> 1, e = task & 1;
+          float* h0 = u_h0 + io * 64 + 32 * e;
+          float* h1 = u_h1 + io * 64 + 32 * e;
+          {
+            const int o = 32 * e + lane;
+            const float* pq = s_part + (size_t)io * 64 + o;
+            const size_t st = (size_t)own_max * 64;
+            float sum;
+            if (C == 8) sum = ((pq[0] + pq[st]) + (pq[2 * st] + pq[3 * st])) + ((pq[4 * st] + pq[5 * st]) + (pq[6 * st] + pq[7 * st]));
+            else if (C == 4) sum = (pq[0] + pq[st]) + (pq[2 * st] + pq[3 * st]);
+            else if (C == 2) sum = pq[0] + pq[st];
+            else sum = pq[0];
+            h0[lane] = fmaxf(b0[o] + sum, 0.f);
           }
-        }
-        __syncthreads();
-        // hidden 2 -> e_self (shared memory) | e_vain (back into u_h0)
-        for (int it = tid; it < n_own * 64; it += IK_THREADS) {
-          const int q = it & 7, kq = (it >> 3) & 3, e = (it >> 5) & 1, io = it >> 6;
-          float4 acc = splitk_32(u_h1 + io * 64 + 32 * e, Wp(e ? off.fovv_w2 : off.fovs_w2), q, kq);
-          if (kq == 0) {
-            const float4 bb = *reinterpret_cast<const float4*>(Wp(e ? off.fovv_b2 : off.fovs_b2) + 4 * q);
-            float* o = e ? (u_h0 + io * 64 + 4 * q) : (s_eself + io * 32 + 4 * q);
-            o[0] = acc.x + bb.x; o[1] = acc.y + bb.y; o[2] = acc.z + bb.z; o[3] = acc.w + bb.w;
+          __syncwarp();
+          {  // hidden 1 -> hidden 2
+            const float4 acc = splitk_32(h0, Wp(e ? off.fovv_w1 : off.fovs_w1), q, kq);
+            if (kq == 0) {
+              const float4 bb = *reinterpret_cast<const float4*>(Wp(e ? off.fovv_b1 : off.fovs_b1) + 4 * q);
+              *reinterpret_cast<float4*>(h1 + 4 * q) = make_float4(fmaxf(acc.x + bb.x, 0.f), fmaxf(acc.y + bb.y, 0.f),
+                                                                  fmaxf(acc.z + bb.z, 0.f), fmaxf(acc.w + bb.w, 0.f));
+            }
           }
-        }
-        __syncthreads();
-        // vain_proj = b0 + W0[11:43]^T e_vain (agent_encoder.py:57-60), stored into every CTA of the cluster (strand kq -> CTAs
-        // kq and kq + 4: the four strands hold the same sum after the shuffles)
-        for (int it = tid; it < n_own * 32; it += IK_THREADS) {
-          const int q = it & 7, kq = (it >> 3) & 3, io = it >> 5;
-          float4 acc = splitk_32(u_h0 + io * 64, Wp(off.ag_w0v), q, kq);
-          const float4 bb = *reinterpret_cast<const float4*>(Wp(off.ag_b0) + 4 * q);
-          const float4 v = make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w);
-          for (int c = kq; c < C; c += 4)
-            *reinterpret_cast<float4*>(cluster.map_shared_rank(s_vp, (unsigned)c) + (size_t)(own_lo + io) * 32 + 4 * q) = v;
+          __syncwarp();
+          {  // hidden 2 -> e_self (shared memory) | e_vain (back into h0)
+            const float4 acc = splitk_32(h1, Wp(e ? off.fovv_w2 : off.fovs_w2), q, kq);
+            if (kq == 0) {
+              const float4 bb = *reinterpret_cast<const float4*>(Wp(e ? off.fovv_b2 : off.fovs_b2) + 4 * q);
+              *reinterpret_cast<float4*>((e ? h0 : s_eself + io * 32) + 4 * q) =
+                  make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w);
+            }
+          }
+          if (e) {
+            // vain_proj = b0 + W0[11:43]^T e_vain (agent_encoder.py:57-60), stored into every CTA of the cluster (strand kq ->
+            // CTAs kq and kq + 4: the four strands hold the same sum after the shuffles)
+            __syncwarp();
+            const float4 acc = splitk_32(h0, Wp(off.ag_w0v), q, kq);
+            const float4 bb = *reinterpret_cast<const float4*>(Wp(off.ag_b0) + 4 * q);
+            const float4 v = make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w);
+            for (int c = kq; c < C; c += 4)
+              *reinterpret_cast<float4*>(cluster.map_shared_rank(s_vp, (unsigned)c) + (size_t)(own_lo + io) * 32 + 4 * q) = v;
+          }
         }
       }
       IK_MARK(4)
