@@ -734,15 +734,15 @@ struct StepProfiler {
   }
 };
 
-// batches up to this many instances take the per-instance kernel (CTRM_INSTANCE_MAX_BATCH moves the threshold, 0 = never)
-static int instance_kernel_max_batch() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CTRM_INSTANCE_MAX_BATCH");
-    v = e ? atoi(e) : 64;  // measured (profiles/r2_instance_kernel.md): 2 CTAs per instance still win at 64 instances, 1 CTA does not at 148
-    if (v < 0) v = 0;
-  }
-  return v;
+// batches up to this many instances take the per-instance kernel (CTRM_INSTANCE_MAX_BATCH moves the threshold, 0 = never).
+// Default: the number of SMs — one CTA per instance still has every instance resident at once and measured 133 ms against the
+// batch path's 148 ms at 148 instances (profiles/r2_instance_kernel.md); a second wave of clusters doubles its time.
+static int instance_kernel_max_batch(int device) {
+  const char* e = getenv("CTRM_INSTANCE_MAX_BATCH");
+  if (e) return atoi(e) > 0 ? atoi(e) : 0;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 64;
+  return sms;
 }
 // CTAs per instance: 0 = chosen by the launcher (the largest of 8, 4, 2, 1 that keeps every cluster resident at once);
 // CTRM_INSTANCE_CLUSTER pins 1, 2, 4 or 8
@@ -897,7 +897,7 @@ extern "C" int ctrm_build_roadmaps(ctrm_ctx* c, const ctrm_params* p, const ctrm
   }
   if (bt.tab_uniforms != nullptr)
     return ctrm_fail(CTRM_ERR_ARG, "per-step uniform tables are only supported through ctrm_cvae_sample (stage entry point)");
-  const bool inst_candidate = c->step_mode == 3 || (c->step_mode == 0 && !c->profile && bt.B <= instance_kernel_max_batch());
+  const bool inst_candidate = c->step_mode == 3 || (c->step_mode == 0 && !c->profile && bt.B <= instance_kernel_max_batch(c->device));
   c->t_arena.trim();
   const bool nn = (bt.tab_teacher == nullptr) || c->trace;
   // reset the roadmap store and the roll-out state

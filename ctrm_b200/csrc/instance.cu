@@ -193,6 +193,20 @@ __device__ __forceinline__ float4 splitk_32(const float* __restrict__ x, const f
   return acc;
 }
 
+// a 32 -> 4 head (W: [32][4], the last column is padding): lane = (output lane & 3, strand of four inputs lane >> 2); every
+// lane returns bias + sum for its output.  Whole warps call this together.
+__device__ __forceinline__ float head4(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias, int lane) {
+  const int col = lane & 3, st = lane >> 2;
+  const float4 xv = *reinterpret_cast<const float4*>(x + 4 * st);
+  float acc = xv.x * W[(4 * st) * 4 + col];
+  acc = fmaf(xv.y, W[(4 * st + 1) * 4 + col], acc);
+  acc = fmaf(xv.z, W[(4 * st + 2) * 4 + col], acc);
+  acc = fmaf(xv.w, W[(4 * st + 3) * 4 + col], acc);
+#pragma unroll
+  for (int d = 4; d <= 16; d <<= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+  return acc + bias[col];
+}
+
 // D[16 x 8] += A[16 x 16] . B[16 x 8], bf16 operands, fp32 accumulators (warp-level mma.sync)
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -711,12 +725,23 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
         IK_MARK(9)
         // ---- role 0: indicator -> argmax (learned_sampler.py:99-104).  roles 1..3: the prior for indicator value v = role - 1
         //      (cvae.py:57-68, :132-136; sqrt of the clamped probabilities, cvae_tc.cu) and the decoder's first layer without its
-        //      z rows — the three values side by side instead of waiting for the argmax (a phase costs what its longest warp
-        //      costs: three short warps beat one warp that shares the weight loads)
+        //      z rows — the three values side by side instead of waiting for the argmax.  Every layer in split-K form (strands
+        //      of 8 or 16 inputs that meet by shuffle, vectors handed on through shared memory): chains of 8-16 FMAs instead of
+        //      32-64, and a third fewer instructions than a lane-per-column layer fed by shuffles.
+        float* vA = gs.hA + gw * 128;  // this warp's vectors (the pair MLP's scratch is free by now): [32] in, [32] hidden, [64] z
+        float* vB = vA + 32;
+        float* vZ = vA + 64;
+        const int sq = lane & 7, skq = lane >> 3;  // splitk_32 layout
         if (gw == 0) {
-          float h = fmaxf(gs.p0[lane] + Wp(off.ind_b0)[lane], 0.f);
-          h = fmaxf(warp_layer32(h, Wp(off.ind_w1), 32, lane, Wp(off.ind_b1)[lane]), 0.f);
-          const float lg = warp_layer32(h, Wp(off.ind_w2), 4, lane & 3, Wp(off.ind_b2)[lane & 3]);
+          vA[lane] = fmaxf(gs.p0[lane] + Wp(off.ind_b0)[lane], 0.f);
+          __syncwarp();
+          const float4 h = splitk_32(vA, Wp(off.ind_w1), sq, skq);
+          if (skq == 0) {
+            const float4 bb = *reinterpret_cast<const float4*>(Wp(off.ind_b1) + 4 * sq);
+            *reinterpret_cast<float4*>(vB + 4 * sq) = make_float4(fmaxf(h.x + bb.x, 0.f), fmaxf(h.y + bb.y, 0.f), fmaxf(h.z + bb.z, 0.f), fmaxf(h.w + bb.w, 0.f));
+          }
+          __syncwarp();
+          const float lg = head4(vB, Wp(off.ind_w2), Wp(off.ind_b2), lane);
           const float l0 = __shfl_sync(0xFFFFFFFFu, lg, 0), l1 = __shfl_sync(0xFFFFFFFFu, lg, 1), l2 = __shfl_sync(0xFFFFFFFFu, lg, 2);
           int ind = 0;
           float best = l0;
@@ -726,38 +751,95 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
         } else {
           const int v = gw - 1;
           gs.d0[v * 32 + lane] = (gs.p0[64 + lane] + Wp(off.dec_b0)[lane]) + Wp(off.dec_w0)[(64 + CTRM_DIM_X + v) * 32 + lane];
-          float he = fmaxf((gs.p0[32 + lane] + Wp(off.enc_b0)[lane]) + Wp(off.enc_w0)[(CTRM_DIM_X + v) * 32 + lane], 0.f);
-          he = fmaxf(warp_layer32(he, Wp(off.enc_w1), 32, lane, Wp(off.enc_b1)[lane]), 0.f);
-          const float g0 = warp_layer32(he, Wp(off.enc_w2), 64, lane, Wp(off.enc_b2)[lane]);
-          const float g1 = warp_layer32(he, Wp(off.enc_w2), 64, 32 + lane, Wp(off.enc_b2)[32 + lane]);
-          const float mx = warp_max(fmaxf(g0, g1));
-          const float lse = logf(warp_sum(expf(g0 - mx) + expf(g1 - mx)));
-          const float q0 = expf((g0 - mx) - lse), q1 = expf((g1 - mx) - lse);  // probs = exp(log_softmax)
-          const float ps = warp_sum(q0 + q1);                                  // Categorical normalises probs / sum
-          gs.sp[v * 64 + lane] = sqrtf(fminf(fmaxf(q0 / ps, eps), 1.f - eps));
-          gs.sp[v * 64 + 32 + lane] = sqrtf(fminf(fmaxf(q1 / ps, eps), 1.f - eps));
+          vA[lane] = fmaxf((gs.p0[32 + lane] + Wp(off.enc_b0)[lane]) + Wp(off.enc_w0)[(CTRM_DIM_X + v) * 32 + lane], 0.f);
+          __syncwarp();
+          const float4 h = splitk_32(vA, Wp(off.enc_w1), sq, skq);
+          if (skq == 0) {
+            const float4 bb = *reinterpret_cast<const float4*>(Wp(off.enc_b1) + 4 * sq);
+            *reinterpret_cast<float4*>(vB + 4 * sq) = make_float4(fmaxf(h.x + bb.x, 0.f), fmaxf(h.y + bb.y, 0.f), fmaxf(h.z + bb.z, 0.f), fmaxf(h.w + bb.w, 0.f));
+          }
+          __syncwarp();
+          // 32 -> 64 logits: lane = (four columns q16, strand of 16 inputs); both half-warps end up with all 64 logits
+          const int q16 = lane & 15, s2 = lane >> 4;
+          float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+          {
+            const float* W2 = Wp(off.enc_w2);
+#pragma unroll 8
+            for (int kk = 0; kk < 16; ++kk) {
+              const int k = 16 * s2 + kk;
+              const float4 w = *reinterpret_cast<const float4*>(W2 + k * 64 + 4 * q16);
+              const float x = vB[k];
+              gq.x = fmaf(x, w.x, gq.x); gq.y = fmaf(x, w.y, gq.y); gq.z = fmaf(x, w.z, gq.z); gq.w = fmaf(x, w.w, gq.w);
+            }
+            gq.x += __shfl_xor_sync(0xFFFFFFFFu, gq.x, 16); gq.y += __shfl_xor_sync(0xFFFFFFFFu, gq.y, 16);
+            gq.z += __shfl_xor_sync(0xFFFFFFFFu, gq.z, 16); gq.w += __shfl_xor_sync(0xFFFFFFFFu, gq.w, 16);
+            const float4 bb = *reinterpret_cast<const float4*>(Wp(off.enc_b2) + 4 * q16);
+            gq.x += bb.x; gq.y += bb.y; gq.z += bb.z; gq.w += bb.w;
+          }
+          // log_softmax -> probs -> Categorical's normalisation -> sqrt of the clamped probabilities; reductions over 16 lanes
+          auto red16_max = [&](float x) {
+#pragma unroll
+            for (int d = 8; d >= 1; d >>= 1) x = fmaxf(x, __shfl_xor_sync(0xFFFFFFFFu, x, d));
+            return x;
+          };
+          auto red16_sum = [&](float x) {
+#pragma unroll
+            for (int d = 8; d >= 1; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+            return x;
+          };
+          const float mx = red16_max(fmaxf(fmaxf(gq.x, gq.y), fmaxf(gq.z, gq.w)));
+          const float lse = logf(red16_sum((expf(gq.x - mx) + expf(gq.y - mx)) + (expf(gq.z - mx) + expf(gq.w - mx))));
+          float4 pq = make_float4(expf((gq.x - mx) - lse), expf((gq.y - mx) - lse), expf((gq.z - mx) - lse), expf((gq.w - mx) - lse));
+          const float ps = red16_sum((pq.x + pq.y) + (pq.z + pq.w));
+          if (s2 == 0)
+            *reinterpret_cast<float4*>(gs.sp + v * 64 + 4 * q16) =
+                make_float4(sqrtf(fminf(fmaxf(pq.x / ps, eps), 1.f - eps)), sqrtf(fminf(fmaxf(pq.y / ps, eps), 1.f - eps)),
+                            sqrtf(fminf(fmaxf(pq.z / ps, eps), 1.f - eps)), sqrtf(fminf(fmaxf(pq.w / ps, eps), 1.f - eps)));
         }
         group_bar(g);
         IK_MARK(10)
         // ---- K relaxed one-hot samples and the decoder, one warp per copy: z_i = sqrt(p_i / E_i) / sum (temperature 2,
-        //      cvae_tc.cu), lane holds latents 2 lane and 2 lane + 1
+        //      cvae_tc.cu), lane holds latents 2 lane and 2 lane + 1; decoder layers in split-K form
         for (int k = dk0; k < bt.K; k += 4) {
           const int ind = gs.ind;
           const float* sp = gs.sp + ind * 64;
           if (gw == 0 || k != dk0) gumbel_rsqrt(k, &rsa, &rsb);
-          const float ra = sp[2 * lane] * rsa, rb = sp[2 * lane + 1] * rsb;
+          const float2 sp2 = *reinterpret_cast<const float2*>(sp + 2 * lane);
+          const float ra = sp2.x * rsa, rb = sp2.y * rsb;
           const float inv = 1.f / warp_sum(ra + rb);
-          const float za = fminf(ra * inv, 1.f), zb = fminf(rb * inv, 1.f);
-          const float* Wz = Wp(off.dec_w0);
-          float h = gs.d0[ind * 32 + lane], h1 = 0.f;  // two chains: even and odd latents
-#pragma unroll 4
-          for (int m = 0; m < 32; ++m) {
-            h = fmaf(__shfl_sync(0xFFFFFFFFu, za, m), Wz[(2 * m) * 32 + lane], h);
-            h1 = fmaf(__shfl_sync(0xFFFFFFFFu, zb, m), Wz[(2 * m + 1) * 32 + lane], h1);
+          __syncwarp();
+          *reinterpret_cast<float2*>(vZ + 2 * lane) = make_float2(fminf(ra * inv, 1.f), fminf(rb * inv, 1.f));
+          __syncwarp();
+          {  // 64 -> 32: lane = (four columns, strand of 16 latents)
+            const float* Wz = Wp(off.dec_w0);
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int kk = 0; kk < 16; ++kk) {
+              const int m = 16 * skq + kk;
+              const float4 w = *reinterpret_cast<const float4*>(Wz + m * 32 + 4 * sq);
+              const float z = vZ[m];
+              h.x = fmaf(z, w.x, h.x); h.y = fmaf(z, w.y, h.y); h.z = fmaf(z, w.z, h.z); h.w = fmaf(z, w.w, h.w);
+            }
+#pragma unroll
+            for (int d = 8; d <= 16; d <<= 1) {
+              h.x += __shfl_xor_sync(0xFFFFFFFFu, h.x, d); h.y += __shfl_xor_sync(0xFFFFFFFFu, h.y, d);
+              h.z += __shfl_xor_sync(0xFFFFFFFFu, h.z, d); h.w += __shfl_xor_sync(0xFFFFFFFFu, h.w, d);
+            }
+            if (skq == 0) {
+              const float4 d0 = *reinterpret_cast<const float4*>(gs.d0 + ind * 32 + 4 * sq);
+              *reinterpret_cast<float4*>(vA + 4 * sq) = make_float4(fmaxf(h.x + d0.x, 0.f), fmaxf(h.y + d0.y, 0.f), fmaxf(h.z + d0.z, 0.f), fmaxf(h.w + d0.w, 0.f));
+            }
           }
-          h = fmaxf(h + h1, 0.f);
-          h = fmaxf(warp_layer32(h, Wp(off.dec_w1), 32, lane, Wp(off.dec_b1)[lane]), 0.f);
-          const float o = warp_layer32(h, Wp(off.dec_w2), 4, lane & 3, Wp(off.dec_b2)[lane & 3]);
+          __syncwarp();
+          {
+            const float4 h = splitk_32(vA, Wp(off.dec_w1), sq, skq);
+            if (skq == 0) {
+              const float4 bb = *reinterpret_cast<const float4*>(Wp(off.dec_b1) + 4 * sq);
+              *reinterpret_cast<float4*>(vB + 4 * sq) = make_float4(fmaxf(h.x + bb.x, 0.f), fmaxf(h.y + bb.y, 0.f), fmaxf(h.z + bb.z, 0.f), fmaxf(h.w + bb.w, 0.f));
+            }
+          }
+          __syncwarp();
+          const float o = head4(vB, Wp(off.dec_w2), Wp(off.dec_b2), lane);
           if (lane < 3) s_samples[((size_t)io * bt.K + k) * 3 + lane] = o;
         }
         group_bar(g);

@@ -238,9 +238,9 @@ int ctrm_get_instance_steps(ctrm_ctx* ctx, int32_t* h_steps /*[B]*/);
 int ctrm_set_profile(ctrm_ctx* ctx, int enable);
 
 /* which kernels run the roll-out loop (learned_sampler.py:65-196):
- *   0 = chosen by batch size (default): a few hundred instances or fewer take the per-instance kernel (3) when the batch
- *       fits its limits (<= 64 agents per instance, K <= 8, temperature 2, <= 15 neighbours), larger batches the batch path
- *       with select + merge as (2) from ~20k agents and as (1) below;
+ *   0 = chosen by batch size (default): up to one instance per SM (148 on B200; CTRM_INSTANCE_MAX_BATCH overrides) takes the
+ *       per-instance kernel (3) when the batch fits its limits (<= 64 agents per instance, K <= 8, temperature 2,
+ *       <= 15 neighbours), larger batches the batch path with select + merge as (2) from ~20k agents and as (1) below;
  *   1 = batch path (one kernel sequence per step over all instances), select + merge one warp per agent;
  *   2 = batch path, select + merge one thread per agent (throughput, large batches);
  *   3 = per-instance kernel: one thread-block cluster per instance runs all N_traj x max_T steps inside ONE launch (single-

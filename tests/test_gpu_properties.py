@@ -80,6 +80,7 @@ def test_full_size_batch_properties_and_batch_independence():
     instances = [_gen(46 + i, 21, 30, 10) for i in range(96)]
     bld = RoadmapBuilder(WEIGHTS, 0)
     try:
+        bld.set_step_kernel(1)  # the batch path (a batch of up to one instance per SM would take the per-instance kernel, tested below)
         csr = bld.build(instances, seed=7, **prm).copy()
         nv = ne = 0
         for b in range(0, 96, 5):
@@ -94,7 +95,6 @@ def test_full_size_batch_properties_and_batch_independence():
         assert np.array_equal(csr.pos.view(np.uint64), again.pos.view(np.uint64))
         # an instance built alone (same instance id) equals its result inside the batch
         b = 37
-        bld.set_step_kernel(1)  # the batch path (a single instance would take the per-instance kernel, tested below)
         alone = bld.build([instances[b]], seed=7, instance_id_base=b, **prm).copy()
         bld.set_step_kernel(0)
         a0, a1 = int(csr.agent_off[b]), int(csr.agent_off[b + 1])
