@@ -6,28 +6,26 @@
 // dependent MMA round trips (12-18 us per kernel, 63 us per step, 96 ms for one 28-agent instance).  Here the N_traj x max_T
 // steps of an instance never leave the chip: a cluster of C = 1, 2, 4 or 8 CTAs owns the instance, every CTA keeps all network
 // weights but the FOV encoders' first layer resident in shared memory (92 KB fp32), the agents are split evenly over the CTAs,
-// and everything the CTAs exchange travels through DISTRIBUTED SHARED MEMORY (stores into the consumer's shared memory, then one
-// barrier.cluster) — a step has four cluster barriers and no global-memory round trip between its phases:
+// and what the CTAs exchange travels through DISTRIBUTED SHARED MEMORY (stores into the consumer's shared memory, then one
+// barrier.cluster) — a step has two cluster barriers and no global-memory round trip between its phases:
 //
 //   gate     which agents take the learned branch (learned_sampler.py:148-157), every CTA for all agents
-//   raster   FOV crops of the own agents as bits (cost_to_go.cpp:109-186): a warp builds six 32-bit words with six
-//            coalesced loads per lane and a ballot each, and stores every word into the CTA that owns its K-slice
+//   fov L0   a warp = (own agent, quarter of the 2 F^2 inputs): it builds six 32-bit words of crop bits (cost_to_go.cpp:109-186;
+//            six coalesced loads per lane and a ballot each) and, the input being BINARY, evaluates its part of the 2F^2 -> 64
+//            first layers of both FOV encoders (fov_encoder.py:34-59) as TABLE LOOK-UPS: for every byte of crop bits one row of
+//            a prebuilt table lut[byte position][256 patterns][64] (the sum of the weight rows of the set bits, summed in
+//            float64 at ctrm_load_weights, 6 MB, L2-resident) — 24 independent 256-byte loads and adds per warp instead of a
+//            K = 722 contraction; the 185 KB of first-layer weights never enter the SM
+//   fov tail own agents: the four quarter sums added as a fixed tree (the result does not depend on C), 32->32->32 tails,
+//            vain_proj stored into EVERY CTA's shared memory
 //   -- cluster barrier 1 --
-//   fov L0   the 2F^2 -> 64 first layers of both FOV encoders (fov_encoder.py:34-59) on the tensor cores (mma.sync, bf16 x 3 =
-//            fp32-exact weights, 0/1 activations): K is cut into 8 slices of 96 inputs, CTA r multiplies the slices it owns for
-//            ALL agents (C = 8: its slice's B fragments are resident; smaller clusters stream the prebuilt fragment image through
-//            L2) and stores the partial sums into the shared memory of the CTA that owns the agent
-//   -- cluster barrier 2 --
-//   fov tail own agents: the partials summed as a fixed binary tree over the slices (the result does not depend on C),
-//            32->32->32 tails, vain_proj stored into EVERY CTA's shared memory
-//   -- cluster barrier 3 --
 //   agent    the 16 warps form four GROUPS of four warps; a group takes one own agent at a time through
 //            comm (k nearest neighbours, pair features compiled.py:30-97, AgentEncoder 43->32->32->42 on the k+1 pairs, attention
 //            softmax and message sum, format_input.py:212-277), cvae (indicator + argmax, the prior for all three indicator
 //            values side by side, K relaxed one-hot samples, decoder; cvae.py:57-79, :128-138; learned_sampler.py:99-121) and
 //            the step (select, then merge_samples with the parents / children / merge candidates / goal test on one warp each),
 //            synchronised by named barriers of 128 threads; the agent's next position and arrival flag are stored into every CTA
-//   -- cluster barrier 4 --
+//   -- cluster barrier 2 --
 //   advance  every CTA advances its own copy of (k_traj, t, makespan) and of all positions
 //
 // The MLPs run on the CUDA cores in plain fp32 (FMA, fixed summation orders): at 28 rows per step a 128-row MMA tile with a
@@ -36,7 +34,6 @@
 // geometry, draws and roadmap updates use the device functions of the batch path (rollout.cuh) — the same bits for every fp64
 // operation, verdict and counter.  Under teacher forcing the two paths are bit-identical.
 #include <cooperative_groups.h>
-#include <cuda_bf16.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -57,28 +54,27 @@ namespace cg = cooperative_groups;
 #define IK_WARPS 16
 #define IK_GROUPS 4    // groups of four warps: one own agent at a time through comm, cvae and the step
 #define IK_NMAX 64     // agents per instance
-#define IK_SLICES 8    // K-slices of the FOV first layer (96 inputs each)
 #define IK_WORDS 24    // 32-bit words of one agent's crop bits
 #define IK_PMAX 16     // pairs per agent: itself + at most 15 neighbours
 #define IK_OBS_MAX 64  // obstacles staged per group in shared memory (more: read through L1)
 #define IK_KMAX 8      // CVAE candidates per agent
 #define IK_NPROF 16
-#define IK_FRAG_SLICE (8 * 6 * 3 * 32)  // uint2 entries of one K-slice of the fragment image: [n-tile][k-step][bf16 part][lane]
+#define IK_BYTES (4 * IK_WORDS)  // byte positions of the crop bits = rows of 256 patterns in the first-layer table
 
 // byte offsets of the shared-memory regions (computed by the host, ik_layout)
 struct IkLayout {
-  int cur, prev, goal, nxt, bits, vp, eself, part, radf, speedf, flags, w0f, pack, samples, nl, vcnt, obs, prof, U, total;
+  int cur, prev, goal, nxt, vp, eself, l0p, radf, speedf, flags, pack, samples, nl, vcnt, obs, prof, U, total;
 };
 
 struct InstArgs {
   const float* blob;
-  const uint2* w0img;  // [IK_SLICES][IK_FRAG_SLICE] mma.sync B fragments of the FOV first layer, bf16 x 3 (instance_w0_image_kernel)
+  const float* lut;    // [IK_BYTES][256][64] FOV first layer as a table over the bytes of the crop bits (instance_w0_image_kernel)
   ctrm_weight_offsets_t off;
   int F, num_neighbors, use_k_neighbor, include_self;
   int nn;        // run the networks (0: teacher-forced run that does not record the CVAE output)
   int C;         // CTAs per instance
   int n_w;       // floats of the blob from fov_b0 on (resident in shared memory)
-  int w0_frag;   // the CTA's K-slice of the fragment image is resident in shared memory (C = 8: one slice per CTA)
+  int l0_split;  // a warp takes a quarter of an agent's inputs (few agents per CTA) instead of a whole agent
   int vc_smem;   // the own agents' layer counts live in shared memory during the roll-outs
   int own_max;   // ceil(n_max / C)
   IkLayout lay;
@@ -207,54 +203,22 @@ __device__ __forceinline__ float head4(const float* __restrict__ x, const float*
   return acc + bias[col];
 }
 
-// D[16 x 8] += A[16 x 16] . B[16 x 8], bf16 operands, fp32 accumulators (warp-level mma.sync)
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-// two crop bits -> two bf16 values (0.0 / 1.0) in one register
-__device__ __forceinline__ uint32_t bits2_bf16(uint32_t t) { return (t & 1u) * 0x3F80u + ((t >> 1) & 1u) * 0x3F800000u; }
-// part `sp` (0 hi, 1 mid, 2 lo) of the three-way bf16 split of an fp32 weight: hi + mid + lo == w to 24 bits
-__device__ __forceinline__ uint32_t bf16_part(float w, int sp) {
-  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-  const float r1 = w - __bfloat162float(hi);
-  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(mid);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
-  return (uint32_t)__bfloat16_as_ushort(sp == 0 ? hi : (sp == 1 ? mid : lo));
-}
-
-// the prebuilt B fragments of the FOV first layer: [slice][n-tile of 8 columns][k-step of 16][bf16 part][lane] (mma.m16n8k16 col)
-__global__ void instance_w0_image_kernel(const float* __restrict__ W0, int KD, uint2* __restrict__ img) {
+// The FOV encoders' first layer as a table over the BYTES of the binary input: lut[p][v][c] = sum over the set bits i of v of
+// W0[8 p + i][c] (rows past 2 F^2 count as zero), summed in float64 and rounded once.
+__global__ void instance_w0_image_kernel(const float* __restrict__ W0, int KD, float* __restrict__ lut) {
   const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gidx >= IK_SLICES * IK_FRAG_SLICE) return;
-  const int s = gidx / IK_FRAG_SLICE, idx = gidx - s * IK_FRAG_SLICE;
-  const int ln = idx & 31, sp = (idx >> 5) % 3, ks = (idx / 96) % 6, nt = idx / 576;
-  const int col = 8 * nt + (ln >> 2), k0 = 96 * s + 16 * ks + 2 * (ln & 3);
-  auto wv = [&](int j) { return j < KD ? W0[(size_t)j * 64 + col] : 0.f; };
-  img[gidx] = make_uint2(bf16_part(wv(k0), sp) | (bf16_part(wv(k0 + 1), sp) << 16),
-                         bf16_part(wv(k0 + 8), sp) | (bf16_part(wv(k0 + 9), sp) << 16));
+  if (gidx >= IK_BYTES * 256 * 64) return;
+  const int c = gidx & 63, v = (gidx >> 6) & 255, p = gidx >> 14;
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = 8 * p + i;
+    if (((v >> i) & 1) && j < KD) acc += (double)W0[(size_t)j * 64 + c];
+  }
+  lut[gidx] = (float)acc;
 }
 
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
-
-// one K-slice of the FOV first layer for a 16-agent m-tile and an 8-column n-tile: fragments f[ks][part]
-__device__ __forceinline__ void l0_slice_mma(const uint32_t* __restrict__ s_bits, int r0, int r1, int slice, int tig,
-                                             const uint2 (&f)[18], float (&p)[4]) {
-  float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int ks = 0; ks < 6; ++ks) {
-    const int widx = 3 * slice + (ks >> 1), sh = 16 * (ks & 1) + 2 * tig;
-    const uint32_t x0 = s_bits[r0 * IK_WORDS + widx] >> sh, x1 = s_bits[r1 * IK_WORDS + widx] >> sh;
-    const uint32_t a[4] = {bits2_bf16(x0), bits2_bf16(x1), bits2_bf16(x0 >> 8), bits2_bf16(x1 >> 8)};
-    mma_bf16_16816(accH, a, f[3 * ks].x, f[3 * ks].y);
-    mma_bf16_16816(accL, a, f[3 * ks + 1].x, f[3 * ks + 1].y);
-    mma_bf16_16816(accL, a, f[3 * ks + 2].x, f[3 * ks + 2].y);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p[i] = accH[i] + accL[i];
-}
 
 // valid_edge(loc, goal) of learned_sampler.py:182-183 for one warp: bit 0 = the swept test ran (counted by the reference's
 // collision counter), bit 1 = the agent arrives
@@ -287,7 +251,6 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
   const int M = bt.M, F = ia.F, FF = F * F, KD = 2 * FF, buf = (F - 1) / 2;
   const int own_lo = (r * n) / C, own_hi = ((r + 1) * n) / C, n_own = own_hi - own_lo;  // even split, sizes differ by at most one
   const int own_max = ia.own_max;
-  const int spc = IK_SLICES / C, s_lo = r * spc;  // K-slices of this CTA
   const ctrm_weight_offsets_t& off = ia.off;
   const IkLayout& ly_ = ia.lay;
 
@@ -297,18 +260,14 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
   double* s_prev = reinterpret_cast<double*>(ik_smem + ly_.prev);
   double* s_goal = reinterpret_cast<double*>(ik_smem + ly_.goal);
   double* s_nxt = reinterpret_cast<double*>(ik_smem + ly_.nxt);      // [2][IK_NMAX][2]: stored by the owners, by step parity
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(ik_smem + ly_.bits);  // [IK_NMAX][IK_WORDS], the words of this CTA's slices
   float* s_vp = reinterpret_cast<float*>(ik_smem + ly_.vp);           // [IK_NMAX][32] vain_proj of all agents
   float* s_eself = reinterpret_cast<float*>(ik_smem + ly_.eself);     // [own][32]
-  float* s_part = reinterpret_cast<float*>(ik_smem + ly_.part);       // [C][own_max][64] partial sums, stored by the slice owners
+  float* s_l0p = reinterpret_cast<float*>(ik_smem + ly_.l0p);         // first-layer sums: [own][4 quarters][64] (l0_split) or [own][64]
   float* s_radf = reinterpret_cast<float*>(ik_smem + ly_.radf);
   float* s_speedf = reinterpret_cast<float*>(ik_smem + ly_.speedf);
   uint8_t* s_arrived = ik_smem + ly_.flags;             // [IK_NMAX]
   uint8_t* s_learned = s_arrived + IK_NMAX;             // [IK_NMAX]
   uint8_t* s_arrn = s_learned + IK_NMAX;                // [2][IK_NMAX] arrival flags after the step, stored by the owners
-  uint8_t* s_owner = s_arrn + 2 * IK_NMAX;              // [IK_NMAX] CTA that owns the agent
-  uint8_t* s_oidx = s_owner + IK_NMAX;                  // [IK_NMAX] its index among that CTA's agents
-  uint2* s_w0f = ia.w0_frag ? reinterpret_cast<uint2*>(ik_smem + ly_.w0f) : nullptr;
   double* s_pack = reinterpret_cast<double*>(ik_smem + ly_.pack);      // own agents' constants (Batch::agent_pack)
   float* s_samples = reinterpret_cast<float*>(ik_smem + ly_.samples);  // own agents' CVAE samples of the step
   int32_t* s_nl = reinterpret_cast<int32_t*>(ik_smem + ly_.nl);
@@ -329,9 +288,6 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
     s_goal[2 * i] = bt.goals[2 * (a0 + i)]; s_goal[2 * i + 1] = bt.goals[2 * (a0 + i) + 1];
     s_radf[i] = (float)bt.rads[a0 + i];
     s_speedf[i] = (float)bt.speeds[a0 + i];
-    const int ow = (i * C + C - 1) / n;  // the r with r * n / C <= i < (r + 1) * n / C
-    s_owner[i] = (uint8_t)ow;
-    s_oidx[i] = (uint8_t)(i - (ow * n) / C);
   }
   for (int i = tid; i < n_own * 6; i += IK_THREADS) s_pack[i] = bt.agent_pack[6 * (size_t)(a0 + own_lo) + i];
   // the own agents' layer counts and sizes in shared memory (TimedRoadmap(start): one layer with the start vertex), written
@@ -340,8 +296,6 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
     for (int i = tid; i < n_own * bt.L; i += IK_THREADS) s_vcnt[i] = (i % bt.L) == 0 ? 1 : 0;
     for (int i = tid; i < n_own; i += IK_THREADS) s_nl[i] = 1;
   }
-  if (s_w0f != nullptr)
-    for (int idx = tid; idx < IK_FRAG_SLICE; idx += IK_THREADS) s_w0f[idx] = __ldg(&ia.w0img[(size_t)s_lo * IK_FRAG_SLICE + idx]);
   __syncthreads();
 
   int t = 1, kt = 0, makespan = 0, steps = 0;
@@ -406,127 +360,77 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
     IK_MARK(0)
 
     if (ia.nn && any_learned) {
-      // ================= raster: crop bits of the OWN agents; task = (own agent, six consecutive words = two K-slices): lane l reads input
-      // 32 w + l of word w, so a load instruction covers 32 consecutive crop cells (two or three map rows), and a ballot is
-      // the word.  The centre's cost is loaded beside the crop (whether it is inside the map is known without it).
+      // ================= FOV crops and first layers of the OWN agents.  A warp builds six consecutive 32-bit words of an agent's
+      // crop bits: lane l reads input 32 w + l of word w, so a load instruction covers 32 consecutive crop cells (two or three map
+      // rows), and a ballot is the word (the centre's cost is loaded beside the crop: whether it is inside the map is known
+      // without it).  The same warp then adds up the table rows of the words' 24 bytes, lane = two of the 64 columns: 24
+      // independent 8-byte loads per lane, summed in byte order.  Quarter sums q0..q3 are combined as (q0 + q1) + (q2 + q3), by the
+      // tail (l0_split: a warp per quarter) or by the warp itself (a warp per agent), so the result does not depend on the split.
       {
         const uint8_t* occ = bt.occ + (size_t)b * M * M;
         const unsigned invF = 65536u / (unsigned)F + 1u;  // jj / F == (jj * invF) >> 16 for jj < F * F, F <= 41
-        for (int task = warp; task < n_own * 4; task += IK_WARPS) {
-          const int io = task >> 2, oct = task & 3, i = own_lo + io;
+        const int n_bytes = (KD + 7) >> 3;                // byte positions that hold inputs
+        const int split = ia.l0_split;
+        for (int task = warp; task < (split ? 4 * n_own : n_own); task += IK_WARPS) {
+          const int io = split ? task >> 2 : task, i = own_lo + io;
           const int cx0 = grid_cell(s_cur[2 * i], M), cy0 = grid_cell(s_cur[2 * i + 1], M);
           const bool centre_in = cx0 < M && cy0 < M;
           const uint16_t* cf = bt.ctg + (size_t)(a0 + i) * ctg_field_elems(M, 1);
           const int cc = centre_in ? (int)__ldg(&cf[ctg_index(cx0, cy0, M, 1)]) : -1;
           const int cx = cx0 - buf, cy = cy0 - buf;
-          int vc[6], vo[6];
-          bool isc[6];
+          float2 qs[4];
+#pragma unroll 1
+          for (int oct = split ? (task & 3) : 0; oct < (split ? (task & 3) + 1 : 4); ++oct) {
+            int vc[6], vo[6];
+            bool isc[6];
 #pragma unroll
-          for (int e = 0; e < 6; ++e) {
-            const int j = 32 * (6 * oct + e) + lane;
-            const int ch = j >= FF ? 1 : 0, jj = j - ch * FF;
-            const int xf = (int)(((unsigned)jj * invF) >> 16), yf = jj - xf * F;
-            const int x = cx + xf, y = cy + yf;
-            const bool ok = j < KD && centre_in && x >= 0 && x < M && y >= 0 && y < M;
-            isc[e] = ch != 0;
-            vc[e] = CTRM_UNREACH;
-            vo[e] = 1;
-            // a word lies in one channel except the one that straddles F^2: warp-uniform tests skip the other channel's index math
-            if (32 * (6 * oct + e) + 31 >= FF) vc[e] = (ok && ch) ? (int)__ldg(&cf[ctg_index(x, y, M, 1)]) : CTRM_UNREACH;
-            if (32 * (6 * oct + e) < FF) vo[e] = (ok && !ch) ? (int)__ldg(&occ[x * M + y]) : 1;
-          }
-          uint32_t mine = 0u;
+            for (int e = 0; e < 6; ++e) {
+              const int j = 32 * (6 * oct + e) + lane;
+              const int ch = j >= FF ? 1 : 0, jj = j - ch * FF;
+              const int xf = (int)(((unsigned)jj * invF) >> 16), yf = jj - xf * F;
+              const int x = cx + xf, y = cy + yf;
+              const bool ok = j < KD && centre_in && x >= 0 && x < M && y >= 0 && y < M;
+              isc[e] = ch != 0;
+              vc[e] = CTRM_UNREACH;
+              vo[e] = 1;
+              // a word lies in one channel except the one that straddles F^2: warp-uniform tests skip the other channel's index math
+              if (32 * (6 * oct + e) + 31 >= FF) vc[e] = (ok && ch) ? (int)__ldg(&cf[ctg_index(x, y, M, 1)]) : CTRM_UNREACH;
+              if (32 * (6 * oct + e) < FF) vo[e] = (ok && !ch) ? (int)__ldg(&occ[x * M + y]) : 1;
+            }
+            uint32_t mine = 0u;
 #pragma unroll
-          for (int e = 0; e < 6; ++e) {
-            const bool bit = isc[e] ? (vc[e] != CTRM_UNREACH && (cc == CTRM_UNREACH || vc[e] < cc)) : (vo[e] == 0);
-            const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
-            if (lane == e) mine = word;
+            for (int e = 0; e < 6; ++e) {
+              const bool bit = isc[e] ? (vc[e] != CTRM_UNREACH && (cc == CTRM_UNREACH || vc[e] < cc)) : (vo[e] == 0);
+              const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+              if (lane == e) mine = word;
+            }
+            // table rows of this quarter's bytes (byte positions 24 oct .. 24 oct + 23)
+            float2 v[24];
+            const float2* lut = reinterpret_cast<const float2*>(ia.lut) + lane;
+#pragma unroll
+            for (int gb = 0; gb < 24; ++gb) {
+              const uint32_t word = __shfl_sync(0xFFFFFFFFu, mine, gb >> 2);
+              const int pos = 24 * oct + gb;
+              v[gb] = pos < n_bytes ? __ldg(lut + ((size_t)pos * 256 + ((word >> (8 * (gb & 3))) & 0xFFu)) * 32) : make_float2(0.f, 0.f);
+            }
+            float2 acc = v[0];
+#pragma unroll
+            for (int gb = 1; gb < 24; ++gb) { acc.x += v[gb].x; acc.y += v[gb].y; }
+            if (split) {
+              *reinterpret_cast<float2*>(s_l0p + ((size_t)(io * 4 + oct)) * 64 + 2 * lane) = acc;
+            } else {
+              if (oct == 0) qs[0] = acc; else if (oct == 1) qs[1] = acc; else if (oct == 2) qs[2] = acc; else qs[3] = acc;
+            }
           }
-          if (lane < 6) {
-            const int w = 6 * oct + lane;
-            uint32_t* dst = cluster.map_shared_rank(s_bits, (unsigned)((w / 3) / spc));
-            dst[i * IK_WORDS + w] = mine;
-          }
+          if (!split)
+            *reinterpret_cast<float2*>(s_l0p + (size_t)io * 64 + 2 * lane) =
+                make_float2((qs[0].x + qs[1].x) + (qs[2].x + qs[3].x), (qs[0].y + qs[1].y) + (qs[2].y + qs[3].y));
         }
       }
       IK_MARK(1)
-      IK_CLUSTER_SYNC();  // every agent's bits of this CTA's slices have arrived
-      IK_MARK(2)
-      // ================= fov L0 on the tensor cores: A = crop bits as bf16 0/1 (exact), B = the three-way bf16 split of W0
-      // (exact to 24 bits), fp32 accumulators, the large (hi) and the small (mid, lo) products in separate accumulators.
-      // task = (n-tile of 8 columns, m-tile of 16 agents); the CTA's slices are summed as a binary tree in slice order.
-      {
-        const int gid = lane >> 2, tig = lane & 3;
-        const int n_mt = (n + 15) >> 4;
-        for (int task = warp; task < 8 * n_mt; task += IK_WARPS) {
-          const int nt = task & 7, mt = task >> 3;
-          const int r0 = 16 * mt + gid, r1 = r0 + 8;
-          float tot[4] = {0.f, 0.f, 0.f, 0.f};
-          if (s_w0f != nullptr) {  // one resident slice
-            uint2 f[18];
-#pragma unroll
-            for (int q = 0; q < 18; ++q) f[q] = s_w0f[(nt * 18 + q) * 32 + lane];
-            l0_slice_mma(s_bits, r0, r1, s_lo, tig, f, tot);
-          } else {
-            float l0v[4], l1v[4], l2v[4];
-            uint2 f[18], fn[18];
-            const uint2* img = ia.w0img + (size_t)nt * 18 * 32 + lane;
-#pragma unroll
-            for (int q = 0; q < 18; ++q) f[q] = __ldg(img + (size_t)s_lo * IK_FRAG_SLICE + q * 32);
-#pragma unroll 1
-            for (int si = 0; si < spc; ++si) {
-              {
-                if (si + 1 < spc) {
-#pragma unroll
-                  for (int q = 0; q < 18; ++q) fn[q] = __ldg(img + (size_t)(s_lo + si + 1) * IK_FRAG_SLICE + q * 32);
-                }
-                float p[4];
-                l0_slice_mma(s_bits, r0, r1, s_lo + si, tig, f, p);
-                // binary-tree carry: slices (0 1) (2 3) ... then pairs of pairs
-                if (si & 1) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) p[i] = l0v[i] + p[i];
-                  if (si & 2) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) p[i] = l1v[i] + p[i];
-                    if (si & 4) {
-#pragma unroll
-                      for (int i = 0; i < 4; ++i) p[i] = l2v[i] + p[i];
-                    } else {
-#pragma unroll
-                      for (int i = 0; i < 4; ++i) l2v[i] = p[i];
-                    }
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) l1v[i] = p[i];
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) l0v[i] = p[i];
-                }
-                if (si + 1 == spc) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) tot[i] = p[i];
-                }
-#pragma unroll
-                for (int q = 0; q < 18; ++q) f[q] = fn[q];
-              }
-            }
-          }
-          const int col = 8 * nt + 2 * tig;
-          if (r0 < n) {
-            float* dst = cluster.map_shared_rank(s_part, (unsigned)s_owner[r0]);
-            *reinterpret_cast<float2*>(dst + ((size_t)r * own_max + s_oidx[r0]) * 64 + col) = make_float2(tot[0], tot[1]);
-          }
-          if (r1 < n) {
-            float* dst = cluster.map_shared_rank(s_part, (unsigned)s_owner[r1]);
-            *reinterpret_cast<float2*>(dst + ((size_t)r * own_max + s_oidx[r1]) * 64 + col) = make_float2(tot[2], tot[3]);
-          }
-        }
-      }
-      IK_CLUSTER_SYNC();
+      __syncthreads();  // the first-layer sums of the own agents are in place
       IK_MARK(3)
-      // ================= fov tails of the own agents: warp = (own agent, encoder), the whole chain partial sums -> hidden 1 ->
+      // ================= fov tails of the own agents: warp = (own agent, encoder), the whole chain quarter sums -> hidden 1 ->
       // hidden 2 -> embedding (-> vain_proj) inside the warp with __syncwarp between the layers — no block-wide barrier
       {
         const float* b0 = Wp(off.fov_b0);
@@ -537,13 +441,13 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
           float* h1 = u_h1 + io * 64 + 32 * e;
           {
             const int o = 32 * e + lane;
-            const float* pq = s_part + (size_t)io * 64 + o;
-            const size_t st = (size_t)own_max * 64;
             float sum;
-            if (C == 8) sum = ((pq[0] + pq[st]) + (pq[2 * st] + pq[3 * st])) + ((pq[4 * st] + pq[5 * st]) + (pq[6 * st] + pq[7 * st]));
-            else if (C == 4) sum = (pq[0] + pq[st]) + (pq[2 * st] + pq[3 * st]);
-            else if (C == 2) sum = pq[0] + pq[st];
-            else sum = pq[0];
+            if (ia.l0_split) {
+              const float* pq = s_l0p + (size_t)io * 256 + o;
+              sum = (pq[0] + pq[64]) + (pq[128] + pq[192]);
+            } else {
+              sum = s_l0p[(size_t)io * 64 + o];
+            }
             h0[lane] = fmaxf(b0[o] + sum, 0.f);
           }
           __syncwarp();
@@ -1126,11 +1030,11 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-size_t instance_w0_image_bytes() { return (size_t)IK_SLICES * IK_FRAG_SLICE * sizeof(uint2); }
+size_t instance_w0_image_bytes() { return (size_t)IK_BYTES * 256 * 64 * sizeof(float); }
 
 int launch_instance_w0_image(const float* d_blob, const ctrm_weight_offsets_t& off, int F, uint8_t* d_image, cudaStream_t st) {
-  const int total = IK_SLICES * IK_FRAG_SLICE;
-  instance_w0_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_blob + off.fov_w0, 2 * F * F, reinterpret_cast<uint2*>(d_image));
+  const int total = IK_BYTES * 256 * 64;
+  instance_w0_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_blob + off.fov_w0, 2 * F * F, reinterpret_cast<float*>(d_image));
   CTRM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1138,10 +1042,10 @@ int launch_instance_w0_image(const float* d_blob, const ctrm_weight_offsets_t& o
 // shared memory of one CTA at cluster size C; fills the layout-dependent fields of `ia`
 static size_t instance_smem_bytes(InstArgs& ia, int n_max, int K, int L, int C) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
-  ia.w0_frag = C == 8 ? 1 : 0;  // one K-slice per CTA: its mma.sync fragments stay resident
   const int own = (n_max + C - 1) / C;
   ia.own_max = own;
   ia.vc_smem = (size_t)own * L * 4 <= 12288 ? 1 : 0;
+  ia.l0_split = own <= 16 ? 1 : 0;  // a warp per quarter of an agent's inputs while the quarter sums (1 KB per agent) stay small
   size_t s = al((size_t)ia.n_w * 4);
   auto take = [&](size_t bytes) { const size_t at = s; s += al(bytes); return (int)at; };
   IkLayout& y = ia.lay;
@@ -1149,14 +1053,12 @@ static size_t instance_smem_bytes(InstArgs& ia, int n_max, int K, int L, int C) 
   y.prev = take(IK_NMAX * 2 * 8);
   y.goal = take(IK_NMAX * 2 * 8);
   y.nxt = take(2 * IK_NMAX * 2 * 8);
-  y.bits = take(IK_NMAX * IK_WORDS * 4);
   y.vp = take(IK_NMAX * 32 * 4);
   y.eself = take((size_t)own * 32 * 4);
-  y.part = take((size_t)C * own * 64 * 4);
+  y.l0p = take((size_t)own * (ia.l0_split ? 4 : 1) * 64 * 4);
   y.radf = take(IK_NMAX * 4);
   y.speedf = take(IK_NMAX * 4);
-  y.flags = take(6 * IK_NMAX);
-  y.w0f = ia.w0_frag ? take((size_t)IK_FRAG_SLICE * 8) : 0;
+  y.flags = take(4 * IK_NMAX);
   y.pack = take((size_t)own * 6 * 8);
   y.samples = take((size_t)own * K * 3 * 4);
   y.nl = take((size_t)own * 4);
@@ -1225,10 +1127,10 @@ static int launch_instance_with(Kernel narrow, Kernel wide, SmemAttrCache& attr_
 int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, cudaStream_t st) {
   if (bt.B <= 0) return 0;
   if (C != 0 && C != 1 && C != 2 && C != 4 && C != 8) return ctrm_fail(-1, "instance kernel: cluster size must be 0 (auto), 1, 2, 4 or 8");
-  if (m.inst_w0_img == nullptr) return ctrm_fail(-1, "instance kernel: fragment image of the FOV first layer missing");
+  if (m.inst_w0_img == nullptr) return ctrm_fail(-1, "instance kernel: table of the FOV first layer missing");
   InstArgs ia;
   ia.blob = m.blob;
-  ia.w0img = reinterpret_cast<const uint2*>(m.inst_w0_img);
+  ia.lut = reinterpret_cast<const float*>(m.inst_w0_img);
   ia.off = m.off;
   ia.F = m.desc.fov_size;
   ia.num_neighbors = m.desc.num_neighbors;
@@ -1237,7 +1139,7 @@ int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, c
   ia.nn = nn;
   ia.C = 1;
   ia.n_w = m.off.total - m.off.fov_b0;
-  ia.w0_frag = 0;
+  ia.l0_split = 0;
   ia.vc_smem = 0;
   ia.own_max = bt.n_max;
   ia.lay = IkLayout{};
@@ -1258,8 +1160,8 @@ int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, c
     CTRM_CUDA_OK(cudaStreamSynchronize(st));
     CTRM_CUDA_OK(cudaMemcpy(h.data(), ia.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(ia.prof);
-    static const char* names[IK_NPROF] = {"gate", "raster", "bar1", "fov_l0+bar2", "fov_tail", "bar3", "rank", "pair_mlp", "softmax",
-                                          "cvae_l0", "prior", "decode", "select", "merge", "bar4", "advance"};
+    static const char* names[IK_NPROF] = {"gate", "raster+fov_l0", "-", "sync", "fov_tail", "bar1", "rank", "pair_mlp", "softmax",
+                                          "cvae_l0", "prior", "decode", "select", "merge", "bar2", "advance"};
     for (size_t cta : {(size_t)0, (size_t)bt.B * Cu - 1}) {
       fprintf(stderr, "[instance kernel] C=%d CTA %zu Mcycles:", Cu, cta);
       for (int i = 0; i < IK_NPROF; ++i) fprintf(stderr, " %s %.2f", names[i], 1e-6 * (double)h[cta * IK_NPROF + i]);

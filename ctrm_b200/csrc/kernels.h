@@ -26,7 +26,7 @@ struct DevModel {
   const uint8_t* decode_img;
   const uint8_t* agent_img;
   const uint8_t* fov_img;
-  const uint8_t* inst_w0_img;  // mma.sync B fragments of the FOV first layer for the per-instance kernel (instance.cu)
+  const uint8_t* inst_w0_img;  // the FOV first layer as a table over the bytes of the binary input, for the per-instance kernel (instance.cu)
 };
 size_t fov_encode_image_bytes();
 int launch_fov_encode_image(const float* d_blob, const ctrm_weight_offsets_t& off, uint8_t* d_image, cudaStream_t st);
