@@ -520,6 +520,7 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
         }
         group_bar(g);
         IK_MARK(6)
+        if (prof) s_prof[2] += 1000000;  // occurrences of the learned chain on thread 0's agent (printed in millions)
         // ---- a warp takes four (agent, slot) pair rows through the pair features (compiled.py:30-97; slot 0 = the agent
         //      itself, slot s = its s-th nearest) and the three layers of AgentEncoder (agent_encoder.py:34-65), lane = column
         {
@@ -578,6 +579,22 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
           gumbel_rsqrt(dk0, &rsa, &rsb);
           asm volatile("" : "+f"(rsa), "+f"(rsb));  // materialise here, beside the softmax: the compiler would sink it to its use
         }
+        // ... and start the first layers of indicator | encoder_input | decoder (x rows): role = net + 1, lane = (k strand, four
+        // columns) in the conflict-free layout of splitk_32.  Inputs 0..39 of X (self_info, e_self) do not depend on the attention:
+        // their part is summed here, the 32 comm inputs follow once the softmax warp has written them
+        const int l0q = lane & 7, l0kq = lane >> 3;
+        const float* l0W = gw == 1 ? Wp(off.ind_w0) : (gw == 2 ? Wp(off.enc_w0) : Wp(off.dec_w0) + 64 * 32);
+        float4 l0acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gw != 0) {
+#pragma unroll 5
+          for (int kk = 0; kk < 10; ++kk) {
+            const int k = 10 * l0kq + kk;
+            const float4 w = *reinterpret_cast<const float4*>(l0W + k * 32 + 4 * l0q);
+            const float v = k < 8 ? gs.X[k] : s_eself[io * 32 + k - 8];
+            l0acc.x = fmaf(v, w.x, l0acc.x); l0acc.y = fmaf(v, w.y, l0acc.y); l0acc.z = fmaf(v, w.z, l0acc.z); l0acc.w = fmaf(v, w.w, l0acc.w);
+          }
+          asm volatile("" : "+f"(l0acc.x), "+f"(l0acc.y), "+f"(l0acc.z), "+f"(l0acc.w));
+        }
         if (gw == 0) {
           const float* y0 = gs.y;
           const int s = lane;
@@ -605,25 +622,21 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
         }
         group_bar(g);
         IK_MARK(8)
-        // ---- first layers of indicator | encoder_input | decoder (x rows) side by side: warp = net, lane = (k strand of 18, four
-        //      columns) in the conflict-free layout of splitk_32
-        if (gt < 96) {
-          const int net = gt >> 5, kq = (gt >> 3) & 3, q = gt & 7;
-          const float* Wm = net == 0 ? Wp(off.ind_w0) : (net == 1 ? Wp(off.enc_w0) : Wp(off.dec_w0) + 64 * 32);
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 6
-          for (int kk = 0; kk < CTRM_DIM_X / 4; ++kk) {
-            const int k = (CTRM_DIM_X / 4) * kq + kk;
-            const float4 w = *reinterpret_cast<const float4*>(Wm + k * 32 + 4 * q);
+        // ---- the comm part of the first layers (inputs 40..71), the strands meet by shuffle
+        if (gw != 0) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const int k = 40 + 8 * l0kq + kk;
+            const float4 w = *reinterpret_cast<const float4*>(l0W + k * 32 + 4 * l0q);
             const float v = gs.X[k];
-            acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y); acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+            l0acc.x = fmaf(v, w.x, l0acc.x); l0acc.y = fmaf(v, w.y, l0acc.y); l0acc.z = fmaf(v, w.z, l0acc.z); l0acc.w = fmaf(v, w.w, l0acc.w);
           }
 #pragma unroll
           for (int d = 8; d <= 16; d <<= 1) {
-            acc.x += __shfl_xor_sync(0xFFFFFFFFu, acc.x, d); acc.y += __shfl_xor_sync(0xFFFFFFFFu, acc.y, d);
-            acc.z += __shfl_xor_sync(0xFFFFFFFFu, acc.z, d); acc.w += __shfl_xor_sync(0xFFFFFFFFu, acc.w, d);
+            l0acc.x += __shfl_xor_sync(0xFFFFFFFFu, l0acc.x, d); l0acc.y += __shfl_xor_sync(0xFFFFFFFFu, l0acc.y, d);
+            l0acc.z += __shfl_xor_sync(0xFFFFFFFFu, l0acc.z, d); l0acc.w += __shfl_xor_sync(0xFFFFFFFFu, l0acc.w, d);
           }
-          if (kq == 0) *reinterpret_cast<float4*>(gs.p0 + 32 * net + 4 * q) = acc;
+          if (l0kq == 0) *reinterpret_cast<float4*>(gs.p0 + 32 * (gw - 1) + 4 * l0q) = l0acc;
         }
         group_bar(g);
         IK_MARK(9)
@@ -1160,7 +1173,7 @@ int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, c
     CTRM_CUDA_OK(cudaStreamSynchronize(st));
     CTRM_CUDA_OK(cudaMemcpy(h.data(), ia.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(ia.prof);
-    static const char* names[IK_NPROF] = {"gate", "raster+fov_l0", "-", "sync", "fov_tail", "bar1", "rank", "pair_mlp", "softmax",
+    static const char* names[IK_NPROF] = {"gate", "raster+fov_l0", "#learned", "sync", "fov_tail", "bar1", "rank", "pair_mlp", "softmax",
                                           "cvae_l0", "prior", "decode", "select", "merge", "bar2", "advance"};
     for (size_t cta : {(size_t)0, (size_t)bt.B * Cu - 1}) {
       fprintf(stderr, "[instance kernel] C=%d CTA %zu Mcycles:", Cu, cta);
