@@ -63,7 +63,7 @@ namespace cg = cooperative_groups;
 
 // byte offsets of the shared-memory regions (computed by the host, ik_layout)
 struct IkLayout {
-  int cur, prev, goal, nxt, vp, eself, l0p, radf, speedf, flags, pack, samples, nl, vcnt, obs, prof, U, total;
+  int cur, prev, goal, nxt, vp, eself, l0p, radf, speedf, flags, pack, samples, nl, vcnt, obs, prof, pre, U, total;
 };
 
 struct InstArgs {
@@ -75,10 +75,17 @@ struct InstArgs {
   int C;         // CTAs per instance
   int n_w;       // floats of the blob from fov_b0 on (resident in shared memory)
   int l0_split;  // a warp takes a quarter of an agent's inputs (few agents per CTA) instead of a whole agent
+  int pre_rank;  // the neighbours of the own learned agents are ranked beside the FOV tails (PreAgent records)
   int vc_smem;   // the own agents' layer counts live in shared memory during the roll-outs
   int own_max;   // ceil(n_max / C)
   IkLayout lay;
   long long* prof;  // optional [B * C][IK_NPROF] clock cycles per phase (CTRM_INSTANCE_PROF=1)
+};
+
+// neighbour order of one own agent, ranked beside the FOV tails by a warp that has none (it depends on positions only)
+struct __align__(16) PreAgent {
+  unsigned long long key[IK_NMAX];
+  int order[IK_PMAX];
 };
 
 // scratch of one group (one agent at a time)
@@ -273,6 +280,7 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
   int32_t* s_nl = reinterpret_cast<int32_t*>(ik_smem + ly_.nl);
   int32_t* s_vcnt = ia.vc_smem ? reinterpret_cast<int32_t*>(ik_smem + ly_.vcnt) : nullptr;
   double* s_obs = reinterpret_cast<double*>(ik_smem + ly_.obs);        // [IK_GROUPS][3 * IK_OBS_MAX]
+  PreAgent* s_pre = reinterpret_cast<PreAgent*>(ik_smem + ly_.pre);  // [own_max] when ia.pre_rank
   uint8_t* U = ik_smem + ly_.U;
   GroupScratch& gs = reinterpret_cast<GroupScratch*>(U)[g];  // agent phases
   float* u_h0 = reinterpret_cast<float*>(U);                 // fov tail: [own agents][64]
@@ -435,7 +443,28 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
       {
         const float* b0 = Wp(off.fov_b0);
         const int q = lane & 7, kq = lane >> 3;
-        for (int task = warp; task < 2 * n_own; task += IK_WARPS) {
+        for (int task = warp; task < (ia.pre_rank ? 3 : 2) * n_own; task += IK_WARPS) {
+          if (task >= 2 * n_own) {
+            // ---- a warp without a tail: k nearest neighbours of an own learned agent (format_input.py:239-243:
+            //      float32(sqrt_f64(dx^2 + dy^2)) keys, ties by index, self first)
+            const int pio = task - 2 * n_own, i = own_lo + pio;
+            if (!(s_learned[i] & 1)) continue;
+            PreAgent& pa = s_pre[pio];
+            const double cix = s_cur[2 * i], ciy = s_cur[2 * i + 1];
+            for (int j = lane; j < n; j += 32) {
+              const double dx = f64sub(s_cur[2 * j], cix), dy = f64sub(s_cur[2 * j + 1], ciy);
+              const float d = __double2float_rn(__dsqrt_rn(f64add(f64mul(dx, dx), f64mul(dy, dy))));
+              pa.key[j] = (j == i) ? 0ull : (((unsigned long long)(__float_as_uint(d) + 1u) << 32) | (unsigned)j);
+            }
+            __syncwarp();
+            for (int j = lane; j < n; j += 32) {
+              const unsigned long long kj = pa.key[j];
+              int rank = 0;
+              for (int j2 = 0; j2 < n; ++j2) rank += pa.key[j2] < kj ? 1 : 0;
+              if (rank <= k_nb) pa.order[rank] = j;
+            }
+            continue;
+          }
           const int io = task >> 1, e = task & 1;
           float* h0 = u_h0 + io * 64 + 32 * e;
           float* h1 = u_h1 + io * 64 + 32 * e;
@@ -498,6 +527,8 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
       if (ia.nn && learned) {
         // ---- k nearest neighbours (format_input.py:239-243): float32(sqrt_f64(dx^2 + dy^2)) keys, ties by index, self first
         const double cix = s_cur[2 * i], ciy = s_cur[2 * i + 1];
+        const int* p_order = ia.pre_rank ? s_pre[io].order : gs.order;
+        if (!ia.pre_rank) {
         if (gt < n) {
           const int j = gt;
           const double dx = f64sub(s_cur[2 * j], cix), dy = f64sub(s_cur[2 * j + 1], ciy);
@@ -519,6 +550,7 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
           if (act && part == 0 && rank <= k_nb) gs.order[rank] = j;
         }
         group_bar(g);
+        }
         IK_MARK(6)
         if (prof) s_prof[2] += 1000000;  // occurrences of the learned chain on thread 0's agent (printed in millions)
         // ---- a warp takes four (agent, slot) pair rows through the pair features (compiled.py:30-97; slot 0 = the agent
@@ -529,7 +561,7 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
             const int s = p0 + lane;
             float* info = gs.info + s * 12;
             if (s <= k_nb) {
-              const int j = gs.order[s];
+              const int j = p_order[s];
               ik_nvm(f64sub(s_cur[2 * j], cix), f64sub(s_cur[2 * j + 1], ciy), info + 0);
               ik_nvm(f64sub(s_goal[2 * j], cix), f64sub(s_goal[2 * j + 1], ciy), info + 3);
               ik_nvm(f64sub(s_prev[2 * j], cix), f64sub(s_prev[2 * j + 1], ciy), info + 6);
@@ -1078,6 +1110,11 @@ static size_t instance_smem_bytes(InstArgs& ia, int n_max, int K, int L, int C) 
   y.vcnt = ia.vc_smem ? take((size_t)own * L * 4) : 0;
   y.obs = take((size_t)IK_GROUPS * 3 * IK_OBS_MAX * 8);
   y.prof = take(IK_NPROF * 8);
+  {  // the PreAgent records if they still fit
+    const size_t u_bytes = std::max((size_t)IK_GROUPS * sizeof(GroupScratch), (size_t)own * 128 * 4);
+    ia.pre_rank = s + al((size_t)own * sizeof(PreAgent)) + al(u_bytes) <= (size_t)227 * 1024 ? 1 : 0;
+    y.pre = ia.pre_rank ? take((size_t)own * sizeof(PreAgent)) : 0;
+  }
   y.U = take(std::max((size_t)IK_GROUPS * sizeof(GroupScratch), (size_t)own * 128 * 4));
   y.total = (int)s;
   return s;
@@ -1153,6 +1190,7 @@ int launch_instance_rollout(const DevModel& m, const Batch& bt, int nn, int C, c
   ia.C = 1;
   ia.n_w = m.off.total - m.off.fov_b0;
   ia.l0_split = 0;
+  ia.pre_rank = 0;
   ia.vc_smem = 0;
   ia.own_max = bt.n_max;
   ia.lay = IkLayout{};
