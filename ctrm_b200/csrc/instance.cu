@@ -63,7 +63,7 @@ namespace cg = cooperative_groups;
 
 // byte offsets of the shared-memory regions (computed by the host, ik_layout)
 struct IkLayout {
-  int cur, prev, goal, nxt, vp, eself, l0p, radf, speedf, flags, pack, samples, nl, vcnt, obs, prof, pre, U, total;
+  int cur, prev, goal, nxt, vp, eself, l0p, radf, speedf, flags, pack, samples, nl, vcnt, obs, prof, pre, wvf, U, total;
 };
 
 struct InstArgs {
@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
   int32_t* s_vcnt = ia.vc_smem ? reinterpret_cast<int32_t*>(ik_smem + ly_.vcnt) : nullptr;
   double* s_obs = reinterpret_cast<double*>(ik_smem + ly_.obs);        // [IK_GROUPS][3 * IK_OBS_MAX]
   PreAgent* s_pre = reinterpret_cast<PreAgent*>(ik_smem + ly_.pre);  // [own_max] when ia.pre_rank
+  float* s_wvf = reinterpret_cast<float*>(ik_smem + ly_.wvf);  // [32][32] + [32]: vain tail's last layer fused with agent.mlp.0's vain rows
   uint8_t* U = ik_smem + ly_.U;
   GroupScratch& gs = reinterpret_cast<GroupScratch*>(U)[g];  // agent phases
   float* u_h0 = reinterpret_cast<float*>(U);                 // fov tail: [own agents][64]
@@ -303,6 +304,16 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
   if (s_vcnt != nullptr) {
     for (int i = tid; i < n_own * bt.L; i += IK_THREADS) s_vcnt[i] = (i % bt.L) == 0 ? 1 : 0;
     for (int i = tid; i < n_own; i += IK_THREADS) s_nl[i] = 1;
+  }
+  __syncthreads();
+  // vain_proj = b0 + W0v^T (W2v^T h + b2v) (fov_encoder.py:34-59, agent_encoder.py:57-60) has no non-linearity between its two
+  // layers: one 32 x 32 layer with the product matrix (summed in float64) instead of two in a row on every step's critical path
+  for (int idx = tid; idx < 33 * 32; idx += IK_THREADS) {
+    const int k = idx >> 5, c2 = idx & 31;  // k = 32: the bias row
+    double acc = k == 32 ? (double)Wp(off.ag_b0)[c2] : 0.0;
+    for (int c = 0; c < 32; ++c)
+      acc += (double)(k == 32 ? Wp(off.fovv_b2)[c] : Wp(off.fovv_w2)[k * 32 + c]) * (double)Wp(off.ag_w0v)[c * 32 + c2];
+    s_wvf[idx] = (float)acc;
   }
   __syncthreads();
 
@@ -489,23 +500,18 @@ __global__ void __launch_bounds__(IK_THREADS, 1) instance_rollout_kernel(Batch b
             }
           }
           __syncwarp();
-          {  // hidden 2 -> e_self (shared memory) | e_vain (back into h0)
-            const float4 acc = splitk_32(h1, Wp(e ? off.fovv_w2 : off.fovs_w2), q, kq);
-            if (kq == 0) {
-              const float4 bb = *reinterpret_cast<const float4*>(Wp(e ? off.fovv_b2 : off.fovs_b2) + 4 * q);
-              *reinterpret_cast<float4*>((e ? h0 : s_eself + io * 32) + 4 * q) =
-                  make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w);
-            }
-          }
-          if (e) {
-            // vain_proj = b0 + W0[11:43]^T e_vain (agent_encoder.py:57-60), stored into every CTA of the cluster (strand kq ->
-            // CTAs kq and kq + 4: the four strands hold the same sum after the shuffles)
-            __syncwarp();
-            const float4 acc = splitk_32(h0, Wp(off.ag_w0v), q, kq);
-            const float4 bb = *reinterpret_cast<const float4*>(Wp(off.ag_b0) + 4 * q);
+          {  // hidden 2 -> e_self (shared memory) | vain_proj = b0 + W0[11:43]^T e_vain (agent_encoder.py:57-60) through the fused
+             // matrix, stored into every CTA of the cluster (strand kq -> CTAs kq and kq + 4: the four strands hold the same sum
+             // after the shuffles)
+            const float4 acc = splitk_32(h1, e ? s_wvf : Wp(off.fovs_w2), q, kq);
+            const float4 bb = *reinterpret_cast<const float4*>((e ? s_wvf + 32 * 32 : Wp(off.fovs_b2)) + 4 * q);
             const float4 v = make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w);
-            for (int c = kq; c < C; c += 4)
-              *reinterpret_cast<float4*>(cluster.map_shared_rank(s_vp, (unsigned)c) + (size_t)(own_lo + io) * 32 + 4 * q) = v;
+            if (e) {
+              for (int c = kq; c < C; c += 4)
+                *reinterpret_cast<float4*>(cluster.map_shared_rank(s_vp, (unsigned)c) + (size_t)(own_lo + io) * 32 + 4 * q) = v;
+            } else if (kq == 0) {
+              *reinterpret_cast<float4*>(s_eself + io * 32 + 4 * q) = v;
+            }
           }
         }
       }
@@ -1110,6 +1116,7 @@ static size_t instance_smem_bytes(InstArgs& ia, int n_max, int K, int L, int C) 
   y.vcnt = ia.vc_smem ? take((size_t)own * L * 4) : 0;
   y.obs = take((size_t)IK_GROUPS * 3 * IK_OBS_MAX * 8);
   y.prof = take(IK_NPROF * 8);
+  y.wvf = take(33 * 32 * 4);
   {  // the PreAgent records if they still fit
     const size_t u_bytes = std::max((size_t)IK_GROUPS * sizeof(GroupScratch), (size_t)own * 128 * 4);
     ia.pre_rank = s + al((size_t)own * sizeof(PreAgent)) + al(u_bytes) <= (size_t)227 * 1024 ? 1 : 0;
