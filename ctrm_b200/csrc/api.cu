@@ -735,7 +735,7 @@ struct StepProfiler {
 };
 
 // batches up to this many instances take the per-instance kernel (CTRM_INSTANCE_MAX_BATCH moves the threshold, 0 = never).
-// Default: the number of SMs — one CTA per instance still has every instance resident at once and measured 133 ms against the
+// Default: the number of SMs — one CTA per instance still has every instance resident at once and measured 114 ms against the
 // batch path's 148 ms at 148 instances (profiles/r2_instance_kernel.md); a second wave of clusters doubles its time.
 static int instance_kernel_max_batch(int device) {
   const char* e = getenv("CTRM_INSTANCE_MAX_BATCH");
