@@ -108,9 +108,9 @@ def test_full_size_batch_properties_and_batch_independence():
 
 def test_instance_kernel_properties_and_cluster_sizes():
     """The per-instance cluster kernel (ctrm_set_step_kernel 3; the default for small batches) free-running at the headline
-    roll-out sizes: every edge valid, deterministic, an instance's result independent of the batch it is built in, and — for
-    the cluster sizes that evaluate the FOV first layer on the CUDA cores (1, 2, 4 CTAs per instance; 8 uses mma.sync) —
-    independent of the cluster size"""
+    roll-out sizes: every edge valid, deterministic, an instance's result independent of the batch it is built in and of the
+    cluster size (1, 2, 4, 8 CTAs per instance: a warp per agent or per quarter of its FOV inputs, the step as one warp or
+    one group of four warps per agent — the same sums in the same order, the same fp64 operations)"""
     import os
 
     from ctrm_b200 import RoadmapBuilder
@@ -142,7 +142,7 @@ def test_instance_kernel_properties_and_cluster_sizes():
             os.environ["CTRM_INSTANCE_CLUSTER"] = str(c)
             by_c[c] = bld.build(instances, seed=3, **prm).copy()
         assert same(by_c[8], csr)
-        assert same(by_c[1], by_c[2]) and same(by_c[1], by_c[4])
+        assert same(by_c[1], by_c[2]) and same(by_c[1], by_c[4]) and same(by_c[1], by_c[8])
         for b in (0, 5):
             _check_instance(by_c[1], b, instances[b])
         # the default choice for a handful of instances is this kernel
